@@ -1,0 +1,223 @@
+/* qtb200.h -- C ABI of the B200-native QuantTorch quantized-forward kernels.
+ *
+ * One shared library (libqtb200.so, built by __graft_entry__.build() with
+ * nvcc -gencode arch=compute_100a,code=sm_100a).  Plain C: device pointers,
+ * sizes, POD structs, a cudaStream_t passed as void*.  No torch types.
+ *
+ * The reference (Enderdead/Pytorch_Quantize_impls, "QuantTorch") has no FFI of
+ * its own: every quantized layer is a Python fake-quant op followed by a dense
+ * fp32 torch.nn.functional.linear / conv2d.  Each entry point below therefore
+ * cites the reference Python code (path:line under /root/reference) whose work
+ * it replaces; the Python binding a maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative QT_E* code on failure;
+ *     qt_last_error() returns a thread-local message for the last failure.
+ *   - all data pointers are DEVICE pointers owned by the caller; nothing is
+ *     allocated, freed or synchronised inside the library; every launch goes
+ *     to the stream passed in (stream-ordered, re-entrant, thread-safe).
+ *   - matrices are row-major; "ld" arguments are in ELEMENTS of that matrix.
+ *   - bit-packed rows: bit i of uint32 word j <-> column 32 j + i; 1 <-> +1.
+ */
+#ifndef QTB200_H
+#define QTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QT_VERSION 100
+
+enum {
+  QT_OK = 0,
+  QT_EINVAL = -1,      /* bad argument (null pointer, misaligned ld, unsupported bit width ...) */
+  QT_ECUDA = -2,       /* CUDA runtime / driver error (message holds cudaGetErrorString) */
+  QT_EUNSUPPORTED = -3 /* device is not sm_100 or shape not supported by the requested kernel */
+};
+
+int qt_version(void);
+const char* qt_last_error(void);
+/* sm major/minor, SM count, 1 if tcgen05 kernels can run on `device`. */
+int qt_device_caps(int device, int* sm_major, int* sm_minor, int* num_sms, int* has_tcgen05);
+
+/* ------------------------------------------------------------------------
+ * Activation quantizers (elementwise + per-row reductions), one pass over x.
+ * Replaces the 3..10 separate ATen elementwise passes of
+ *   safeSign                     QuantTorch/functions/common.py:4-7
+ *   BinaryConnectDeterministic   QuantTorch/functions/binary_connect.py:22-28
+ *   TernaryConnectDeterministic  QuantTorch/functions/terner_connect.py:24-27
+ *   _quantize / DorefaQuant      QuantTorch/functions/dorefa_connect.py:11-25,49-63
+ *   _quantOpXnor (dim=1)         QuantTorch/functions/xnor_connect.py:20-28
+ *   LogQuant / LinQuant          QuantTorch/functions/log_lin_connect.py:29-32,61-68
+ * and additionally emits the low-bit operand the contraction kernels consume.
+ * ---------------------------------------------------------------------- */
+enum {
+  QT_Q_SIGN = 0,     /* +1 iff !(x<0)                         codes {-1,+1}          */
+  QT_Q_TERNARY = 1,  /* x>=.5 -> 1, -.5<=x<.5 -> 0, else -1   codes {-1,0,+1}        */
+  QT_Q_DOREFA = 2,   /* c = rint((2^k-1) x), y = fl(1/n) c    codes c (unclamped)    */
+  QT_Q_XNOR_ROW = 3, /* sign(x) * mean(x,row)  (torch.sign)   codes {-1,0,+1}, row_scale = mean */
+  QT_Q_LOG = 4,      /* sign(x) 2^clamp(round(log2|x|), fsr-2^bw, fsr)   (fp32 only) */
+  QT_Q_LIN = 5,      /* sign(x) clamp(round(|x|/step) step, 0, 2^fsr)    (fp32 only) */
+  QT_Q_SPLIT = 6     /* no quantisation: bf16 hi/lo split of x (codes_bf16 = hi plane, plane 1 = lo) */
+};
+
+typedef struct QtActQuant {
+  int mode;             /* QT_Q_* */
+  int bit_width;        /* DoReFa k (2..8), Log/Lin bit width */
+  int fsr;              /* Log/Lin full-scale range */
+  int with_sign;        /* Log/Lin */
+  const float* x;       /* [rows, ld_x] fp32 */
+  int64_t rows, cols, ld_x;
+  float* y;             /* optional fp32 fake-quant result [rows, ld_y] (the reference op's return value) */
+  int64_t ld_y;
+  void* codes;          /* optional low-bit operand, [rows, ld_codes] of int8/uint8 or bf16 (see codes_kind);
+                           columns cols..ld_codes-1 are zero-filled */
+  int codes_kind;       /* 0 = none, 1 = int8, 2 = uint8, 3 = bf16, 4 = bf16 hi/lo planes (plane stride = rows*ld_codes) */
+  int64_t ld_codes;
+  uint32_t* bits;       /* optional bit-packed sign rows [rows, ld_bits] (QT_Q_SIGN only) */
+  int64_t ld_bits;
+  int32_t* row_sum;     /* optional [rows]: sum over columns of the integer codes */
+  float* row_scale;     /* optional [rows]: QT_Q_XNOR_ROW row mean */
+  int32_t* overflow;    /* optional device flag, OR-ed with 1 when a code does not fit the int8/uint8 lane */
+} QtActQuant;
+
+int qt_quant_act(const QtActQuant* p, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Weight quantizers / packers: fp32 master weights [n, k] -> k-bit HBM format.
+ *   BinaryNet  sign bits                     binary_layers.py:42-46 (bin_op on W)
+ *   Terner     two bit planes (nz, sign)     terner_layers.py:47-51
+ *   DoReFa     k-bit codes c in [0, 2^k-1]   dorefa_connect.py:99-111 (nnQuantWeight)
+ *              k == 1: sign bits + scalar E = mean|W|
+ *   XnorNet    sign/nz planes + alpha[k] = mean(|W|, dim 0)   xnor_connect.py:111-112
+ * `stats` is a small device scratch (>= 16 floats) that receives the reductions:
+ *   stats[0] = max|tanh W| (DoReFa k>=2)  stats[1] = mean|W| (DoReFa k==1)
+ *   stats[2] = number of exact zeros (as float)   stats[3] = max|W|
+ * ---------------------------------------------------------------------- */
+enum {
+  QT_W_SIGN = 0,     /* packed: bits[n, ldw]                                  */
+  QT_W_TERNARY = 1,  /* packed: nz[n, ldw] then sign[n, ldw] (plane stride n*ldw words) */
+  QT_W_DOREFA = 2,   /* packed: codes, lane bits = 1,2,4,8 (k=3 -> 4, k=5..7 -> 8), little-endian within a byte */
+  QT_W_XNOR = 3      /* packed: nz/sign planes as ternary (torch.sign keeps zeros) + alpha[k] */
+};
+
+typedef struct QtWeightPack {
+  int mode;          /* QT_W_* */
+  int bit_width;     /* DoReFa k */
+  const float* w;    /* [n, ld_w] fp32 */
+  int64_t n, k, ld_w;
+  void* packed;      /* see mode */
+  int64_t ld_packed; /* row stride of `packed` in BYTES (multiple of 4) */
+  float* alpha;      /* QT_W_XNOR: [k]; written unless alpha_is_input */
+  int alpha_is_input; /* 1: alpha was computed by the caller (XNORConv2d per-tap alpha, xnor_connect.py:140) */
+  float* stats;      /* device scratch, >= 16 floats */
+  float* wq;         /* optional fp32 fake-quant weights [n, ld_w] (what the reference's weight op returns) */
+} QtWeightPack;
+
+int qt_pack_weight(const QtWeightPack* p, void* stream);
+
+/* alpha[c] = mean over the n rows of |w[r, c]|  (torch.mean(torch.abs(W), 0), xnor_connect.py:111). */
+int qt_col_absmean(const float* w, int64_t n, int64_t k, int64_t ld_w, float* alpha, void* stream);
+
+/* Expand a packed weight matrix into the transient operand the tensor-core
+ * kernels read (written and re-read through L2; never the persistent format).
+ *   kind 1: int8  centred codes  (sign: +-1, ternary: -1/0/1, DoReFa k<=7: 2c-n)
+ *   kind 2: uint8 raw codes c    (DoReFa k == 8; zero point handled in the epilogue)
+ *   kind 3: bf16 exact values of kind 1
+ *   kind 4: bf16 hi/lo planes of alpha[k] * sign (XnorNet; plane stride = n*ld_out elements)
+ */
+typedef struct QtWeightExpand {
+  int mode, bit_width;
+  const void* packed;
+  int64_t n, k, ld_packed;
+  const float* alpha;   /* QT_W_XNOR */
+  void* out;
+  int out_kind;
+  int64_t ld_out;       /* elements; columns k..ld_out-1 are zero-filled */
+} QtWeightExpand;
+
+int qt_expand_weight(const QtWeightExpand* p, void* stream);
+
+/* ------------------------------------------------------------------------
+ * im2col gather for the conv layers (binary_layers.py:103-106, terner_layers.py:89-92,
+ * dorefa_layers.py:77-82, xnor_connect.py:139-146).  Input NCHW, zero padding
+ * (a padded tap contributes exactly 0, as F.conv2d does).  Output row m =
+ * (b, oh, ow), column = (c, kh, kw) of group `g`; element type = 1, 2 or 4 bytes
+ * (int8/uint8 codes, bf16, fp32).  Optional row_sum of int8/uint8 codes.
+ * ---------------------------------------------------------------------- */
+typedef struct QtIm2col {
+  const void* x;     /* [B, C, H, W] */
+  int elem_bytes;    /* 1, 2, 4 */
+  int is_unsigned;   /* for row_sum of 1-byte codes */
+  int64_t B, C, H, W;
+  int kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int groups, group;           /* channels [group*C/groups, (group+1)*C/groups) */
+  int64_t OH, OW;
+  void* out;                   /* [B*OH*OW, ld_out] */
+  int64_t ld_out;              /* elements; columns beyond (C/groups)*kh*kw zero-filled */
+  int32_t* row_sum;            /* optional */
+} QtIm2col;
+
+int qt_im2col(const QtIm2col* p, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Contractions.  All compute  D[m, n] = sum_k A[m, k] * W[n, k]  (i.e. x . W^T,
+ * the F.linear call at binary_layers.py:44, terner_layers.py:49, dorefa_layers.py:43,
+ * xnor_connect.py:115) and apply the fused epilogue
+ *     t = acc_mul * acc + rs_mul * row_sum[m]                (integer kernels; exact)
+ *     y = float(t) * scale * row_scale[m] * col_scale[n] + bias[n]
+ * Output addressing:
+ *     out_mode 0 (row major) : out[m * ldo + n]
+ *     out_mode 1 (NCHW)      : out[((m / P) * ldo + n) * P + m % P],  P = nchw_inner (= OH*OW), ldo = total
+ *                              output channels (a conv group writes at out + group_offset * P)
+ * acc_out (optional, integer kernels) receives the raw int32 accumulators [M, N] row major.
+ * ---------------------------------------------------------------------- */
+typedef struct QtEpilogue {
+  const float* bias;      /* [N] or NULL */
+  const float* row_scale; /* [M] or NULL */
+  const float* col_scale; /* [N] or NULL */
+  const int32_t* row_sum; /* [M] or NULL */
+  float scale;
+  int32_t acc_mul, rs_mul;
+  float* out;
+  int64_t ldo;
+  int out_mode;
+  int64_t nchw_inner;
+  int32_t* acc_out;
+} QtEpilogue;
+
+/* 1-bit x 1-bit: acc = K - 2 popc(a ^ w).  CUDA-core XNOR + popcount. */
+int qt_gemm_b1b1(const uint32_t* a_bits, int64_t lda_words, const uint32_t* w_bits, int64_t ldw_words,
+                 int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, void* stream);
+
+/* 1-bit activations x ternary weights (two planes): acc = popc(nz) - 2 popc(nz & (a ^ s)). */
+int qt_gemm_b1t2(const uint32_t* a_bits, int64_t lda_words, const uint32_t* w_nz, const uint32_t* w_sign,
+                 int64_t ldw_words, int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, void* stream);
+
+/* 8-bit codes x 8-bit codes -> int32.  backend: 0 = auto, 1 = tcgen05 (kind::i8, TMA + TMEM),
+ * 2 = CUDA-core dp4a fallback (any shape).  lda/ldw in bytes; tcgen05 needs them % 16 == 0. */
+int qt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* w, int w_signed, int64_t ldw,
+               int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream);
+
+/* bf16 planes x bf16 planes -> fp32.  D = sum over passes p of A[pa[p]] . W[pw[p]]^T.
+ * Planes are [M, lda] / [N, ldw] bf16 matrices `a_plane_stride` / `w_plane_stride` elements apart.
+ * backend as above (2 = CUDA-core fp32 FMA fallback). */
+int qt_gemm_bf16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
+                 int64_t w_plane_stride, int npass, const int* pa, const int* pw,
+                 int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream);
+
+/* fp32 x fp32 CUDA-core GEMM (D = A . W^T), the always-available exact-fp32 route used for
+ * ragged first layers; same epilogue. */
+int qt_gemm_f32(const float* a, int64_t lda, const float* w, int64_t ldw,
+                int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, void* stream);
+
+/* Number of kernel launches issued by this library on the calling thread since the last reset
+ * (bench.py's gpu_launches). */
+int64_t qt_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QTB200_H */

@@ -1,0 +1,16 @@
+"""pytorch_quantize_impls_b200 -- B200-native quantized forward path behind the QuantTorch surface.
+
+    import pytorch_quantize_impls_b200 as QuantTorch
+    QuantTorch.layers.LinearBin(...), QuantTorch.functions.BinaryConnect(), QuantTorch.BinaryNet.LinearBin ...
+
+Unlike the reference's package init (QuantTorch/__init__.py:1-7) nothing here imports the training / optuna
+tooling; only the hot path (functions, layers, facades) exists.
+"""
+from . import _lib  # noqa: F401  (defines the loud failure when libqtb200.so is missing)
+from . import functions, layers  # noqa: F401
+from . import BinaryNet, DorefaNet, LogLinNet, TernerNet, XnorNet  # noqa: F401
+from ._engine import set_backend  # noqa: F401
+from ._ops import device_caps, set_strict  # noqa: F401
+from .device import device  # noqa: F401
+
+__version__ = '0.1'

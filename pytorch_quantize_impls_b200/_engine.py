@@ -1,0 +1,237 @@
+"""Contraction routing: (activation operand kind) x (weight pack kind) -> kernel + epilogue.
+
+                      | W sign / ternary / dorefa (integer codes) | W xnor (alpha[k] * sign) / real planes
+  --------------------+-------------------------------------------+-----------------------------------------
+  A int8/uint8 codes  | tcgen05 kind::i8 (or XNOR-popcount for    | falls back to the row below (A re-read
+  (Binary/Ter/DoReFa) | 1-bit x 1-bit/ternary when M is small)    | as real values)
+  A bf16 codes (xnor) | tcgen05 kind::f16, 1 pass, row_scale      | 2 passes (W hi, W lo), row_scale
+  A real (untagged)   | bf16 hi/lo split of A, 2 passes           | 3 passes (hi*hi, lo*hi, hi*lo)
+
+Integer accumulators are exact; the bf16 routes carry 16 significant bits per operand (error ~2^-17,
+far inside the 1e-3 relative tolerance of the north star).
+"""
+import os
+
+import torch
+
+from . import _lib as L
+from . import _ops as ops
+
+# M at or below which the 1-bit CUDA-core XNOR+popcount kernels are preferred over expanding the weights
+# for the tensor cores (GEMV-like shapes: the packed weights are read once, 1 bit each).
+POPCOUNT_MAX_M = int(os.environ.get("QTB200_POPCOUNT_MAX_M", "64"))
+_force_backend = {"i8": L.BACKEND_AUTO, "bf16": L.BACKEND_AUTO}
+_force_popcount = [False]
+
+
+def set_backend(i8=None, bf16=None, popcount=None):
+    """Testing/benchmark hook: force 'tcgen05' / 'simt' / 'auto' for the integer and bf16 contractions, and
+    popcount=True to route every 1-bit x {1-bit, ternary} product to the XNOR-popcount kernels."""
+    names = {"auto": L.BACKEND_AUTO, "tcgen05": L.BACKEND_TCGEN05, "simt": L.BACKEND_SIMT, None: None}
+    if i8 is not None:
+        _force_backend["i8"] = names[i8]
+    if bf16 is not None:
+        _force_backend["bf16"] = names[bf16]
+    if popcount is not None:
+        _force_popcount[0] = bool(popcount)
+
+
+def get_tag(x):
+    """Return the ActCodes attached to `x` by an activation quantizer if it still describes x."""
+    tag = getattr(x, "_qt_codes", None)
+    if tag is None:
+        return None
+    if tag.version != x._version or tuple(tag.shape) != tuple(x.shape):
+        return None
+    return tag
+
+
+def attach_tag(y, tag):
+    if tag is not None:
+        tag.version = y._version
+        tag.shape = tuple(y.shape)
+        y._qt_codes = tag
+    return y
+
+
+class _A:
+    """Activation operand handed to the contraction."""
+    __slots__ = ("form", "t", "ld", "signed", "scale", "row_sum", "row_scale", "planes", "bits", "ld_bits")
+
+
+def _a_from_tag(tag):
+    a = _A()
+    a.scale, a.row_sum, a.row_scale, a.bits, a.ld_bits = tag.scale, tag.row_sum, tag.row_scale, tag.bits, tag.ld_bits
+    a.t, a.ld = tag.codes, tag.ld
+    if tag.codes_kind in (L.CODES_I8, L.CODES_U8):
+        a.form, a.signed, a.planes = "i8", tag.codes_kind == L.CODES_I8, 1
+    else:
+        a.form, a.signed, a.planes = "bf16", True, (2 if tag.codes_kind == L.CODES_BF16X2 else 1)
+    return a
+
+
+def _a_split(x2d):
+    _, tag = ops.quant_act(x2d, L.Q_SPLIT, want_y=False, codes_kind=L.CODES_BF16X2, kind="real")
+    return _a_from_tag(tag)
+
+
+def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=None, nchw_inner=1, out_offset=0,
+              acc_out=None):
+    """One GEMM launch (plus the transient weight expansion) for N output columns starting at weight row w_row0."""
+    ldo = N if ldo is None else ldo
+    col_scale = None if pack.col_scale is None else pack.col_scale[w_row0:w_row0 + N]
+    int_w = pack.kind in ("sign", "ternary", "dorefa")
+
+    if a.form == "i8" and int_w:
+        use_pop = (a.bits is not None and pack.kind in ("sign", "ternary") and a.scale == 1.0 and out_mode == 0
+                   and (_force_popcount[0] or (M <= POPCOUNT_MAX_M and _force_backend["i8"] == L.BACKEND_AUTO)))
+        if use_pop:
+            epi = ops.make_epi(out, ldo=ldo, bias=bias, scale=1.0, acc_out=acc_out, out_offset=out_offset)
+            ldw = pack.ld_packed // 4
+            wbits = pack.packed.view(torch.int32)
+            if pack.kind == "sign":
+                ops.gemm_b1b1(a.bits, a.ld_bits, wbits[0, w_row0:], ldw, M, N, K, epi)
+            else:
+                ops.gemm_b1t2(a.bits, a.ld_bits, wbits[0, w_row0:], wbits[1, w_row0:], ldw, M, N, K, epi)
+            return
+        if pack.kind == "dorefa" and pack.bit_width == 8:
+            # raw unsigned codes c, W_q = (2c - 255)/255:  sum a (2c - 255) = 2 sum a c - 255 sum a
+            w, ldw = ops.expand_weight(pack, L.CODES_U8)
+            if a.row_sum is None:
+                raise RuntimeError("internal: 8-bit DoReFa weights need activation row sums")
+            epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
+                               row_sum=a.row_sum, scale=a.scale, acc_mul=2, rs_mul=-255, acc_out=acc_out,
+                               out_offset=out_offset)
+            ops.gemm_i8(a.t, a.signed, a.ld, w[w_row0:], False, ldw, M, N, K, epi, _force_backend["i8"])
+            return
+        w, ldw = ops.expand_weight(pack, L.CODES_I8)
+        epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
+                           scale=a.scale, acc_out=acc_out, out_offset=out_offset)
+        ops.gemm_i8(a.t, a.signed, a.ld, w[w_row0:], True, ldw, M, N, K, epi, _force_backend["i8"])
+        return
+
+    if a.form != "bf16":
+        raise RuntimeError("internal: integer activation codes cannot meet a real-valued weight operand")
+    # bf16 routes
+    if int_w:
+        w, ldw = ops.expand_weight(pack, L.CODES_BF16)
+        wplanes = 1
+    elif pack.kind == "xnor":
+        w, ldw = ops.expand_weight(pack, L.CODES_BF16X2)
+        wplanes = 2
+    else:
+        w, ldw, wplanes = pack.planes, pack.ld_planes, 2
+    passes = [(0, 0)]
+    if a.planes == 2:
+        passes.append((1, 0))
+    if wplanes == 2:
+        passes.append((0, 1))
+    a_stride = a.t.stride(0) if a.t.dim() == 3 else 0
+    w_stride = w.stride(0)
+    epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
+                       row_scale=a.row_scale, scale=a.scale, out_offset=out_offset)
+    ops.gemm_bf16(a.t, a.ld, a_stride, w[0, w_row0:], ldw, w_stride, passes, M, N, K, epi, _force_backend["bf16"])
+
+
+def linear(x, pack, bias):
+    """F.linear(x, W_q, bias) with W_q given as a WeightPack.  x: [..., K] fp32 CUDA tensor."""
+    ops.require_cuda(x, "input")
+    K, N = pack.k, pack.n
+    if x.shape[-1] != K:
+        raise RuntimeError("size mismatch: input has %d features, layer expects %d" % (x.shape[-1], K))
+    lead = x.shape[:-1]
+    tag = get_tag(x) if x.dim() == 2 else None
+    x2d = ops.as_f32c(x).reshape(-1, K)
+    M = x2d.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    if M == 0:
+        return out.reshape(*lead, N)
+    int_w = pack.kind in ("sign", "ternary", "dorefa")
+    a = None
+    if tag is not None:
+        a = _a_from_tag(tag)
+        if a.form == "i8" and not int_w:
+            a = None
+    if a is None:
+        a = _a_split(x2d)
+    if bias is not None:
+        bias = ops.as_f32c(bias)
+    _contract(a, pack, M, N, K, out, bias=bias)
+    return out.reshape(*lead, N)
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
+    """F.conv2d(x, W_q, bias, stride, padding, dilation, groups) via im2col gather + GEMM with an NCHW epilogue."""
+    ops.require_cuda(x, "input")
+    if x.dim() != 4:
+        raise RuntimeError("expected a 4-D NCHW input, got %d-D" % x.dim())
+    B, Cin, H, W = x.shape
+    O, Cg, kh, kw = weight_shape
+    if Cin != Cg * groups:
+        raise RuntimeError("input has %d channels, layer expects %d" % (Cin, Cg * groups))
+    sh, sw = _pair(stride)
+    dh, dw = _pair(dilation)
+    if isinstance(padding, str):
+        if padding == "valid":
+            ph = pw = 0
+        else:
+            tot_h, tot_w = dh * (kh - 1), dw * (kw - 1)
+            if padding != "same" or tot_h % 2 or tot_w % 2 or sh != 1 or sw != 1:
+                raise NotImplementedError("padding=%r is not supported by the quantized conv kernels" % (padding,))
+            ph, pw = tot_h // 2, tot_w // 2
+    else:
+        ph, pw = _pair(padding)
+    OH = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    OW = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    out = torch.empty((B, O, max(OH, 0), max(OW, 0)), dtype=torch.float32, device=x.device)
+    if B == 0 or OH <= 0 or OW <= 0:
+        return out
+    Ng, Kg, P = O // groups, Cg * kh * kw, OH * OW
+    geom = (kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW)
+    int_w = pack.kind in ("sign", "ternary", "dorefa")
+    tag = get_tag(x)
+    if tag is not None and not (tag.codes_kind in (L.CODES_I8, L.CODES_U8) and int_w and tag.rows == 1):
+        tag = None
+    if bias is not None:
+        bias = ops.as_f32c(bias)
+    need_rs = int_w and pack.kind == "dorefa" and pack.bit_width == 8
+
+    if tag is not None:
+        elem, ld = 1, ops.round_up(Kg, 16)
+        src = tag.codes.view(-1)[:x.numel()].view(B, Cin, H, W)
+        planes = [src]
+        dtype = tag.codes.dtype
+    else:
+        elem, ld = 2, ops.round_up(Kg, 8)
+        a0 = _a_split(ops.as_f32c(x).reshape(1, -1))
+        planes = [a0.t[p].view(-1)[:x.numel()].view(B, Cin, H, W) for p in range(2)]
+        dtype = torch.bfloat16
+
+    # bound the transient im2col matrix (~1.5 GiB per chunk of images)
+    per_img = P * ld * elem * len(planes)
+    bchunk = max(1, min(B, (3 << 29) // max(per_img, 1)))
+    for b0 in range(0, B, bchunk):
+        b1 = min(B, b0 + bchunk)
+        nb = b1 - b0
+        M = nb * P
+        for g in range(groups):
+            a = _A()
+            a.bits, a.ld_bits, a.row_scale, a.row_sum = None, 0, None, None
+            a.ld = ld
+            buf = torch.empty((len(planes), M, ld), dtype=dtype, device=x.device)
+            if need_rs and tag is not None:
+                a.row_sum = torch.empty(M, dtype=torch.int32, device=x.device)
+            for pi, src in enumerate(planes):
+                ops.im2col(src[b0:b1], elem, geom, g, buf[pi], ld, row_sum=a.row_sum if pi == 0 else None,
+                           is_unsigned=(dtype == torch.uint8))
+            if tag is not None:
+                a.form, a.t, a.signed, a.scale, a.planes = "i8", buf[0], dtype == torch.int8, tag.scale, 1
+            else:
+                a.form, a.t, a.signed, a.scale, a.planes = "bf16", buf, True, 1.0, 2
+            _contract(a, pack, M, Ng, Kg, out, w_row0=g * Ng, bias=None if bias is None else bias[g * Ng:(g + 1) * Ng],
+                      out_mode=1, ldo=O, nchw_inner=P, out_offset=(b0 * O + g * Ng) * P)
+    return out

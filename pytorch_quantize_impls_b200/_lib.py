@@ -1,0 +1,107 @@
+"""ctypes binding of libqtb200.so (the C ABI declared in include/qtb200.h).
+
+There is no CPU fallback: if the library is missing, or a call is made with a
+non-CUDA tensor, this module raises.  The oracle under ``oracle/`` is test
+infrastructure and is never imported from here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libqtb200.so")
+
+# ---- enums (mirror include/qtb200.h) -------------------------------------
+Q_SIGN, Q_TERNARY, Q_DOREFA, Q_XNOR_ROW, Q_LOG, Q_LIN, Q_SPLIT = range(7)
+W_SIGN, W_TERNARY, W_DOREFA, W_XNOR = range(4)
+CODES_NONE, CODES_I8, CODES_U8, CODES_BF16, CODES_BF16X2 = range(5)
+BACKEND_AUTO, BACKEND_TCGEN05, BACKEND_SIMT = 0, 1, 2
+
+vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
+
+
+class QtActQuant(C.Structure):
+    _fields_ = [("mode", i32), ("bit_width", i32), ("fsr", i32), ("with_sign", i32),
+                ("x", vp), ("rows", i64), ("cols", i64), ("ld_x", i64),
+                ("y", vp), ("ld_y", i64),
+                ("codes", vp), ("codes_kind", i32), ("ld_codes", i64),
+                ("bits", vp), ("ld_bits", i64),
+                ("row_sum", vp), ("row_scale", vp), ("overflow", vp)]
+
+
+class QtWeightPack(C.Structure):
+    _fields_ = [("mode", i32), ("bit_width", i32), ("w", vp), ("n", i64), ("k", i64), ("ld_w", i64),
+                ("packed", vp), ("ld_packed", i64), ("alpha", vp), ("alpha_is_input", i32),
+                ("stats", vp), ("wq", vp)]
+
+
+class QtWeightExpand(C.Structure):
+    _fields_ = [("mode", i32), ("bit_width", i32), ("packed", vp), ("n", i64), ("k", i64), ("ld_packed", i64),
+                ("alpha", vp), ("out", vp), ("out_kind", i32), ("ld_out", i64)]
+
+
+class QtIm2col(C.Structure):
+    _fields_ = [("x", vp), ("elem_bytes", i32), ("is_unsigned", i32),
+                ("B", i64), ("C", i64), ("H", i64), ("W", i64),
+                ("kh", i32), ("kw", i32), ("stride_h", i32), ("stride_w", i32), ("pad_h", i32), ("pad_w", i32),
+                ("dil_h", i32), ("dil_w", i32), ("groups", i32), ("group", i32),
+                ("OH", i64), ("OW", i64), ("out", vp), ("ld_out", i64), ("row_sum", vp)]
+
+
+class QtEpilogue(C.Structure):
+    _fields_ = [("bias", vp), ("row_scale", vp), ("col_scale", vp), ("row_sum", vp),
+                ("scale", f32), ("acc_mul", C.c_int32), ("rs_mul", C.c_int32),
+                ("out", vp), ("ldo", i64), ("out_mode", i32), ("nchw_inner", i64), ("acc_out", vp)]
+
+
+# every symbol include/qtb200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "qt_version": (i32, []),
+    "qt_last_error": (C.c_char_p, []),
+    "qt_device_caps": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "qt_quant_act": (i32, [C.POINTER(QtActQuant), vp]),
+    "qt_pack_weight": (i32, [C.POINTER(QtWeightPack), vp]),
+    "qt_col_absmean": (i32, [vp, i64, i64, i64, vp, vp]),
+    "qt_expand_weight": (i32, [C.POINTER(QtWeightExpand), vp]),
+    "qt_im2col": (i32, [C.POINTER(QtIm2col), vp]),
+    "qt_gemm_b1b1": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
+    "qt_gemm_b1t2": (i32, [vp, i64, vp, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
+    "qt_gemm_i8": (i32, [vp, i32, i64, vp, i32, i64, i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
+    "qt_gemm_bf16": (i32, [vp, i64, i64, vp, i64, i64, i32, C.POINTER(i32), C.POINTER(i32),
+                           i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
+    "qt_gemm_f32": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
+    "qt_launch_count": (i64, [i32]),
+}
+
+_lib = None
+
+
+class QtError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise loudly if the CUDA library is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "pytorch_quantize_impls_b200: %s is missing. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc, sm_100a). "
+                "There is no CPU or PyTorch fallback for the quantized kernels." % LIB_PATH)
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().qt_last_error().decode("utf-8", "replace")
+        raise QtError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def launch_count(reset=False):
+    return int(lib().qt_launch_count(1 if reset else 0))

@@ -1,0 +1,264 @@
+"""Tensor-level wrappers over the C ABI: torch is used only for device memory and streams."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_strict = False
+
+
+def set_strict(flag: bool):
+    """strict=True: after every k-bit activation quantizer, synchronise and raise if a code left its
+    8-bit lane (the reference's _quantize does not clamp, dorefa_connect.py:24-25).  Default False:
+    the sticky device flag is kept on the operand and can be inspected with ActCodes.check()."""
+    global _strict
+    _strict = bool(flag)
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(
+            "pytorch_quantize_impls_b200: %s must be a CUDA tensor (got %s); the quantized kernels are "
+            "sm_100a CUDA code and there is no CPU fallback" % (what, getattr(t, "device", type(t))))
+
+
+def as_f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class ActCodes:
+    """Low-bit activation operand produced by an activation quantizer and consumed by the next layer.
+
+    kind        'sign' | 'ternary' | 'dorefa' | 'xnor'
+    codes       int8/uint8 [rows, ld] or bf16 [rows, ld] tensor (K-major, zero padded)
+    scale       value = scale * code  (DoReFa: fl(1/n); others 1.0)
+    row_sum     int32 [rows] sum of codes (for unsigned-weight zero points), or None
+    row_scale   fp32 [rows] (XnorNet row mean), or None
+    bits        uint32 [rows, ld_bits] packed signs (kind 'sign'), or None
+    shape       shape of the fp32 tensor the codes describe (e.g. NCHW)
+    """
+    __slots__ = ("kind", "bit_width", "codes", "codes_kind", "rows", "cols", "ld", "scale", "row_sum",
+                 "row_scale", "bits", "ld_bits", "overflow", "shape", "version")
+
+    def check(self):
+        if self.overflow is not None and int(self.overflow.item()) != 0:
+            raise RuntimeError("quantized activation code overflowed its 8-bit lane "
+                               "(inputs of a k-bit DoReFa quantizer must lie in [0, 1])")
+
+
+def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_kind=L.CODES_NONE,
+              want_bits=False, want_row_sum=False, want_row_scale=False, kind=None):
+    """Run one activation-quantizer pass.  Returns (y or None, ActCodes or None)."""
+    require_cuda(x, "input")
+    x = as_f32c(x)
+    shape = tuple(x.shape)
+    rows = shape[0] if x.dim() == 2 else 1      # N-D tensors (NCHW activations) are one dense row
+    cols = x.numel() // max(rows, 1) if rows else 0
+    dev = x.device
+    y = torch.empty_like(x) if want_y else None
+    a = L.QtActQuant()
+    a.mode, a.bit_width, a.fsr, a.with_sign = mode, bit_width, fsr, int(with_sign)
+    a.x, a.rows, a.cols, a.ld_x = _p(x), rows, cols, cols
+    a.y, a.ld_y = _p(y), cols
+    codes = bits = row_sum = row_scale = overflow = None
+    ld = ldb = 0
+    if codes_kind in (L.CODES_I8, L.CODES_U8):
+        ld = round_up(max(cols, 1), 16)
+        codes = torch.empty((rows, ld), dtype=torch.int8 if codes_kind == L.CODES_I8 else torch.uint8, device=dev)
+        overflow = torch.zeros(1, dtype=torch.int32, device=dev) if mode == L.Q_DOREFA else None
+    elif codes_kind == L.CODES_BF16:
+        ld = round_up(max(cols, 1), 8)
+        codes = torch.empty((rows, ld), dtype=torch.bfloat16, device=dev)
+    elif codes_kind == L.CODES_BF16X2:
+        ld = round_up(max(cols, 1), 8)
+        codes = torch.empty((2, rows, ld), dtype=torch.bfloat16, device=dev)
+    if want_bits:
+        ldb = round_up((cols + 31) // 32, 4)
+        bits = torch.empty((rows, ldb), dtype=torch.int32, device=dev)
+    if want_row_sum:
+        row_sum = torch.empty(rows, dtype=torch.int32, device=dev)
+    if want_row_scale:
+        row_scale = torch.empty(rows, dtype=torch.float32, device=dev)
+    a.codes, a.codes_kind, a.ld_codes = _p(codes), codes_kind, ld
+    a.bits, a.ld_bits = _p(bits), ldb
+    a.row_sum, a.row_scale, a.overflow = _p(row_sum), _p(row_scale), _p(overflow)
+    if rows and cols:
+        L.check(L.lib().qt_quant_act(C.byref(a), _stream()), "qt_quant_act")
+    tag = None
+    if codes is not None or bits is not None:
+        tag = ActCodes()
+        tag.kind, tag.bit_width = kind, bit_width
+        tag.codes, tag.codes_kind, tag.rows, tag.cols, tag.ld = codes, codes_kind, rows, cols, ld
+        tag.scale = 1.0
+        tag.row_sum, tag.row_scale, tag.bits, tag.ld_bits = row_sum, row_scale, bits, ldb
+        tag.overflow, tag.shape, tag.version = overflow, shape, None
+        if _strict:
+            tag.check()
+    return y, tag
+
+
+class WeightPack:
+    """k-bit weight matrix resident in HBM (the persistent format) + what the epilogue needs."""
+    __slots__ = ("kind", "bit_width", "n", "k", "packed", "ld_packed", "alpha", "stats", "col_scale",
+                 "planes", "ld_planes", "wq")
+
+    def nbytes(self):
+        t = self.packed if self.packed is not None else self.planes
+        return t.numel() * t.element_size()
+
+
+def _lane_bits(k):
+    return 1 if k <= 1 else 2 if k <= 2 else 4 if k <= 4 else 8
+
+
+def pack_weight(w2d, kind, bit_width=1, want_wq=False, alpha=None):
+    """fp32 [n, k] master weights -> packed k-bit HBM format (one reduction pass + one pack pass)."""
+    require_cuda(w2d, "weight")
+    w2d = as_f32c(w2d)
+    n, k = w2d.shape
+    dev = w2d.device
+    mode = {"sign": L.W_SIGN, "ternary": L.W_TERNARY, "dorefa": L.W_DOREFA, "xnor": L.W_XNOR}[kind]
+    lane = _lane_bits(bit_width) if kind == "dorefa" else 1
+    ld_packed = round_up((k * lane + 7) // 8, 16)          # bytes, 16-byte rows
+    planes = 2 if kind in ("ternary", "xnor") else 1
+    p = WeightPack()
+    p.kind, p.bit_width, p.n, p.k = kind, bit_width, n, k
+    p.packed = torch.empty((planes, n, ld_packed), dtype=torch.uint8, device=dev)
+    p.ld_packed = ld_packed
+    p.stats = torch.empty(16, dtype=torch.float32, device=dev)
+    p.alpha = None
+    if kind == "xnor":
+        p.alpha = alpha if alpha is not None else torch.empty(k, dtype=torch.float32, device=dev)
+    p.wq = torch.empty_like(w2d) if want_wq else None
+    p.planes, p.ld_planes, p.col_scale = None, 0, None
+    a = L.QtWeightPack()
+    a.mode, a.bit_width = mode, bit_width
+    a.w, a.n, a.k, a.ld_w = _p(w2d), n, k, k
+    a.packed, a.ld_packed = _p(p.packed), ld_packed
+    a.alpha, a.alpha_is_input = _p(p.alpha), 1 if alpha is not None else 0
+    a.stats, a.wq = _p(p.stats), _p(p.wq)
+    L.check(L.lib().qt_pack_weight(C.byref(a), _stream()), "qt_pack_weight")
+    if kind == "dorefa":
+        # per-output-column scale kept on the device (no host sync):
+        #   k == 1 : E = mean|W|            (dorefa_connect.py:100-102)
+        #   k >= 2 : 1/n, or 0 when W is all zeros (dorefa_connect.py:106-107)
+        if bit_width == 1:
+            p.col_scale = p.stats[1:2].expand(n).contiguous()
+        else:
+            inv_n = 1.0 / float(2 ** bit_width - 1)
+            p.col_scale = torch.where(p.stats[3:4] == 0, torch.zeros_like(p.stats[3:4]),
+                                      torch.full_like(p.stats[3:4], inv_n)).expand(n).contiguous()
+    return p
+
+
+def pack_real_weight(wq2d):
+    """Arbitrary fp32 weights -> two bf16 planes (hi, lo) [2, n, ld]: the 'real' weight operand
+    (LogLin quantized values are exact in the hi plane)."""
+    require_cuda(wq2d, "weight")
+    _, tag = quant_act(as_f32c(wq2d), L.Q_SPLIT, want_y=False, codes_kind=L.CODES_BF16X2, kind="real")
+    p = WeightPack()
+    p.kind, p.bit_width, p.n, p.k = "real", 32, wq2d.shape[0], wq2d.shape[1]
+    p.packed, p.ld_packed, p.alpha, p.stats, p.col_scale, p.wq = None, 0, None, None, None, None
+    p.planes, p.ld_planes = tag.codes, tag.ld
+    return p
+
+
+def col_absmean(w2d):
+    require_cuda(w2d, "weight")
+    w2d = as_f32c(w2d)
+    n, k = w2d.shape
+    out = torch.empty(k, dtype=torch.float32, device=w2d.device)
+    L.check(L.lib().qt_col_absmean(_p(w2d), n, k, k, _p(out), _stream()), "qt_col_absmean")
+    return out
+
+
+def expand_weight(p, out_kind):
+    """Packed k-bit weights -> transient tensor-core operand (lives in L2 between the two kernels)."""
+    dev = p.packed.device
+    ld = round_up(p.k, 16)
+    if out_kind == L.CODES_I8:
+        out = torch.empty((p.n, ld), dtype=torch.int8, device=dev)
+    elif out_kind == L.CODES_U8:
+        out = torch.empty((p.n, ld), dtype=torch.uint8, device=dev)
+    elif out_kind == L.CODES_BF16:
+        out = torch.empty((1, p.n, ld), dtype=torch.bfloat16, device=dev)
+    else:
+        out = torch.empty((2, p.n, ld), dtype=torch.bfloat16, device=dev)
+    mode = {"sign": L.W_SIGN, "ternary": L.W_TERNARY, "dorefa": L.W_DOREFA, "xnor": L.W_XNOR}[p.kind]
+    a = L.QtWeightExpand()
+    a.mode, a.bit_width = mode, p.bit_width
+    a.packed, a.n, a.k, a.ld_packed = _p(p.packed), p.n, p.k, p.ld_packed
+    a.alpha, a.out, a.out_kind, a.ld_out = _p(p.alpha), _p(out), out_kind, ld
+    L.check(L.lib().qt_expand_weight(C.byref(a), _stream()), "qt_expand_weight")
+    return out, ld
+
+
+def im2col(x4d, elem_bytes, geom, group, out, ld_out, row_sum=None, is_unsigned=False):
+    """geom = (kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW)."""
+    B, Cc, H, W = x4d.shape
+    kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW = geom
+    a = L.QtIm2col()
+    a.x, a.elem_bytes, a.is_unsigned = _p(x4d), elem_bytes, int(is_unsigned)
+    a.B, a.C, a.H, a.W = B, Cc, H, W
+    a.kh, a.kw, a.stride_h, a.stride_w, a.pad_h, a.pad_w, a.dil_h, a.dil_w = kh, kw, sh, sw, ph, pw, dh, dw
+    a.groups, a.group, a.OH, a.OW = groups, group, OH, OW
+    a.out, a.ld_out, a.row_sum = _p(out), ld_out, _p(row_sum)
+    L.check(L.lib().qt_im2col(C.byref(a), _stream()), "qt_im2col")
+
+
+def make_epi(out, *, ldo, out_mode=0, nchw_inner=1, bias=None, row_scale=None, col_scale=None, row_sum=None,
+             scale=1.0, acc_mul=1, rs_mul=0, acc_out=None, out_offset=0):
+    e = L.QtEpilogue()
+    e.bias, e.row_scale, e.col_scale, e.row_sum = _p(bias), _p(row_scale), _p(col_scale), _p(row_sum)
+    e.scale, e.acc_mul, e.rs_mul = float(scale), int(acc_mul), int(rs_mul)
+    e.out = None if out is None else C.c_void_p(out.data_ptr() + 4 * out_offset)
+    e.ldo, e.out_mode, e.nchw_inner = ldo, out_mode, nchw_inner
+    e.acc_out = _p(acc_out)
+    return e
+
+
+def gemm_b1b1(a_bits, lda, w_bits, ldw, M, N, K, epi):
+    L.check(L.lib().qt_gemm_b1b1(_p(a_bits), lda, _p(w_bits), ldw, M, N, K, C.byref(epi), _stream()), "qt_gemm_b1b1")
+
+
+def gemm_b1t2(a_bits, lda, w_nz, w_sign, ldw, M, N, K, epi):
+    L.check(L.lib().qt_gemm_b1t2(_p(a_bits), lda, _p(w_nz), _p(w_sign), ldw, M, N, K, C.byref(epi), _stream()),
+            "qt_gemm_b1t2")
+
+
+def gemm_i8(a, a_signed, lda, w, w_signed, ldw, M, N, K, epi, backend=L.BACKEND_AUTO):
+    L.check(L.lib().qt_gemm_i8(_p(a), int(a_signed), lda, _p(w), int(w_signed), ldw, M, N, K, C.byref(epi),
+                               backend, _stream()), "qt_gemm_i8")
+
+
+def gemm_bf16(a, lda, a_plane_stride, w, ldw, w_plane_stride, passes, M, N, K, epi, backend=L.BACKEND_AUTO):
+    n = len(passes)
+    pa = (C.c_int * n)(*[p[0] for p in passes])
+    pw = (C.c_int * n)(*[p[1] for p in passes])
+    L.check(L.lib().qt_gemm_bf16(_p(a), lda, a_plane_stride, _p(w), ldw, w_plane_stride, n, pa, pw, M, N, K,
+                                 C.byref(epi), backend, _stream()), "qt_gemm_bf16")
+
+
+def gemm_f32(a, lda, w, ldw, M, N, K, epi):
+    L.check(L.lib().qt_gemm_f32(_p(a), lda, _p(w), ldw, M, N, K, C.byref(epi), _stream()), "qt_gemm_f32")
+
+
+def device_caps(device=0):
+    maj, mnr, sms, tc = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    L.check(L.lib().qt_device_caps(device, C.byref(maj), C.byref(mnr), C.byref(sms), C.byref(tc)), "qt_device_caps")
+    return dict(sm_major=maj.value, sm_minor=mnr.value, num_sms=sms.value, has_tcgen05=bool(tc.value))

@@ -1,0 +1,443 @@
+// tcgen05 contraction core for sm_100a:  D[M,N] = sum_passes A_p[M,K] . W_p[N,K]^T  with a fused epilogue.
+//
+//   * operands are K-major byte matrices in HBM/L2 (int8/uint8 codes, or bf16 planes), fetched by TMA
+//     (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage shared-memory ring guarded by
+//     full/empty mbarriers;
+//   * one elected thread issues tcgen05.mma (kind::i8 -> s32, kind::f16/bf16 -> f32), 128 x BN x 32 B per
+//     instruction, accumulators live in TMEM (2 x BN columns: double buffered across output tiles);
+//   * four epilogue warps drain TMEM with tcgen05.ld (32x32b.x32), apply the integer-exact affine
+//     + scale/bias epilogue and store fp32 straight to the row-major or NCHW output, overlapping the
+//     next tile's main loop;
+//   * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule with M fastest so that
+//     concurrently running CTAs share the same weight tile in L2.
+#include <cuda.h>
+#include <mutex>
+#include "qt_common.cuh"
+
+namespace qt {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK_BYTES = 128;          // one 128B swizzle row of K per stage
+constexpr int TC_THREADS = 192;           // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+
+struct TcArgs {
+  int64_t M, N;
+  int num_kblocks;      // per pass
+  int npass;
+  int pa[4], pw[4];
+  int64_t a_plane_rows, w_plane_rows;
+  uint32_t idesc;
+  int is_int;
+  Epi ep;
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// K-major, 128B-swizzled operand tile: 8-row atoms of 1024 B (SBO), LBO unused, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;   // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, int KIND, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcArgs g) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK_BYTES;
+  constexpr uint32_t W_BYTES = BN * TC_BK_BYTES;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + W_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8u * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = g.tiles_m * g.tiles_n;
+  const int iters = g.npass * g.num_kblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile % g.tiles_m, tn = tile / g.tiles_m;
+        for (int pass = 0; pass < g.npass; ++pass) {
+          const int a_row = (int)(g.pa[pass] * g.a_plane_rows) + tm * TC_BM;
+          const int w_row = (int)(g.pw[pass] * g.w_plane_rows) + tn * BN;
+          for (int kb = 0; kb < g.num_kblocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            tma_load_2d(sa, &map_a, full_bar(stage), kb * TC_BK_BYTES, a_row);
+            tma_load_2d(sa + A_BYTES, &map_w, full_bar(stage), kb * TC_BK_BYTES, w_row);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK_BYTES / 32; ++k) {
+            // +32 B along K inside the swizzle atom == +2 in the (addr >> 4) field
+            tc_mma<KIND>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), g.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));     // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(as));          // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int lane_grp = warp & 3;         // TMEM lane quadrant this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    const Epi& e = g.ep;
+    const bool vec_ok = (e.out != nullptr) && e.out_mode == 0 && (e.ldo % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(e.out) & 15) == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile % g.tiles_m, tn = tile / g.tiles_m;
+      const int64_t m = (int64_t)tm * TC_BM + lane_grp * 32 + lane;
+      const int64_t n_tile = (int64_t)tn * BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const bool row_ok = m < g.M;
+      float rscale = 1.f;
+      int32_t rsum = 0;
+      int64_t nchw_base = 0;
+      if (row_ok) {
+        if (e.row_scale) rscale = __ldg(e.row_scale + m);
+        if (e.row_sum) rsum = e.rs_mul * __ldg(e.row_sum + m);
+        if (e.out_mode == 1) {
+          int64_t img = m / e.nchw_inner, r = m - img * e.nchw_inner;
+          nchw_base = img * e.ldo * e.nchw_inner + r;
+        }
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n_tile + c0 >= g.N) break;     // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t)(as * BN + c0) + ((uint32_t)(lane_grp * 32) << 16), r);
+        if (!row_ok) continue;
+        const int64_t n0 = n_tile + c0;
+        if (g.is_int && e.acc_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < g.N) e.acc_out[m * g.N + n0 + j] = (int32_t)r[j];
+        }
+        if (!e.out) continue;
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int64_t n = n0 + j;
+          float v;
+          if (g.is_int) v = (float)(e.acc_mul * (int32_t)r[j] + rsum);
+          else v = __uint_as_float(r[j]);
+          v = v * e.scale * rscale;
+          if (n < g.N) {
+            if (e.col_scale) v *= __ldg(e.col_scale + n);
+            if (e.bias) v += __ldg(e.bias + n);
+          }
+          y[j] = v;
+        }
+        if (e.out_mode == 0) {
+          float* o = e.out + m * e.ldo + n0;
+          if (vec_ok && n0 + 32 <= g.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < g.N) o[j] = y[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < g.N) e.out[nchw_base + (n0 + j) * e.nchw_inner] = y[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// 2-D byte matrix [rows, row_bytes] with row pitch ld_bytes; box = 128 B x box_rows, 128B swizzle, zero OOB fill.
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t row_bytes, uint64_t ld_bytes, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return QT_ECUDA; }
+  cuuint64_t dims[2] = {row_bytes, rows};
+  cuuint64_t strides[1] = {ld_bytes};
+  cuuint32_t box[2] = {TC_BK_BYTES, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return QT_ECUDA; }
+  return QT_OK;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int KIND, int STAGES>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK_BYTES + BN * TC_BK_BYTES) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, KIND, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  g.tiles_m = (int)ceil_div(g.M, TC_BM);
+  g.tiles_n = (int)ceil_div(g.N, BN);
+  int grid = std::min(g.tiles_m * g.tiles_n, num_sms());
+  tc_gemm_kernel<BN, KIND, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mw, g);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+template <int KIND>
+static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream) {
+  if (bn == 64) return launch_tc<64, KIND, 8>(ma, mw, g, stream);
+  if (bn == 128) return launch_tc<128, KIND, 6>(ma, mw, g, stream);
+  return launch_tc<256, KIND, 4>(ma, mw, g, stream);
+}
+
+static int pick_bn(int64_t N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }
+
+static bool tc_available() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, maj = 0, min = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev);
+    ok = (maj == 10 && min == 0) ? 1 : 0;
+  }
+  return ok == 1;
+}
+
+int simt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* w, int w_signed, int64_t ldw,
+                 int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, cudaStream_t stream);
+int simt_gemm_bf16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
+                   int64_t w_plane_stride, int npass, const int* pa, const int* pw,
+                   int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, cudaStream_t stream);
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace qt
+
+using namespace qt;
+
+extern "C" int qt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* w, int w_signed, int64_t ldw,
+                          int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(a && w, "qt_gemm_i8: null operand");
+  QT_REQUIRE(M >= 0 && N >= 0 && K > 0 && lda >= K && ldw >= K, "qt_gemm_i8: bad shape");
+  if (int rc = check_epi(ep, M, N)) return rc;
+  if (M == 0 || N == 0) return QT_OK;
+  const bool tc_ok = tc_available() && lda % 16 == 0 && ldw % 16 == 0 && al16(a) && al16(w) &&
+                     M < (1ll << 31) && N < (1ll << 31);
+  if (backend == 1 && !tc_ok) { set_error("qt_gemm_i8: tcgen05 backend needs sm_100 and 16-byte aligned operands/pitches"); return QT_EUNSUPPORTED; }
+  const bool use_tc = backend == 1 || (backend == 0 && tc_ok && (double)M * (double)N * (double)K >= 1.0e7);
+  if (!use_tc) return simt_gemm_i8(a, a_signed, lda, w, w_signed, ldw, M, N, K, ep, stream);
+
+  const int bn = pick_bn(N);
+  CUtensorMap ma, mw;
+  if (int rc = make_map(&ma, a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, TC_BM)) return rc;
+  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn)) return rc;
+  TcArgs g{};
+  g.M = M; g.N = N; g.num_kblocks = (int)ceil_div(K, TC_BK_BYTES); g.npass = 1; g.pa[0] = g.pw[0] = 0;
+  g.a_plane_rows = g.w_plane_rows = 0; g.is_int = 1; g.ep = make_epi(ep, M, N);
+  // instruction descriptor: D = s32 (2 << 4), A/B = s8 (1) or u8 (0) at bits 7 / 10, K-major both, N >> 3 at 17, M >> 4 at 24
+  g.idesc = (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((w_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) |
+            ((uint32_t)(TC_BM >> 4) << 24);
+  return dispatch_tc<0>(ma, mw, g, bn, stream);
+}
+
+extern "C" int qt_gemm_bf16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
+                            int64_t w_plane_stride, int npass, const int* pa, const int* pw,
+                            int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(a && w && pa && pw, "qt_gemm_bf16: null operand");
+  QT_REQUIRE(npass >= 1 && npass <= 4, "qt_gemm_bf16: npass must be 1..4");
+  QT_REQUIRE(M >= 0 && N >= 0 && K > 0 && lda >= K && ldw >= K, "qt_gemm_bf16: bad shape");
+  if (int rc = check_epi(ep, M, N)) return rc;
+  QT_REQUIRE(ep->out, "qt_gemm_bf16: needs ep->out");
+  if (M == 0 || N == 0) return QT_OK;
+  int max_pa = 0, max_pw = 0;
+  for (int i = 0; i < npass; ++i) { max_pa = std::max(max_pa, pa[i]); max_pw = std::max(max_pw, pw[i]); }
+  bool tc_ok = tc_available() && (lda * 2) % 16 == 0 && (ldw * 2) % 16 == 0 && al16(a) && al16(w);
+  if (max_pa > 0) tc_ok = tc_ok && a_plane_stride % lda == 0;
+  if (max_pw > 0) tc_ok = tc_ok && w_plane_stride % ldw == 0;
+  if (backend == 1 && !tc_ok) { set_error("qt_gemm_bf16: tcgen05 backend needs sm_100, 16-byte aligned pitches and plane strides that are whole rows"); return QT_EUNSUPPORTED; }
+  const bool use_tc = backend == 1 || (backend == 0 && tc_ok && (double)M * (double)N * (double)K >= 1.0e7);
+  if (!use_tc) return simt_gemm_bf16(a, lda, a_plane_stride, w, ldw, w_plane_stride, npass, pa, pw, M, N, K, ep, stream);
+
+  const int bn = pick_bn(N);
+  TcArgs g{};
+  g.a_plane_rows = max_pa > 0 ? a_plane_stride / lda : 0;
+  g.w_plane_rows = max_pw > 0 ? w_plane_stride / ldw : 0;
+  const uint64_t a_rows = (uint64_t)(max_pa * g.a_plane_rows + M), w_rows = (uint64_t)(max_pw * g.w_plane_rows + N);
+  CUtensorMap ma, mw;
+  if (int rc = make_map(&ma, a, a_rows, (uint64_t)K * 2, (uint64_t)lda * 2, TC_BM)) return rc;
+  if (int rc = make_map(&mw, w, w_rows, (uint64_t)K * 2, (uint64_t)ldw * 2, (uint32_t)bn)) return rc;
+  g.M = M; g.N = N; g.num_kblocks = (int)ceil_div(K * 2, TC_BK_BYTES); g.npass = npass;
+  for (int i = 0; i < npass; ++i) { g.pa[i] = pa[i]; g.pw[i] = pw[i]; }
+  g.is_int = 0; g.ep = make_epi(ep, M, N);
+  // D = f32 (1 << 4), A/B = bf16 (1) at bits 7 / 10
+  g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  return dispatch_tc<1>(ma, mw, g, bn, stream);
+}

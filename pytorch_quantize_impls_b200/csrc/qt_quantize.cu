@@ -1,0 +1,685 @@
+// Activation quantizers, weight packers/expanders and the im2col gather.
+// All kernels are HBM-bound streaming passes: 128-bit coalesced loads, one warp per row (or row chunk),
+// warp-shuffle reductions, and every derived output (fp32 fake-quant value, low-bit codes, packed bits,
+// row sums) produced from a single read of the fp32 source.
+#include <math.h>
+#include "qt_common.cuh"
+
+namespace qt {
+
+// ---------------------------------------------------------------------------------------------
+// per-element quantizer semantics (must match oracle/quanttorch_oracle.py bit for bit)
+// ---------------------------------------------------------------------------------------------
+struct QParams {
+  int mode;
+  float n;        // DoReFa 2^k - 1
+  float inv_n;    // fl(1 / n)
+  float lo_e, hi_e;  // Log: exponent clamp
+  float step, maxv;  // Lin
+  int with_sign;
+};
+
+struct QOut {
+  float y;     // fake-quant fp32 value (what the reference op returns)
+  float code;  // integer-valued code
+};
+
+__device__ __forceinline__ float sign3(float x) { return (float)((x > 0.f) - (x < 0.f)); }  // torch.sign (NaN -> 0)
+__device__ __forceinline__ float sign_safe(float x) { return (x < 0.f) ? -1.f : 1.f; }      // safeSign
+
+__device__ __forceinline__ QOut quant_elem(const QParams& q, float x, float row_mean) {
+  QOut o;
+  switch (q.mode) {
+    case QT_Q_SIGN: {
+      o.y = o.code = sign_safe(x);
+      break;
+    }
+    case QT_Q_TERNARY: {
+      float s = sign_safe(x);
+      float t = x - 0.5f * s;
+      o.y = o.code = (s + sign_safe(t)) * 0.5f;
+      break;
+    }
+    case QT_Q_DOREFA: {
+      float c = rintf(q.n * x);  // torch.round == round-half-to-even
+      o.code = c;
+      o.y = q.inv_n * c;
+      break;
+    }
+    case QT_Q_XNOR_ROW: {
+      float s = sign3(x);
+      o.code = s;
+      o.y = s * row_mean;
+      break;
+    }
+    case QT_Q_LOG: {
+      float e = fminf(fmaxf(rintf(log2f(fabsf(x))), q.lo_e), q.hi_e);
+      float p = exp2f(e);
+      o.y = q.with_sign ? sign3(x) * p : p;
+      o.code = 0.f;
+      break;
+    }
+    case QT_Q_LIN: {
+      if (q.with_sign) {
+        o.y = sign3(x) * fminf(fmaxf(rintf(fabsf(x) / q.step) * q.step, 0.f), q.maxv);
+      } else {
+        o.y = fminf(fmaxf(rintf(x / q.step) * q.step, 0.f), q.maxv);
+      }
+      o.code = 0.f;
+      break;
+    }
+    default: {  // QT_Q_SPLIT
+      o.y = x;
+      o.code = x;
+      break;
+    }
+  }
+  return o;
+}
+
+struct ActArgs {
+  QParams q;
+  const float* x;
+  int64_t rows, cols, ld_x;
+  float* y;
+  int64_t ld_y;
+  void* codes;
+  int codes_kind;
+  int64_t ld_codes;
+  uint32_t* bits;
+  int64_t ld_bits;
+  int32_t* row_sum;
+  float* row_scale;
+  int32_t* overflow;
+  int64_t chunk;    // columns per warp task (multiple of 128)
+  int nchunks;
+};
+
+__device__ __forceinline__ int code_to_lane(float c, int kind, bool& ovf) {
+  // kind 1: int8, kind 2: uint8.  NaN / out-of-lane codes saturate and raise the sticky overflow flag.
+  float lo = (kind == 1) ? -128.f : 0.f, hi = (kind == 1) ? 127.f : 255.f;
+  if (!(c >= lo && c <= hi)) {
+    ovf = true;
+    c = (c != c) ? 0.f : fminf(fmaxf(c, lo), hi);
+  }
+  return (int)c;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) act_quant_kernel(ActArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t task = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (task >= a.rows * a.nchunks) return;
+  const int64_t row = task / a.nchunks;
+  const int chunk_id = (int)(task - row * a.nchunks);
+  const int64_t c0 = (int64_t)chunk_id * a.chunk;
+  const int64_t c1 = min(a.cols, c0 + a.chunk);
+  const float* xr = a.x + row * a.ld_x;
+
+  float row_mean = 0.f;
+  if (a.q.mode == QT_Q_XNOR_ROW) {  // never chunked: the whole row is reduced by this warp
+    double s = 0.0;
+    if (VEC) {
+      for (int64_t c = 4 * lane; c < a.cols; c += 128) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
+        s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+      }
+    } else {
+      for (int64_t c = lane; c < a.cols; c += 32) s += (double)__ldg(xr + c);
+    }
+    s = warp_sum_d(s);
+    row_mean = (float)(s / (double)a.cols);
+    if (a.row_scale && lane == 0) a.row_scale[row] = row_mean;
+  }
+
+  int isum = 0;
+  bool ovf = false;
+  float* yr = a.y ? a.y + row * a.ld_y : nullptr;
+  int8_t* c8 = (a.codes_kind == 1 || a.codes_kind == 2) ? reinterpret_cast<int8_t*>(a.codes) + row * a.ld_codes : nullptr;
+  __nv_bfloat16* cb = (a.codes_kind >= 3) ? reinterpret_cast<__nv_bfloat16*>(a.codes) + row * a.ld_codes : nullptr;
+  __nv_bfloat16* cb_lo = (a.codes_kind == 4) ? cb + a.rows * a.ld_codes : nullptr;
+  uint32_t* br = a.bits ? a.bits + row * a.ld_bits : nullptr;
+
+  if (VEC) {
+    for (int64_t base = c0; base < c1; base += 128) {
+      const int64_t c = base + 4 * lane;
+      const bool valid = c < c1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) v = __ldg(reinterpret_cast<const float4*>(xr + c));
+      QOut o0 = quant_elem(a.q, v.x, row_mean), o1 = quant_elem(a.q, v.y, row_mean);
+      QOut o2 = quant_elem(a.q, v.z, row_mean), o3 = quant_elem(a.q, v.w, row_mean);
+      if (valid) {
+        if (yr) *reinterpret_cast<float4*>(yr + c) = make_float4(o0.y, o1.y, o2.y, o3.y);
+        if (c8) {
+          int k0 = code_to_lane(o0.code, a.codes_kind, ovf), k1 = code_to_lane(o1.code, a.codes_kind, ovf);
+          int k2 = code_to_lane(o2.code, a.codes_kind, ovf), k3 = code_to_lane(o3.code, a.codes_kind, ovf);
+          isum += k0 + k1 + k2 + k3;
+          uint32_t w = (uint32_t)(k0 & 0xff) | ((uint32_t)(k1 & 0xff) << 8) | ((uint32_t)(k2 & 0xff) << 16) |
+                       ((uint32_t)(k3 & 0xff) << 24);
+          *reinterpret_cast<uint32_t*>(c8 + c) = w;
+        } else if (cb) {
+          __nv_bfloat16 h0 = __float2bfloat16_rn(o0.code), h1 = __float2bfloat16_rn(o1.code);
+          __nv_bfloat16 h2 = __float2bfloat16_rn(o2.code), h3 = __float2bfloat16_rn(o3.code);
+          __nv_bfloat162 p0(h0, h1), p1(h2, h3);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&p0);
+          u.y = *reinterpret_cast<uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(cb + c) = u;
+          if (cb_lo) {
+            __nv_bfloat162 q0(__float2bfloat16_rn(o0.code - __bfloat162float(h0)),
+                              __float2bfloat16_rn(o1.code - __bfloat162float(h1)));
+            __nv_bfloat162 q1(__float2bfloat16_rn(o2.code - __bfloat162float(h2)),
+                              __float2bfloat16_rn(o3.code - __bfloat162float(h3)));
+            uint2 l;
+            l.x = *reinterpret_cast<uint32_t*>(&q0);
+            l.y = *reinterpret_cast<uint32_t*>(&q1);
+            *reinterpret_cast<uint2*>(cb_lo + c) = l;
+          }
+          isum += (int)o0.code + (int)o1.code + (int)o2.code + (int)o3.code;
+        }
+      }
+      if (br) {  // 4 bits per lane -> 4 words per 128-column step
+        uint32_t nib = 0;
+        if (valid) nib = (uint32_t)(o0.code > 0.f) | ((uint32_t)(o1.code > 0.f) << 1) |
+                         ((uint32_t)(o2.code > 0.f) << 2) | ((uint32_t)(o3.code > 0.f) << 3);
+        uint32_t w = nib << (4 * (lane & 7));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        const int64_t widx = (base >> 5) + (lane >> 3);
+        if ((lane & 7) == 0 && widx * 32 < c1) br[widx] = w;
+      }
+    }
+  } else {
+    for (int64_t base = c0; base < c1; base += 32) {
+      const int64_t c = base + lane;
+      const bool valid = c < c1;
+      float v = valid ? __ldg(xr + c) : 0.f;
+      QOut o = quant_elem(a.q, v, row_mean);
+      if (valid) {
+        if (yr) yr[c] = o.y;
+        if (c8) {
+          int k = code_to_lane(o.code, a.codes_kind, ovf);
+          isum += k;
+          c8[c] = (int8_t)k;
+        } else if (cb) {
+          __nv_bfloat16 h = __float2bfloat16_rn(o.code);
+          cb[c] = h;
+          if (cb_lo) cb_lo[c] = __float2bfloat16_rn(o.code - __bfloat162float(h));
+          isum += (int)o.code;
+        }
+      }
+      if (br) {
+        uint32_t w = __ballot_sync(0xffffffffu, valid && o.code > 0.f);
+        if (lane == 0) br[base >> 5] = w;
+      }
+    }
+  }
+
+  // zero-fill the padding columns / words (last chunk only)
+  if (chunk_id == a.nchunks - 1) {
+    if (c8) for (int64_t c = a.cols + lane; c < a.ld_codes; c += 32) c8[c] = 0;
+    if (cb) for (int64_t c = a.cols + lane; c < a.ld_codes; c += 32) {
+      cb[c] = __float2bfloat16_rn(0.f);
+      if (cb_lo) cb_lo[c] = __float2bfloat16_rn(0.f);
+    }
+    if (br) for (int64_t w = ((a.cols + 31) >> 5) + lane; w < a.ld_bits; w += 32) br[w] = 0u;
+  }
+  if (a.row_sum) {
+    isum = warp_sum_i(isum);
+    if (lane == 0) {
+      if (a.nchunks == 1) a.row_sum[row] = isum;
+      else atomicAdd(a.row_sum + row, isum);
+    }
+  }
+  if (a.overflow) {
+    unsigned any = __ballot_sync(0xffffffffu, ovf);
+    if (any && lane == 0) atomicOr(a.overflow, 1);
+  }
+}
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// weight-side reductions
+// ---------------------------------------------------------------------------------------------
+// stats[0] = max|tanh w|, stats[1] = sum|w| (then turned into the mean), stats[2] = #zeros, stats[3] = max|w|
+__global__ void __launch_bounds__(256) weight_stats_kernel(const float* __restrict__ w, int64_t n, int64_t k, int64_t ld,
+                                                           float* stats, double* dsum) {
+  double s = 0.0;
+  float mx = 0.f;
+  int zeros = 0;
+  const int64_t total = n * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / k, c = i - r * k;
+    float v = __ldg(w + r * ld + c);
+    float av = fabsf(v);
+    s += (double)av;
+    mx = fmaxf(mx, av);
+    zeros += (v == 0.f);
+  }
+  // tanh is monotone, so max|tanh w| = |tanh(max|w|)|; evaluated once, in double, below.
+  s = warp_sum_d(s);
+  zeros = warp_sum_i(zeros);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(dsum, s);
+    atomicAdd(reinterpret_cast<int*>(stats + 8), zeros);
+    atomicMax(reinterpret_cast<int*>(stats + 3), __float_as_int(mx));  // non-negative floats order as ints
+  }
+}
+
+__global__ void weight_stats_finish_kernel(float* stats, const double* dsum, double count) {
+  float mx = stats[3];
+  stats[0] = (float)tanh((double)mx);
+  stats[1] = (float)(*dsum / count);
+  stats[2] = (float)(*reinterpret_cast<int*>(stats + 8));
+}
+
+// alpha[k] = mean over rows of |w[:, k]|  (xnor_connect.py:111, DIM = 0)
+__global__ void __launch_bounds__(256) col_absmean_kernel(const float* __restrict__ w, int64_t n, int64_t k, int64_t ld,
+                                                          float* __restrict__ alpha) {
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  double s = 0.0;
+  if (c < k)
+    for (int64_t r = ty; r < n; r += 8) s += (double)fabsf(__ldg(w + r * ld + c));
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < k) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    alpha[c] = (float)(t / (double)n);
+  }
+}
+
+struct PackArgs {
+  int mode, bit_width, lane_bits;
+  const float* w;
+  int64_t n, k, ld_w;
+  uint8_t* packed;
+  int64_t ld_packed;  // bytes
+  const float* stats;
+  float* wq;
+  const float* alpha;
+};
+
+// DoReFa weight code, dorefa_connect.py:108-110: c = round(n * (tanh(w) / (2 max|tanh w|) + 0.5))
+__device__ __forceinline__ float dorefa_wcode(float w, float two_maxt, float n) {
+  float t = (float)tanh((double)w);
+  t = t / two_maxt + 0.5f;
+  return rintf(n * t);
+}
+
+// One warp per row; lanes stride over 32-column groups so that every lane owns whole output words.
+__global__ void __launch_bounds__(256) weight_pack_kernel(PackArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= a.n) return;
+  const float* wr = a.w + row * a.ld_w;
+  float* qr = a.wq ? a.wq + row * a.ld_w : nullptr;
+  uint8_t* pr = a.packed + row * a.ld_packed;
+  const int64_t words = a.ld_packed / 4;
+
+  if (a.mode == QT_W_SIGN || (a.mode == QT_W_DOREFA && a.bit_width == 1)) {
+    const float e = (a.mode == QT_W_DOREFA) ? a.stats[1] : 1.f;
+    uint32_t* out = reinterpret_cast<uint32_t*>(pr);
+    for (int64_t base = 0; base < words * 32; base += 32) {
+      int64_t c = base + lane;
+      bool valid = c < a.k;
+      float v = valid ? __ldg(wr + c) : -1.f;
+      bool pos = !(v < 0.f);
+      if (valid && qr) qr[c] = (pos ? 1.f : -1.f) * e;
+      uint32_t wbits = __ballot_sync(0xffffffffu, valid && pos);
+      if (lane == 0) out[base >> 5] = wbits;
+    }
+  } else if (a.mode == QT_W_TERNARY || a.mode == QT_W_XNOR) {
+    uint32_t* nz = reinterpret_cast<uint32_t*>(pr);
+    uint32_t* sg = reinterpret_cast<uint32_t*>(pr + a.n * a.ld_packed);
+    for (int64_t base = 0; base < words * 32; base += 32) {
+      int64_t c = base + lane;
+      bool valid = c < a.k;
+      float v = valid ? __ldg(wr + c) : 0.f;
+      float t;
+      if (a.mode == QT_W_TERNARY) {
+        float s = sign_safe(v);
+        t = (s + sign_safe(v - 0.5f * s)) * 0.5f;
+        if (valid && qr) qr[c] = t;
+      } else {
+        t = sign3(v);
+        if (valid && qr) qr[c] = t * __ldg(a.alpha + c);
+      }
+      uint32_t bnz = __ballot_sync(0xffffffffu, valid && t != 0.f);
+      uint32_t bsg = __ballot_sync(0xffffffffu, valid && t > 0.f);
+      if (lane == 0) {
+        nz[base >> 5] = bnz;
+        sg[base >> 5] = bsg;
+      }
+    }
+  } else {  // DoReFa k >= 2
+    const float n = (float)((1 << a.bit_width) - 1);
+    const float two_maxt = 2.f * a.stats[0];
+    const float inv_n = 1.0f / n;
+    const int per_word = 32 / a.lane_bits;
+    uint32_t* out = reinterpret_cast<uint32_t*>(pr);
+    for (int64_t wi = lane; wi < words; wi += 32) {
+      uint32_t acc = 0;
+      for (int j = 0; j < per_word; ++j) {
+        int64_t c = wi * per_word + j;
+        if (c < a.k) {
+          float code = dorefa_wcode(__ldg(wr + c), two_maxt, n);
+          if (qr) qr[c] = 2.f * (inv_n * code) - 1.f;
+          acc |= ((uint32_t)code & ((1u << a.lane_bits) - 1u)) << (j * a.lane_bits);
+        }
+      }
+      out[wi] = acc;
+    }
+  }
+}
+
+struct ExpandArgs {
+  int mode, bit_width, lane_bits;
+  const uint8_t* packed;
+  int64_t n, k, ld_packed;
+  const float* alpha;
+  void* out;
+  int out_kind;
+  int64_t ld_out;
+};
+
+__device__ __forceinline__ float packed_value(const ExpandArgs& a, const uint8_t* pr, int64_t c) {
+  if (a.mode == QT_W_SIGN || (a.mode == QT_W_DOREFA && a.bit_width == 1)) {
+    uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c >> 5));
+    return ((w >> (c & 31)) & 1u) ? 1.f : -1.f;
+  }
+  if (a.mode == QT_W_TERNARY || a.mode == QT_W_XNOR) {
+    uint32_t nz = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c >> 5));
+    uint32_t sg = __ldg(reinterpret_cast<const uint32_t*>(pr + a.n * a.ld_packed) + (c >> 5));
+    if (!((nz >> (c & 31)) & 1u)) return 0.f;
+    return ((sg >> (c & 31)) & 1u) ? 1.f : -1.f;
+  }
+  const int per_word = 32 / a.lane_bits;
+  uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(pr) + c / per_word);
+  uint32_t code = (w >> ((c % per_word) * a.lane_bits)) & ((1u << a.lane_bits) - 1u);
+  if (a.out_kind == 2) return (float)code;                       // raw unsigned code
+  return 2.f * (float)code - (float)((1 << a.bit_width) - 1);    // centred 2c - n
+}
+
+// Each thread produces 16 consecutive output columns of one row.
+__global__ void __launch_bounds__(256) weight_expand_kernel(ExpandArgs a) {
+  const int64_t groups_per_row = a.ld_out / 16;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= a.n * groups_per_row) return;
+  const int64_t row = gid / groups_per_row, c0 = (gid - row * groups_per_row) * 16;
+  const uint8_t* pr = a.packed + row * a.ld_packed;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    int64_t c = c0 + j;
+    v[j] = (c < a.k) ? packed_value(a, pr, c) : 0.f;
+  }
+  if (a.out_kind == 1 || a.out_kind == 2) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      w[q] = ((uint32_t)((int)v[4 * q] & 0xff)) | ((uint32_t)((int)v[4 * q + 1] & 0xff) << 8) |
+             ((uint32_t)((int)v[4 * q + 2] & 0xff) << 16) | ((uint32_t)((int)v[4 * q + 3] & 0xff) << 24);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out) + row * a.ld_out + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ld_out + c0;
+    __nv_bfloat16* o2 = o + a.n * a.ld_out;
+    __align__(16) __nv_bfloat16 h[16], l[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float x = v[j];
+      if (a.out_kind == 4) x *= (c0 + j < a.k) ? __ldg(a.alpha + c0 + j) : 0.f;
+      h[j] = __float2bfloat16_rn(x);
+      l[j] = __float2bfloat16_rn(x - __bfloat162float(h[j]));
+    }
+    reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(h)[0];
+    reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(h)[1];
+    if (a.out_kind == 4) {
+      reinterpret_cast<uint4*>(o2)[0] = reinterpret_cast<uint4*>(l)[0];
+      reinterpret_cast<uint4*>(o2)[1] = reinterpret_cast<uint4*>(l)[1];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col
+// ---------------------------------------------------------------------------------------------
+struct Im2colArgs {
+  const uint8_t* x;
+  int eb;
+  int64_t B, C, H, W, OH, OW;
+  int kh, kw, sh, sw, ph, pw, dh, dw;
+  int64_t c_begin, cg;   // first channel of the group, channels per group
+  uint8_t* out;
+  int64_t ld_out, kcols;
+};
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
+  const int64_t vec_per_row = a.ld_out / VEC;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t M = a.B * a.OH * a.OW;
+  if (gid >= M * vec_per_row) return;
+  const int64_t m = gid / vec_per_row, col0 = (gid - m * vec_per_row) * VEC;
+  const int64_t b = m / (a.OH * a.OW), r = m - b * (a.OH * a.OW);
+  const int64_t oh = r / a.OW, ow = r - oh * a.OW;
+  const T* x = reinterpret_cast<const T*>(a.x);
+  __align__(16) T v[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    int64_t col = col0 + j;
+    T val = T(0);
+    if (col < a.kcols) {
+      int64_t c = col / (a.kh * a.kw);
+      int rem = (int)(col - c * (a.kh * a.kw));
+      int ky = rem / a.kw, kx = rem - ky * a.kw;
+      int64_t ih = oh * a.sh - a.ph + (int64_t)ky * a.dh;
+      int64_t iw = ow * a.sw - a.pw + (int64_t)kx * a.dw;
+      if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W)
+        val = x[((b * a.C + a.c_begin + c) * a.H + ih) * a.W + iw];
+    }
+    v[j] = val;
+  }
+  T* o = reinterpret_cast<T*>(a.out) + m * a.ld_out + col0;
+  if (sizeof(T) * VEC == 16) {
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = v[j];
+  }
+}
+
+template <bool UNSIGNED>
+__global__ void __launch_bounds__(256) rowsum_i8_kernel(const uint8_t* __restrict__ a, int64_t rows, int64_t ld,
+                                                        int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(a + row * ld);
+  int s = 0;
+  for (int64_t i = lane; i < ld / 4; i += 32) {
+    uint32_t w = __ldg(p + i);
+    if (UNSIGNED) s = __dp4a(w, 0x01010101u, (unsigned)s);
+    else s = __dp4a((int)w, 0x01010101, s);
+  }
+  s = warp_sum_i(s);
+  if (lane == 0) out[row] = s;
+}
+
+}  // namespace qt
+
+using namespace qt;
+
+extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(p && p->x, "qt_quant_act: null argument");
+  QT_REQUIRE(p->mode >= QT_Q_SIGN && p->mode <= QT_Q_SPLIT, "qt_quant_act: bad mode %d", p->mode);
+  QT_REQUIRE(p->rows >= 0 && p->cols >= 0 && p->ld_x >= p->cols, "qt_quant_act: bad shape");
+  if (p->rows == 0 || p->cols == 0) return QT_OK;
+  ActArgs a;
+  a.q.mode = p->mode;
+  a.q.n = a.q.inv_n = 1.f;
+  a.q.lo_e = a.q.hi_e = a.q.step = a.q.maxv = 0.f;
+  a.q.with_sign = p->with_sign;
+  if (p->mode == QT_Q_DOREFA) {
+    QT_REQUIRE(p->bit_width >= 2 && p->bit_width <= 16, "qt_quant_act: DoReFa bit width %d not in 2..16", p->bit_width);
+    a.q.n = (float)((1 << p->bit_width) - 1);
+    a.q.inv_n = 1.0f / a.q.n;
+    if (p->codes_kind == 1 || p->codes_kind == 2)
+      QT_REQUIRE(p->bit_width <= 8, "qt_quant_act: 8-bit code lanes need bit width <= 8");
+  }
+  if (p->mode == QT_Q_LOG) {
+    a.q.lo_e = (float)(p->fsr - (1 << p->bit_width));
+    a.q.hi_e = (float)p->fsr;
+  }
+  if (p->mode == QT_Q_LIN) {
+    a.q.step = ldexpf(1.f, p->fsr - p->bit_width);
+    a.q.maxv = ldexpf(1.f, p->fsr);
+  }
+  if (p->mode == QT_Q_SPLIT) QT_REQUIRE(p->codes_kind == 4, "qt_quant_act: QT_Q_SPLIT needs codes_kind 4");
+  if (p->mode == QT_Q_LOG || p->mode == QT_Q_LIN)
+    QT_REQUIRE(p->codes_kind == 0 && !p->bits, "qt_quant_act: Log/Lin quantizers produce fp32 only");
+  QT_REQUIRE(p->codes_kind >= 0 && p->codes_kind <= 4, "qt_quant_act: bad codes_kind");
+  if (p->codes_kind) QT_REQUIRE(p->codes && p->ld_codes >= p->cols, "qt_quant_act: bad codes buffer");
+  if (p->bits) QT_REQUIRE(p->mode == QT_Q_SIGN && p->ld_bits * 32 >= p->cols, "qt_quant_act: bits need QT_Q_SIGN and ld_bits*32 >= cols");
+  if (p->y) QT_REQUIRE(p->ld_y >= p->cols, "qt_quant_act: ld_y < cols");
+  a.x = p->x; a.rows = p->rows; a.cols = p->cols; a.ld_x = p->ld_x;
+  a.y = p->y; a.ld_y = p->ld_y; a.codes = p->codes; a.codes_kind = p->codes_kind; a.ld_codes = p->ld_codes;
+  a.bits = p->bits; a.ld_bits = p->ld_bits; a.row_sum = p->row_sum; a.row_scale = p->row_scale; a.overflow = p->overflow;
+
+  bool vec = (p->cols % 4 == 0) && (p->ld_x % 4 == 0) && aligned(p->x, 16);
+  if (p->y) vec = vec && (p->ld_y % 4 == 0) && aligned(p->y, 16);
+  if (p->codes_kind == 1 || p->codes_kind == 2) vec = vec && (p->ld_codes % 4 == 0) && aligned(p->codes, 4);
+  if (p->codes_kind >= 3) vec = vec && (p->ld_codes % 4 == 0) && aligned(p->codes, 8) && ((p->rows * p->ld_codes) % 4 == 0);
+
+  // split long rows into chunks when there are too few rows to fill the machine
+  a.chunk = p->cols; a.nchunks = 1;
+  if (p->mode != QT_Q_XNOR_ROW && p->cols > 8192 && p->rows < 4096) {
+    a.chunk = 4096;
+    a.nchunks = (int)ceil_div(p->cols, a.chunk);
+  }
+  if (a.nchunks > 1 && p->row_sum) QT_CUDA_OK(cudaMemsetAsync(p->row_sum, 0, sizeof(int32_t) * p->rows, stream));
+  const int warps_per_block = 8;
+  int64_t tasks = p->rows * a.nchunks;
+  dim3 grid((unsigned)ceil_div(tasks, warps_per_block)), block(32 * warps_per_block);
+  if (vec) act_quant_kernel<true><<<grid, block, 0, stream>>>(a);
+  else act_quant_kernel<false><<<grid, block, 0, stream>>>(a);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+static int lane_bits_for(int k) { return k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : 8; }
+
+extern "C" int qt_pack_weight(const QtWeightPack* p, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(p && p->w && p->packed && p->stats, "qt_pack_weight: null argument");
+  QT_REQUIRE(p->mode >= QT_W_SIGN && p->mode <= QT_W_XNOR, "qt_pack_weight: bad mode %d", p->mode);
+  QT_REQUIRE(p->n > 0 && p->k > 0 && p->ld_w >= p->k, "qt_pack_weight: bad shape");
+  QT_REQUIRE(p->ld_packed % 4 == 0, "qt_pack_weight: ld_packed must be a multiple of 4 bytes");
+  PackArgs a;
+  a.mode = p->mode; a.bit_width = p->bit_width; a.lane_bits = 1;
+  if (p->mode == QT_W_DOREFA) {
+    QT_REQUIRE(p->bit_width >= 1 && p->bit_width <= 8, "qt_pack_weight: DoReFa bit width %d not in 1..8", p->bit_width);
+    a.lane_bits = lane_bits_for(p->bit_width);
+  }
+  QT_REQUIRE(p->ld_packed * 8 >= p->k * a.lane_bits, "qt_pack_weight: ld_packed too small");
+  if (p->mode == QT_W_XNOR) QT_REQUIRE(p->alpha, "qt_pack_weight: QT_W_XNOR needs alpha");
+  a.w = p->w; a.n = p->n; a.k = p->k; a.ld_w = p->ld_w;
+  a.packed = (uint8_t*)p->packed; a.ld_packed = p->ld_packed; a.stats = p->stats; a.wq = p->wq; a.alpha = p->alpha;
+
+  // reductions: stats[0..3] + int zero counter at stats[8] + double accumulator at stats[12..13]
+  QT_CUDA_OK(cudaMemsetAsync(p->stats, 0, 16 * sizeof(float), stream));
+  double* dsum = reinterpret_cast<double*>(p->stats + 12);
+  QT_REQUIRE(aligned(dsum, 8), "qt_pack_weight: stats must be 8-byte aligned");
+  int blocks = (int)std::min<int64_t>(ceil_div(p->n * p->k, 256 * 8), 148 * 8);
+  weight_stats_kernel<<<blocks, 256, 0, stream>>>(p->w, p->n, p->k, p->ld_w, p->stats, dsum);
+  QT_LAUNCH_CHECK();
+  weight_stats_finish_kernel<<<1, 1, 0, stream>>>(p->stats, dsum, (double)p->n * (double)p->k);
+  QT_LAUNCH_CHECK();
+  if (p->mode == QT_W_XNOR && !p->alpha_is_input) {
+    col_absmean_kernel<<<(unsigned)ceil_div(p->k, 32), 256, 0, stream>>>(p->w, p->n, p->k, p->ld_w, p->alpha);
+    QT_LAUNCH_CHECK();
+  }
+  weight_pack_kernel<<<(unsigned)ceil_div(p->n, 8), 256, 0, stream>>>(a);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+extern "C" int qt_col_absmean(const float* w, int64_t n, int64_t k, int64_t ld_w, float* alpha, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(w && alpha && n > 0 && k > 0 && ld_w >= k, "qt_col_absmean: bad argument");
+  col_absmean_kernel<<<(unsigned)ceil_div(k, 32), 256, 0, stream>>>(w, n, k, ld_w, alpha);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+extern "C" int qt_expand_weight(const QtWeightExpand* p, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(p && p->packed && p->out, "qt_expand_weight: null argument");
+  QT_REQUIRE(p->mode >= QT_W_SIGN && p->mode <= QT_W_XNOR, "qt_expand_weight: bad mode");
+  QT_REQUIRE(p->out_kind >= 1 && p->out_kind <= 4, "qt_expand_weight: bad out_kind");
+  QT_REQUIRE(p->ld_out % 16 == 0 && p->ld_out >= p->k, "qt_expand_weight: ld_out must be a multiple of 16 and >= k");
+  QT_REQUIRE(aligned(p->out, 16), "qt_expand_weight: out must be 16-byte aligned");
+  if (p->out_kind == 4) QT_REQUIRE(p->alpha && p->mode == QT_W_XNOR, "qt_expand_weight: kind 4 needs XNOR alpha");
+  if (p->out_kind == 2) QT_REQUIRE(p->mode == QT_W_DOREFA && p->bit_width >= 2, "qt_expand_weight: uint8 codes are DoReFa only");
+  if (p->out_kind == 1 && p->mode == QT_W_DOREFA) QT_REQUIRE(p->bit_width <= 7, "qt_expand_weight: centred int8 codes need k <= 7");
+  ExpandArgs a;
+  a.mode = p->mode; a.bit_width = p->bit_width;
+  a.lane_bits = (p->mode == QT_W_DOREFA) ? lane_bits_for(p->bit_width) : 1;
+  a.packed = (const uint8_t*)p->packed; a.n = p->n; a.k = p->k; a.ld_packed = p->ld_packed; a.alpha = p->alpha;
+  a.out = p->out; a.out_kind = p->out_kind; a.ld_out = p->ld_out;
+  int64_t threads = p->n * (p->ld_out / 16);
+  weight_expand_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, stream>>>(a);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+extern "C" int qt_im2col(const QtIm2col* p, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(p && p->x && p->out, "qt_im2col: null argument");
+  QT_REQUIRE(p->elem_bytes == 1 || p->elem_bytes == 2 || p->elem_bytes == 4, "qt_im2col: elem_bytes must be 1, 2 or 4");
+  QT_REQUIRE(p->groups >= 1 && p->C % p->groups == 0 && p->group >= 0 && p->group < p->groups, "qt_im2col: bad groups");
+  Im2colArgs a;
+  a.x = (const uint8_t*)p->x; a.eb = p->elem_bytes;
+  a.B = p->B; a.C = p->C; a.H = p->H; a.W = p->W; a.OH = p->OH; a.OW = p->OW;
+  a.kh = p->kh; a.kw = p->kw; a.sh = p->stride_h; a.sw = p->stride_w; a.ph = p->pad_h; a.pw = p->pad_w;
+  a.dh = p->dil_h; a.dw = p->dil_w;
+  a.cg = p->C / p->groups; a.c_begin = a.cg * p->group;
+  a.out = (uint8_t*)p->out; a.ld_out = p->ld_out; a.kcols = a.cg * p->kh * p->kw;
+  QT_REQUIRE(p->ld_out >= a.kcols, "qt_im2col: ld_out < C/groups*kh*kw");
+  const int64_t M = p->B * p->OH * p->OW;
+  if (M == 0) return QT_OK;
+  const int vec = 16 / p->elem_bytes;
+  QT_REQUIRE(p->ld_out % vec == 0 && aligned(p->out, 16), "qt_im2col: ld_out*elem_bytes must be a multiple of 16, out 16B aligned");
+  int64_t threads = M * (p->ld_out / vec);
+  unsigned blocks = (unsigned)ceil_div(threads, 256);
+  if (p->elem_bytes == 1) im2col_kernel<uint8_t, 16><<<blocks, 256, 0, stream>>>(a);
+  else if (p->elem_bytes == 2) im2col_kernel<uint16_t, 8><<<blocks, 256, 0, stream>>>(a);
+  else im2col_kernel<uint32_t, 4><<<blocks, 256, 0, stream>>>(a);
+  QT_LAUNCH_CHECK();
+  if (p->row_sum) {
+    QT_REQUIRE(p->elem_bytes == 1, "qt_im2col: row_sum needs 1-byte codes");
+    if (p->is_unsigned) rowsum_i8_kernel<true><<<(unsigned)ceil_div(M, 8), 256, 0, stream>>>(a.out, M, p->ld_out, p->row_sum);
+    else rowsum_i8_kernel<false><<<(unsigned)ceil_div(M, 8), 256, 0, stream>>>(a.out, M, p->ld_out, p->row_sum);
+    QT_LAUNCH_CHECK();
+  }
+  return QT_OK;
+}

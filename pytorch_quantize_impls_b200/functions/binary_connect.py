@@ -1,0 +1,137 @@
+"""BinaryConnect / BinaryNet ops -- surface of QuantTorch/functions/binary_connect.py."""
+import warnings as _warnings
+
+import torch
+
+from .. import _engine as eng
+from .. import _lib as L
+from .. import _ops as ops
+from .common import TaggingFunction, front, safeSign, ste_clip
+
+
+class BinaryConnectDeterministic(TaggingFunction):
+    """r_b = sign(r) (0 -> +1); backward 1_{|r|<=1.001}.  binary_connect.py:14-38.
+
+    Besides the fp32 +-1 tensor the forward emits int8 codes and packed sign bits in the same pass; the next
+    LinearBin / BinConv2d / LinearTer / LinearDorefa contracts on those."""
+
+    @staticmethod
+    def forward(ctx, input):
+        ctx.save_for_backward(input)
+        y, tag = ops.quant_act(input, L.Q_SIGN, want_y=True, codes_kind=L.CODES_I8,
+                               want_bits=(input.dim() == 2), kind="sign")
+        TaggingFunction._leave(tag)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, = ctx.saved_tensors
+        return ste_clip(grad_output, input)
+
+
+class BinaryConnectStochastic(torch.autograd.Function):
+    """+1 with probability hardsigmoid(r); binary_connect.py:42-71.  Device Philox stream (torch.rand_like),
+    so it is statistically, not bitwise, comparable with the CPU reference (as the reference's own test does)."""
+
+    @staticmethod
+    def forward(ctx, input):
+        ops.require_cuda(input, "input")
+        ctx.save_for_backward(input)
+        z = torch.rand_like(input, requires_grad=False)
+        p = (torch.clamp(input, -1, 1) + 1) / 2
+        return -1.0 + 2.0 * (z < p).float()
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, = ctx.saved_tensors
+        return ste_clip(grad_output, input)
+
+
+def BinaryConnect(stochastic=False):
+    """nn.Module wrapping the binarization op (binary_connect.py:74-83)."""
+    return front(BinaryConnectStochastic if stochastic else BinaryConnectDeterministic)
+
+
+def _sign_pack(weight):
+    return ops.pack_weight(weight.detach().reshape(weight.shape[0], -1), "sign")
+
+
+class BinaryDense(TaggingFunction):
+    """y = x . sign(W)^T + b with explicit backward, binary_connect.py:86-112."""
+
+    @staticmethod
+    def forward(ctx, input, weight, bias=None):
+        ctx.save_for_backward(input, weight, bias)
+        return eng.linear(input, _sign_pack(weight), bias)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, weight, bias = ctx.saved_tensors
+        weight_b = safeSign(weight)
+        grad_input = grad_weight = grad_bias = None
+        if ctx.needs_input_grad[0]:
+            grad_input = grad_output.mm(weight_b)
+        if ctx.needs_input_grad[1]:
+            grad_weight = grad_output.t().mm(input)
+        if bias is not None and ctx.needs_input_grad[2]:
+            grad_bias = grad_output.sum(0).squeeze(0)
+        return grad_input, grad_weight, grad_bias
+
+
+def BinaryConv2d(stride=1, padding=1, dilation=1, groups=1):
+    """DEPRECATED functional conv (binary_connect.py:116-153); kept for surface parity."""
+    _warnings.warn("Deprecated conv op !", DeprecationWarning, stacklevel=2)
+
+    class _BinaryConv2d(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, input, weight, bias=None):
+            ctx.save_for_backward(input, weight, bias)
+            return eng.conv2d(input, _sign_pack(weight), bias, tuple(weight.shape), stride, padding, dilation, groups)
+
+        @staticmethod
+        def backward(ctx, grad_output):
+            input, weight, bias = ctx.saved_tensors
+            weight_b = safeSign(weight)
+            gi = gw = gb = None
+            if ctx.needs_input_grad[0]:
+                gi = torch.nn.grad.conv2d_input(input.size(), weight_b, grad_output, stride=stride, padding=padding,
+                                                dilation=dilation, groups=groups)
+            if ctx.needs_input_grad[1]:
+                gw = torch.nn.grad.conv2d_weight(input, weight.shape, grad_output, stride=stride, padding=padding,
+                                                 dilation=dilation, groups=groups)
+            if bias is not None and ctx.needs_input_grad[2]:
+                gb = grad_output.sum((0, 2, 3))
+            return (gi, gw, gb) if bias is not None else (gi, gw)
+
+    return _BinaryConv2d
+
+
+def AP2(x):
+    """sign(x) * 2^round(log2|x|), binary_connect.py:157-169 (shift-BN primitive; torch ops, off the measured path)."""
+    two = torch.ones_like(x) * 2
+    return safeSign(x) * torch.pow(two, torch.round(torch.log2(torch.abs(x))))
+
+
+class ShiftBatch(torch.autograd.Function):
+    """Shift-based batch-norm primitive, binary_connect.py:173-214 (off the measured path; torch ops)."""
+
+    @staticmethod
+    def forward(ctx, input, running_mean, running_var, weight, bias, eps):
+        inputs_mu = input - running_mean
+        sqrtvar = torch.sqrt(running_var + eps)
+        norm_inputs = inputs_mu * AP2(1 / sqrtvar)
+        out = norm_inputs * AP2(weight) + bias
+        ctx.save_for_backward(input, weight, sqrtvar, norm_inputs)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, weight, sqrtvar, norm_inputs = ctx.saved_tensors
+        gi = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gi = grad_output * weight / sqrtvar
+        if ctx.needs_input_grad[3]:
+            gw = grad_output * norm_inputs
+        if ctx.needs_input_grad[4]:
+            gb = grad_output.sum(0).squeeze(0)
+        return gi, None, None, gw, gb, None

@@ -1,0 +1,138 @@
+"""Shared machinery of the quantized layers.
+
+The reference repeats the same train()/forward pattern in every layer class
+(binary_layers.py:30-46, terner_layers.py:30-51, dorefa_layers.py:29-45, log_lin_layers.py:22-42);
+here it lives once, parameterised by two hooks:
+    _weight_op(w)   differentiable fake-quant of the fp32 weights (the reference's bin_op / ter_op / weight_op)
+    _make_pack(w)   k-bit HBM pack of the fp32 master weights
+"""
+import torch
+
+from .. import _engine as eng
+from .. import _ops as ops
+
+
+class QLayer():
+    """Marker base class, QuantTorch/layers/common.py:1-9."""
+
+    def get_quant_weight(self):
+        raise NotImplementedError
+
+    def set_quant_weight(self):
+        raise NotImplementedError
+
+    def restore_weight(self):
+        raise NotImplementedError
+
+
+class _EvalState:
+    __slots__ = ("pack", "version", "ptr")
+
+
+class _Contraction(torch.autograd.Function):
+    """Forward = low-bit kernels; backward = the reference's autograd semantics (F.linear / F.conv2d of the
+    fake-quantized weight, STE through the weight op), evaluated with torch ops."""
+
+    @staticmethod
+    def forward(ctx, input, weight, bias, layer):
+        ctx.layer = layer
+        ctx.save_for_backward(input, weight, bias)
+        return layer._run_kernels(input)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, weight, bias = ctx.saved_tensors
+        layer = ctx.layer
+        gi = gw = gb = None
+        with torch.enable_grad():
+            w = weight.detach().requires_grad_(True)
+            wq = layer._weight_op(w) if layer.training else w
+        wqd = wq.detach()
+        if layer._is_conv:
+            kw = dict(stride=layer.stride, padding=layer.padding, dilation=layer.dilation, groups=layer.groups)
+            if ctx.needs_input_grad[0]:
+                gi = torch.nn.grad.conv2d_input(input.shape, wqd, grad_output, **kw)
+            if ctx.needs_input_grad[1]:
+                gwq = torch.nn.grad.conv2d_weight(input, weight.shape, grad_output, **kw)
+            if bias is not None and ctx.needs_input_grad[2]:
+                gb = grad_output.sum((0, 2, 3))
+        else:
+            g2 = grad_output.reshape(-1, grad_output.shape[-1])
+            if ctx.needs_input_grad[0]:
+                gi = (g2 @ wqd).reshape(input.shape)
+            if ctx.needs_input_grad[1]:
+                gwq = g2.t() @ input.reshape(-1, input.shape[-1])
+            if bias is not None and ctx.needs_input_grad[2]:
+                gb = g2.sum(0)
+        if ctx.needs_input_grad[1]:
+            if wq is w:
+                gw = gwq
+            else:
+                gw, = torch.autograd.grad(wq, w, gwq)
+        return gi, gw, gb, None
+
+
+class QuantLayerMixin(QLayer):
+    _is_conv = False
+    _eval_state = None
+
+    # ---- hooks -------------------------------------------------------------------------
+    def _weight_op(self, w):
+        raise NotImplementedError
+
+    def _make_pack(self, w):
+        raise NotImplementedError
+
+    # ---- weight-swap train()/eval(), e.g. binary_layers.py:30-40 --------------------------
+    def train(self, mode=True):
+        if self.training == mode:
+            return self
+        self.training = mode
+        if mode:
+            self.weight.data.copy_(self.weight.org.data)
+            self._eval_state = None
+        else:
+            if not hasattr(self.weight, 'org'):
+                self.weight.org = self.weight.data.clone()
+            self.weight.org.data.copy_(self.weight.data)
+            st = _EvalState()
+            st.pack = self._make_pack(self.weight)            # packed once, from the fp32 master weights
+            with torch.no_grad():
+                self.weight.data.copy_(self._weight_op(self.weight).detach())
+            st.version, st.ptr = self.weight._version, self.weight.data_ptr()
+            self._eval_state = st
+        return self
+
+    def _current_pack(self):
+        if self.training:
+            return self._make_pack(self.weight)               # the reference re-quantizes W on every call
+        st = self._eval_state
+        if st is not None and st.version == self.weight._version and st.ptr == self.weight.data_ptr():
+            return st.pack
+        # eval mode with weights that train(False) did not produce (state_dict loaded in eval mode, .to() after
+        # eval, ...): the reference contracts with the stored values as they are -> real-valued weight operand
+        st = _EvalState()
+        st.pack = ops.pack_real_weight(self.weight.detach().reshape(self.weight.shape[0], -1))
+        st.version, st.ptr = self.weight._version, self.weight.data_ptr()
+        self._eval_state = st
+        return st.pack
+
+    def _run_kernels(self, input):
+        pack = self._current_pack()
+        if self._is_conv:
+            return eng.conv2d(input, pack, self.bias, tuple(self.weight.shape), self.stride, self.padding,
+                              self.dilation, self.groups)
+        return eng.linear(input, pack, self.bias)
+
+    def forward(self, input):
+        ops.require_cuda(input, "input")
+        needs_grad = torch.is_grad_enabled() and (
+            input.requires_grad or self.weight.requires_grad or (self.bias is not None and self.bias.requires_grad))
+        if needs_grad:
+            return _Contraction.apply(input, self.weight, self.bias, self)
+        return self._run_kernels(input)
+
+
+def check_convert(other, cls, name):
+    if not isinstance(other, cls):
+        raise TypeError("Expected a {} ! Receive:  {}".format(name, other.__class__))
