@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- quantized-GEMM throughput of the QuantTorch hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): XnorNet 3-layer MLP 4096-4096-4096-1000, 1-bit weights / 1-bit activations,
+batch 8192 per GPU, synthetic N(0,1) inputs (seed 1234), random-init weights.  One "step" = one forward pass of
+    nnQuantXnor(1) -> LinearXNOR -> nnQuantXnor(1) -> LinearXNOR -> nnQuantXnor(1) -> LinearXNOR
+over one batch.  metric = quantized-GEMM GOPS = 2*B*sum(K_l*N_l) / time (logical low-bit contraction).
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract plus `roofline`, `cpu_baseline`, `e2e`, `clocks`,
+`gpu_launches` and an `extra` object with the north-star LinearBin 4096x4096 batch 8192 layer and a DoReFa-4 layer.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS = [4096, 4096, 4096, 1000]
+BATCH = 8192
+MACS_PER_ROW = sum(DIMS[i] * DIMS[i + 1] for i in range(3))
+WORKLOAD = "XnorNet 3-layer MLP 4096-4096-4096-1000, 1-bit W / 1-bit A, batch 8192 per GPU (BASELINE configs[1])"
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["src"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (the reference is pure Python on torch; oracle/ restates it)
+# --------------------------------------------------------------------------------------------
+def cpu_reference_gops(batch, reps, warmup=1, seed=1234):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import quanttorch_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(seed)
+    ws = [torch.empty(DIMS[i + 1], DIMS[i]).uniform_(-DIMS[i] ** -0.5, DIMS[i] ** -0.5, generator=g) for i in range(3)]
+    bs = [torch.empty(DIMS[i + 1]).uniform_(-1, 1, generator=g) for i in range(3)]
+    x = torch.randn(batch, DIMS[0], generator=g)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + reps):
+            t0 = time.perf_counter()
+            O.xnor_mlp_forward(x, ws, bs)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    ops = 2.0 * batch * MACS_PER_ROW
+    return dict(times=times, gops_best=ops / min(times) / 1e9, gops_mean=ops / (sum(times) / len(times)) / 1e9,
+                cores=cores, batch=batch)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 1024
+    r = cpu_reference_gops(sample_b, reps=max(args.steps, 1), warmup=max(args.warmup, 1))
+    ms = 1e3 * sum(r["times"]) / len(r["times"])
+    sample = "oracle port of the reference CPU path, batch %d rows of the same MLP per step, %d torch threads" % (
+        sample_b, r["cores"])
+    line = {
+        "impl": "reference", "metric": "quantized_gemm_gops", "value": round(r["gops_mean"], 2), "unit": "GOPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_batch": sample_b},
+        "cpu_baseline": {"value": round(r["gops_mean"], 2), "unit": "GOPS", "cores": r["cores"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": round(r["gops_mean"], 2), "unit": "GOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def build_xnor_mlp(Q, torch, dev, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    lays = []
+    for i in range(3):
+        l = Q.layers.LinearXNOR(DIMS[i], DIMS[i + 1])
+        l.weight.data.uniform_(-DIMS[i] ** -0.5, DIMS[i] ** -0.5, generator=g)
+        l.bias.data.uniform_(-1, 1, generator=g)
+        lays.append(l)
+    mods = []
+    for l in lays:
+        mods += [Q.functions.nnQuantXnor(1), l]
+    net = torch.nn.Sequential(*mods).to(dev)
+    net.eval()          # inference: weights packed once (2 bit planes + alpha[k]) at the train(False) swap
+    return net
+
+
+class GemmTimer:
+    """CUDA-event timing of every tensor-core GEMM launch inside the timed region (current stream)."""
+
+    def __init__(self, torch, ops):
+        self.torch, self.ops, self.ev, self.on = torch, ops, [], False
+        self._orig_bf16, self._orig_i8 = ops.gemm_bf16, ops.gemm_i8
+
+    def _wrap(self, fn, kind):
+        def inner(*a, **k):
+            if not self.on:
+                return fn(*a, **k)
+            s, e = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn(*a, **k)
+            e.record()
+            M, N, K = (a[7], a[8], a[9]) if kind == "bf16" else (a[6], a[7], a[8])
+            self.ev.append((kind, M, N, K, s, e))
+        return inner
+
+    def install(self):
+        self.ops.gemm_bf16 = self._wrap(self._orig_bf16, "bf16")
+        self.ops.gemm_i8 = self._wrap(self._orig_i8, "i8")
+
+    def summary(self):
+        out = {}
+        for kind, M, N, K, s, e in self.ev:
+            out.setdefault((kind, M, N, K), []).append(s.elapsed_time(e))
+        return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import pytorch_quantize_impls_b200 as Q
+    from pytorch_quantize_impls_b200 import _lib, _ops
+    pk = peaks()
+
+    net = build_xnor_mlp(Q, torch, dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    NBUF = 3   # rotate over 3 x 134 MB inputs (> 126 MB L2) so no step finds its input in L2
+    x_host = [torch.randn(BATCH, DIMS[0], generator=g).pin_memory() for _ in range(NBUF)]
+    x_dev = [t.to(dev) for t in x_host]
+    gathered = torch.empty(world * BATCH, DIMS[-1], device=dev) if world > 1 else None
+    out_host = torch.empty(BATCH, DIMS[-1]).pin_memory()
+    timer = GemmTimer(torch, _ops)
+    timer.install()
+
+    def step(i, x=None):
+        y = net(x_dev[i % NBUF] if x is None else x)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y)      # the only collective: logits
+        return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        barrier()
+        _lib.launch_count(reset=True)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        timer.on = True
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        timer.on = False
+        launches = _lib.launch_count(reset=True)
+        ms_total = e0.elapsed_time(e1)
+        t = torch.tensor([ms_total], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / args.steps
+
+        # end-to-end through the public nn.Module API with HOST buffers: H2D of the batch and D2H of the logits
+        # are inside the timed region, every step
+        xe = torch.empty(BATCH, DIMS[0], device=dev)
+        for i in range(2):
+            xe.copy_(x_host[i % NBUF], non_blocking=True); out_host.copy_(step(i, xe), non_blocking=True)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for i in range(args.steps):
+            xe.copy_(x_host[i % NBUF], non_blocking=True)
+            y = step(i, xe)
+            out_host.copy_(y, non_blocking=True)
+        e3.record()
+        barrier()
+        t = torch.tensor([e2.elapsed_time(e3)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item()) / args.steps
+        clocks = sampler.stop() if rank == 0 else None
+
+        extra = {}
+        if rank == 0:
+            extra = extra_layers(Q, torch, dev, pk, _ops)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ops_step = 2.0 * BATCH * MACS_PER_ROW * world
+    value = ops_step / (ms_step * 1e-3) / 1e9
+    e2e = ops_step / (ms_e2e * 1e-3) / 1e9
+
+    # roofline of the dominant kernel: the bf16 tcgen05 GEMM of the 4096x4096 layers (2 of the 3 contractions)
+    summ = timer.summary()
+    dom = max(summ.items(), key=lambda kv: sum(kv[1]))
+    (kind, M, N, K), durs = dom
+    avg_ms = sum(durs) / len(durs)
+    flops = 2.0 * M * N * K                         # algorithmic: the logical 1-bit contraction, once
+    achieved = flops / (avg_ms * 1e-3) / 1e12
+    peak = pk["bf16_tflops_sustained"]
+    gemm_ms_per_step = sum(sum(v) for v in summ.values()) / args.steps
+    roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<256, bf16, 4 stages> M=%d N=%d K=%d (2 passes: W hi/lo)" % (M, N, K),
+                "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk["src"] == "measured" else "fallback",
+                "avg_launch_ms": round(avg_ms, 4), "gemm_share_of_step": round(gemm_ms_per_step / ms_step, 3),
+                "traffic": None}
+
+    cb = cpu_reference_gops(2048, reps=3, warmup=1)
+    cpu_baseline = {"value": round(cb["gops_best"], 2), "unit": "GOPS", "cores": cb["cores"], "kind": "port",
+                    "sample": "oracle port (torch CPU, %d threads) of the same MLP forward on a 2048-row batch, best of 3"
+                              % cb["cores"]}
+    line = {
+        "metric": "quantized_gemm_gops", "value": round(value, 1), "unit": "GOPS", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "mode": "eval (weights pre-packed: 2 bit planes + alpha[k])",
+                   "l2": "inputs rotate over 3 device buffers of 134 MB each (> 126 MB L2)",
+                   "images_per_sec": round(BATCH * world / (ms_step * 1e-3), 1),
+                   "collective": "all_gather of fp32 logits" if world > 1 else "none"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": {"value": round(e2e, 1), "unit": "GOPS", "ms_per_step": round(ms_e2e, 4),
+                "h2d_bytes_per_step": BATCH * DIMS[0] * 4, "d2h_bytes_per_step": BATCH * DIMS[-1] * 4},
+        "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_fn(torch, fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def extra_layers(Q, torch, dev, pk, _ops):
+    """North-star layer (BinaryConnect -> LinearBin 4096x4096, batch 8192) and a DoReFa W4A4 layer of the same shape."""
+    M = K = N = None
+    out = {}
+    M, K, N = 8192, 4096, 4096
+    g = torch.Generator().manual_seed(99)
+    xs = [torch.randn(M, K, generator=g).to(dev) for _ in range(2)]
+    bytes_module = 4.0 * M * K + N * K / 8 + 4 * N + 4.0 * M * N      # fp32 in, 1-bit W, fp32 out
+    ops_ = 2.0 * M * K * N
+    lay = Q.layers.LinearBin(K, N).to(dev)
+    lay.bias.data.uniform_(-1, 1)
+    lay.eval()
+    act = Q.functions.BinaryConnect()
+    i = [0]
+
+    def f():
+        i[0] += 1
+        return lay(act(xs[i[0] % 2]))
+    for name, kw in (("tcgen05_i8", dict(i8="tcgen05")), ("xnor_popcount_cuda_core", dict(popcount=True))):
+        Q.set_backend(**kw)
+        ms = time_fn(torch, f, iters=5 if name.startswith("xnor") else 20)
+        out["linearbin_4096x4096_b8192_" + name] = {
+            "ms": round(ms, 4), "gops": round(ops_ / ms / 1e6, 1),
+            "hbm_gbs_algorithmic": round(bytes_module / ms / 1e6, 1),
+            "hbm_frac": round(bytes_module / ms / 1e6 / pk["hbm_gbs"], 4)}
+        Q.set_backend(i8="auto", popcount=False)
+    # contraction kernel alone on pre-quantized operands
+    xq = act(xs[0])
+    ms = time_fn(torch, lambda: lay(xq), iters=20)
+    out["linearbin_4096x4096_b8192_contraction_only"] = {"ms": round(ms, 4), "tops": round(ops_ / ms / 1e9, 1)}
+    xu = [torch.rand(M, K, generator=g).to(dev) for _ in range(2)]
+    ld = Q.layers.LinearDorefa(K, N, bit_width=4).to(dev)
+    ld.eval()
+    qa = Q.functions.nnDorefaQuant(4)
+
+    def fd():
+        i[0] += 1
+        return ld(qa(xu[i[0] % 2]))
+    ms = time_fn(torch, fd, iters=20)
+    out["lineardorefa_w4a4_4096x4096_b8192"] = {"ms": round(ms, 4), "gops": round(ops_ / ms / 1e6, 1)}
+    xq4 = qa(xu[0])
+    ms = time_fn(torch, lambda: ld(xq4), iters=20)
+    out["lineardorefa_w4a4_contraction_only"] = {"ms": round(ms, 4), "tops": round(ops_ / ms / 1e9, 1)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

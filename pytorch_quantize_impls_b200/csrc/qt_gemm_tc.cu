@@ -5,9 +5,9 @@
 //     full/empty mbarriers;
 //   * one elected thread issues tcgen05.mma (kind::i8 -> s32, kind::f16/bf16 -> f32), 128 x BN x 32 B per
 //     instruction, accumulators live in TMEM (2 x BN columns: double buffered across output tiles);
-//   * four epilogue warps drain TMEM with tcgen05.ld (32x32b.x32), apply the integer-exact affine
-//     + scale/bias epilogue and store fp32 straight to the row-major or NCHW output, overlapping the
-//     next tile's main loop;
+//   * eight epilogue warps drain TMEM with tcgen05.ld (32x32b.x32), apply the integer-exact affine +
+//     scale/bias epilogue and write fp32 through 128B-swizzled smem tiles + cp.async.bulk.tensor stores
+//     (row-major output) or coalesced per-column stores (NCHW output), overlapping the next tile's main loop;
 //   * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule with M fastest so that
 //     concurrently running CTAs share the same weight tile in L2.
 #include <cuda.h>
@@ -18,7 +18,7 @@ namespace qt {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK_BYTES = 128;          // one 128B swizzle row of K per stage
-constexpr int TC_THREADS = 192;           // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int TC_THREADS = 320;           // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..9 epilogue
 
 struct TcArgs {
   int64_t M, N;
@@ -30,6 +30,7 @@ struct TcArgs {
   int is_int;
   Epi ep;
   int tiles_m, tiles_n;
+  int tma_store;        // 1: row-major fp32 output goes through swizzled smem + cp.async.bulk.tensor store
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -60,6 +61,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -109,7 +122,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 template <int BN, int KIND, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcArgs g) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_out, TcArgs g) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK_BYTES;
   constexpr uint32_t W_BYTES = BN * TC_BK_BYTES;
   constexpr uint32_t STAGE_BYTES = A_BYTES + W_BYTES;
@@ -117,27 +131,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  constexpr uint32_t EPI_BYTES = 8 * 4096;         // 8 epilogue warps x (32 rows x 128 B) staging tile
+  const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = epi_base + EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8u * (2 * STAGES + 4));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + EPI_BYTES + 8u * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    if (g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -204,24 +222,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     __syncwarp();
   } else {
-    const int lane_grp = warp & 3;         // TMEM lane quadrant this warp may access
+    // ---- epilogue: 8 warps.  Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quadrant split
+    // the BN accumulator columns in halves, so each SM sub-partition always has a second warp to hide latencies.
+    const int ew = warp - 2;
+    const int lane_grp = warp & 3;
+    const int half = ew >> 2;
+    constexpr int CHUNKS = BN / 32;
+    constexpr int CH_PER_WARP = CHUNKS / 2;
     int as = 0;
     uint32_t aphase = 0;
     const Epi& e = g.ep;
     const bool vec_ok = (e.out != nullptr) && e.out_mode == 0 && (e.ldo % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(e.out) & 15) == 0);
+    const uint32_t my_buf = epi_base + (uint32_t)ew * 4096u;   // this warp's 32 x 128 B staging tile
+    const int N32 = (int)g.N;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile % g.tiles_m, tn = tile / g.tiles_m;
       const int64_t m = (int64_t)tm * TC_BM + lane_grp * 32 + lane;
-      const int64_t n_tile = (int64_t)tn * BN;
+      const int n_tile = tn * BN;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const bool row_ok = m < g.M;
-      float rscale = 1.f;
+      float mul = e.scale;
       int32_t rsum = 0;
       int64_t nchw_base = 0;
       if (row_ok) {
-        if (e.row_scale) rscale = __ldg(e.row_scale + m);
+        if (e.row_scale) mul *= __ldg(e.row_scale + m);
         if (e.row_sum) rsum = e.rs_mul * __ldg(e.row_sum + m);
         if (e.out_mode == 1) {
           int64_t img = m / e.nchw_inner, r = m - img * e.nchw_inner;
@@ -229,46 +255,65 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n_tile + c0 >= g.N) break;     // warp-uniform
+      for (int ci = 0; ci < CH_PER_WARP; ++ci) {
+        const int c0 = (half * CH_PER_WARP + ci) * 32;
+        const int n0 = n_tile + c0;
+        if (n0 >= N32) break;     // warp-uniform
         uint32_t r[32];
         tmem_ld32(tmem_base + (uint32_t)(as * BN + c0) + ((uint32_t)(lane_grp * 32) << 16), r);
-        if (!row_ok) continue;
-        const int64_t n0 = n_tile + c0;
-        if (g.is_int && e.acc_out) {
+        // per-column scale / bias of this chunk: one coalesced load per lane, broadcast by shuffle below
+        const int nl = n0 + lane;
+        float cs_l = 1.f, b_l = 0.f;
+        if (nl < N32) {
+          if (e.col_scale) cs_l = __ldg(e.col_scale + nl);
+          if (e.bias) b_l = __ldg(e.bias + nl);
+        }
+        if (KIND == 0 && e.acc_out && row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + j < g.N) e.acc_out[m * g.N + n0 + j] = (int32_t)r[j];
+            if (n0 + j < N32) e.acc_out[m * g.N + n0 + j] = (int32_t)r[j];
         }
         if (!e.out) continue;
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int64_t n = n0 + j;
           float v;
-          if (g.is_int) v = (float)(e.acc_mul * (int32_t)r[j] + rsum);
+          if (KIND == 0) v = (float)(e.acc_mul * (int32_t)r[j] + rsum);
           else v = __uint_as_float(r[j]);
-          v = v * e.scale * rscale;
-          if (n < g.N) {
-            if (e.col_scale) v *= __ldg(e.col_scale + n);
-            if (e.bias) v += __ldg(e.bias + n);
-          }
-          y[j] = v;
+          // y = acc * (scale * row_scale) * col_scale + bias; with scale = row/col scale = 1 the multiply is exact and
+          // float(acc) + bias is one rounding (BinaryNet / Terner bit-exactness)
+          const float cs = __shfl_sync(0xffffffffu, cs_l, j), bb = __shfl_sync(0xffffffffu, b_l, j);
+          y[j] = (v * mul) * cs + bb;
         }
-        if (e.out_mode == 0) {
+        if (g.tma_store) {
+          // registers (one output row per lane) -> 128B-swizzled smem tile -> one bulk tensor store per 32x32 block:
+          // every global write is a full 128-byte line; M/N tails are clipped by the tensor map.
+          if (lane == 0) tma_store_wait_read0();      // the previous store has finished reading this buffer
+          __syncwarp();
+          const uint32_t rowaddr = my_buf + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(rowaddr + (uint32_t)((j ^ (lane & 7)) << 4), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&map_out, my_buf, n0, tm * TC_BM + lane_grp * 32);
+        } else if (e.out_mode == 0) {
+          if (!row_ok) continue;
           float* o = e.out + m * e.ldo + n0;
-          if (vec_ok && n0 + 32 <= g.N) {
+          if (vec_ok && n0 + 32 <= N32) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (n0 + j < g.N) o[j] = y[j];
+              if (n0 + j < N32) o[j] = y[j];
           }
         } else {
+          if (!row_ok) continue;
+          float* o = e.out + nchw_base + (int64_t)n0 * e.nchw_inner;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + j < g.N) e.out[nchw_base + (n0 + j) * e.nchw_inner] = y[j];
+            if (n0 + j < N32) o[(int64_t)j * e.nchw_inner] = y[j];   // lanes = consecutive pixels: coalesced per column
         }
       }
       tc_fence_before();
@@ -276,6 +321,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (g.tma_store && lane == 0) tma_store_wait_all();   // all bulk stores of this warp have completed
   }
 
   tc_fence_before();
@@ -307,14 +353,15 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D byte matrix [rows, row_bytes] with row pitch ld_bytes; box = 128 B x box_rows, 128B swizzle, zero OOB fill.
-static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t row_bytes, uint64_t ld_bytes, uint32_t box_rows) {
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t row_bytes, uint64_t ld_bytes, uint32_t box_rows,
+                    bool f32 = false) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return QT_ECUDA; }
-  cuuint64_t dims[2] = {row_bytes, rows};
+  cuuint64_t dims[2] = {f32 ? row_bytes / 4 : row_bytes, rows};
   cuuint64_t strides[1] = {ld_bytes};
-  cuuint32_t box[2] = {TC_BK_BYTES, box_rows};
+  cuuint32_t box[2] = {f32 ? 32u : (cuuint32_t)TC_BK_BYTES, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return QT_ECUDA; }
@@ -334,7 +381,14 @@ static int num_sms() {
 
 template <int BN, int KIND, int STAGES>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK_BYTES + BN * TC_BK_BYTES) + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK_BYTES + BN * TC_BK_BYTES) + 4 * 2 * 4096 + 1024 + 256;
+  // output tensor map (row-major fp32): only when every row pitch / base is 16-byte aligned
+  CUtensorMap mo = ma;
+  g.tma_store = 0;
+  if (g.ep.out && g.ep.out_mode == 0 && g.ep.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(g.ep.out) & 15) == 0) {
+    if (int rc = make_map(&mo, g.ep.out, (uint64_t)g.M, (uint64_t)g.N * 4, (uint64_t)g.ep.ldo * 4, 32, true)) return rc;
+    g.tma_store = 1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, KIND, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -343,7 +397,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
   g.tiles_m = (int)ceil_div(g.M, TC_BM);
   g.tiles_n = (int)ceil_div(g.N, BN);
   int grid = std::min(g.tiles_m * g.tiles_n, num_sms());
-  tc_gemm_kernel<BN, KIND, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mw, g);
+  tc_gemm_kernel<BN, KIND, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }

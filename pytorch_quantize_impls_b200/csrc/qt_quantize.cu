@@ -152,15 +152,26 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActArgs a) {
   uint32_t* br = a.bits ? a.bits + row * a.ld_bits : nullptr;
 
   if (VEC) {
-    for (int64_t base = c0; base < c1; base += 128) {
+    constexpr int U = 4;   // 4 independent 16-byte loads in flight per lane (2 KB per warp) before any use
+    for (int64_t base0 = c0; base0 < c1; base0 += 128 * U) {
+     float4 vv[U];
+#pragma unroll
+     for (int u = 0; u < U; ++u) {
+       const int64_t cu = base0 + u * 128 + 4 * lane;
+       vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+       if (cu < c1) vv[u] = __ldcs(reinterpret_cast<const float4*>(xr + cu));
+     }
+#pragma unroll
+     for (int u = 0; u < U; ++u) {
+      const int64_t base = base0 + u * 128;
+      if (base >= c1) break;   // warp-uniform
       const int64_t c = base + 4 * lane;
       const bool valid = c < c1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) v = __ldg(reinterpret_cast<const float4*>(xr + c));
+      const float4 v = vv[u];
       QOut o0 = quant_elem(a.q, v.x, row_mean), o1 = quant_elem(a.q, v.y, row_mean);
       QOut o2 = quant_elem(a.q, v.z, row_mean), o3 = quant_elem(a.q, v.w, row_mean);
       if (valid) {
-        if (yr) *reinterpret_cast<float4*>(yr + c) = make_float4(o0.y, o1.y, o2.y, o3.y);
+        if (yr) __stcs(reinterpret_cast<float4*>(yr + c), make_float4(o0.y, o1.y, o2.y, o3.y));   // streamed: never re-read here
         if (c8) {
           int k0 = code_to_lane(o0.code, a.codes_kind, ovf), k1 = code_to_lane(o1.code, a.codes_kind, ovf);
           int k2 = code_to_lane(o2.code, a.codes_kind, ovf), k3 = code_to_lane(o3.code, a.codes_kind, ovf);
@@ -200,6 +211,7 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActArgs a) {
         const int64_t widx = (base >> 5) + (lane >> 3);
         if ((lane & 7) == 0 && widx * 32 < c1) br[widx] = w;
       }
+     }
     }
   } else {
     for (int64_t base = c0; base < c1; base += 32) {
