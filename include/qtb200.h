@@ -74,7 +74,8 @@ typedef struct QtActQuant {
   int64_t ld_y;
   void* codes;          /* optional low-bit operand, [rows, ld_codes] of int8/uint8 or bf16 (see codes_kind);
                            columns cols..ld_codes-1 are zero-filled */
-  int codes_kind;       /* 0 = none, 1 = int8, 2 = uint8, 3 = bf16, 4 = bf16 hi/lo planes (plane stride = rows*ld_codes) */
+  int codes_kind;       /* 0 = none, 1 = int8, 2 = uint8, 3 = bf16, 4 = bf16 hi/lo planes (plane stride = rows*ld_codes),
+                           5 = fp16 */
   int64_t ld_codes;
   uint32_t* bits;       /* optional bit-packed sign rows [rows, ld_bits] (QT_Q_SIGN only) */
   int64_t ld_bits;
@@ -127,6 +128,9 @@ int qt_col_absmean(const float* w, int64_t n, int64_t k, int64_t ld_w, float* al
  *   kind 2: uint8 raw codes c    (DoReFa k == 8; zero point handled in the epilogue)
  *   kind 3: bf16 exact values of kind 1
  *   kind 4: bf16 hi/lo planes of alpha[k] * sign (XnorNet; plane stride = n*ld_out elements)
+ *   kind 5: fp16 alpha[k] * sign, one plane (XnorNet fast route; pass alpha pre-normalised to max 1 so that the
+ *           values sit in fp16's normal range, and put the max back through the epilogue's col_scale)
+ *   kind 6: fp16 exact values of kind 1 (integers up to 255 are exact in fp16)
  */
 typedef struct QtWeightExpand {
   int mode, bit_width;
@@ -201,12 +205,12 @@ int qt_gemm_b1t2(const uint32_t* a_bits, int64_t lda_words, const uint32_t* w_nz
 int qt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* w, int w_signed, int64_t ldw,
                int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream);
 
-/* bf16 planes x bf16 planes -> fp32.  D = sum over passes p of A[pa[p]] . W[pw[p]]^T.
- * Planes are [M, lda] / [N, ldw] bf16 matrices `a_plane_stride` / `w_plane_stride` elements apart.
- * backend as above (2 = CUDA-core fp32 FMA fallback). */
-int qt_gemm_bf16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
-                 int64_t w_plane_stride, int npass, const int* pa, const int* pw,
-                 int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream);
+/* 16-bit float planes x 16-bit float planes -> fp32.  D = sum over passes p of A[pa[p]] . W[pw[p]]^T.
+ * fmt 0: bf16, fmt 1: fp16 (both operands).  Planes are [M, lda] / [N, ldw] matrices `a_plane_stride` /
+ * `w_plane_stride` elements apart.  backend as above (2 = CUDA-core fp32 FMA fallback). */
+int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
+                int64_t w_plane_stride, int fmt, int npass, const int* pa, const int* pw,
+                int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream);
 
 /* fp32 x fp32 CUDA-core GEMM (D = A . W^T), the always-available exact-fp32 route used for
  * ragged first layers; same epilogue. */

@@ -22,6 +22,19 @@ from . import _ops as ops
 POPCOUNT_MAX_M = int(os.environ.get("QTB200_POPCOUNT_MAX_M", "64"))
 _force_backend = {"i8": L.BACKEND_AUTO, "bf16": L.BACKEND_AUTO}
 _force_popcount = [False]
+# XnorNet product precision: "fp16" = one fp16 tensor pass (alpha[k]*sign rounded to 11 bits, ~1e-4 of max|y|),
+# "bf16x2" = two bf16 passes over hi/lo weight planes (~1e-5).  Both are inside the 1e-3 tolerance.
+_xnor_mode = ["fp16"]
+
+
+def set_xnor_mode(mode):
+    if mode not in ("fp16", "bf16x2"):
+        raise ValueError("xnor mode must be 'fp16' or 'bf16x2'")
+    _xnor_mode[0] = mode
+
+
+def xnor_codes_kind():
+    return L.CODES_F16 if _xnor_mode[0] == "fp16" else L.CODES_BF16
 
 
 def set_backend(i8=None, bf16=None, popcount=None):
@@ -65,6 +78,8 @@ def _a_from_tag(tag):
     a.t, a.ld = tag.codes, tag.ld
     if tag.codes_kind in (L.CODES_I8, L.CODES_U8):
         a.form, a.signed, a.planes = "i8", tag.codes_kind == L.CODES_I8, 1
+    elif tag.codes_kind == L.CODES_F16:
+        a.form, a.signed, a.planes = "fp16", True, 1
     else:
         a.form, a.signed, a.planes = "bf16", True, (2 if tag.codes_kind == L.CODES_BF16X2 else 1)
     return a
@@ -110,6 +125,20 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
         ops.gemm_i8(a.t, a.signed, a.ld, w[w_row0:], True, ldw, M, N, K, epi, _force_backend["i8"])
         return
 
+    if a.form == "fp16":
+        # XnorNet activations (+-1 / 0 codes in fp16, row_scale = mean): one fp16 tensor pass
+        if int_w:
+            w, ldw = ops.expand_weight(pack, L.CODES_F16_EXACT)
+        elif pack.kind == "xnor":
+            w, ldw = ops.expand_weight(pack, L.CODES_F16)
+            col_scale = pack.alpha_max[w_row0:w_row0 + N]
+        else:
+            raise RuntimeError("internal: fp16 activation codes cannot meet a real-valued weight operand")
+        epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
+                           row_scale=a.row_scale, scale=a.scale, out_offset=out_offset)
+        ops.gemm_f16(a.t, a.ld, 0, w[0, w_row0:], ldw, w.stride(0), [(0, 0)], M, N, K, epi, _force_backend["bf16"],
+                     fmt=L.FMT_FP16)
+        return
     if a.form != "bf16":
         raise RuntimeError("internal: integer activation codes cannot meet a real-valued weight operand")
     # bf16 routes
@@ -130,7 +159,7 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
     w_stride = w.stride(0)
     epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
                        row_scale=a.row_scale, scale=a.scale, out_offset=out_offset)
-    ops.gemm_bf16(a.t, a.ld, a_stride, w[0, w_row0:], ldw, w_stride, passes, M, N, K, epi, _force_backend["bf16"])
+    ops.gemm_f16(a.t, a.ld, a_stride, w[0, w_row0:], ldw, w_stride, passes, M, N, K, epi, _force_backend["bf16"])
 
 
 def linear(x, pack, bias):
@@ -150,7 +179,7 @@ def linear(x, pack, bias):
     a = None
     if tag is not None:
         a = _a_from_tag(tag)
-        if a.form == "i8" and not int_w:
+        if (a.form == "i8" and not int_w) or (a.form == "fp16" and pack.kind == "real"):
             a = None
     if a is None:
         a = _a_split(x2d)

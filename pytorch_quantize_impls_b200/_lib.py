@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libqtb200.so")
 # ---- enums (mirror include/qtb200.h) -------------------------------------
 Q_SIGN, Q_TERNARY, Q_DOREFA, Q_XNOR_ROW, Q_LOG, Q_LIN, Q_SPLIT = range(7)
 W_SIGN, W_TERNARY, W_DOREFA, W_XNOR = range(4)
-CODES_NONE, CODES_I8, CODES_U8, CODES_BF16, CODES_BF16X2 = range(5)
+CODES_NONE, CODES_I8, CODES_U8, CODES_BF16, CODES_BF16X2, CODES_F16, CODES_F16_EXACT = range(7)
+FMT_BF16, FMT_FP16 = 0, 1
 BACKEND_AUTO, BACKEND_TCGEN05, BACKEND_SIMT = 0, 1, 2
 
 vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
@@ -66,8 +67,8 @@ SYMBOLS = {
     "qt_gemm_b1b1": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_gemm_b1t2": (i32, [vp, i64, vp, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_gemm_i8": (i32, [vp, i32, i64, vp, i32, i64, i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
-    "qt_gemm_bf16": (i32, [vp, i64, i64, vp, i64, i64, i32, C.POINTER(i32), C.POINTER(i32),
-                           i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
+    "qt_gemm_f16": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, C.POINTER(i32), C.POINTER(i32),
+                          i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
     "qt_gemm_f32": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_launch_count": (i64, [i32]),
 }

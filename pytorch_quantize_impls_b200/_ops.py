@@ -84,6 +84,9 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
     elif codes_kind == L.CODES_BF16:
         ld = round_up(max(cols, 1), 8)
         codes = torch.empty((rows, ld), dtype=torch.bfloat16, device=dev)
+    elif codes_kind == L.CODES_F16:
+        ld = round_up(max(cols, 1), 8)
+        codes = torch.empty((rows, ld), dtype=torch.float16, device=dev)
     elif codes_kind == L.CODES_BF16X2:
         ld = round_up(max(cols, 1), 8)
         codes = torch.empty((2, rows, ld), dtype=torch.bfloat16, device=dev)
@@ -114,8 +117,8 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
 
 class WeightPack:
     """k-bit weight matrix resident in HBM (the persistent format) + what the epilogue needs."""
-    __slots__ = ("kind", "bit_width", "n", "k", "packed", "ld_packed", "alpha", "stats", "col_scale",
-                 "planes", "ld_planes", "wq")
+    __slots__ = ("kind", "bit_width", "n", "k", "packed", "ld_packed", "alpha", "alpha_norm", "alpha_max", "stats",
+                 "col_scale", "planes", "ld_planes", "wq")
 
     def nbytes(self):
         t = self.packed if self.packed is not None else self.planes
@@ -146,6 +149,7 @@ def pack_weight(w2d, kind, bit_width=1, want_wq=False, alpha=None):
         p.alpha = alpha if alpha is not None else torch.empty(k, dtype=torch.float32, device=dev)
     p.wq = torch.empty_like(w2d) if want_wq else None
     p.planes, p.ld_planes, p.col_scale = None, 0, None
+    p.alpha_norm = p.alpha_max = None
     a = L.QtWeightPack()
     a.mode, a.bit_width = mode, bit_width
     a.w, a.n, a.k, a.ld_w = _p(w2d), n, k, k
@@ -153,6 +157,11 @@ def pack_weight(w2d, kind, bit_width=1, want_wq=False, alpha=None):
     a.alpha, a.alpha_is_input = _p(p.alpha), 1 if alpha is not None else 0
     a.stats, a.wq = _p(p.stats), _p(p.wq)
     L.check(L.lib().qt_pack_weight(C.byref(a), _stream()), "qt_pack_weight")
+    if kind == "xnor":
+        # fp16 fast route: alpha normalised to max 1 (fp16 normal range); the max goes back in through col_scale
+        amax = torch.clamp_min(p.alpha.max(), 1e-30)
+        p.alpha_norm = (p.alpha / amax).contiguous()
+        p.alpha_max = amax.reshape(1).expand(n).contiguous()
     if kind == "dorefa":
         # per-output-column scale kept on the device (no host sync):
         #   k == 1 : E = mean|W|            (dorefa_connect.py:100-102)
@@ -174,6 +183,7 @@ def pack_real_weight(wq2d):
     p = WeightPack()
     p.kind, p.bit_width, p.n, p.k = "real", 32, wq2d.shape[0], wq2d.shape[1]
     p.packed, p.ld_packed, p.alpha, p.stats, p.col_scale, p.wq = None, 0, None, None, None, None
+    p.alpha_norm = p.alpha_max = None
     p.planes, p.ld_planes = tag.codes, tag.ld
     return p
 
@@ -197,13 +207,16 @@ def expand_weight(p, out_kind):
         out = torch.empty((p.n, ld), dtype=torch.uint8, device=dev)
     elif out_kind == L.CODES_BF16:
         out = torch.empty((1, p.n, ld), dtype=torch.bfloat16, device=dev)
+    elif out_kind in (L.CODES_F16, L.CODES_F16_EXACT):
+        out = torch.empty((1, p.n, ld), dtype=torch.float16, device=dev)
     else:
         out = torch.empty((2, p.n, ld), dtype=torch.bfloat16, device=dev)
     mode = {"sign": L.W_SIGN, "ternary": L.W_TERNARY, "dorefa": L.W_DOREFA, "xnor": L.W_XNOR}[p.kind]
     a = L.QtWeightExpand()
     a.mode, a.bit_width = mode, p.bit_width
     a.packed, a.n, a.k, a.ld_packed = _p(p.packed), p.n, p.k, p.ld_packed
-    a.alpha, a.out, a.out_kind, a.ld_out = _p(p.alpha), _p(out), out_kind, ld
+    a.alpha = _p(p.alpha_norm if out_kind == L.CODES_F16 else p.alpha)
+    a.out, a.out_kind, a.ld_out = _p(out), out_kind, ld
     L.check(L.lib().qt_expand_weight(C.byref(a), _stream()), "qt_expand_weight")
     return out, ld
 
@@ -246,12 +259,13 @@ def gemm_i8(a, a_signed, lda, w, w_signed, ldw, M, N, K, epi, backend=L.BACKEND_
                                backend, _stream()), "qt_gemm_i8")
 
 
-def gemm_bf16(a, lda, a_plane_stride, w, ldw, w_plane_stride, passes, M, N, K, epi, backend=L.BACKEND_AUTO):
+def gemm_f16(a, lda, a_plane_stride, w, ldw, w_plane_stride, passes, M, N, K, epi, backend=L.BACKEND_AUTO,
+             fmt=L.FMT_BF16):
     n = len(passes)
     pa = (C.c_int * n)(*[p[0] for p in passes])
     pw = (C.c_int * n)(*[p[1] for p in passes])
-    L.check(L.lib().qt_gemm_bf16(_p(a), lda, a_plane_stride, _p(w), ldw, w_plane_stride, n, pa, pw, M, N, K,
-                                 C.byref(epi), backend, _stream()), "qt_gemm_bf16")
+    L.check(L.lib().qt_gemm_f16(_p(a), lda, a_plane_stride, _p(w), ldw, w_plane_stride, fmt, n, pa, pw, M, N, K,
+                                C.byref(epi), backend, _stream()), "qt_gemm_f16")
 
 
 def gemm_f32(a, lda, w, ldw, M, N, K, epi):

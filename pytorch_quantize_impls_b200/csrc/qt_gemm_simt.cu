@@ -6,6 +6,7 @@
 // These are the any-shape routes (ragged K, tiny M, first layers); the large aligned shapes go to the
 // tcgen05 kernels in qt_gemm_tc.cu.
 #include <type_traits>
+#include <cuda_fp16.h>
 #include "qt_common.cuh"
 
 namespace qt {
@@ -46,6 +47,16 @@ struct OpBf16x2 {
   __device__ static __forceinline__ void mac(Acc& acc, uint32_t a, uint32_t w, uint32_t) {
     acc = fmaf(__uint_as_float(a << 16), __uint_as_float(w << 16), acc);
     acc = fmaf(__uint_as_float(a & 0xffff0000u), __uint_as_float(w & 0xffff0000u), acc);
+  }
+};
+
+struct OpFp16x2 {
+  using Acc = float;
+  static constexpr bool kHasAux = false;
+  __device__ static __forceinline__ void mac(Acc& acc, uint32_t a, uint32_t w, uint32_t) {
+    float2 fa = __half22float2(*reinterpret_cast<__half2*>(&a)), fw = __half22float2(*reinterpret_cast<__half2*>(&w));
+    acc = fmaf(fa.x, fw.x, acc);
+    acc = fmaf(fa.y, fw.y, acc);
   }
 };
 
@@ -203,18 +214,19 @@ int simt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* w, int w_
   return launch_simt<OpDp4a<false, false>>(g, stream);
 }
 
-int simt_gemm_bf16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
-                   int64_t w_plane_stride, int npass, const int* pa, const int* pw,
-                   int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, cudaStream_t stream) {
+int simt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
+                  int64_t w_plane_stride, int fmt, int npass, const int* pa, const int* pw,
+                  int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, cudaStream_t stream) {
   QT_REQUIRE(lda % 2 == 0 && ldw % 2 == 0 && a_plane_stride % 2 == 0 && w_plane_stride % 2 == 0,
-             "qt_gemm_bf16: strides must be even");
-  QT_REQUIRE(lda >= ((K + 1) / 2) * 2 && ldw >= ((K + 1) / 2) * 2, "qt_gemm_bf16: rows must be zero-padded to 2 elements");
+             "qt_gemm_f16: strides must be even");
+  QT_REQUIRE(lda >= ((K + 1) / 2) * 2 && ldw >= ((K + 1) / 2) * 2, "qt_gemm_f16: rows must be zero-padded to 2 elements");
   SimtArgs g{};
   g.a = (const uint32_t*)a; g.w = (const uint32_t*)w;
   g.lda = lda / 2; g.ldw = ldw / 2; g.M = M; g.N = N; g.kwords = (K + 1) / 2; g.K = K;
   g.npass = npass; g.a_plane = a_plane_stride / 2; g.w_plane = w_plane_stride / 2;
   for (int i = 0; i < npass; ++i) { g.pa[i] = pa[i]; g.pw[i] = pw[i]; }
   g.finish = 0; g.ep = make_epi(ep, M, N);
+  if (fmt == 1) return launch_simt<OpFp16x2>(g, stream);
   return launch_simt<OpBf16x2>(g, stream);
 }
 

@@ -425,9 +425,9 @@ static bool tc_available() {
 
 int simt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* w, int w_signed, int64_t ldw,
                  int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, cudaStream_t stream);
-int simt_gemm_bf16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
-                   int64_t w_plane_stride, int npass, const int* pa, const int* pw,
-                   int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, cudaStream_t stream);
+int simt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
+                  int64_t w_plane_stride, int fmt, int npass, const int* pa, const int* pw,
+                  int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, cudaStream_t stream);
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -461,24 +461,25 @@ extern "C" int qt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* 
   return dispatch_tc<0>(ma, mw, g, bn, stream);
 }
 
-extern "C" int qt_gemm_bf16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
-                            int64_t w_plane_stride, int npass, const int* pa, const int* pw,
-                            int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream_) {
+extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
+                           int64_t w_plane_stride, int fmt, int npass, const int* pa, const int* pw,
+                           int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  QT_REQUIRE(a && w && pa && pw, "qt_gemm_bf16: null operand");
-  QT_REQUIRE(npass >= 1 && npass <= 4, "qt_gemm_bf16: npass must be 1..4");
-  QT_REQUIRE(M >= 0 && N >= 0 && K > 0 && lda >= K && ldw >= K, "qt_gemm_bf16: bad shape");
+  QT_REQUIRE(a && w && pa && pw, "qt_gemm_f16: null operand");
+  QT_REQUIRE(npass >= 1 && npass <= 4, "qt_gemm_f16: npass must be 1..4");
+  QT_REQUIRE(fmt == 0 || fmt == 1, "qt_gemm_f16: fmt must be 0 (bf16) or 1 (fp16)");
+  QT_REQUIRE(M >= 0 && N >= 0 && K > 0 && lda >= K && ldw >= K, "qt_gemm_f16: bad shape");
   if (int rc = check_epi(ep, M, N)) return rc;
-  QT_REQUIRE(ep->out, "qt_gemm_bf16: needs ep->out");
+  QT_REQUIRE(ep->out, "qt_gemm_f16: needs ep->out");
   if (M == 0 || N == 0) return QT_OK;
   int max_pa = 0, max_pw = 0;
   for (int i = 0; i < npass; ++i) { max_pa = std::max(max_pa, pa[i]); max_pw = std::max(max_pw, pw[i]); }
   bool tc_ok = tc_available() && (lda * 2) % 16 == 0 && (ldw * 2) % 16 == 0 && al16(a) && al16(w);
   if (max_pa > 0) tc_ok = tc_ok && a_plane_stride % lda == 0;
   if (max_pw > 0) tc_ok = tc_ok && w_plane_stride % ldw == 0;
-  if (backend == 1 && !tc_ok) { set_error("qt_gemm_bf16: tcgen05 backend needs sm_100, 16-byte aligned pitches and plane strides that are whole rows"); return QT_EUNSUPPORTED; }
+  if (backend == 1 && !tc_ok) { set_error("qt_gemm_f16: tcgen05 backend needs sm_100, 16-byte aligned pitches and plane strides that are whole rows"); return QT_EUNSUPPORTED; }
   const bool use_tc = backend == 1 || (backend == 0 && tc_ok && (double)M * (double)N * (double)K >= 1.0e7);
-  if (!use_tc) return simt_gemm_bf16(a, lda, a_plane_stride, w, ldw, w_plane_stride, npass, pa, pw, M, N, K, ep, stream);
+  if (!use_tc) return simt_gemm_f16(a, lda, a_plane_stride, w, ldw, w_plane_stride, fmt, npass, pa, pw, M, N, K, ep, stream);
 
   const int bn = pick_bn(N);
   TcArgs g{};
@@ -491,7 +492,8 @@ extern "C" int qt_gemm_bf16(const void* a, int64_t lda, int64_t a_plane_stride, 
   g.M = M; g.N = N; g.num_kblocks = (int)ceil_div(K * 2, TC_BK_BYTES); g.npass = npass;
   for (int i = 0; i < npass; ++i) { g.pa[i] = pa[i]; g.pw[i] = pw[i]; }
   g.is_int = 0; g.ep = make_epi(ep, M, N);
-  // D = f32 (1 << 4), A/B = bf16 (1) at bits 7 / 10
-  g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  // D = f32 (1 << 4), A/B = bf16 (1) or fp16 (0) at bits 7 / 10
+  const uint32_t f = fmt == 0 ? 1u : 0u;
+  g.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   return dispatch_tc<1>(ma, mw, g, bn, stream);
 }

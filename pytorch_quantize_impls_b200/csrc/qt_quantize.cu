@@ -3,6 +3,7 @@
 // warp-shuffle reductions, and every derived output (fp32 fake-quant value, low-bit codes, packed bits,
 // row sums) produced from a single read of the fp32 source.
 #include <math.h>
+#include <cuda_fp16.h>
 #include "qt_common.cuh"
 
 namespace qt {
@@ -27,9 +28,10 @@ struct QOut {
 __device__ __forceinline__ float sign3(float x) { return (float)((x > 0.f) - (x < 0.f)); }  // torch.sign (NaN -> 0)
 __device__ __forceinline__ float sign_safe(float x) { return (x < 0.f) ? -1.f : 1.f; }      // safeSign
 
+template <int MODE>
 __device__ __forceinline__ QOut quant_elem(const QParams& q, float x, float row_mean) {
   QOut o;
-  switch (q.mode) {
+  switch (MODE) {
     case QT_Q_SIGN: {
       o.y = o.code = sign_safe(x);
       break;
@@ -116,8 +118,8 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(256) act_quant_kernel(ActArgs a) {
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t task = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (task >= a.rows * a.nchunks) return;
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActArgs a) {
   const float* xr = a.x + row * a.ld_x;
 
   float row_mean = 0.f;
-  if (a.q.mode == QT_Q_XNOR_ROW) {  // never chunked: the whole row is reduced by this warp
+  if (MODE == QT_Q_XNOR_ROW) {  // never chunked: the whole row is reduced by this warp
     double s = 0.0;
     if (VEC) {
       for (int64_t c = 4 * lane; c < a.cols; c += 128) {
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActArgs a) {
   float* yr = a.y ? a.y + row * a.ld_y : nullptr;
   int8_t* c8 = (a.codes_kind == 1 || a.codes_kind == 2) ? reinterpret_cast<int8_t*>(a.codes) + row * a.ld_codes : nullptr;
   __nv_bfloat16* cb = (a.codes_kind >= 3) ? reinterpret_cast<__nv_bfloat16*>(a.codes) + row * a.ld_codes : nullptr;
+  const bool f16 = a.codes_kind == 5;   // same 2-byte lanes, IEEE half encoding
   __nv_bfloat16* cb_lo = (a.codes_kind == 4) ? cb + a.rows * a.ld_codes : nullptr;
   uint32_t* br = a.bits ? a.bits + row * a.ld_bits : nullptr;
 
@@ -168,8 +171,8 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActArgs a) {
       const int64_t c = base + 4 * lane;
       const bool valid = c < c1;
       const float4 v = vv[u];
-      QOut o0 = quant_elem(a.q, v.x, row_mean), o1 = quant_elem(a.q, v.y, row_mean);
-      QOut o2 = quant_elem(a.q, v.z, row_mean), o3 = quant_elem(a.q, v.w, row_mean);
+      QOut o0 = quant_elem<MODE>(a.q, v.x, row_mean), o1 = quant_elem<MODE>(a.q, v.y, row_mean);
+      QOut o2 = quant_elem<MODE>(a.q, v.z, row_mean), o3 = quant_elem<MODE>(a.q, v.w, row_mean);
       if (valid) {
         if (yr) __stcs(reinterpret_cast<float4*>(yr + c), make_float4(o0.y, o1.y, o2.y, o3.y));   // streamed: never re-read here
         if (c8) {
@@ -186,6 +189,11 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActArgs a) {
           uint2 u;
           u.x = *reinterpret_cast<uint32_t*>(&p0);
           u.y = *reinterpret_cast<uint32_t*>(&p1);
+          if (f16) {
+            __half2 q0 = __floats2half2_rn(o0.code, o1.code), q1 = __floats2half2_rn(o2.code, o3.code);
+            u.x = *reinterpret_cast<uint32_t*>(&q0);
+            u.y = *reinterpret_cast<uint32_t*>(&q1);
+          }
           *reinterpret_cast<uint2*>(cb + c) = u;
           if (cb_lo) {
             __nv_bfloat162 q0(__float2bfloat16_rn(o0.code - __bfloat162float(h0)),
@@ -218,7 +226,7 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActArgs a) {
       const int64_t c = base + lane;
       const bool valid = c < c1;
       float v = valid ? __ldg(xr + c) : 0.f;
-      QOut o = quant_elem(a.q, v, row_mean);
+      QOut o = quant_elem<MODE>(a.q, v, row_mean);
       if (valid) {
         if (yr) yr[c] = o.y;
         if (c8) {
@@ -227,6 +235,10 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActArgs a) {
           c8[c] = (int8_t)k;
         } else if (cb) {
           __nv_bfloat16 h = __float2bfloat16_rn(o.code);
+          if (f16) {
+            __half hh = __float2half_rn(o.code);
+            h = *reinterpret_cast<__nv_bfloat16*>(&hh);
+          }
           cb[c] = h;
           if (cb_lo) cb_lo[c] = __float2bfloat16_rn(o.code - __bfloat162float(h));
           isum += (int)o.code;
@@ -458,9 +470,15 @@ __global__ void __launch_bounds__(256) weight_expand_kernel(ExpandArgs a) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float x = v[j];
-      if (a.out_kind == 4) x *= (c0 + j < a.k) ? __ldg(a.alpha + c0 + j) : 0.f;
-      h[j] = __float2bfloat16_rn(x);
-      l[j] = __float2bfloat16_rn(x - __bfloat162float(h[j]));
+      if (a.out_kind == 4 || a.out_kind == 5) x *= (c0 + j < a.k) ? __ldg(a.alpha + c0 + j) : 0.f;
+      if (a.out_kind >= 5) {
+        __half hh = __float2half_rn(x);
+        h[j] = *reinterpret_cast<__nv_bfloat16*>(&hh);
+        l[j] = h[j];
+      } else {
+        h[j] = __float2bfloat16_rn(x);
+        l[j] = __float2bfloat16_rn(x - __bfloat162float(h[j]));
+      }
     }
     reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(h)[0];
     reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(h)[1];
@@ -569,7 +587,7 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   if (p->mode == QT_Q_SPLIT) QT_REQUIRE(p->codes_kind == 4, "qt_quant_act: QT_Q_SPLIT needs codes_kind 4");
   if (p->mode == QT_Q_LOG || p->mode == QT_Q_LIN)
     QT_REQUIRE(p->codes_kind == 0 && !p->bits, "qt_quant_act: Log/Lin quantizers produce fp32 only");
-  QT_REQUIRE(p->codes_kind >= 0 && p->codes_kind <= 4, "qt_quant_act: bad codes_kind");
+  QT_REQUIRE(p->codes_kind >= 0 && p->codes_kind <= 5, "qt_quant_act: bad codes_kind");
   if (p->codes_kind) QT_REQUIRE(p->codes && p->ld_codes >= p->cols, "qt_quant_act: bad codes buffer");
   if (p->bits) QT_REQUIRE(p->mode == QT_Q_SIGN && p->ld_bits * 32 >= p->cols, "qt_quant_act: bits need QT_Q_SIGN and ld_bits*32 >= cols");
   if (p->y) QT_REQUIRE(p->ld_y >= p->cols, "qt_quant_act: ld_y < cols");
@@ -592,8 +610,21 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   const int warps_per_block = 8;
   int64_t tasks = p->rows * a.nchunks;
   dim3 grid((unsigned)ceil_div(tasks, warps_per_block)), block(32 * warps_per_block);
-  if (vec) act_quant_kernel<true><<<grid, block, 0, stream>>>(a);
-  else act_quant_kernel<false><<<grid, block, 0, stream>>>(a);
+#define QT_ACT_LAUNCH(MODE_)                                                              \
+  case MODE_:                                                                            \
+    if (vec) act_quant_kernel<MODE_, true><<<grid, block, 0, stream>>>(a);               \
+    else act_quant_kernel<MODE_, false><<<grid, block, 0, stream>>>(a);                  \
+    break;
+  switch (p->mode) {
+    QT_ACT_LAUNCH(QT_Q_SIGN)
+    QT_ACT_LAUNCH(QT_Q_TERNARY)
+    QT_ACT_LAUNCH(QT_Q_DOREFA)
+    QT_ACT_LAUNCH(QT_Q_XNOR_ROW)
+    QT_ACT_LAUNCH(QT_Q_LOG)
+    QT_ACT_LAUNCH(QT_Q_LIN)
+    QT_ACT_LAUNCH(QT_Q_SPLIT)
+  }
+#undef QT_ACT_LAUNCH
   QT_LAUNCH_CHECK();
   return QT_OK;
 }
@@ -647,10 +678,10 @@ extern "C" int qt_expand_weight(const QtWeightExpand* p, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   QT_REQUIRE(p && p->packed && p->out, "qt_expand_weight: null argument");
   QT_REQUIRE(p->mode >= QT_W_SIGN && p->mode <= QT_W_XNOR, "qt_expand_weight: bad mode");
-  QT_REQUIRE(p->out_kind >= 1 && p->out_kind <= 4, "qt_expand_weight: bad out_kind");
+  QT_REQUIRE(p->out_kind >= 1 && p->out_kind <= 6, "qt_expand_weight: bad out_kind");
   QT_REQUIRE(p->ld_out % 16 == 0 && p->ld_out >= p->k, "qt_expand_weight: ld_out must be a multiple of 16 and >= k");
   QT_REQUIRE(aligned(p->out, 16), "qt_expand_weight: out must be 16-byte aligned");
-  if (p->out_kind == 4) QT_REQUIRE(p->alpha && p->mode == QT_W_XNOR, "qt_expand_weight: kind 4 needs XNOR alpha");
+  if (p->out_kind == 4 || p->out_kind == 5) QT_REQUIRE(p->alpha && p->mode == QT_W_XNOR, "qt_expand_weight: kinds 4/5 need XNOR alpha");
   if (p->out_kind == 2) QT_REQUIRE(p->mode == QT_W_DOREFA && p->bit_width >= 2, "qt_expand_weight: uint8 codes are DoReFa only");
   if (p->out_kind == 1 && p->mode == QT_W_DOREFA) QT_REQUIRE(p->bit_width <= 7, "qt_expand_weight: centred int8 codes need k <= 7");
   ExpandArgs a;

@@ -22,8 +22,8 @@ def _quantOpXnor(dim=1):
         @staticmethod
         def forward(ctx, input):
             if dim == 1 and input.dim() == 2:
-                # fused device pass: row mean (fp64 accumulate) + sign + bf16 codes for the next layer
-                y, tag = ops.quant_act(input, L.Q_XNOR_ROW, want_y=True, codes_kind=L.CODES_BF16,
+                # fused device pass: row mean (fp64 accumulate) + sign + fp16 (or bf16) codes for the next layer
+                y, tag = ops.quant_act(input, L.Q_XNOR_ROW, want_y=True, codes_kind=eng.xnor_codes_kind(),
                                        want_row_scale=True, kind="xnor")
                 ctx.save_for_backward(input, tag.row_scale)
                 TaggingFunction._leave(tag)

@@ -162,13 +162,20 @@ def test_linear_xnor_golden(Q, golden):
     N, K = c["w"].shape
     lay = _set(Q.layers.LinearXNOR(K, N).cuda(), c["w"], c["b"])
     with torch.no_grad():
-        xq = Q.functions.QuantXnor(cu(c["x"]), 1)
-        assert relerr(xq, c["xq"]) < 2e-6
-        for be in ("simt", "tcgen05"):
-            Q.set_backend(bf16=be)
-            assert relerr(lay(xq), c["out"]) < 2e-5, be
-            assert relerr(lay(cu(c["x"])), c["out_real"]) < 5e-5, be
+        for mode, tol in (("fp16", 5e-4), ("bf16x2", 2e-5)):
+            Q.set_xnor_mode(mode)                          # one fp16 pass (11-bit alpha*sign) vs two bf16 passes
+            xq = Q.functions.QuantXnor(cu(c["x"]), 1)
+            assert relerr(xq, c["xq"]) < 2e-6
+            for be in ("simt", "tcgen05"):
+                Q.set_backend(bf16=be)
+                assert relerr(lay(xq), c["out"]) < tol, (mode, be)
+                assert relerr(lay(cu(c["x"])), c["out_real"]) < 5e-5, be
         Q.set_backend(bf16="auto")
+        Q.set_xnor_mode("fp16")
+        # XnorNet activations feeding an integer-weight layer (fp16 exact-code route)
+        lb = _set(Q.layers.LinearBin(K, N).cuda(), c["w"], c["b"])
+        ref = O.linear_bin(c["xq"], c["w"], c["b"])
+        assert relerr(lb(Q.functions.QuantXnor(cu(c["x"]), 1)), ref) < 2e-5
         lay.train(False)                                  # the reference raises NameError here; ours swaps
         assert relerr(lay.weight.data, O.xnor_weight(c["w"])) < 1e-6
         lay.train(True)
@@ -275,7 +282,7 @@ def test_gemm_bf16_planes(Q, M, N, K, backend):
     _, ta = ops.quant_act(x.cuda(), L.Q_SPLIT, want_y=False, codes_kind=L.CODES_BF16X2, kind="real")
     pw = ops.pack_real_weight(w.cuda())
     out = torch.empty(M, N).cuda()
-    ops.gemm_bf16(ta.codes, ta.ld, ta.codes.stride(0), pw.planes, pw.ld_planes, pw.planes.stride(0),
+    ops.gemm_f16(ta.codes, ta.ld, ta.codes.stride(0), pw.planes, pw.ld_planes, pw.planes.stride(0),
                   [(0, 0), (1, 0), (0, 1)], M, N, K, ops.make_epi(out, ldo=N),
                   L.BACKEND_SIMT if backend == "simt" else L.BACKEND_TCGEN05)
     ref = x.double() @ w.double().t()
