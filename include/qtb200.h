@@ -60,7 +60,7 @@ enum {
   QT_Q_XNOR_ROW = 3, /* sign(x) * mean(x,row)  (torch.sign)   codes {-1,0,+1}, row_scale = mean */
   QT_Q_LOG = 4,      /* sign(x) 2^clamp(round(log2|x|), fsr-2^bw, fsr)   (fp32 only) */
   QT_Q_LIN = 5,      /* sign(x) clamp(round(|x|/step) step, 0, 2^fsr)    (fp32 only) */
-  QT_Q_SPLIT = 6     /* no quantisation: bf16 hi/lo split of x (codes_bf16 = hi plane, plane 1 = lo) */
+  QT_Q_SPLIT = 6     /* no quantisation: bf16 hi/lo (codes_kind 4) or hi/mid/lo (codes_kind 6) split of x */
 };
 
 typedef struct QtActQuant {
@@ -75,13 +75,16 @@ typedef struct QtActQuant {
   void* codes;          /* optional low-bit operand, [rows, ld_codes] of int8/uint8 or bf16 (see codes_kind);
                            columns cols..ld_codes-1 are zero-filled */
   int codes_kind;       /* 0 = none, 1 = int8, 2 = uint8, 3 = bf16, 4 = bf16 hi/lo planes (plane stride = rows*ld_codes),
-                           5 = fp16 */
+                           5 = fp16, 6 = bf16 hi/mid/lo planes (24 significant bits: the fp32-faithful split) */
   int64_t ld_codes;
   uint32_t* bits;       /* optional bit-packed sign rows [rows, ld_bits] (QT_Q_SIGN only) */
   int64_t ld_bits;
   int32_t* row_sum;     /* optional [rows]: sum over columns of the integer codes */
   float* row_scale;     /* optional [rows]: QT_Q_XNOR_ROW row mean */
   int32_t* overflow;    /* optional device flag, OR-ed with 1 when a code does not fit the int8/uint8 lane */
+  int64_t nhwc_c;       /* 0: codes are row-major [rows, ld_codes].  C > 0: x (and y) are NCHW with rows = B images of
+                           C channels x (cols / C) pixels, and the int8/uint8 codes are written channels-last
+                           [B, H*W, C] (dense) -- the layout the conv gather / TMA im2col reads with 16-byte vectors */
 } QtActQuant;
 
 int qt_quant_act(const QtActQuant* p, void* stream);
@@ -146,13 +149,16 @@ int qt_expand_weight(const QtWeightExpand* p, void* stream);
 
 /* ------------------------------------------------------------------------
  * im2col gather for the conv layers (binary_layers.py:103-106, terner_layers.py:89-92,
- * dorefa_layers.py:77-82, xnor_connect.py:139-146).  Input NCHW, zero padding
- * (a padded tap contributes exactly 0, as F.conv2d does).  Output row m =
- * (b, oh, ow), column = (c, kh, kw) of group `g`; element type = 1, 2 or 4 bytes
- * (int8/uint8 codes, bf16, fp32).  Optional row_sum of int8/uint8 codes.
+ * dorefa_layers.py:77-82, xnor_connect.py:139-146).  Input NCHW (nhwc = 0) or channels-last NHWC
+ * (nhwc = 1, 16-byte vector copies when C/groups * elem_bytes % 16 == 0), zero padding
+ * (a padded tap contributes exactly 0, as F.conv2d does).  Output row m = (b, oh, ow),
+ * column = (kh, kw, c) of group `g` -- channel fastest, so weights are packed from
+ * W.permute(0, 2, 3, 1); element type = 1, 2 or 4 bytes (int8/uint8 codes, bf16, fp32).
+ * Optional row_sum of int8/uint8 codes.
  * ---------------------------------------------------------------------- */
 typedef struct QtIm2col {
-  const void* x;     /* [B, C, H, W] */
+  const void* x;     /* [B, C, H, W] or [B, H, W, C] */
+  int nhwc;          /* input layout */
   int elem_bytes;    /* 1, 2, 4 */
   int is_unsigned;   /* for row_sum of 1-byte codes */
   int64_t B, C, H, W;

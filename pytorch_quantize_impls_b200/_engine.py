@@ -5,10 +5,10 @@
   A int8/uint8 codes  | tcgen05 kind::i8 (or XNOR-popcount for    | falls back to the row below (A re-read
   (Binary/Ter/DoReFa) | 1-bit x 1-bit/ternary when M is small)    | as real values)
   A bf16 codes (xnor) | tcgen05 kind::f16, 1 pass, row_scale      | 2 passes (W hi, W lo), row_scale
-  A real (untagged)   | bf16 hi/lo split of A, 2 passes           | 3 passes (hi*hi, lo*hi, hi*lo)
+  A real (untagged)   | bf16 hi/mid/lo split of A, 3 passes       | 5 passes (3 A planes x W hi, 2 x W lo)
 
-Integer accumulators are exact; the bf16 routes carry 16 significant bits per operand (error ~2^-17,
-far inside the 1e-3 relative tolerance of the north star).
+Integer accumulators are exact; the real-activation route carries 24 significant bits of the activation
+(fp32-faithful), real-valued weights 16 bits (error ~2^-17), far inside the 1e-3 tolerance of the north star.
 """
 import os
 
@@ -81,12 +81,14 @@ def _a_from_tag(tag):
     elif tag.codes_kind == L.CODES_F16:
         a.form, a.signed, a.planes = "fp16", True, 1
     else:
-        a.form, a.signed, a.planes = "bf16", True, (2 if tag.codes_kind == L.CODES_BF16X2 else 1)
+        a.form, a.signed = "bf16", True
+        a.planes = {L.CODES_BF16X2: 2, L.CODES_BF16X3: 3}.get(tag.codes_kind, 1)
     return a
 
 
 def _a_split(x2d):
-    _, tag = ops.quant_act(x2d, L.Q_SPLIT, want_y=False, codes_kind=L.CODES_BF16X2, kind="real")
+    """fp32 activations -> bf16 hi/mid/lo planes (3 x 8 = 24 significant bits: as faithful as the fp32 source)."""
+    _, tag = ops.quant_act(x2d, L.Q_SPLIT, want_y=False, codes_kind=L.CODES_BF16X3, kind="real")
     return _a_from_tag(tag)
 
 
@@ -150,11 +152,10 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
         wplanes = 2
     else:
         w, ldw, wplanes = pack.planes, pack.ld_planes, 2
-    passes = [(0, 0)]
-    if a.planes == 2:
-        passes.append((1, 0))
+    # every (A plane, W plane) product whose magnitude is above ~2^-24 of the leading term
+    passes = [(i, 0) for i in range(a.planes)]
     if wplanes == 2:
-        passes.append((0, 1))
+        passes += [(i, 1) for i in range(min(a.planes, 2))]
     a_stride = a.t.stride(0) if a.t.dim() == 3 else 0
     w_stride = w.stride(0)
     epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
@@ -223,7 +224,7 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
     geom = (kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW)
     int_w = pack.kind in ("sign", "ternary", "dorefa")
     tag = get_tag(x)
-    if tag is not None and not (tag.codes_kind in (L.CODES_I8, L.CODES_U8) and int_w and tag.rows == 1):
+    if tag is not None and not (tag.codes_kind in (L.CODES_I8, L.CODES_U8) and int_w and tag.layout == "nhwc"):
         tag = None
     if bias is not None:
         bias = ops.as_f32c(bias)
@@ -231,13 +232,12 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
 
     if tag is not None:
         elem, ld = 1, ops.round_up(Kg, 16)
-        src = tag.codes.view(-1)[:x.numel()].view(B, Cin, H, W)
-        planes = [src]
+        planes = [tag.codes]                     # [B, H, W, C] channels-last codes
         dtype = tag.codes.dtype
     else:
         elem, ld = 2, ops.round_up(Kg, 8)
         a0 = _a_split(ops.as_f32c(x).reshape(1, -1))
-        planes = [a0.t[p].view(-1)[:x.numel()].view(B, Cin, H, W) for p in range(2)]
+        planes = [a0.t[p].view(-1)[:x.numel()].view(B, Cin, H, W) for p in range(a0.planes)]
         dtype = torch.bfloat16
 
     # bound the transient im2col matrix (~1.5 GiB per chunk of images)
@@ -256,11 +256,11 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
                 a.row_sum = torch.empty(M, dtype=torch.int32, device=x.device)
             for pi, src in enumerate(planes):
                 ops.im2col(src[b0:b1], elem, geom, g, buf[pi], ld, row_sum=a.row_sum if pi == 0 else None,
-                           is_unsigned=(dtype == torch.uint8))
+                           is_unsigned=(dtype == torch.uint8), nhwc=tag is not None)
             if tag is not None:
                 a.form, a.t, a.signed, a.scale, a.planes = "i8", buf[0], dtype == torch.int8, tag.scale, 1
             else:
-                a.form, a.t, a.signed, a.scale, a.planes = "bf16", buf, True, 1.0, 2
+                a.form, a.t, a.signed, a.scale, a.planes = "bf16", buf, True, 1.0, len(planes)
             _contract(a, pack, M, Ng, Kg, out, w_row0=g * Ng, bias=None if bias is None else bias[g * Ng:(g + 1) * Ng],
                       out_mode=1, ldo=O, nchw_inner=P, out_offset=(b0 * O + g * Ng) * P)
     return out

@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libqtb200.so")
 # ---- enums (mirror include/qtb200.h) -------------------------------------
 Q_SIGN, Q_TERNARY, Q_DOREFA, Q_XNOR_ROW, Q_LOG, Q_LIN, Q_SPLIT = range(7)
 W_SIGN, W_TERNARY, W_DOREFA, W_XNOR = range(4)
-CODES_NONE, CODES_I8, CODES_U8, CODES_BF16, CODES_BF16X2, CODES_F16, CODES_F16_EXACT = range(7)
+CODES_NONE, CODES_I8, CODES_U8, CODES_BF16, CODES_BF16X2, CODES_F16, CODES_BF16X3 = range(7)
+CODES_F16_EXACT = 6      # qt_expand_weight out_kind 6 (fp16 exact integer codes)
 FMT_BF16, FMT_FP16 = 0, 1
 BACKEND_AUTO, BACKEND_TCGEN05, BACKEND_SIMT = 0, 1, 2
 
@@ -26,7 +27,7 @@ class QtActQuant(C.Structure):
                 ("y", vp), ("ld_y", i64),
                 ("codes", vp), ("codes_kind", i32), ("ld_codes", i64),
                 ("bits", vp), ("ld_bits", i64),
-                ("row_sum", vp), ("row_scale", vp), ("overflow", vp)]
+                ("row_sum", vp), ("row_scale", vp), ("overflow", vp), ("nhwc_c", i64)]
 
 
 class QtWeightPack(C.Structure):
@@ -41,7 +42,7 @@ class QtWeightExpand(C.Structure):
 
 
 class QtIm2col(C.Structure):
-    _fields_ = [("x", vp), ("elem_bytes", i32), ("is_unsigned", i32),
+    _fields_ = [("x", vp), ("nhwc", i32), ("elem_bytes", i32), ("is_unsigned", i32),
                 ("B", i64), ("C", i64), ("H", i64), ("W", i64),
                 ("kh", i32), ("kw", i32), ("stride_h", i32), ("stride_w", i32), ("pad_h", i32), ("pad_w", i32),
                 ("dil_h", i32), ("dil_w", i32), ("groups", i32), ("group", i32),

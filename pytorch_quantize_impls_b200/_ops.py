@@ -53,7 +53,7 @@ class ActCodes:
     shape       shape of the fp32 tensor the codes describe (e.g. NCHW)
     """
     __slots__ = ("kind", "bit_width", "codes", "codes_kind", "rows", "cols", "ld", "scale", "row_sum",
-                 "row_scale", "bits", "ld_bits", "overflow", "shape", "version")
+                 "row_scale", "bits", "ld_bits", "overflow", "shape", "version", "layout")
 
     def check(self):
         if self.overflow is not None and int(self.overflow.item()) != 0:
@@ -77,7 +77,17 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
     a.y, a.ld_y = _p(y), cols
     codes = bits = row_sum = row_scale = overflow = None
     ld = ldb = 0
-    if codes_kind in (L.CODES_I8, L.CODES_U8):
+    layout = "rows"
+    if x.dim() == 4 and codes_kind in (L.CODES_I8, L.CODES_U8) and not want_bits and not want_row_sum:
+        # conv activations: channels-last codes [B, H, W, C] (what the conv gather reads with 16-byte vectors)
+        layout = "nhwc"
+        Bn, Cn, Hn, Wn = shape
+        rows, cols = Bn, Cn * Hn * Wn
+        a.rows, a.cols, a.ld_x, a.ld_y, a.nhwc_c = rows, cols, cols, cols, Cn
+        codes = torch.empty((Bn, Hn, Wn, Cn), dtype=torch.int8 if codes_kind == L.CODES_I8 else torch.uint8, device=dev)
+        overflow = torch.zeros(1, dtype=torch.int32, device=dev) if mode == L.Q_DOREFA else None
+        ld = cols
+    elif codes_kind in (L.CODES_I8, L.CODES_U8):
         ld = round_up(max(cols, 1), 16)
         codes = torch.empty((rows, ld), dtype=torch.int8 if codes_kind == L.CODES_I8 else torch.uint8, device=dev)
         overflow = torch.zeros(1, dtype=torch.int32, device=dev) if mode == L.Q_DOREFA else None
@@ -87,9 +97,9 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
     elif codes_kind == L.CODES_F16:
         ld = round_up(max(cols, 1), 8)
         codes = torch.empty((rows, ld), dtype=torch.float16, device=dev)
-    elif codes_kind == L.CODES_BF16X2:
+    elif codes_kind in (L.CODES_BF16X2, L.CODES_BF16X3):
         ld = round_up(max(cols, 1), 8)
-        codes = torch.empty((2, rows, ld), dtype=torch.bfloat16, device=dev)
+        codes = torch.empty((2 if codes_kind == L.CODES_BF16X2 else 3, rows, ld), dtype=torch.bfloat16, device=dev)
     if want_bits:
         ldb = round_up((cols + 31) // 32, 4)
         bits = torch.empty((rows, ldb), dtype=torch.int32, device=dev)
@@ -109,7 +119,7 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
         tag.codes, tag.codes_kind, tag.rows, tag.cols, tag.ld = codes, codes_kind, rows, cols, ld
         tag.scale = 1.0
         tag.row_sum, tag.row_scale, tag.bits, tag.ld_bits = row_sum, row_scale, bits, ldb
-        tag.overflow, tag.shape, tag.version = overflow, shape, None
+        tag.overflow, tag.shape, tag.version, tag.layout = overflow, shape, None, layout
         if _strict:
             tag.check()
     return y, tag
@@ -221,12 +231,22 @@ def expand_weight(p, out_kind):
     return out, ld
 
 
-def im2col(x4d, elem_bytes, geom, group, out, ld_out, row_sum=None, is_unsigned=False):
-    """geom = (kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW)."""
-    B, Cc, H, W = x4d.shape
+def conv_weight_2d(w):
+    """[O, C/g, kh, kw] conv weights -> [O, kh*kw*C/g] with the channel fastest: the K order of qt_im2col."""
+    if w.dim() != 4:
+        return w.reshape(w.shape[0], -1)
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def im2col(x4d, elem_bytes, geom, group, out, ld_out, row_sum=None, is_unsigned=False, nhwc=False):
+    """geom = (kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW); x4d is [B,C,H,W] (nhwc=False) or [B,H,W,C]."""
+    if nhwc:
+        B, H, W, Cc = x4d.shape
+    else:
+        B, Cc, H, W = x4d.shape
     kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW = geom
     a = L.QtIm2col()
-    a.x, a.elem_bytes, a.is_unsigned = _p(x4d), elem_bytes, int(is_unsigned)
+    a.x, a.nhwc, a.elem_bytes, a.is_unsigned = _p(x4d), int(nhwc), elem_bytes, int(is_unsigned)
     a.B, a.C, a.H, a.W = B, Cc, H, W
     a.kh, a.kw, a.stride_h, a.stride_w, a.pad_h, a.pad_w, a.dil_h, a.dil_w = kh, kw, sh, sw, ph, pw, dh, dw
     a.groups, a.group, a.OH, a.OW = groups, group, OH, OW

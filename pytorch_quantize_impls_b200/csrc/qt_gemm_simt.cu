@@ -69,7 +69,7 @@ struct SimtArgs {
   int64_t K;             // logical K (popcount kernels)
   int npass;             // bf16 planes: passes
   int64_t a_plane, w_plane;  // plane strides in words
-  int pa[4], pw[4];
+  int pa[8], pw[8];
   int finish;            // 0: plain, 1: K - 2 acc, 2: nzcount - 2 acc
   Epi ep;
 };

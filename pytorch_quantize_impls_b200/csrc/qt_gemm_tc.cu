@@ -24,7 +24,7 @@ struct TcArgs {
   int64_t M, N;
   int num_kblocks;      // per pass
   int npass;
-  int pa[4], pw[4];
+  int pa[8], pw[8];
   int64_t a_plane_rows, w_plane_rows;
   uint32_t idesc;
   int is_int;
@@ -466,7 +466,7 @@ extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, c
                            int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   QT_REQUIRE(a && w && pa && pw, "qt_gemm_f16: null operand");
-  QT_REQUIRE(npass >= 1 && npass <= 4, "qt_gemm_f16: npass must be 1..4");
+  QT_REQUIRE(npass >= 1 && npass <= 8, "qt_gemm_f16: npass must be 1..8");
   QT_REQUIRE(fmt == 0 || fmt == 1, "qt_gemm_f16: fmt must be 0 (bf16) or 1 (fp16)");
   QT_REQUIRE(M >= 0 && N >= 0 && K > 0 && lda >= K && ldw >= K, "qt_gemm_f16: bad shape");
   if (int rc = check_epi(ep, M, N)) return rc;

@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
   int8_t* c8 = (a.codes_kind == 1 || a.codes_kind == 2) ? reinterpret_cast<int8_t*>(a.codes) + row * a.ld_codes : nullptr;
   __nv_bfloat16* cb = (a.codes_kind >= 3) ? reinterpret_cast<__nv_bfloat16*>(a.codes) + row * a.ld_codes : nullptr;
   const bool f16 = a.codes_kind == 5;   // same 2-byte lanes, IEEE half encoding
-  __nv_bfloat16* cb_lo = (a.codes_kind == 4) ? cb + a.rows * a.ld_codes : nullptr;
+  __nv_bfloat16* cb_lo = (a.codes_kind == 4 || a.codes_kind == 6) ? cb + a.rows * a.ld_codes : nullptr;
+  __nv_bfloat16* cb_lo2 = (a.codes_kind == 6) ? cb_lo + a.rows * a.ld_codes : nullptr;
   uint32_t* br = a.bits ? a.bits + row * a.ld_bits : nullptr;
 
   if (VEC) {
@@ -204,6 +205,16 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
             l.x = *reinterpret_cast<uint32_t*>(&q0);
             l.y = *reinterpret_cast<uint32_t*>(&q1);
             *reinterpret_cast<uint2*>(cb_lo + c) = l;
+            if (cb_lo2) {
+              __nv_bfloat162 r0(__float2bfloat16_rn(o0.code - __bfloat162float(h0) - __bfloat162float(q0.x)),
+                                __float2bfloat16_rn(o1.code - __bfloat162float(h1) - __bfloat162float(q0.y)));
+              __nv_bfloat162 r1(__float2bfloat16_rn(o2.code - __bfloat162float(h2) - __bfloat162float(q1.x)),
+                                __float2bfloat16_rn(o3.code - __bfloat162float(h3) - __bfloat162float(q1.y)));
+              uint2 l2;
+              l2.x = *reinterpret_cast<uint32_t*>(&r0);
+              l2.y = *reinterpret_cast<uint32_t*>(&r1);
+              *reinterpret_cast<uint2*>(cb_lo2 + c) = l2;
+            }
           }
           isum += (int)o0.code + (int)o1.code + (int)o2.code + (int)o3.code;
         }
@@ -240,7 +251,11 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
             h = *reinterpret_cast<__nv_bfloat16*>(&hh);
           }
           cb[c] = h;
-          if (cb_lo) cb_lo[c] = __float2bfloat16_rn(o.code - __bfloat162float(h));
+          if (cb_lo) {
+            __nv_bfloat16 m = __float2bfloat16_rn(o.code - __bfloat162float(h));
+            cb_lo[c] = m;
+            if (cb_lo2) cb_lo2[c] = __float2bfloat16_rn(o.code - __bfloat162float(h) - __bfloat162float(m));
+          }
           isum += (int)o.code;
         }
       }
@@ -257,6 +272,7 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
     if (cb) for (int64_t c = a.cols + lane; c < a.ld_codes; c += 32) {
       cb[c] = __float2bfloat16_rn(0.f);
       if (cb_lo) cb_lo[c] = __float2bfloat16_rn(0.f);
+      if (cb_lo2) cb_lo2[c] = __float2bfloat16_rn(0.f);
     }
     if (br) for (int64_t w = ((a.cols + 31) >> 5) + lane; w < a.ld_bits; w += 32) br[w] = 0u;
   }
@@ -265,6 +281,59 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
     if (lane == 0) {
       if (a.nchunks == 1) a.row_sum[row] = isum;
       else atomicAdd(a.row_sum + row, isum);
+    }
+  }
+  if (a.overflow) {
+    unsigned any = __ballot_sync(0xffffffffu, ovf);
+    if (any && lane == 0) atomicOr(a.overflow, 1);
+  }
+}
+
+// Channels-last code emitter for NCHW activations (conv inputs).  One CTA = one image x 128 channels x 32 pixels:
+// coalesced fp32 reads along the pixel axis (one warp = 32 consecutive pixels of one channel), the fp32 fake-quant
+// result is written with the same pattern, codes are transposed through a 4 KB shared tile and leave as 128-byte
+// channel runs per pixel (16 bytes per thread).
+struct NhwcArgs {
+  QParams q;
+  const float* x;
+  float* y;
+  int8_t* codes;
+  int codes_kind;
+  int64_t B, C, HW;
+  int32_t* overflow;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) act_quant_nhwc_kernel(NhwcArgs a) {
+  __shared__ __align__(16) int8_t tile[32][128 + 16];   // [pixel][channel], +16 keeps rows 16-byte aligned and de-conflicts banks
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t p0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 128, b = blockIdx.z;
+  const float* xb = a.x + b * a.C * a.HW;
+  float* yb = a.y ? a.y + b * a.C * a.HW : nullptr;
+  bool ovf = false;
+  const int64_t p = p0 + lane;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int cl = warp * 16 + i;
+    const int64_t c = c0 + cl;
+    int code = 0;
+    if (c < a.C && p < a.HW) {
+      QOut o = quant_elem<MODE>(a.q, __ldcs(xb + c * a.HW + p), 0.f);
+      if (yb) __stcs(yb + c * a.HW + p, o.y);
+      code = code_to_lane(o.code, a.codes_kind, ovf);
+    }
+    tile[lane][cl] = (int8_t)code;
+  }
+  __syncthreads();
+  // write phase: thread -> (pixel = tid / 8, 16 channels = tid % 8)
+  const int px = threadIdx.x >> 3, cg = (threadIdx.x & 7) * 16;
+  const int64_t pp = p0 + px;
+  if (pp < a.HW && c0 + cg < a.C) {
+    int8_t* dst = a.codes + (b * a.HW + pp) * a.C + c0 + cg;
+    if ((a.C & 15) == 0) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&tile[px][cg]);
+    } else {
+      for (int j = 0; j < 16 && c0 + cg + j < a.C; ++j) dst[j] = tile[px][cg + j];
     }
   }
   if (a.overflow) {
@@ -443,7 +512,8 @@ __device__ __forceinline__ float packed_value(const ExpandArgs& a, const uint8_t
   return 2.f * (float)code - (float)((1 << a.bit_width) - 1);    // centred 2c - n
 }
 
-// Each thread produces 16 consecutive output columns of one row.
+// Each thread produces 16 consecutive output columns of one row; the packed bits/codes those 16 columns need are
+// fetched once (1, 2 or 4 words) and unpacked in registers.
 __global__ void __launch_bounds__(256) weight_expand_kernel(ExpandArgs a) {
   const int64_t groups_per_row = a.ld_out / 16;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -451,10 +521,34 @@ __global__ void __launch_bounds__(256) weight_expand_kernel(ExpandArgs a) {
   const int64_t row = gid / groups_per_row, c0 = (gid - row * groups_per_row) * 16;
   const uint8_t* pr = a.packed + row * a.ld_packed;
   float v[16];
+  const bool one_bit = a.mode == QT_W_SIGN || (a.mode == QT_W_DOREFA && a.bit_width == 1);
+  if (c0 >= a.k) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    int64_t c = c0 + j;
-    v[j] = (c < a.k) ? packed_value(a, pr, c) : 0.f;
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  } else if (one_bit) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c0 >> 5)) >> (c0 & 31);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (c0 + j < a.k) ? (((w >> j) & 1u) ? 1.f : -1.f) : 0.f;
+  } else if (a.mode == QT_W_TERNARY || a.mode == QT_W_XNOR) {
+    const uint32_t nz = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c0 >> 5)) >> (c0 & 31);
+    const uint32_t sg = __ldg(reinterpret_cast<const uint32_t*>(pr + a.n * a.ld_packed) + (c0 >> 5)) >> (c0 & 31);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (c0 + j < a.k && ((nz >> j) & 1u)) ? (((sg >> j) & 1u) ? 1.f : -1.f) : 0.f;
+  } else {
+    const int lb = a.lane_bits;                      // 2, 4 or 8 -> 16 columns span 1, 2 or 4 words
+    const int nwords = lb / 2;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(pr) + (c0 * lb) / 32;
+    uint32_t wds[4] = {0, 0, 0, 0};
+    for (int i = 0; i < nwords; ++i) wds[i] = __ldg(wp + i);
+    const uint32_t mask = (1u << lb) - 1u;
+    const float n = (float)((1 << a.bit_width) - 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int bit = j * lb;
+      const uint32_t code = (wds[bit >> 5] >> (bit & 31)) & mask;
+      float x = (a.out_kind == 2) ? (float)code : 2.f * (float)code - n;
+      v[j] = (c0 + j < a.k) ? x : 0.f;
+    }
   }
   if (a.out_kind == 1 || a.out_kind == 2) {
     uint32_t w[4];
@@ -500,7 +594,30 @@ struct Im2colArgs {
   int64_t c_begin, cg;   // first channel of the group, channels per group
   uint8_t* out;
   int64_t ld_out, kcols;
+  int nhwc;
 };
+
+// NHWC fast path: every 16-byte vector of an output row is 16 bytes of one pixel's channel run (or zeros).
+__global__ void __launch_bounds__(256) im2col_nhwc_vec_kernel(Im2colArgs a) {
+  const int64_t vec_per_row = (a.ld_out * a.eb) / 16;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t M = a.B * a.OH * a.OW;
+  if (gid >= M * vec_per_row) return;
+  const int64_t m = gid / vec_per_row, v = gid - m * vec_per_row;
+  const int64_t col0 = v * (16 / a.eb);
+  uint4 val = make_uint4(0, 0, 0, 0);
+  if (col0 < a.kcols) {
+    const int64_t b = m / (a.OH * a.OW), r = m - b * (a.OH * a.OW);
+    const int64_t oh = r / a.OW, ow = r - oh * a.OW;
+    const int tap = (int)(col0 / a.cg);
+    const int64_t c = col0 - (int64_t)tap * a.cg;
+    const int ky = tap / a.kw, kx = tap - ky * a.kw;
+    const int64_t ih = oh * a.sh - a.ph + (int64_t)ky * a.dh, iw = ow * a.sw - a.pw + (int64_t)kx * a.dw;
+    if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W)
+      val = __ldg(reinterpret_cast<const uint4*>(a.x + (((b * a.H + ih) * a.W + iw) * a.C + a.c_begin + c) * a.eb));
+  }
+  *reinterpret_cast<uint4*>(a.out + (m * a.ld_out) * a.eb + v * 16) = val;
+}
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
@@ -518,13 +635,14 @@ __global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
     int64_t col = col0 + j;
     T val = T(0);
     if (col < a.kcols) {
-      int64_t c = col / (a.kh * a.kw);
-      int rem = (int)(col - c * (a.kh * a.kw));
-      int ky = rem / a.kw, kx = rem - ky * a.kw;
+      int tap = (int)(col / a.cg);
+      int64_t c = col - (int64_t)tap * a.cg;           // column = (kh, kw, c): channel fastest
+      int ky = tap / a.kw, kx = tap - ky * a.kw;
       int64_t ih = oh * a.sh - a.ph + (int64_t)ky * a.dh;
       int64_t iw = ow * a.sw - a.pw + (int64_t)kx * a.dw;
       if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W)
-        val = x[((b * a.C + a.c_begin + c) * a.H + ih) * a.W + iw];
+        val = a.nhwc ? x[((b * a.H + ih) * a.W + iw) * a.C + a.c_begin + c]
+                     : x[((b * a.C + a.c_begin + c) * a.H + ih) * a.W + iw];
     }
     v[j] = val;
   }
@@ -584,10 +702,10 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
     a.q.step = ldexpf(1.f, p->fsr - p->bit_width);
     a.q.maxv = ldexpf(1.f, p->fsr);
   }
-  if (p->mode == QT_Q_SPLIT) QT_REQUIRE(p->codes_kind == 4, "qt_quant_act: QT_Q_SPLIT needs codes_kind 4");
+  if (p->mode == QT_Q_SPLIT) QT_REQUIRE(p->codes_kind == 4 || p->codes_kind == 6, "qt_quant_act: QT_Q_SPLIT needs codes_kind 4 or 6");
   if (p->mode == QT_Q_LOG || p->mode == QT_Q_LIN)
     QT_REQUIRE(p->codes_kind == 0 && !p->bits, "qt_quant_act: Log/Lin quantizers produce fp32 only");
-  QT_REQUIRE(p->codes_kind >= 0 && p->codes_kind <= 5, "qt_quant_act: bad codes_kind");
+  QT_REQUIRE(p->codes_kind >= 0 && p->codes_kind <= 6, "qt_quant_act: bad codes_kind");
   if (p->codes_kind) QT_REQUIRE(p->codes && p->ld_codes >= p->cols, "qt_quant_act: bad codes buffer");
   if (p->bits) QT_REQUIRE(p->mode == QT_Q_SIGN && p->ld_bits * 32 >= p->cols, "qt_quant_act: bits need QT_Q_SIGN and ld_bits*32 >= cols");
   if (p->y) QT_REQUIRE(p->ld_y >= p->cols, "qt_quant_act: ld_y < cols");
@@ -595,6 +713,22 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   a.y = p->y; a.ld_y = p->ld_y; a.codes = p->codes; a.codes_kind = p->codes_kind; a.ld_codes = p->ld_codes;
   a.bits = p->bits; a.ld_bits = p->ld_bits; a.row_sum = p->row_sum; a.row_scale = p->row_scale; a.overflow = p->overflow;
 
+  if (p->nhwc_c > 0) {
+    QT_REQUIRE(p->codes && (p->codes_kind == 1 || p->codes_kind == 2), "qt_quant_act: NHWC output needs int8/uint8 codes");
+    QT_REQUIRE(p->mode == QT_Q_SIGN || p->mode == QT_Q_TERNARY || p->mode == QT_Q_DOREFA, "qt_quant_act: NHWC output: SIGN/TERNARY/DOREFA only");
+    QT_REQUIRE(p->cols % p->nhwc_c == 0 && p->ld_x == p->cols && (!p->y || p->ld_y == p->cols) && !p->bits && !p->row_sum,
+               "qt_quant_act: NHWC output needs dense NCHW input and no bits / row sums");
+    NhwcArgs n;
+    n.q = a.q; n.x = p->x; n.y = p->y; n.codes = (int8_t*)p->codes; n.codes_kind = p->codes_kind;
+    n.B = p->rows; n.C = p->nhwc_c; n.HW = p->cols / p->nhwc_c; n.overflow = p->overflow;
+    QT_REQUIRE(n.B <= 65535 && ceil_div(n.C, 128) <= 65535, "qt_quant_act: NHWC grid too large");
+    dim3 grid((unsigned)ceil_div(n.HW, 32), (unsigned)ceil_div(n.C, 128), (unsigned)n.B);
+    if (p->mode == QT_Q_SIGN) act_quant_nhwc_kernel<QT_Q_SIGN><<<grid, 256, 0, stream>>>(n);
+    else if (p->mode == QT_Q_TERNARY) act_quant_nhwc_kernel<QT_Q_TERNARY><<<grid, 256, 0, stream>>>(n);
+    else act_quant_nhwc_kernel<QT_Q_DOREFA><<<grid, 256, 0, stream>>>(n);
+    QT_LAUNCH_CHECK();
+    return QT_OK;
+  }
   bool vec = (p->cols % 4 == 0) && (p->ld_x % 4 == 0) && aligned(p->x, 16);
   if (p->y) vec = vec && (p->ld_y % 4 == 0) && aligned(p->y, 16);
   if (p->codes_kind == 1 || p->codes_kind == 2) vec = vec && (p->ld_codes % 4 == 0) && aligned(p->codes, 4);
@@ -707,6 +841,7 @@ extern "C" int qt_im2col(const QtIm2col* p, void* stream_) {
   a.dh = p->dil_h; a.dw = p->dil_w;
   a.cg = p->C / p->groups; a.c_begin = a.cg * p->group;
   a.out = (uint8_t*)p->out; a.ld_out = p->ld_out; a.kcols = a.cg * p->kh * p->kw;
+  a.nhwc = p->nhwc;
   QT_REQUIRE(p->ld_out >= a.kcols, "qt_im2col: ld_out < C/groups*kh*kw");
   const int64_t M = p->B * p->OH * p->OW;
   if (M == 0) return QT_OK;
@@ -714,7 +849,9 @@ extern "C" int qt_im2col(const QtIm2col* p, void* stream_) {
   QT_REQUIRE(p->ld_out % vec == 0 && aligned(p->out, 16), "qt_im2col: ld_out*elem_bytes must be a multiple of 16, out 16B aligned");
   int64_t threads = M * (p->ld_out / vec);
   unsigned blocks = (unsigned)ceil_div(threads, 256);
-  if (p->elem_bytes == 1) im2col_kernel<uint8_t, 16><<<blocks, 256, 0, stream>>>(a);
+  const bool fast = p->nhwc && ((a.cg * p->elem_bytes) % 16 == 0) && ((p->C * p->elem_bytes) % 16 == 0) && aligned(p->x, 16);
+  if (fast) im2col_nhwc_vec_kernel<<<blocks, 256, 0, stream>>>(a);
+  else if (p->elem_bytes == 1) im2col_kernel<uint8_t, 16><<<blocks, 256, 0, stream>>>(a);
   else if (p->elem_bytes == 2) im2col_kernel<uint16_t, 8><<<blocks, 256, 0, stream>>>(a);
   else im2col_kernel<uint32_t, 4><<<blocks, 256, 0, stream>>>(a);
   QT_LAUNCH_CHECK();

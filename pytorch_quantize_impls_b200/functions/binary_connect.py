@@ -53,7 +53,7 @@ def BinaryConnect(stochastic=False):
 
 
 def _sign_pack(weight):
-    return ops.pack_weight(weight.detach().reshape(weight.shape[0], -1), "sign")
+    return ops.pack_weight(ops.conv_weight_2d(weight.detach()), "sign")
 
 
 class BinaryDense(TaggingFunction):

@@ -136,7 +136,7 @@ def nnQuantWeight(bit_width=3):
 
 def dorefa_pack(weight, bit_width):
     """k-bit HBM pack of a layer weight (rows = out features / channels)."""
-    return ops.pack_weight(weight.detach().reshape(weight.shape[0], -1), "dorefa", bit_width)
+    return ops.pack_weight(ops.conv_weight_2d(weight.detach()), "dorefa", bit_width)
 
 
 def _functional_weight(weight, bit_width, max_abs):
@@ -184,7 +184,7 @@ def QuantConv2d(stride=1, padding=1, dilation=1, groups=1, bit_width=3):
             max_weight = torch.max(torch.abs(weight))
             weight_q = _functional_weight(weight, bit_width, torch.tanh(max_weight))
             ctx.save_for_backward(input, weight, weight_q, max_weight, bias)
-            pack = ops.pack_real_weight(weight_q.reshape(weight.shape[0], -1))
+            pack = ops.pack_real_weight(ops.conv_weight_2d(weight_q))
             return eng.conv2d(input, pack, bias, tuple(weight.shape), stride, padding, dilation, groups)
 
         @staticmethod

@@ -90,7 +90,7 @@ def TernaryConv2d(stochastic=True, stride=1, padding=1, dilation=1, groups=1):
         def forward(ctx, input, weight, bias=None):
             weight_t = _functional_ternary(weight, stochastic)
             ctx.save_for_backward(input, weight, weight_t, bias)
-            pack = ops.pack_real_weight(weight_t.reshape(weight.shape[0], -1))
+            pack = ops.pack_real_weight(ops.conv_weight_2d(weight_t))
             return eng.conv2d(input, pack, bias, tuple(weight.shape), stride, padding, dilation, groups)
 
         @staticmethod

@@ -92,10 +92,10 @@ def xnor_conv_pack(weight, dim=(0, 1)):
     w = weight.detach()
     if sorted(d % 4 for d in dim) == [0, 1]:
         a_tap = ops.col_absmean(w.reshape(O * Cg, kh * kw))           # [kh*kw]
-        alpha_k = a_tap.repeat(Cg).contiguous()                       # column (c, kh, kw) -> alpha[kh, kw]
-        return ops.pack_weight(w.reshape(O, -1), "xnor", alpha=alpha_k)
+        alpha_k = a_tap.repeat_interleave(Cg).contiguous()            # column (kh, kw, c) -> alpha[kh, kw]
+        return ops.pack_weight(ops.conv_weight_2d(w), "xnor", alpha=alpha_k)
     mean_weight = torch.mean(torch.abs(w), list(dim), keepdim=True)   # general `dim`: real-valued weight operand
-    return ops.pack_real_weight((torch.sign(w) * mean_weight).reshape(O, -1))
+    return ops.pack_real_weight(ops.conv_weight_2d(torch.sign(w) * mean_weight))
 
 
 def XNORDense(dim=[0, 1]):

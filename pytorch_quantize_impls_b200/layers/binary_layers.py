@@ -19,9 +19,9 @@ class _BinMixin(QuantLayerMixin):
 
     def _make_pack(self, w):
         if self.deterministic:
-            return ops.pack_weight(w.detach().reshape(w.shape[0], -1), "sign")
+            return ops.pack_weight(ops.conv_weight_2d(w.detach()), "sign")
         # stochastic binarisation draws new +-1 weights each call; pack the drawn signs
-        return ops.pack_weight(self.bin_op.apply(w.detach()).reshape(w.shape[0], -1), "sign")
+        return ops.pack_weight(ops.conv_weight_2d(self.bin_op.apply(w.detach())), "sign")
 
 
 class LinearBin(_BinMixin, torch.nn.Linear):

@@ -112,7 +112,7 @@ class QuantLayerMixin(QLayer):
         # eval mode with weights that train(False) did not produce (state_dict loaded in eval mode, .to() after
         # eval, ...): the reference contracts with the stored values as they are -> real-valued weight operand
         st = _EvalState()
-        st.pack = ops.pack_real_weight(self.weight.detach().reshape(self.weight.shape[0], -1))
+        st.pack = ops.pack_real_weight(ops.conv_weight_2d(self.weight.detach()))
         st.version, st.ptr = self.weight._version, self.weight.data_ptr()
         self._eval_state = st
         return st.pack

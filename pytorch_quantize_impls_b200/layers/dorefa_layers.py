@@ -15,11 +15,11 @@ class _DorefaMixin(QuantLayerMixin):
         return self.weight_op.forward(w)
 
     def _make_pack(self, w):
-        w2 = w.detach().reshape(w.shape[0], -1)
+        w2 = ops.conv_weight_2d(w.detach())
         if 1 <= self.bit_width <= 8:
             return ops.pack_weight(w2, "dorefa", self.bit_width)     # k-bit codes (+ E / 1/n column scale)
         with torch.no_grad():                                        # k == 32 (or 9..16): real-valued operand
-            return ops.pack_real_weight(self.weight_op.forward(w.detach()).reshape(w.shape[0], -1))
+            return ops.pack_real_weight(ops.conv_weight_2d(self.weight_op.forward(w.detach())))
 
 
 class LinearDorefa(_DorefaMixin, torch.nn.Linear):

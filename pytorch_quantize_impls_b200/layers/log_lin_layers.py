@@ -16,7 +16,7 @@ class _LogLinMixin(QuantLayerMixin):
     def _make_pack(self, w):
         with torch.no_grad():
             wq = self.weight_op.forward(w.detach())
-        return ops.pack_real_weight(wq.reshape(w.shape[0], -1))
+        return ops.pack_real_weight(ops.conv_weight_2d(wq))
 
     def clamp(self):
         self.weight.data.clamp_(-1 * 2 ** (self.fsr), 2 ** (self.fsr))

@@ -18,11 +18,11 @@ class _TerMixin(QuantLayerMixin):
         return self.ter_op.apply(w)
 
     def _make_pack(self, w):
-        w2 = w.detach().reshape(w.shape[0], -1)
+        w2 = ops.conv_weight_2d(w.detach())
         if self.deterministic:
             return ops.pack_weight(w2, "ternary")
         # stochastic: the drawn values are already in {-1, 0, 1}; the deterministic packer maps them to themselves
-        return ops.pack_weight(self.ter_op.apply(w.detach()).reshape(w.shape[0], -1), "ternary")
+        return ops.pack_weight(ops.conv_weight_2d(self.ter_op.apply(w.detach())), "ternary")
 
 
 class LinearTer(_TerMixin, torch.nn.Linear):

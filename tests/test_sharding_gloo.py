@@ -43,9 +43,9 @@ def test_sharded_forward_matches_single_process(batch):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, batch, q)) for r in range(2)]
     for p in procs:
         p.start()
-    y = q.get(timeout=120)
+    y = q.get(timeout=600)
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=600)
         assert p.exitcode == 0
     torch.manual_seed(5)
     x = torch.randn(batch, 64); w = torch.randn(10, 64) * 0.3; b = torch.rand(10)
