@@ -230,18 +230,18 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
         bias = ops.as_f32c(bias)
     need_rs = int_w and pack.kind == "dorefa" and pack.bit_width == 8
 
+    xf = None
     if tag is not None:
-        elem, ld = 1, ops.round_up(Kg, 16)
-        planes = [tag.codes]                     # [B, H, W, C] channels-last codes
+        elem, ld, nplanes = 1, ops.round_up(Kg, 16), 1
         dtype = tag.codes.dtype
     else:
-        elem, ld = 2, ops.round_up(Kg, 8)
-        a0 = _a_split(ops.as_f32c(x).reshape(1, -1))
-        planes = [a0.t[p].view(-1)[:x.numel()].view(B, Cin, H, W) for p in range(a0.planes)]
+        # real-valued input (first layers): fused gather + bf16 hi/mid/lo split straight from the fp32 NCHW tensor
+        elem, ld, nplanes = 2, ops.round_up(Kg, 8), 3
+        xf = ops.as_f32c(x)
         dtype = torch.bfloat16
 
     # bound the transient im2col matrix (~1.5 GiB per chunk of images)
-    per_img = P * ld * elem * len(planes)
+    per_img = P * ld * elem * nplanes
     bchunk = max(1, min(B, (3 << 29) // max(per_img, 1)))
     for b0 in range(0, B, bchunk):
         b1 = min(B, b0 + bchunk)
@@ -251,16 +251,16 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
             a = _A()
             a.bits, a.ld_bits, a.row_scale, a.row_sum = None, 0, None, None
             a.ld = ld
-            buf = torch.empty((len(planes), M, ld), dtype=dtype, device=x.device)
-            if need_rs and tag is not None:
-                a.row_sum = torch.empty(M, dtype=torch.int32, device=x.device)
-            for pi, src in enumerate(planes):
-                ops.im2col(src[b0:b1], elem, geom, g, buf[pi], ld, row_sum=a.row_sum if pi == 0 else None,
-                           is_unsigned=(dtype == torch.uint8), nhwc=tag is not None)
+            buf = torch.empty((nplanes, M, ld), dtype=dtype, device=x.device)
             if tag is not None:
+                if need_rs:
+                    a.row_sum = torch.empty(M, dtype=torch.int32, device=x.device)
+                ops.im2col(tag.codes[b0:b1], 1, geom, g, buf[0], ld, row_sum=a.row_sum,
+                           is_unsigned=(dtype == torch.uint8), nhwc=True)
                 a.form, a.t, a.signed, a.scale, a.planes = "i8", buf[0], dtype == torch.int8, tag.scale, 1
             else:
-                a.form, a.t, a.signed, a.scale, a.planes = "bf16", buf, True, 1.0, len(planes)
+                ops.im2col(xf[b0:b1], 4, geom, g, buf, ld, split3=True)
+                a.form, a.t, a.signed, a.scale, a.planes = "bf16", buf, True, 1.0, 3
             _contract(a, pack, M, Ng, Kg, out, w_row0=g * Ng, bias=None if bias is None else bias[g * Ng:(g + 1) * Ng],
                       out_mode=1, ldo=O, nchw_inner=P, out_offset=(b0 * O + g * Ng) * P)
     return out

@@ -46,7 +46,7 @@ class QtIm2col(C.Structure):
                 ("B", i64), ("C", i64), ("H", i64), ("W", i64),
                 ("kh", i32), ("kw", i32), ("stride_h", i32), ("stride_w", i32), ("pad_h", i32), ("pad_w", i32),
                 ("dil_h", i32), ("dil_w", i32), ("groups", i32), ("group", i32),
-                ("OH", i64), ("OW", i64), ("out", vp), ("ld_out", i64), ("row_sum", vp)]
+                ("OH", i64), ("OW", i64), ("out", vp), ("ld_out", i64), ("row_sum", vp), ("split3", i32)]
 
 
 class QtEpilogue(C.Structure):

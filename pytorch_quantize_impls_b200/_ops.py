@@ -238,7 +238,7 @@ def conv_weight_2d(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
 
-def im2col(x4d, elem_bytes, geom, group, out, ld_out, row_sum=None, is_unsigned=False, nhwc=False):
+def im2col(x4d, elem_bytes, geom, group, out, ld_out, row_sum=None, is_unsigned=False, nhwc=False, split3=False):
     """geom = (kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW); x4d is [B,C,H,W] (nhwc=False) or [B,H,W,C]."""
     if nhwc:
         B, H, W, Cc = x4d.shape
@@ -250,7 +250,7 @@ def im2col(x4d, elem_bytes, geom, group, out, ld_out, row_sum=None, is_unsigned=
     a.B, a.C, a.H, a.W = B, Cc, H, W
     a.kh, a.kw, a.stride_h, a.stride_w, a.pad_h, a.pad_w, a.dil_h, a.dil_w = kh, kw, sh, sw, ph, pw, dh, dw
     a.groups, a.group, a.OH, a.OW = groups, group, OH, OW
-    a.out, a.ld_out, a.row_sum = _p(out), ld_out, _p(row_sum)
+    a.out, a.ld_out, a.row_sum, a.split3 = _p(out), ld_out, _p(row_sum), int(split3)
     L.check(L.lib().qt_im2col(C.byref(a), _stream()), "qt_im2col")
 
 

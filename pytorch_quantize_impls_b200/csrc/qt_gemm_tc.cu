@@ -445,7 +445,7 @@ extern "C" int qt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* 
   const bool tc_ok = tc_available() && lda % 16 == 0 && ldw % 16 == 0 && al16(a) && al16(w) &&
                      M < (1ll << 31) && N < (1ll << 31);
   if (backend == 1 && !tc_ok) { set_error("qt_gemm_i8: tcgen05 backend needs sm_100 and 16-byte aligned operands/pitches"); return QT_EUNSUPPORTED; }
-  const bool use_tc = backend == 1 || (backend == 0 && tc_ok && (double)M * (double)N * (double)K >= 1.0e7);
+  const bool use_tc = backend == 1 || (backend == 0 && tc_ok && (double)M * (double)N * (double)K >= 2.0e5);
   if (!use_tc) return simt_gemm_i8(a, a_signed, lda, w, w_signed, ldw, M, N, K, ep, stream);
 
   const int bn = pick_bn(N);
@@ -478,7 +478,7 @@ extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, c
   if (max_pa > 0) tc_ok = tc_ok && a_plane_stride % lda == 0;
   if (max_pw > 0) tc_ok = tc_ok && w_plane_stride % ldw == 0;
   if (backend == 1 && !tc_ok) { set_error("qt_gemm_f16: tcgen05 backend needs sm_100, 16-byte aligned pitches and plane strides that are whole rows"); return QT_EUNSUPPORTED; }
-  const bool use_tc = backend == 1 || (backend == 0 && tc_ok && (double)M * (double)N * (double)K >= 1.0e7);
+  const bool use_tc = backend == 1 || (backend == 0 && tc_ok && (double)M * (double)N * (double)K >= 2.0e5);
   if (!use_tc) return simt_gemm_f16(a, lda, a_plane_stride, w, ldw, w_plane_stride, fmt, npass, pa, pw, M, N, K, ep, stream);
 
   const int bn = pick_bn(N);

@@ -655,6 +655,53 @@ __global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
   }
 }
 
+// First-layer gather: fp32 NCHW image -> three bf16 planes (hi/mid/lo) of the im2col matrix in one pass.
+// The column -> (input offset, dy, dx) decomposition is tabulated once per CTA in shared memory, so the inner loop is
+// table lookups + L1-resident gathers; each thread emits 8 consecutive columns (one 16-byte store per plane).
+__global__ void __launch_bounds__(256) im2col_split3_kernel(Im2colArgs a, int64_t plane_stride) {
+  extern __shared__ int tab[];                 // [kcols] offset, [kcols] (dy << 16 | dx)
+  int* toff = tab;
+  int* tdyx = tab + a.kcols;
+  for (int col = threadIdx.x; col < a.kcols; col += blockDim.x) {
+    int tap = col / (int)a.cg, c = col - tap * (int)a.cg;
+    int ky = tap / a.kw, kx = tap - ky * a.kw;
+    int dy = ky * a.dh, dx = kx * a.dw;
+    toff[col] = (int)(((a.c_begin + c) * a.H + dy) * a.W + dx);
+    tdyx[col] = (dy << 16) | dx;
+  }
+  __syncthreads();
+  const int64_t vec_per_row = a.ld_out / 8;
+  const int64_t M = a.B * a.OH * a.OW;
+  for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < M * vec_per_row;
+       gid += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = gid / vec_per_row;
+    const int col0 = (int)(gid - m * vec_per_row) * 8;
+    const int64_t b = m / (a.OH * a.OW), r = m - b * (a.OH * a.OW);
+    const int oh = (int)(r / a.OW), ow = (int)(r - (int64_t)oh * a.OW);
+    const int ih0 = oh * a.sh - a.ph, iw0 = ow * a.sw - a.pw;
+    const float* xb = reinterpret_cast<const float*>(a.x) + b * a.C * a.H * a.W + (int64_t)ih0 * a.W + iw0;
+    __align__(16) __nv_bfloat16 h[8], mi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = col0 + j;
+      float v = 0.f;
+      if (col < a.kcols) {
+        const int dyx = tdyx[col];
+        const int ih = ih0 + (dyx >> 16), iw = iw0 + (dyx & 0xffff);
+        if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W) v = __ldg(xb + toff[col]);
+      }
+      h[j] = __float2bfloat16_rn(v);
+      float r1 = v - __bfloat162float(h[j]);
+      mi[j] = __float2bfloat16_rn(r1);
+      lo[j] = __float2bfloat16_rn(r1 - __bfloat162float(mi[j]));
+    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + m * a.ld_out + col0;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
+    *reinterpret_cast<uint4*>(o + plane_stride) = *reinterpret_cast<uint4*>(mi);
+    *reinterpret_cast<uint4*>(o + 2 * plane_stride) = *reinterpret_cast<uint4*>(lo);
+  }
+}
+
 template <bool UNSIGNED>
 __global__ void __launch_bounds__(256) rowsum_i8_kernel(const uint8_t* __restrict__ a, int64_t rows, int64_t ld,
                                                         int32_t* __restrict__ out) {
@@ -845,6 +892,16 @@ extern "C" int qt_im2col(const QtIm2col* p, void* stream_) {
   QT_REQUIRE(p->ld_out >= a.kcols, "qt_im2col: ld_out < C/groups*kh*kw");
   const int64_t M = p->B * p->OH * p->OW;
   if (M == 0) return QT_OK;
+  if (p->split3) {
+    QT_REQUIRE(p->elem_bytes == 4 && !p->nhwc && !p->row_sum, "qt_im2col: split3 needs fp32 NCHW input and no row sums");
+    QT_REQUIRE(p->ld_out % 8 == 0 && aligned(p->out, 16) && (M * p->ld_out) % 8 == 0, "qt_im2col: split3 needs ld_out % 8 == 0");
+    QT_REQUIRE(a.kcols <= 4096 && p->C * p->H * p->W < (1ll << 31), "qt_im2col: split3 supports up to 4096 gathered columns");
+    int64_t vecs = M * (p->ld_out / 8);
+    unsigned nb = (unsigned)std::min<int64_t>(ceil_div(vecs, 256), 148 * 16);
+    im2col_split3_kernel<<<nb, 256, 2 * a.kcols * sizeof(int), stream>>>(a, M * p->ld_out);
+    QT_LAUNCH_CHECK();
+    return QT_OK;
+  }
   const int vec = 16 / p->elem_bytes;
   QT_REQUIRE(p->ld_out % vec == 0 && aligned(p->out, 16), "qt_im2col: ld_out*elem_bytes must be a multiple of 16, out 16B aligned");
   int64_t threads = M * (p->ld_out / vec);
