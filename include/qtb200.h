@@ -214,6 +214,27 @@ int qt_gemm_b1t2(const uint32_t* a_bits, int64_t lda_words, const uint32_t* w_nz
 int qt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* w, int w_signed, int64_t ldw,
                int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream);
 
+/* Implicit-GEMM convolution (F.conv2d at binary_layers.py:105-106, terner_layers.py:91-92, dorefa_layers.py:79,81) on
+ * channels-last 8-bit activation codes x_nhwc[B, H, W, C]: the A operand is fetched by TMA in im2col mode (no im2col
+ * matrix is ever materialised; padding taps are zero-filled by the hardware), K runs over (kh, kw, c) with the channel
+ * fastest, `w` is the expanded weight operand [N, kh*kw*C/groups] of conv group `group` (ldw bytes per row).
+ * Same epilogue (use out_mode = 1 for NCHW output).  Returns QT_EUNSUPPORTED when (C/groups) % 32 != 0 or the device is
+ * not sm_100: callers then use qt_im2col + qt_gemm_i8. */
+typedef struct QtConvGeom {
+  int64_t B, C, H, W;
+  int kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int groups, group;
+  int64_t OH, OW;
+} QtConvGeom;
+
+int qt_conv_i8(const void* x_nhwc, int a_signed, const QtConvGeom* g, const void* w, int w_signed, int64_t ldw,
+               int64_t N, const QtEpilogue* ep, void* stream);
+
+/* Per-output-pixel sum of the 8-bit codes under the filter window of conv group `group` (zero padding contributes 0):
+ * row_sum[m] = sum_{kh,kw,c} x_nhwc[b, ih, iw, c].  It is the activation row sum the unsigned-weight (DoReFa-8) zero point
+ * needs when the conv runs as an implicit GEMM and no im2col matrix exists.  `chan_sum` is int32 scratch of B*H*W elements. */
+int qt_patch_rowsum(const void* x_nhwc, int is_unsigned, const QtConvGeom* g, int32_t* chan_sum, int32_t* row_sum, void* stream);
+
 /* 16-bit float planes x 16-bit float planes -> fp32.  D = sum over passes p of A[pa[p]] . W[pw[p]]^T.
  * fmt 0: bf16, fmt 1: fp16 (both operands).  Planes are [M, lda] / [N, ldw] matrices `a_plane_stride` /
  * `w_plane_stride` elements apart.  backend as above (2 = CUDA-core fp32 FMA fallback). */

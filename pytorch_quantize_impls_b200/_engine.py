@@ -22,6 +22,7 @@ from . import _ops as ops
 POPCOUNT_MAX_M = int(os.environ.get("QTB200_POPCOUNT_MAX_M", "64"))
 _force_backend = {"i8": L.BACKEND_AUTO, "bf16": L.BACKEND_AUTO}
 _force_popcount = [False]
+_implicit_conv = [os.environ.get("QTB200_IMPLICIT_CONV", "1") != "0"]
 # XnorNet product precision: "fp16" = one fp16 tensor pass (alpha[k]*sign rounded to 11 bits, ~1e-4 of max|y|),
 # "bf16x2" = two bf16 passes over hi/lo weight planes (~1e-5).  Both are inside the 1e-3 tolerance.
 _xnor_mode = ["fp16"]
@@ -35,6 +36,11 @@ def set_xnor_mode(mode):
 
 def xnor_codes_kind():
     return L.CODES_F16 if _xnor_mode[0] == "fp16" else L.CODES_BF16
+
+
+def set_implicit_conv(flag):
+    """True (default): conv layers on channels-last codes use the TMA-im2col implicit GEMM; False: explicit gather."""
+    _implicit_conv[0] = bool(flag)
 
 
 def set_backend(i8=None, bf16=None, popcount=None):
@@ -229,6 +235,26 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
     if bias is not None:
         bias = ops.as_f32c(bias)
     need_rs = int_w and pack.kind == "dorefa" and pack.bit_width == 8
+
+    # implicit GEMM: TMA im2col straight from the channels-last codes (no im2col matrix is materialised)
+    if (tag is not None and _implicit_conv[0] and Cg % 32 == 0 and Cin % 16 == 0
+            and _force_backend["i8"] != L.BACKEND_SIMT):
+        a_signed = tag.codes_kind == L.CODES_I8
+        # DoReFa-8 weights stay unsigned codes c; the zero point needs the per-pixel patch sums of the activation codes
+        w, ldw = ops.expand_weight(pack, L.CODES_U8 if need_rs else L.CODES_I8)
+        col_scale = pack.col_scale
+        done = True
+        for g in range(groups):
+            rs = ops.patch_rowsum(tag.codes, not a_signed, geom, g) if need_rs else None
+            epi = ops.make_epi(out, ldo=O, out_mode=1, nchw_inner=P, bias=None if bias is None else bias[g * Ng:(g + 1) * Ng],
+                               col_scale=None if col_scale is None else col_scale[g * Ng:(g + 1) * Ng],
+                               row_sum=rs, acc_mul=2 if need_rs else 1, rs_mul=-255 if need_rs else 0,
+                               scale=tag.scale, out_offset=g * Ng * P)
+            if not ops.conv_i8(tag.codes, a_signed, geom, g, w[g * Ng:], not need_rs, ldw, Ng, epi):
+                done = False
+                break
+        if done:
+            return out
 
     xf = None
     if tag is not None:

@@ -49,6 +49,12 @@ class QtIm2col(C.Structure):
                 ("OH", i64), ("OW", i64), ("out", vp), ("ld_out", i64), ("row_sum", vp), ("split3", i32)]
 
 
+class QtConvGeom(C.Structure):
+    _fields_ = [("B", i64), ("C", i64), ("H", i64), ("W", i64),
+                ("kh", i32), ("kw", i32), ("stride_h", i32), ("stride_w", i32), ("pad_h", i32), ("pad_w", i32),
+                ("dil_h", i32), ("dil_w", i32), ("groups", i32), ("group", i32), ("OH", i64), ("OW", i64)]
+
+
 class QtEpilogue(C.Structure):
     _fields_ = [("bias", vp), ("row_scale", vp), ("col_scale", vp), ("row_sum", vp),
                 ("scale", f32), ("acc_mul", C.c_int32), ("rs_mul", C.c_int32),
@@ -68,6 +74,8 @@ SYMBOLS = {
     "qt_gemm_b1b1": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_gemm_b1t2": (i32, [vp, i64, vp, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_gemm_i8": (i32, [vp, i32, i64, vp, i32, i64, i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
+    "qt_conv_i8": (i32, [vp, i32, C.POINTER(QtConvGeom), vp, i32, i64, i64, C.POINTER(QtEpilogue), vp]),
+    "qt_patch_rowsum": (i32, [vp, i32, C.POINTER(QtConvGeom), vp, vp, vp]),
     "qt_gemm_f16": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, C.POINTER(i32), C.POINTER(i32),
                           i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
     "qt_gemm_f32": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),

@@ -288,6 +288,28 @@ def gemm_f16(a, lda, a_plane_stride, w, ldw, w_plane_stride, passes, M, N, K, ep
                                 C.byref(epi), backend, _stream()), "qt_gemm_f16")
 
 
+def conv_i8(x_nhwc, a_signed, geom, group, w, w_signed, ldw, N, epi):
+    """Implicit-GEMM conv on channels-last codes; returns False when the shape needs the explicit im2col route."""
+    B, H, W, Cc = x_nhwc.shape
+    kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW = geom
+    g = L.QtConvGeom(B, Cc, H, W, kh, kw, sh, sw, ph, pw, dh, dw, groups, group, OH, OW)
+    rc = L.lib().qt_conv_i8(_p(x_nhwc), int(a_signed), C.byref(g), _p(w), int(w_signed), ldw, N, C.byref(epi), _stream())
+    if rc == -3:
+        return False
+    L.check(rc, "qt_conv_i8")
+    return True
+
+
+def patch_rowsum(x_nhwc, is_unsigned, geom, group):
+    B, H, W, Cc = x_nhwc.shape
+    kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW = geom
+    g = L.QtConvGeom(B, Cc, H, W, kh, kw, sh, sw, ph, pw, dh, dw, groups, group, OH, OW)
+    S = torch.empty(B * H * W, dtype=torch.int32, device=x_nhwc.device)
+    rs = torch.empty(B * OH * OW, dtype=torch.int32, device=x_nhwc.device)
+    L.check(L.lib().qt_patch_rowsum(_p(x_nhwc), int(is_unsigned), C.byref(g), _p(S), _p(rs), _stream()), "qt_patch_rowsum")
+    return rs
+
+
 def gemm_f32(a, lda, w, ldw, M, N, K, epi):
     L.check(L.lib().qt_gemm_f32(_p(a), lda, _p(w), ldw, M, N, K, C.byref(epi), _stream()), "qt_gemm_f32")
 

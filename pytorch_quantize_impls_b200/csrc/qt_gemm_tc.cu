@@ -31,6 +31,11 @@ struct TcArgs {
   Epi ep;
   int tiles_m, tiles_n;
   int tma_store;        // 1: row-major fp32 output goes through swizzled smem + cp.async.bulk.tensor store
+  // implicit-GEMM conv (IM2COL kernels): A rows are output pixels (b, oh, ow), K runs over (kh, kw, c-blocks)
+  int cv_OW, cv_OHW;            // output width, output pixels per image
+  int cv_sh, cv_sw, cv_ph, cv_pw, cv_dh, cv_dw, cv_kw;
+  int cv_cblocks;               // channel blocks (of BKB bytes) per filter tap
+  int cv_c0;                    // first channel of the conv group
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -60,6 +65,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// TMA im2col load: 128 output pixels x BKB channel bytes of filter tap (off_w, off_h), starting at base pixel (w, h) of
+// image n (coordinates in the padded "bounding box" space); out-of-image taps are zero-filled by the hardware.
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -98,12 +112,14 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
 }
 
 // K-major, 128B-swizzled operand tile: 8-row atoms of 1024 B (SBO), LBO unused, descriptor version 1 (sm_100).
+template <int BKB>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  // rows of BKB bytes, BKB-byte swizzle (128 / 64 / 32), 8-row atoms -> SBO = 8 * BKB
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)((8u * BKB) >> 4) << 32;
   d |= 1ull << 46;
-  d |= 2ull << 61;   // SWIZZLE_128B
+  d |= (uint64_t)(BKB == 128 ? 2 : (BKB == 64 ? 4 : 6)) << 61;   // SWIZZLE_128B / 64B / 32B
   return d;
 }
 
@@ -120,12 +136,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN, int KIND, int STAGES>
+template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_out, TcArgs g) {
-  constexpr uint32_t A_BYTES = TC_BM * TC_BK_BYTES;
-  constexpr uint32_t W_BYTES = BN * TC_BK_BYTES;
+  constexpr uint32_t A_BYTES = TC_BM * BKB;
+  constexpr uint32_t W_BYTES = BN * BKB;
   constexpr uint32_t STAGE_BYTES = A_BYTES + W_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
@@ -180,12 +196,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int pass = 0; pass < g.npass; ++pass) {
           const int a_row = (int)(g.pa[pass] * g.a_plane_rows) + tm * TC_BM;
           const int w_row = (int)(g.pw[pass] * g.w_plane_rows) + tn * BN;
+          int cv_n = 0, cv_h = 0, cv_w = 0;
+          if (IM2COL) {   // first output pixel of this M tile -> base position of its filter window
+            const int m0 = tm * TC_BM;
+            cv_n = m0 / g.cv_OHW;
+            const int r = m0 - cv_n * g.cv_OHW;
+            const int oh = r / g.cv_OW;
+            cv_h = oh * g.cv_sh - g.cv_ph;
+            cv_w = (r - oh * g.cv_OW) * g.cv_sw - g.cv_pw;
+          }
           for (int kb = 0; kb < g.num_kblocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), STAGE_BYTES);
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            tma_load_2d(sa, &map_a, full_bar(stage), kb * TC_BK_BYTES, a_row);
-            tma_load_2d(sa + A_BYTES, &map_w, full_bar(stage), kb * TC_BK_BYTES, w_row);
+            if (IM2COL) {
+              const int tap = kb / g.cv_cblocks, cb = kb - tap * g.cv_cblocks;
+              const int ky = tap / g.cv_kw, kx = tap - ky * g.cv_kw;
+              tma_load_im2col(sa, &map_a, full_bar(stage), g.cv_c0 + cb * BKB, cv_w, cv_h, cv_n,
+                              (uint16_t)(kx * g.cv_dw), (uint16_t)(ky * g.cv_dh));
+            } else {
+              tma_load_2d(sa, &map_a, full_bar(stage), kb * BKB, a_row);
+            }
+            tma_load_2d(sa + A_BYTES, &map_w, full_bar(stage), kb * BKB, w_row);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -206,10 +238,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+          const uint64_t adesc = make_smem_desc<BKB>(sa);
+          const uint64_t bdesc = make_smem_desc<BKB>(sa + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BK_BYTES / 32; ++k) {
+          for (int k = 0; k < BKB / 32; ++k) {
             // +32 B along K inside the swizzle atom == +2 in the (addr >> 4) field
             tc_mma<KIND>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), g.idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
@@ -353,19 +385,40 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D byte matrix [rows, row_bytes] with row pitch ld_bytes; box = 128 B x box_rows, 128B swizzle, zero OOB fill.
+static CUtensorMapSwizzle swizzle_for(int bkb) {
+  return bkb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bkb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
 static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t row_bytes, uint64_t ld_bytes, uint32_t box_rows,
-                    bool f32 = false) {
+                    bool f32 = false, int bkb = TC_BK_BYTES) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return QT_ECUDA; }
   cuuint64_t dims[2] = {f32 ? row_bytes / 4 : row_bytes, rows};
   cuuint64_t strides[1] = {ld_bytes};
-  cuuint32_t box[2] = {f32 ? 32u : (cuuint32_t)TC_BK_BYTES, box_rows};
+  cuuint32_t box[2] = {f32 ? 32u : (cuuint32_t)bkb, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_for(bkb), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return QT_ECUDA; }
   return QT_OK;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn get_encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeIm2colFn)p;
+  });
+  return fn;
 }
 
 static int g_num_sms = 0;
@@ -379,9 +432,9 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int KIND, int STAGES>
+template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK_BYTES + BN * TC_BK_BYTES) + 4 * 2 * 4096 + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * BKB + BN * BKB) + 4 * 2 * 4096 + 1024 + 256;
   // output tensor map (row-major fp32): only when every row pitch / base is 16-byte aligned
   CUtensorMap mo = ma;
   g.tma_store = 0;
@@ -391,13 +444,13 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
   }
   static bool attr_set = false;
   if (!attr_set) {
-    QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, KIND, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, KIND, STAGES, BKB, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   g.tiles_m = (int)ceil_div(g.M, TC_BM);
   g.tiles_n = (int)ceil_div(g.N, BN);
   int grid = std::min(g.tiles_m * g.tiles_n, num_sms());
-  tc_gemm_kernel<BN, KIND, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
+  tc_gemm_kernel<BN, KIND, STAGES, BKB, IM2COL><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }
@@ -496,4 +549,64 @@ extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, c
   const uint32_t f = fmt == 0 ? 1u : 0u;
   g.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   return dispatch_tc<1>(ma, mw, g, bn, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// implicit-GEMM convolution on channels-last 8-bit codes (TMA im2col mode feeds the A operand)
+// ---------------------------------------------------------------------------------------------
+namespace qt {
+template <int BKB>
+static int dispatch_conv(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream) {
+  // stage = 128 x BKB (pixels) + BN x BKB (filters); keep ~192 KB of operands in flight
+  if (bn == 64) return launch_tc<64, 0, 8, BKB, true>(ma, mw, g, stream);
+  if (bn == 128) return launch_tc<128, 0, (BKB == 128 ? 6 : 8), BKB, true>(ma, mw, g, stream);
+  return launch_tc<256, 0, (BKB == 128 ? 4 : 8), BKB, true>(ma, mw, g, stream);
+}
+}  // namespace qt
+
+extern "C" int qt_conv_i8(const void* x_nhwc, int a_signed, const QtConvGeom* cg, const void* w, int w_signed, int64_t ldw,
+                          int64_t N, const QtEpilogue* ep, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(x_nhwc && cg && w, "qt_conv_i8: null argument");
+  QT_REQUIRE(cg->groups >= 1 && cg->C % cg->groups == 0 && cg->group >= 0 && cg->group < cg->groups, "qt_conv_i8: bad groups");
+  const int64_t Cg = cg->C / cg->groups, taps = (int64_t)cg->kh * cg->kw, K = taps * Cg;
+  const int64_t P = cg->OH * cg->OW, M = cg->B * P;
+  if (int rc = check_epi(ep, M, N)) return rc;
+  if (M == 0 || N == 0) return QT_OK;
+  const int bkb = (Cg % 128 == 0) ? 128 : ((Cg % 64 == 0) ? 64 : ((Cg % 32 == 0) ? 32 : 0));
+  const bool ok = tc_available() && bkb != 0 && cg->C % 16 == 0 && al16(x_nhwc) && al16(w) && ldw % 16 == 0 && ldw >= K &&
+                  M < (1ll << 31) && cg->dil_w * (cg->kw - 1) < 65536 && cg->dil_h * (cg->kh - 1) < 65536 &&
+                  cg->stride_w <= 8 && cg->stride_h <= 8;
+  if (!ok) { set_error("qt_conv_i8: shape not supported by the TMA im2col path (needs sm_100, C/groups %% 32 == 0, 16-byte aligned operands)"); return QT_EUNSUPPORTED; }
+  EncodeIm2colFn enc = get_encode_im2col_fn();
+  if (!enc) { set_error("cuTensorMapEncodeIm2col entry point not available"); return QT_ECUDA; }
+
+  CUtensorMap ma, mw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cg->C, (cuuint64_t)cg->W, (cuuint64_t)cg->H, (cuuint64_t)cg->B};
+    cuuint64_t strides[3] = {(cuuint64_t)cg->C, (cuuint64_t)cg->W * cg->C, (cuuint64_t)cg->H * cg->W * cg->C};
+    // bounding box of filter-window base positions: [-pad, (size - 1) + pad - (k - 1) * dil]
+    int lower[2] = {-cg->pad_w, -cg->pad_h};
+    int upper[2] = {cg->pad_w - (cg->kw - 1) * cg->dil_w, cg->pad_h - (cg->kh - 1) * cg->dil_h};
+    cuuint32_t estr[4] = {1, (cuuint32_t)cg->stride_w, (cuuint32_t)cg->stride_h, 1};
+    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x_nhwc), dims, strides, lower, upper,
+                     (cuuint32_t)bkb, (cuuint32_t)TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bkb),
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed with CUresult %d", (int)r); return QT_EUNSUPPORTED; }
+  }
+  const int bn = pick_bn(N);
+  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, false, bkb)) return rc;
+  TcArgs g{};
+  g.M = M; g.N = N; g.npass = 1; g.pa[0] = g.pw[0] = 0; g.a_plane_rows = g.w_plane_rows = 0; g.is_int = 1;
+  g.ep = make_epi(ep, M, N);
+  g.cv_cblocks = (int)(Cg / bkb);
+  g.num_kblocks = (int)taps * g.cv_cblocks;
+  g.cv_OW = (int)cg->OW; g.cv_OHW = (int)P;
+  g.cv_sh = cg->stride_h; g.cv_sw = cg->stride_w; g.cv_ph = cg->pad_h; g.cv_pw = cg->pad_w;
+  g.cv_dh = cg->dil_h; g.cv_dw = cg->dil_w; g.cv_kw = cg->kw; g.cv_c0 = (int)(Cg * cg->group);
+  g.idesc = (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((w_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) |
+            ((uint32_t)(TC_BM >> 4) << 24);
+  if (bkb == 128) return dispatch_conv<128>(ma, mw, g, bn, stream);
+  if (bkb == 64) return dispatch_conv<64>(ma, mw, g, bn, stream);
+  return dispatch_conv<32>(ma, mw, g, bn, stream);
 }

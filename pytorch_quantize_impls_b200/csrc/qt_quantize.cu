@@ -719,9 +719,74 @@ __global__ void __launch_bounds__(256) rowsum_i8_kernel(const uint8_t* __restric
   if (lane == 0) out[row] = s;
 }
 
+// S[b, h, w] = sum over the group's channels of the 8-bit codes (one thread per pixel, 16-byte loads, dp4a with ones)
+template <bool UNSIGNED>
+__global__ void __launch_bounds__(256) chan_sum_kernel(const uint8_t* __restrict__ x, int64_t npix, int64_t C, int64_t c0, int64_t cg,
+                                                       int32_t* __restrict__ S) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const uint8_t* px = x + p * C + c0;
+  int s = 0;
+  if ((cg & 15) == 0 && ((C | c0) & 15) == 0) {
+    for (int64_t c = 0; c < cg; c += 16) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(px + c));
+      if (UNSIGNED) {
+        s = __dp4a(v.x, 0x01010101u, (unsigned)s); s = __dp4a(v.y, 0x01010101u, (unsigned)s);
+        s = __dp4a(v.z, 0x01010101u, (unsigned)s); s = __dp4a(v.w, 0x01010101u, (unsigned)s);
+      } else {
+        s = __dp4a((int)v.x, 0x01010101, s); s = __dp4a((int)v.y, 0x01010101, s);
+        s = __dp4a((int)v.z, 0x01010101, s); s = __dp4a((int)v.w, 0x01010101, s);
+      }
+    }
+  } else {
+    for (int64_t c = 0; c < cg; ++c) s += UNSIGNED ? (int)px[c] : (int)(int8_t)px[c];
+  }
+  S[p] = s;
+}
+
+// row_sum[m] = sum over in-image filter taps of S
+__global__ void __launch_bounds__(256) box_sum_kernel(const int32_t* __restrict__ S, Im2colArgs a, int32_t* __restrict__ out) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t M = a.B * a.OH * a.OW;
+  if (m >= M) return;
+  const int64_t b = m / (a.OH * a.OW), r = m - b * (a.OH * a.OW);
+  const int64_t oh = r / a.OW, ow = r - oh * a.OW;
+  int s = 0;
+  for (int ky = 0; ky < a.kh; ++ky) {
+    const int64_t ih = oh * a.sh - a.ph + (int64_t)ky * a.dh;
+    if (ih < 0 || ih >= a.H) continue;
+    for (int kx = 0; kx < a.kw; ++kx) {
+      const int64_t iw = ow * a.sw - a.pw + (int64_t)kx * a.dw;
+      if (iw >= 0 && iw < a.W) s += __ldg(S + (b * a.H + ih) * a.W + iw);
+    }
+  }
+  out[m] = s;
+}
+
 }  // namespace qt
 
 using namespace qt;
+
+extern "C" int qt_patch_rowsum(const void* x_nhwc, int is_unsigned, const QtConvGeom* g, int32_t* chan_sum, int32_t* row_sum,
+                               void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(x_nhwc && g && chan_sum && row_sum, "qt_patch_rowsum: null argument");
+  QT_REQUIRE(g->groups >= 1 && g->C % g->groups == 0 && g->group >= 0 && g->group < g->groups, "qt_patch_rowsum: bad groups");
+  const int64_t npix = g->B * g->H * g->W, cg = g->C / g->groups;
+  if (npix == 0) return QT_OK;
+  if (is_unsigned) chan_sum_kernel<true><<<(unsigned)ceil_div(npix, 256), 256, 0, stream>>>((const uint8_t*)x_nhwc, npix, g->C, cg * g->group, cg, chan_sum);
+  else chan_sum_kernel<false><<<(unsigned)ceil_div(npix, 256), 256, 0, stream>>>((const uint8_t*)x_nhwc, npix, g->C, cg * g->group, cg, chan_sum);
+  QT_LAUNCH_CHECK();
+  Im2colArgs a{};
+  a.B = g->B; a.C = g->C; a.H = g->H; a.W = g->W; a.OH = g->OH; a.OW = g->OW;
+  a.kh = g->kh; a.kw = g->kw; a.sh = g->stride_h; a.sw = g->stride_w; a.ph = g->pad_h; a.pw = g->pad_w;
+  a.dh = g->dil_h; a.dw = g->dil_w;
+  const int64_t M = g->B * g->OH * g->OW;
+  if (M == 0) return QT_OK;
+  box_sum_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, stream>>>(chan_sum, a, row_sum);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
 
 extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;

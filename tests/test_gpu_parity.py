@@ -355,3 +355,42 @@ def test_config2_xnor_mlp_slice(Q):
     with torch.no_grad():
         y = net(x.cuda())
     assert relerr(y, ref) < REL
+
+
+# ------------------------------------------------------------------ implicit-GEMM conv (TMA im2col) vs explicit gather vs oracle
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, C=64, H=14, W=14, O=96, k=3, stride=1, padding=1, dilation=1, groups=1),
+    dict(B=3, C=64, H=15, W=13, O=40, k=3, stride=2, padding=1, dilation=1, groups=1),
+    dict(B=2, C=128, H=9, W=9, O=300, k=3, stride=1, padding=2, dilation=2, groups=1),
+    dict(B=2, C=192, H=12, W=12, O=64, k=5, stride=1, padding=2, dilation=1, groups=1),
+    dict(B=2, C=64, H=10, W=10, O=32, k=1, stride=2, padding=0, dilation=1, groups=1),
+    dict(B=2, C=64, H=8, W=8, O=48, k=3, stride=1, padding=1, dilation=1, groups=2),
+    dict(B=5, C=32, H=7, W=7, O=16, k=3, stride=1, padding=0, dilation=1, groups=1),
+])
+def test_implicit_conv_bit_exact(Q, cfg):
+    c = dict(cfg)
+    B, C, H, W, Oc, k = (c.pop(n) for n in ("B", "C", "H", "W", "O", "k"))
+    g = torch.Generator().manual_seed(Oc * 7 + C)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(Oc, C // c["groups"], k, k, generator=g) * 0.6
+    ref_bin = O_conv(O_fn="conv_bin", x=O.binary_det(x), w=w, **c)
+    ref_ter = O_conv(O_fn="conv_ter", x=O.binary_det(x), w=w, **c)
+    xu = torch.rand(B, C, H, W, generator=g)
+    ref_d4 = O_conv(O_fn="conv_dorefa", x=O.dorefa_quantize(xu, 4), w=w, bit_width=4, **c)
+    ref_d8 = O_conv(O_fn="conv_dorefa", x=O.dorefa_quantize(xu, 8), w=w, bit_width=8, **c)
+    with torch.no_grad():
+        for implicit in (True, False):
+            Q.set_implicit_conv(implicit)
+            lay = Q.layers.BinConv2d(C, Oc, k, bias=False, **c).cuda(); lay.weight.data.copy_(w)
+            assert torch.equal(lay(Q.functions.BinaryConnect()(x.cuda())).cpu(), ref_bin), implicit
+            lay = Q.layers.TerConv2d(C, Oc, k, bias=False, **c).cuda(); lay.weight.data.copy_(w)
+            assert torch.equal(lay(Q.functions.BinaryConnect()(x.cuda())).cpu(), ref_ter), implicit
+            lay = Q.layers.DorefaConv2d(C, Oc, k, bias=False, bit_width=4, **c).cuda(); lay.weight.data.copy_(w)
+            assert relerr(lay(Q.functions.DorefaQuant(xu.cuda(), 4)), ref_d4) < 2e-5, implicit
+            lay = Q.layers.DorefaConv2d(C, Oc, k, bias=False, bit_width=8, **c).cuda(); lay.weight.data.copy_(w)
+            assert relerr(lay(Q.functions.DorefaQuant(xu.cuda(), 8)), ref_d8) < 2e-5, implicit   # uint8 codes + patch sums
+    Q.set_implicit_conv(True)
+
+
+def O_conv(O_fn, x, w, **kw):
+    return getattr(O, O_fn)(x, w, None, **kw)
