@@ -82,6 +82,15 @@ typedef struct QtActQuant {
   int32_t* row_sum;     /* optional [rows]: sum over columns of the integer codes */
   float* row_scale;     /* optional [rows]: QT_Q_XNOR_ROW row mean */
   int32_t* overflow;    /* optional device flag, OR-ed with 1 when a code does not fit the int8/uint8 lane */
+  /* optional fused pre-transform (inference-time BatchNorm + activation clamp in front of the quantizer,
+     e.g. benchmark/BinaryNet/AlexNetBin.py:14-16 `BatchNorm2d -> Hardtanh -> BinaryConnect`):
+       x' = clamp(x * pre_scale[ch] + pre_shift[ch], pre_lo, pre_hi),   ch = (column / pre_hw) % pre_channels
+     pre_scale == NULL disables it; pre_clamp == 0 skips the clamp. */
+  const float* pre_scale;
+  const float* pre_shift;
+  int64_t pre_channels, pre_hw;
+  int pre_clamp;
+  float pre_lo, pre_hi;
   int64_t nhwc_c;       /* 0: codes are row-major [rows, ld_codes].  C > 0: x (and y) are NCHW with rows = B images of
                            C channels x (cols / C) pixels, and the int8/uint8 codes are written channels-last
                            [B, H*W, C] (dense) -- the layout the conv gather / TMA im2col reads with 16-byte vectors */

@@ -11,6 +11,7 @@ Integer accumulators are exact; the real-activation route carries 24 significant
 (fp32-faithful), real-valued weights 16 bits (error ~2^-17), far inside the 1e-3 tolerance of the north star.
 """
 import os
+import threading
 
 import torch
 
@@ -36,6 +37,54 @@ def set_xnor_mode(mode):
 
 def xnor_codes_kind():
     return L.CODES_F16 if _xnor_mode[0] == "fp16" else L.CODES_BF16
+
+
+_code_only = [False]
+
+
+class code_only_activations:
+    """Context manager for fused inference chains: while active (and autograd is off) the activation quantizers
+    (BinaryConnect, TernaryConnect, nnDorefaQuant / DorefaQuant, nnQuantXnor / QuantXnor) skip the fp32 fake-quant
+    tensor and return a storage-less (device='meta') placeholder that only carries the low-bit operand for the next
+    quantized layer.  The layer outputs are bit-identical to the default mode; what is saved is one fp32 write of
+    every activation tensor.  Anything other than a quantized layer that touches the placeholder fails loudly."""
+
+    def __enter__(self):
+        self.prev = _code_only[0]
+        _code_only[0] = True
+        return self
+
+    def __exit__(self, *exc):
+        _code_only[0] = self.prev
+        return False
+
+
+_apply_grad_mode = threading.local()
+
+
+def want_fp32_result(input):
+    """False when the activation quantizer may skip the fp32 fake-quant tensor (code-only mode, autograd off).
+    Inside autograd.Function.forward grad mode is always off, so the mode seen by TaggingFunction.apply is used."""
+    grad_on = getattr(_apply_grad_mode, "value", None)
+    if grad_on is None:
+        grad_on = torch.is_grad_enabled()
+    return not (_code_only[0] and not grad_on and input.dim() in (2, 4))
+
+
+def placeholder_like(input):
+    return torch.empty(input.shape, dtype=torch.float32, device="meta")
+
+
+def tagged_input_device(x):
+    """Device of a layer input; code-only placeholders live on 'meta' and point at their operand's device."""
+    if x.is_meta:
+        tag = get_tag(x)
+        if tag is None:
+            raise RuntimeError("pytorch_quantize_impls_b200: a code-only activation placeholder lost its low-bit operand "
+                               "(it may only be passed to the next quantized layer)")
+        return (tag.codes if tag.codes is not None else tag.bits).device
+    ops.require_cuda(x, "input")
+    return x.device
 
 
 def set_implicit_conv(flag):
@@ -171,15 +220,15 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
 
 def linear(x, pack, bias):
     """F.linear(x, W_q, bias) with W_q given as a WeightPack.  x: [..., K] fp32 CUDA tensor."""
-    ops.require_cuda(x, "input")
+    dev = tagged_input_device(x)
     K, N = pack.k, pack.n
     if x.shape[-1] != K:
         raise RuntimeError("size mismatch: input has %d features, layer expects %d" % (x.shape[-1], K))
     lead = x.shape[:-1]
     tag = get_tag(x) if x.dim() == 2 else None
-    x2d = ops.as_f32c(x).reshape(-1, K)
-    M = x2d.shape[0]
-    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    x2d = None if x.is_meta else ops.as_f32c(x).reshape(-1, K)
+    M = x.numel() // K
+    out = torch.empty((M, N), dtype=torch.float32, device=dev)
     if M == 0:
         return out.reshape(*lead, N)
     int_w = pack.kind in ("sign", "ternary", "dorefa")
@@ -189,6 +238,10 @@ def linear(x, pack, bias):
         if (a.form == "i8" and not int_w) or (a.form == "fp16" and pack.kind == "real"):
             a = None
     if a is None:
+        if x2d is None:
+            raise RuntimeError("pytorch_quantize_impls_b200: this layer cannot consume the code-only activation it was "
+                               "given (operand kind %r vs weight kind %r); leave code_only_activations() for this pair"
+                               % (getattr(tag, "kind", None), pack.kind))
         a = _a_split(x2d)
     if bias is not None:
         bias = ops.as_f32c(bias)
@@ -202,7 +255,7 @@ def _pair(v):
 
 def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
     """F.conv2d(x, W_q, bias, stride, padding, dilation, groups) via im2col gather + GEMM with an NCHW epilogue."""
-    ops.require_cuda(x, "input")
+    dev = tagged_input_device(x)
     if x.dim() != 4:
         raise RuntimeError("expected a 4-D NCHW input, got %d-D" % x.dim())
     B, Cin, H, W = x.shape
@@ -223,7 +276,7 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
         ph, pw = _pair(padding)
     OH = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
     OW = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
-    out = torch.empty((B, O, max(OH, 0), max(OW, 0)), dtype=torch.float32, device=x.device)
+    out = torch.empty((B, O, max(OH, 0), max(OW, 0)), dtype=torch.float32, device=dev)
     if B == 0 or OH <= 0 or OW <= 0:
         return out
     Ng, Kg, P = O // groups, Cg * kh * kw, OH * OW
@@ -235,6 +288,8 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
     if bias is not None:
         bias = ops.as_f32c(bias)
     need_rs = int_w and pack.kind == "dorefa" and pack.bit_width == 8
+    if x.is_meta and tag is None:
+        raise RuntimeError("pytorch_quantize_impls_b200: this conv layer cannot consume the code-only activation it was given")
 
     # implicit GEMM: TMA im2col straight from the channels-last codes (no im2col matrix is materialised)
     if (tag is not None and _implicit_conv[0] and Cg % 32 == 0 and Cin % 16 == 0
@@ -277,10 +332,10 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
             a = _A()
             a.bits, a.ld_bits, a.row_scale, a.row_sum = None, 0, None, None
             a.ld = ld
-            buf = torch.empty((nplanes, M, ld), dtype=dtype, device=x.device)
+            buf = torch.empty((nplanes, M, ld), dtype=dtype, device=dev)
             if tag is not None:
                 if need_rs:
-                    a.row_sum = torch.empty(M, dtype=torch.int32, device=x.device)
+                    a.row_sum = torch.empty(M, dtype=torch.int32, device=dev)
                 ops.im2col(tag.codes[b0:b1], 1, geom, g, buf[0], ld, row_sum=a.row_sum,
                            is_unsigned=(dtype == torch.uint8), nhwc=True)
                 a.form, a.t, a.signed, a.scale, a.planes = "i8", buf[0], dtype == torch.int8, tag.scale, 1

@@ -27,7 +27,9 @@ class QtActQuant(C.Structure):
                 ("y", vp), ("ld_y", i64),
                 ("codes", vp), ("codes_kind", i32), ("ld_codes", i64),
                 ("bits", vp), ("ld_bits", i64),
-                ("row_sum", vp), ("row_scale", vp), ("overflow", vp), ("nhwc_c", i64)]
+                ("row_sum", vp), ("row_scale", vp), ("overflow", vp),
+                ("pre_scale", vp), ("pre_shift", vp), ("pre_channels", i64), ("pre_hw", i64), ("pre_clamp", i32),
+                ("pre_lo", f32), ("pre_hi", f32), ("nhwc_c", i64)]
 
 
 class QtWeightPack(C.Structure):

@@ -62,8 +62,9 @@ class ActCodes:
 
 
 def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_kind=L.CODES_NONE,
-              want_bits=False, want_row_sum=False, want_row_scale=False, kind=None):
-    """Run one activation-quantizer pass.  Returns (y or None, ActCodes or None)."""
+              want_bits=False, want_row_sum=False, want_row_scale=False, kind=None, pre=None):
+    """Run one activation-quantizer pass.  Returns (y or None, ActCodes or None).
+    pre = (scale[C], shift[C], lo, hi) fuses x' = clamp(x*scale[ch] + shift[ch], lo, hi) in front (lo/hi None: no clamp)."""
     require_cuda(x, "input")
     x = as_f32c(x)
     shape = tuple(x.shape)
@@ -75,6 +76,12 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
     a.mode, a.bit_width, a.fsr, a.with_sign = mode, bit_width, fsr, int(with_sign)
     a.x, a.rows, a.cols, a.ld_x = _p(x), rows, cols, cols
     a.y, a.ld_y = _p(y), cols
+    if pre is not None:
+        ps, pt, lo, hi = pre
+        a.pre_scale, a.pre_shift, a.pre_channels = _p(ps), _p(pt), ps.numel()
+        a.pre_hw = 1 if x.dim() == 2 else (x.numel() // (x.shape[0] * x.shape[1]))
+        a.pre_clamp = 0 if lo is None else 1
+        a.pre_lo, a.pre_hi = (0.0, 0.0) if lo is None else (float(lo), float(hi))
     codes = bits = row_sum = row_scale = overflow = None
     ld = ldb = 0
     layout = "rows"

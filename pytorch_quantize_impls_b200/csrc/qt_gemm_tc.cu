@@ -94,6 +94,19 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// Tile rasterisation: M is cut into bands of TC_BAND_M tiles; inside a band the schedule is M-fastest, so the CTAs that
+// run concurrently share a handful of weight tiles AND a band of activation rows small enough to stay L2-resident
+// while the fp32 output streams through (without bands the A operand is re-fetched from HBM once per ~2 weight tiles).
+constexpr int TC_BAND_M = 16;
+__device__ __forceinline__ void tile_coords(const TcArgs& g, int tile, int& tm, int& tn) {
+  const int band_tiles = TC_BAND_M * g.tiles_n;
+  const int band = tile / band_tiles;
+  const int t = tile - band * band_tiles;
+  const int bm = min(TC_BAND_M, g.tiles_m - band * TC_BAND_M);   // last band may be shorter
+  tn = t / bm;
+  tm = band * TC_BAND_M + (t - tn * bm);
+}
+
 template <int KIND>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   if (KIND == 0) {
@@ -192,7 +205,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile % g.tiles_m, tn = tile / g.tiles_m;
+        int tm, tn;
+      tile_coords(g, tile, tm, tn);
         for (int pass = 0; pass < g.npass; ++pass) {
           const int a_row = (int)(g.pa[pass] * g.a_plane_rows) + tm * TC_BM;
           const int w_row = (int)(g.pw[pass] * g.w_plane_rows) + tn * BN;
@@ -269,7 +283,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t my_buf = epi_base + (uint32_t)ew * 4096u;   // this warp's 32 x 128 B staging tile
     const int N32 = (int)g.N;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile % g.tiles_m, tn = tile / g.tiles_m;
+      int tm, tn;
+      tile_coords(g, tile, tm, tn);
       const int64_t m = (int64_t)tm * TC_BM + lane_grp * 32 + lane;
       const int n_tile = tn * BN;
       mbar_wait(tfull_bar(as), aphase);

@@ -18,7 +18,24 @@ struct QParams {
   float lo_e, hi_e;  // Log: exponent clamp
   float step, maxv;  // Lin
   int with_sign;
+  // fused BatchNorm(eval) + clamp in front of the quantizer
+  const float* pre_scale;
+  const float* pre_shift;
+  int64_t pre_channels, pre_hw;
+  int pre_clamp;
+  float pre_lo, pre_hi;
 };
+
+__device__ __forceinline__ float pre_apply(const QParams& q, float x, int64_t ch) {
+  x = fmaf(x, __ldg(q.pre_scale + ch), __ldg(q.pre_shift + ch));
+  if (q.pre_clamp) x = fminf(fmaxf(x, q.pre_lo), q.pre_hi);
+  return x;
+}
+template <bool PRE>
+__device__ __forceinline__ float pre_col(const QParams& q, float x, int64_t col) {
+  if (!PRE) return x;
+  return pre_apply(q, x, (col / q.pre_hw) % q.pre_channels);
+}
 
 struct QOut {
   float y;     // fake-quant fp32 value (what the reference op returns)
@@ -118,7 +135,7 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
-template <int MODE, bool VEC>
+template <int MODE, bool VEC, bool PRE>
 __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t task = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -135,10 +152,11 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
     if (VEC) {
       for (int64_t c = 4 * lane; c < a.cols; c += 128) {
         float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
-        s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+        s += (double)pre_col<PRE>(a.q, v.x, c) + (double)pre_col<PRE>(a.q, v.y, c + 1) + (double)pre_col<PRE>(a.q, v.z, c + 2) +
+             (double)pre_col<PRE>(a.q, v.w, c + 3);
       }
     } else {
-      for (int64_t c = lane; c < a.cols; c += 32) s += (double)__ldg(xr + c);
+      for (int64_t c = lane; c < a.cols; c += 32) s += (double)pre_col<PRE>(a.q, __ldg(xr + c), c);
     }
     s = warp_sum_d(s);
     row_mean = (float)(s / (double)a.cols);
@@ -172,8 +190,8 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
       const int64_t c = base + 4 * lane;
       const bool valid = c < c1;
       const float4 v = vv[u];
-      QOut o0 = quant_elem<MODE>(a.q, v.x, row_mean), o1 = quant_elem<MODE>(a.q, v.y, row_mean);
-      QOut o2 = quant_elem<MODE>(a.q, v.z, row_mean), o3 = quant_elem<MODE>(a.q, v.w, row_mean);
+      QOut o0 = quant_elem<MODE>(a.q, pre_col<PRE>(a.q, v.x, c), row_mean), o1 = quant_elem<MODE>(a.q, pre_col<PRE>(a.q, v.y, c + 1), row_mean);
+      QOut o2 = quant_elem<MODE>(a.q, pre_col<PRE>(a.q, v.z, c + 2), row_mean), o3 = quant_elem<MODE>(a.q, pre_col<PRE>(a.q, v.w, c + 3), row_mean);
       if (valid) {
         if (yr) __stcs(reinterpret_cast<float4*>(yr + c), make_float4(o0.y, o1.y, o2.y, o3.y));   // streamed: never re-read here
         if (c8) {
@@ -236,7 +254,7 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
     for (int64_t base = c0; base < c1; base += 32) {
       const int64_t c = base + lane;
       const bool valid = c < c1;
-      float v = valid ? __ldg(xr + c) : 0.f;
+      float v = valid ? pre_col<PRE>(a.q, __ldg(xr + c), c) : 0.f;
       QOut o = quant_elem<MODE>(a.q, v, row_mean);
       if (valid) {
         if (yr) yr[c] = o.y;
@@ -318,7 +336,9 @@ __global__ void __launch_bounds__(256) act_quant_nhwc_kernel(NhwcArgs a) {
     const int64_t c = c0 + cl;
     int code = 0;
     if (c < a.C && p < a.HW) {
-      QOut o = quant_elem<MODE>(a.q, __ldcs(xb + c * a.HW + p), 0.f);
+      float xv = __ldcs(xb + c * a.HW + p);
+      if (a.q.pre_scale) xv = pre_apply(a.q, xv, c % a.q.pre_channels);
+      QOut o = quant_elem<MODE>(a.q, xv, 0.f);
       if (yb) __stcs(yb + c * a.HW + p, o.y);
       code = code_to_lane(o.code, a.codes_kind, ovf);
     }
@@ -799,6 +819,10 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   a.q.n = a.q.inv_n = 1.f;
   a.q.lo_e = a.q.hi_e = a.q.step = a.q.maxv = 0.f;
   a.q.with_sign = p->with_sign;
+  a.q.pre_scale = p->pre_scale; a.q.pre_shift = p->pre_shift;
+  a.q.pre_channels = p->pre_channels > 0 ? p->pre_channels : 1; a.q.pre_hw = p->pre_hw > 0 ? p->pre_hw : 1;
+  a.q.pre_clamp = p->pre_clamp; a.q.pre_lo = p->pre_lo; a.q.pre_hi = p->pre_hi;
+  if (p->pre_scale) QT_REQUIRE(p->pre_shift && p->pre_channels > 0, "qt_quant_act: pre-transform needs pre_shift and pre_channels");
   if (p->mode == QT_Q_DOREFA) {
     QT_REQUIRE(p->bit_width >= 2 && p->bit_width <= 16, "qt_quant_act: DoReFa bit width %d not in 2..16", p->bit_width);
     a.q.n = (float)((1 << p->bit_width) - 1);
@@ -858,8 +882,13 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   dim3 grid((unsigned)ceil_div(tasks, warps_per_block)), block(32 * warps_per_block);
 #define QT_ACT_LAUNCH(MODE_)                                                              \
   case MODE_:                                                                            \
-    if (vec) act_quant_kernel<MODE_, true><<<grid, block, 0, stream>>>(a);               \
-    else act_quant_kernel<MODE_, false><<<grid, block, 0, stream>>>(a);                  \
+    if (p->pre_scale) {                                                                  \
+      if (vec) act_quant_kernel<MODE_, true, true><<<grid, block, 0, stream>>>(a);       \
+      else act_quant_kernel<MODE_, false, true><<<grid, block, 0, stream>>>(a);          \
+    } else {                                                                             \
+      if (vec) act_quant_kernel<MODE_, true, false><<<grid, block, 0, stream>>>(a);      \
+      else act_quant_kernel<MODE_, false, false><<<grid, block, 0, stream>>>(a);         \
+    }                                                                                    \
     break;
   switch (p->mode) {
     QT_ACT_LAUNCH(QT_Q_SIGN)

@@ -18,10 +18,11 @@ class BinaryConnectDeterministic(TaggingFunction):
     @staticmethod
     def forward(ctx, input):
         ctx.save_for_backward(input)
-        y, tag = ops.quant_act(input, L.Q_SIGN, want_y=True, codes_kind=L.CODES_I8,
+        full = eng.want_fp32_result(input)
+        y, tag = ops.quant_act(input, L.Q_SIGN, want_y=full, codes_kind=L.CODES_I8,
                                want_bits=(input.dim() == 2), kind="sign")
         TaggingFunction._leave(tag)
-        return y
+        return y if full else eng.placeholder_like(input)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -49,7 +50,9 @@ class BinaryConnectStochastic(torch.autograd.Function):
 
 def BinaryConnect(stochastic=False):
     """nn.Module wrapping the binarization op (binary_connect.py:74-83)."""
-    return front(BinaryConnectStochastic if stochastic else BinaryConnectDeterministic)
+    m = front(BinaryConnectStochastic if stochastic else BinaryConnectDeterministic)
+    m._qt_spec = None if stochastic else ("sign", 1)
+    return m
 
 
 def _sign_pack(weight):

@@ -31,7 +31,11 @@ class TaggingFunction(torch.autograd.Function):
     @classmethod
     def apply(cls, *args, **kwargs):
         _tls.pending = None
-        out = super().apply(*args, **kwargs)
+        eng._apply_grad_mode.value = torch.is_grad_enabled()     # grad mode is forced off inside forward()
+        try:
+            out = super().apply(*args, **kwargs)
+        finally:
+            eng._apply_grad_mode.value = None
         tag = getattr(_tls, "pending", None)
         _tls.pending = None
         if tag is not None and isinstance(out, torch.Tensor):

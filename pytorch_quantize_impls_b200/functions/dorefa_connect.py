@@ -9,24 +9,27 @@ from .. import _ops as ops
 from .common import TaggingFunction, _f32, front, safeSign
 
 
-def _quantize_with_codes(x, bit_width):
+def _quantize_with_codes(x, bit_width, pre=None):
     """_quantize (dorefa_connect.py:11-25) on the device.  Returns (y, ActCodes or None).
 
     k == 1 -> safeSign (+ sign codes/bits); k == 32 -> x itself; else y = fl(1/n) * round(n x), no clamp,
     round-half-even, with integer codes c = round(n x) in an int8 lane (k <= 7) or uint8 lane (k == 8) and
     their row sums."""
+    full = eng.want_fp32_result(x)
     if bit_width == 1:
-        return ops.quant_act(x, L.Q_SIGN, want_y=True, codes_kind=L.CODES_I8, want_bits=(x.dim() == 2), kind="sign")
+        y, tag = ops.quant_act(x, L.Q_SIGN, want_y=full, codes_kind=L.CODES_I8, want_bits=(x.dim() == 2), kind="sign",
+                               pre=pre)
+        return (y if full else eng.placeholder_like(x)), tag
     if bit_width == 32:
         ops.require_cuda(x, "input")
         return x, None
     if 2 <= bit_width <= 8:
         kind = L.CODES_I8 if bit_width <= 7 else L.CODES_U8
-        y, tag = ops.quant_act(x, L.Q_DOREFA, bit_width=bit_width, want_y=True, codes_kind=kind,
-                               want_row_sum=(x.dim() == 2), kind="dorefa")
+        y, tag = ops.quant_act(x, L.Q_DOREFA, bit_width=bit_width, want_y=full, codes_kind=kind,
+                               want_row_sum=(x.dim() == 2), kind="dorefa", pre=pre)
         tag.scale = _f32(1.0) / _f32(2 ** bit_width - 1)
         tag.scale = _f32(tag.scale)
-        return y, tag
+        return (y if full else eng.placeholder_like(x)), tag
     if 9 <= bit_width <= 16:                     # no 8-bit lane: fp32 result only
         return ops.quant_act(x, L.Q_DOREFA, bit_width=bit_width, want_y=True)
     raise RuntimeError("bit_width %r not supported (1..16 or 32)" % (bit_width,))
@@ -64,7 +67,9 @@ def _quant_fn(bit_width):
 
 def nnDorefaQuant(bit_width=3):
     """nn.Module with the k-bit activation quantizer inside; identity STE (dorefa_connect.py:28-45)."""
-    return front(_quant_fn(bit_width))
+    m = front(_quant_fn(bit_width))
+    m._qt_spec = ("dorefa", bit_width) if 1 <= bit_width <= 8 else None
+    return m
 
 
 def DorefaQuant(x, bit_width=3):

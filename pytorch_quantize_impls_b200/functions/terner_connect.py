@@ -16,9 +16,10 @@ class TernaryConnectDeterministic(TaggingFunction):
     @staticmethod
     def forward(ctx, input):
         ctx.save_for_backward(input)
-        y, tag = ops.quant_act(input, L.Q_TERNARY, want_y=True, codes_kind=L.CODES_I8, kind="ternary")
+        full = eng.want_fp32_result(input)
+        y, tag = ops.quant_act(input, L.Q_TERNARY, want_y=full, codes_kind=L.CODES_I8, kind="ternary")
         TaggingFunction._leave(tag)
-        return y
+        return y if full else eng.placeholder_like(input)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -45,7 +46,9 @@ class TernaryConnectStochastic(torch.autograd.Function):
 
 def TernaryConnect(stochastic=False):
     """nn.Module wrapping the ternary op (terner_connect.py:67-75)."""
-    return front(TernaryConnectStochastic if stochastic else TernaryConnectDeterministic)
+    m = front(TernaryConnectStochastic if stochastic else TernaryConnectDeterministic)
+    m._qt_spec = None if stochastic else ("ternary", 2)
+    return m
 
 
 def _functional_ternary(weight, stochastic):

@@ -23,11 +23,12 @@ def _quantOpXnor(dim=1):
         def forward(ctx, input):
             if dim == 1 and input.dim() == 2:
                 # fused device pass: row mean (fp64 accumulate) + sign + fp16 (or bf16) codes for the next layer
-                y, tag = ops.quant_act(input, L.Q_XNOR_ROW, want_y=True, codes_kind=eng.xnor_codes_kind(),
+                full = eng.want_fp32_result(input)
+                y, tag = ops.quant_act(input, L.Q_XNOR_ROW, want_y=full, codes_kind=eng.xnor_codes_kind(),
                                        want_row_scale=True, kind="xnor")
                 ctx.save_for_backward(input, tag.row_scale)
                 TaggingFunction._leave(tag)
-                return y
+                return y if full else eng.placeholder_like(input)
             # dim 0 / -1 reduce over the batch: a column/global reduction followed by one elementwise product
             # (not used by the sharded configs -- it would need an all-reduce)
             ops.require_cuda(input, "input")
@@ -63,7 +64,9 @@ def _op(dim):
 
 def nnQuantXnor(dim=1):
     """Module form of QuantXnor (xnor_connect.py:40-52)."""
-    return front(_op(dim))
+    m = front(_op(dim))
+    m._qt_spec = ("xnor", dim) if dim == 1 else None
+    return m
 
 
 def QuantXnor(input, dim=1):

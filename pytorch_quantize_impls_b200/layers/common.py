@@ -109,10 +109,24 @@ class QuantLayerMixin(QLayer):
         st = self._eval_state
         if st is not None and st.version == self.weight._version and st.ptr == self.weight.data_ptr():
             return st.pack
-        # eval mode with weights that train(False) did not produce (state_dict loaded in eval mode, .to() after
-        # eval, ...): the reference contracts with the stored values as they are -> real-valued weight operand
+        # eval mode, but the cached pack no longer describes `weight` (module moved with .to(), deep-copied, state_dict
+        # loaded in eval mode, ...).  If the fp32 master copy made by train(False) is still around and the stored weights
+        # are its quantisation, re-pack from it; if the stored values are themselves a fixed point of the quantizer
+        # (+-1 / {-1,0,1}), pack those; otherwise contract with the stored values as they are (what the reference does
+        # in eval mode) through the real-valued weight operand.
         st = _EvalState()
-        st.pack = ops.pack_real_weight(ops.conv_weight_2d(self.weight.detach()))
+        st.pack = None
+        w = self.weight.detach()
+        org = getattr(self.weight, "org", None)
+        with torch.no_grad():
+            if org is not None and org.shape == w.shape:
+                org = org.to(w.device)
+                if torch.equal(self._weight_op(org), w):
+                    st.pack = self._make_pack(org)
+            if st.pack is None and torch.equal(self._weight_op(w), w):
+                st.pack = self._make_pack(w)
+        if st.pack is None:
+            st.pack = ops.pack_real_weight(ops.conv_weight_2d(w))
         st.version, st.ptr = self.weight._version, self.weight.data_ptr()
         self._eval_state = st
         return st.pack
@@ -125,7 +139,7 @@ class QuantLayerMixin(QLayer):
         return eng.linear(input, pack, self.bias)
 
     def forward(self, input):
-        ops.require_cuda(input, "input")
+        eng.tagged_input_device(input)
         needs_grad = torch.is_grad_enabled() and (
             input.requires_grad or self.weight.requires_grad or (self.bias is not None and self.bias.requires_grad))
         if needs_grad:

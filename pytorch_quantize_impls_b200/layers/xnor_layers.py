@@ -13,7 +13,7 @@ from .common import QuantLayerMixin, _EvalState, check_convert
 
 class _XnorMixin(QuantLayerMixin):
     def forward(self, input):
-        ops.require_cuda(input, "input")
+        eng.tagged_input_device(input)
         pack = None
         st = self._eval_state
         if (not self.training and st is not None and st.version == self.weight._version

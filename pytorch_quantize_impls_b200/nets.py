@@ -89,8 +89,8 @@ class TerBasicBlock(nn.Module):
         super().__init__()
         self.q_in = lib.nnDorefaQuant(act_bits)
         self.conv1 = lib.TerConv2d(in_planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
-        self.q_mid = lib.nnDorefaQuant(act_bits)
+        # BN -> clamp -> quantizer kept as one Sequential so that fusion.fuse_inference can turn it into a single pass
+        self.post1 = nn.Sequential(nn.BatchNorm2d(planes), nn.Hardtanh(0.0, 1.0), lib.nnDorefaQuant(act_bits))
         self.conv2 = lib.TerConv2d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
         self.clip = nn.Hardtanh(0.0, 1.0)
@@ -101,7 +101,7 @@ class TerBasicBlock(nn.Module):
 
     def forward(self, x):                      # x in [0, 1]
         xq = self.q_in(x)
-        out = self.q_mid(self.clip(self.bn1(self.conv1(xq))))
+        out = self.post1(self.conv1(xq))
         out = self.bn2(self.conv2(out))
         out = out + (x if self.shortcut is None else self.shortcut(xq))
         return self.clip(out)
@@ -144,9 +144,12 @@ def vgg_dorefa(bit_width=8, num_classes=10, lib=None):
     k = bit_width
 
     def block(cin, cout, pool, quant=True):
-        m = [lib.DorefaConv2d(cin, cout, kernel_size=3, padding=1, bit_width=k), nn.BatchNorm2d(cout), nn.Hardtanh(0.0, 1.0)]
+        # conv -> [pool] -> BN -> clamp -> quantizer: the ordering of models/Alexnet/Alexnet_Bin.py (pool right after
+        # the conv), which keeps BN/clamp/quantizer adjacent (one fused pass under fusion.fuse_inference)
+        m = [lib.DorefaConv2d(cin, cout, kernel_size=3, padding=1, bit_width=k)]
         if pool:
             m.append(nn.MaxPool2d(kernel_size=2))
+        m += [nn.BatchNorm2d(cout), nn.Hardtanh(0.0, 1.0)]
         if quant:
             m.append(lib.nnDorefaQuant(k))
         return m

@@ -105,3 +105,43 @@ def test_resnet18_ternary_a8():
 def test_vgg_dorefa_w8a8():
     worst, cos = _check("vgg_dorefa", torch.rand(4, 3, 32, 32), _dorefa_q(8), bit_width=8)
     print("vgg layerwise worst rel", worst, "e2e cosine", cos)
+
+
+@pytest.mark.parametrize("builder,x,kw", [
+    ("alexnet_dorefa", torch.rand(2, 3, 224, 224), dict(bit_width=4)),
+    ("resnet18_ternary", torch.rand(2, 3, 96, 96), dict(act_bits=8)),
+    ("vgg_dorefa", torch.rand(4, 3, 32, 32), dict(bit_width=8)),
+])
+def test_fuse_inference_matches_unfused(builder, x, kw):
+    """fusion.fuse_inference (BatchNorm+clamp+quantizer in one pass) and code-only activations against the plain GPU
+    graph: every fused module, fed the input the plain graph saw, reproduces the plain codes up to one level on at most
+    0.1 % of the elements (fma vs three roundings); end-to-end outputs agree in direction."""
+    import pytorch_quantize_impls_b200 as Q
+    net, _ = _build(builder, x, **kw)
+    fused, _ = _build(builder, x, **kw)          # same seeds -> same weights
+    fused = Q.fuse_inference(fused)
+    n_fused = [m for m in fused.modules() if isinstance(m, Q.FusedBNActQuant)]
+    assert len(n_fused) >= 3
+    with torch.no_grad():
+        ref = net(x.cuda())
+        worst = 0.0
+        for fm in n_fused:        # each fused module against its own un-fused composition on a spread-out input
+            C = fm.bn.num_features
+            if isinstance(fm.bn, torch.nn.BatchNorm1d):
+                xin = torch.rand(64, C).cuda() * 3 - 1
+            else:
+                xin = torch.rand(8, C, 6, 6).cuda() * 3 - 1
+            xin = xin * fm.bn.running_var.sqrt().view(1, -1, *([1] * (xin.dim() - 2))) + fm.bn.running_mean.view(1, -1, *([1] * (xin.dim() - 2)))
+            y_plain = fm._compose(xin)
+            y_fused = fm(xin)
+            n = 2 ** fm.quant._qt_spec[1] - 1 if fm.quant._qt_spec[0] == "dorefa" else 1
+            d = ((y_fused - y_plain) * n).abs()
+            assert float(d.max()) <= 1.0 + 1e-4
+            frac = float((d > 0.5).float().mean())
+            worst = max(worst, frac)
+            assert frac <= 1e-3, frac
+            assert y_fused._qt_codes is not None
+        with Q.code_only_activations():
+            y = fused(x.cuda())
+    cos = torch.nn.functional.cosine_similarity(y.flatten(), ref.flatten(), dim=0).item()
+    assert cos > 0.98, cos

@@ -394,3 +394,61 @@ def test_implicit_conv_bit_exact(Q, cfg):
 
 def O_conv(O_fn, x, w, **kw):
     return getattr(O, O_fn)(x, w, None, **kw)
+
+
+# ------------------------------------------------------------------ code-only activation mode (fused inference chains)
+def test_code_only_activations_bit_identical(Q):
+    torch.manual_seed(5)
+    F, Lm = Q.functions, Q.layers
+    x = torch.randn(96, 256).cuda()
+    nets = [
+        torch.nn.Sequential(F.nnQuantXnor(1), Lm.LinearXNOR(256, 128), F.nnQuantXnor(1), Lm.LinearXNOR(128, 10)),
+        torch.nn.Sequential(F.BinaryConnect(), Lm.LinearBin(256, 128), torch.nn.Hardtanh(), F.BinaryConnect(), Lm.LinearTer(128, 10)),
+        torch.nn.Sequential(torch.nn.Hardtanh(0., 1.), F.nnDorefaQuant(4), Lm.LinearDorefa(256, 64, bit_width=4),
+                            torch.nn.Hardtanh(0., 1.), F.nnDorefaQuant(8), Lm.LinearDorefa(64, 10, bit_width=8)),
+    ]
+    xi = torch.rand(3, 64, 9, 9).cuda()
+    convnet = torch.nn.Sequential(F.nnDorefaQuant(4), Lm.DorefaConv2d(64, 32, 3, padding=1, bit_width=4),
+                                  torch.nn.Hardtanh(0., 1.), F.BinaryConnect(), Lm.BinConv2d(32, 8, 3))
+    with torch.no_grad():
+        for net, inp in [(n, x) for n in nets] + [(convnet, xi)]:
+            net = net.cuda().eval()
+            ref = net(inp)
+            with Q.code_only_activations():
+                y = net(inp)
+            assert torch.equal(y, ref)
+        # the placeholder carries no storage: anything but a quantized layer fails loudly
+        with Q.code_only_activations():
+            ph = F.BinaryConnect()(x)
+        assert ph.is_meta and tuple(ph.shape) == tuple(x.shape)
+        with pytest.raises(Exception):
+            (ph + x).sum().item()
+        with pytest.raises(RuntimeError):
+            Lm.LinearXNOR(256, 8).cuda()(ph)          # int8 sign codes cannot feed the alpha[k]-scaled XNOR weights
+    # with autograd on, the quantizers keep returning real tensors
+    with Q.code_only_activations():
+        assert not F.BinaryConnect()(x.clone().requires_grad_(True)).is_meta
+
+
+def test_eval_pack_survives_deepcopy_and_device_roundtrip(Q):
+    """A layer in eval mode that is deep-copied (or moved) no longer matches its cached pack: it must re-derive the
+    k-bit pack (from weight.org, or from the stored +-1 / ternary values) and give bit-identical outputs."""
+    import copy
+    torch.manual_seed(2)
+    x = torch.randn(70, 96).cuda()
+    for cls, kw in ((Q.layers.LinearBin, {}), (Q.layers.LinearTer, {}), (Q.layers.LinearDorefa, dict(bit_width=4))):
+        lay = cls(96, 40, **kw).cuda()
+        lay.weight.data.mul_(3)
+        lay.eval()
+        act = Q.functions.BinaryConnect() if cls is not Q.layers.LinearDorefa else Q.functions.nnDorefaQuant(4)
+        with torch.no_grad():
+            xin = x if cls is not Q.layers.LinearDorefa else x.abs().clamp(0, 1)
+            ref = lay(act(xin))
+            twin = copy.deepcopy(lay)
+            if cls is not Q.layers.LinearDorefa:                 # quantized values are a fixed point -> k-bit pack again
+                assert twin._current_pack().kind in ("sign", "ternary")
+                assert torch.equal(twin(act(xin)), ref)
+            else:                                                # DoReFa values re-enter as real weights (bf16 planes)
+                assert relerr(twin(act(xin)), ref.cpu()) < 1e-4
+            moved = lay.cpu().cuda()                             # weight.org stays behind on the old device
+            assert torch.equal(moved(act(xin)), ref)
