@@ -103,7 +103,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -210,7 +210,6 @@ def run_ours(args):
     x_host = [torch.randn(BATCH, DIMS[0], generator=g).pin_memory() for _ in range(NBUF)]
     x_dev = [t.to(dev) for t in x_host]
     gathered = torch.empty(world * BATCH, DIMS[-1], device=dev) if world > 1 else None
-    out_host = torch.empty(BATCH, DIMS[-1]).pin_memory()
     timer = GemmTimer(torch, _ops)
     timer.install()
 
@@ -251,24 +250,35 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item()) / args.steps
 
-        # end-to-end through the public nn.Module API with HOST buffers: H2D of the batch and D2H of the logits
-        # are inside the timed region, every step
-        xe = torch.empty(BATCH, DIMS[0], device=dev)
-        for i in range(2):
-            xe.copy_(x_host[i % NBUF], non_blocking=True); out_host.copy_(step(i, xe), non_blocking=True)
+        # end-to-end through the public API with HOST buffers: every step copies its batch from pinned host memory and
+        # returns its logits to pinned host memory, inside the timed region.  pipeline.HostPipeline overlaps the H2D of
+        # step i+1 and the D2H of step i-1 with the kernels of step i (separate streams).
+        from pytorch_quantize_impls_b200.pipeline import HostPipeline
+        outs_host = [torch.empty(BATCH, DIMS[-1]).pin_memory() for _ in range(2)]
+        pipe = HostPipeline(lambda xb: step(0, xb), depth=2)
+        ins = [x_host[i % NBUF] for i in range(args.steps)]
+        outs = [outs_host[i % 2] for i in range(args.steps)]
+        pipe.run(ins[:2], outs[:2])
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
-        for i in range(args.steps):
-            xe.copy_(x_host[i % NBUF], non_blocking=True)
-            y = step(i, xe)
-            out_host.copy_(y, non_blocking=True)
+        pipe.run(ins, outs)
         e3.record()
         barrier()
         t = torch.tensor([e2.elapsed_time(e3)], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item()) / args.steps
+        # un-pipelined variant (copy -> compute -> copy on one stream), for reference
+        xe = torch.empty(BATCH, DIMS[0], device=dev)
+        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e6.record()
+        for i in range(args.steps):
+            xe.copy_(x_host[i % NBUF], non_blocking=True)
+            outs_host[0].copy_(step(i, xe), non_blocking=True)
+        e7.record()
+        barrier()
+        ms_e2e_serial = e6.elapsed_time(e7) / args.steps
         clocks = sampler.stop() if rank == 0 else None
 
         # same steps in the default drop-in mode (every quantizer also writes its fp32 fake-quant tensor)
@@ -331,6 +341,8 @@ def run_ours(args):
                    "collective": "all_gather of fp32 logits" if world > 1 else "none"},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": round(e2e, 1), "unit": "GOPS", "ms_per_step": round(ms_e2e, 4),
+                "api": "pipeline.HostPipeline(net).run(pinned inputs, pinned outputs): H2D / kernels / D2H on 3 streams",
+                "ms_per_step_single_stream": round(ms_e2e_serial, 4),
                 "h2d_bytes_per_step": BATCH * DIMS[0] * 4, "d2h_bytes_per_step": BATCH * DIMS[-1] * 4},
         "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
     }

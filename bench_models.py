@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="GLOBAL batch (sharded over ranks)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mode", default="fused", choices=["plain", "fused"],
+                    help="fused: fusion.fuse_inference (BN+clamp+quantizer in one pass) + code_only_activations()")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -40,17 +42,23 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    import contextlib
+    import pytorch_quantize_impls_b200 as Q
     from pytorch_quantize_impls_b200 import _lib, nets, sharding
     builder, kw, shape, dflt, gmac = CONFIGS[args.config]
     B = args.batch or dflt
     torch.manual_seed(1234)
     net = getattr(nets, builder)(**kw).to(dev).eval()
+    if args.mode == "fused":
+        net = Q.fuse_inference(net)
+    mode_ctx = Q.code_only_activations if args.mode == "fused" else contextlib.nullcontext
     g = torch.Generator().manual_seed(1234)
     lo, hi = sharding.shard_bounds(B, rank, world)
     x = torch.rand(hi - lo, *shape, generator=g).to(dev)
 
     def step():
-        y = net(x)
+        with mode_ctx():
+            y = net(x)
         return sharding.gather_logits(y, batch=B)
 
     with torch.no_grad():
@@ -74,7 +82,7 @@ def main():
     ms = float(t.item()) / args.steps
     if rank == 0:
         print(json.dumps({
-            "config": args.config, "n_gpus": world, "global_batch": B, "ms_per_step": round(ms, 3),
+            "config": args.config, "mode": args.mode, "n_gpus": world, "global_batch": B, "ms_per_step": round(ms, 3),
             "images_per_sec": round(B / (ms * 1e-3), 1), "quantized_gops": round(2 * gmac * B / (ms * 1e-3), 1),
             "qt_kernel_launches_per_step": _lib.launch_count() // args.steps, "logits_shape": list(y.shape),
             "finite": bool(torch.isfinite(y).all().item())}), flush=True)

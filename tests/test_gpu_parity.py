@@ -452,3 +452,94 @@ def test_eval_pack_survives_deepcopy_and_device_roundtrip(Q):
                 assert relerr(twin(act(xin)), ref.cpu()) < 1e-4
             moved = lay.cpu().cuda()                             # weight.org stays behind on the old device
             assert torch.equal(moved(act(xin)), ref)
+
+
+# ------------------------------------------------------------------ backward (STE) vs gradients of the live reference
+@pytest.fixture(scope="module")
+def golden_grads():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "quanttorch_ref_grads_v1.npz"))
+    return {k: torch.from_numpy(z[k].copy()) for k in z.files}
+
+
+def _grad_case(gg, name):
+    pre = name + "/"
+    return {k[len(pre):]: v for k, v in gg.items() if k.startswith(pre)}
+
+
+@pytest.mark.parametrize("name", ["lin_bin", "lin_ter", "lin_dorefa1", "lin_dorefa2", "lin_dorefa4", "lin_xnor",
+                                  "conv_bin", "conv_ter", "conv_dorefa3"])
+def test_backward_matches_reference(Q, golden_grads, name):
+    """Forward through the low-bit kernels, backward with the reference's STE semantics: gradients w.r.t. input, weight
+    and bias equal those of the live reference (golden vectors from oracle/gen_golden_grads.py) to 1e-4."""
+    c = _grad_case(golden_grads, name)
+    Lm, F = Q.layers, Q.functions
+    w = c["w"]
+    if name == "lin_bin":
+        lay, act = Lm.LinearBin(w.shape[1], w.shape[0]), F.BinaryConnect()
+    elif name == "lin_ter":
+        lay, act = Lm.LinearTer(w.shape[1], w.shape[0]), F.BinaryConnect()
+    elif name.startswith("lin_dorefa"):
+        k = int(name[-1]); lay, act = Lm.LinearDorefa(w.shape[1], w.shape[0], bit_width=k), F.nnDorefaQuant(k)
+    elif name == "lin_xnor":
+        lay, act = Lm.LinearXNOR(w.shape[1], w.shape[0]), F.nnQuantXnor(1)
+    elif name == "conv_bin":
+        lay, act = Lm.BinConv2d(4, 6, 3, stride=2, padding=1), F.BinaryConnect()
+    elif name == "conv_ter":
+        lay, act = Lm.TerConv2d(4, 6, 3, padding=1), F.BinaryConnect()
+    else:
+        lay, act = Lm.DorefaConv2d(4, 6, 3, padding=1, bit_width=3), F.nnDorefaQuant(3)
+    lay = lay.cuda()
+    lay.weight.data.copy_(w); lay.bias.data.copy_(c["b"])
+    x = c["x"].cuda().requires_grad_(True)
+    y = lay(act(x))
+    assert relerr(y.detach(), c["y"]) < 5e-4
+    (y * c["go"].cuda()).sum().backward()
+    assert relerr(x.grad, c["gx"]) < 1e-4
+    assert relerr(lay.weight.grad, c["gw"]) < 1e-4
+    assert relerr(lay.bias.grad, c["gb"]) < 1e-4
+
+
+def test_host_pipeline_matches_direct(Q):
+    from pytorch_quantize_impls_b200.pipeline import HostPipeline
+    torch.manual_seed(9)
+    net = torch.nn.Sequential(Q.functions.BinaryConnect(), Q.layers.LinearBin(256, 64)).cuda().eval()
+    xs = [torch.randn(128, 256).pin_memory() for _ in range(5)]
+    outs = [torch.empty(128, 64).pin_memory() for _ in range(5)]
+    with torch.no_grad():
+        HostPipeline(net, depth=2).run(xs, outs)
+        torch.cuda.synchronize()
+        for xi, yo in zip(xs, outs):
+            assert torch.equal(net(xi.cuda()).cpu(), yo)
+
+
+def test_stochastic_ops_statistics(Q):
+    """BinaryConnectStochastic / TernaryConnectStochastic: device RNG, so parity is statistical, exactly as the reference's
+    own tests do (BinaryNet/function_test.py:36-44, Terner/function_test.py:30-46)."""
+    x = torch.tensor([0.5, -0.5, 0.0, 0.9, -0.2, 2.0, -3.0]).cuda()
+    acc_b = torch.zeros_like(x); acc_t = torch.zeros_like(x)
+    n = 2000
+    for _ in range(n):
+        acc_b += Q.functions.BinaryConnectStochastic.apply(x)
+        acc_t += Q.functions.TernaryConnectStochastic.apply(x)
+    exp_b = torch.clamp(x, -1, 1)                       # E[+-1] = 2 hardsigmoid(x) - 1
+    exp_t = torch.sign(x) * torch.clamp(x.abs(), max=1.0)
+    assert float((acc_b / n - exp_b).abs().max()) < 0.08
+    assert float((acc_t / n - exp_t).abs().max()) < 0.08
+
+
+def test_edge_shapes(Q):
+    """Empty batch, single row, K smaller than a word, non-contiguous input."""
+    lay = Q.layers.LinearBin(5, 3).cuda()
+    act = Q.functions.BinaryConnect()
+    with torch.no_grad():
+        assert lay(act(torch.zeros(0, 5).cuda())).shape == (0, 3)
+        x = torch.randn(1, 5)
+        assert relerr(lay(act(x.cuda())), O.linear_bin(O.binary_det(x), lay.weight.data.cpu(), lay.bias.data.cpu())) < 1e-6
+        xt = torch.randn(5, 7).cuda().t()                # non-contiguous [7, 5]
+        ref = O.linear_bin(O.binary_det(xt.cpu()), lay.weight.data.cpu(), lay.bias.data.cpu())
+        assert relerr(lay(act(xt)), ref) < 1e-6
+        x3 = torch.randn(2, 4, 5).cuda()                 # leading dims, as F.linear accepts
+        assert lay(x3).shape == (2, 4, 3)
+        conv = Q.layers.BinConv2d(3, 4, 3).cuda()
+        assert conv(torch.randn(0, 3, 8, 8).cuda()).shape == (0, 4, 6, 6)
