@@ -150,10 +150,22 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
   if (MODE == QT_Q_XNOR_ROW) {  // never chunked: the whole row is reduced by this warp
     double s = 0.0;
     if (VEC) {
-      for (int64_t c = 4 * lane; c < a.cols; c += 128) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
-        s += (double)pre_col<PRE>(a.q, v.x, c) + (double)pre_col<PRE>(a.q, v.y, c + 1) + (double)pre_col<PRE>(a.q, v.z, c + 2) +
-             (double)pre_col<PRE>(a.q, v.w, c + 3);
+      // 8 independent 16-byte loads in flight per lane (the reduction is latency-bound otherwise); fp32 partial sums of 4
+      // are folded into the fp64 accumulator
+      for (int64_t c0r = 4 * lane; c0r < a.cols; c0r += 128 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int64_t c = c0r + u * 128;
+          v[u] = (c < a.cols) ? __ldg(reinterpret_cast<const float4*>(xr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int64_t c = c0r + u * 128;
+          if (c < a.cols)
+            s += (double)pre_col<PRE>(a.q, v[u].x, c) + (double)pre_col<PRE>(a.q, v[u].y, c + 1) +
+                 (double)pre_col<PRE>(a.q, v[u].z, c + 2) + (double)pre_col<PRE>(a.q, v[u].w, c + 3);
+        }
       }
     } else {
       for (int64_t c = lane; c < a.cols; c += 32) s += (double)pre_col<PRE>(a.q, __ldg(xr + c), c);
@@ -323,37 +335,54 @@ struct NhwcArgs {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) act_quant_nhwc_kernel(NhwcArgs a) {
-  __shared__ __align__(16) int8_t tile[32][128 + 16];   // [pixel][channel], +16 keeps rows 16-byte aligned and de-conflicts banks
+  // tile[pixel][channel] as 32-bit words of 4 channel codes; 33-word rows make both the transposing stores
+  // (lane = pixel, fixed channel word) and the row reads of the write phase bank-conflict free
+  __shared__ uint32_t tile[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t p0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 128, b = blockIdx.z;
   const float* xb = a.x + b * a.C * a.HW;
   float* yb = a.y ? a.y + b * a.C * a.HW : nullptr;
   bool ovf = false;
   const int64_t p = p0 + lane;
-#pragma unroll 4
+  const bool pix_ok = p < a.HW;
+  // 16 channels per warp: all 16 loads are issued before any is used (64 B in flight per lane)
+  float xv[16];
+#pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const int cl = warp * 16 + i;
-    const int64_t c = c0 + cl;
-    int code = 0;
-    if (c < a.C && p < a.HW) {
-      float xv = __ldcs(xb + c * a.HW + p);
-      if (a.q.pre_scale) xv = pre_apply(a.q, xv, c % a.q.pre_channels);
-      QOut o = quant_elem<MODE>(a.q, xv, 0.f);
-      if (yb) __stcs(yb + c * a.HW + p, o.y);
-      code = code_to_lane(o.code, a.codes_kind, ovf);
+    const int64_t c = c0 + warp * 16 + i;
+    xv[i] = (pix_ok && c < a.C) ? __ldcs(xb + c * a.HW + p) : 0.f;
+  }
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = q4 * 4 + j;
+      const int64_t c = c0 + warp * 16 + i;
+      int code = 0;
+      if (pix_ok && c < a.C) {
+        float v = xv[i];
+        if (a.q.pre_scale) v = pre_apply(a.q, v, c % a.q.pre_channels);
+        QOut o = quant_elem<MODE>(a.q, v, 0.f);
+        if (yb) __stcs(yb + c * a.HW + p, o.y);
+        code = code_to_lane(o.code, a.codes_kind, ovf);
+      }
+      word |= (uint32_t)(code & 0xff) << (8 * j);
     }
-    tile[lane][cl] = (int8_t)code;
+    tile[lane][warp * 4 + q4] = word;
   }
   __syncthreads();
-  // write phase: thread -> (pixel = tid / 8, 16 channels = tid % 8)
-  const int px = threadIdx.x >> 3, cg = (threadIdx.x & 7) * 16;
+  // write phase: thread -> (pixel = tid / 8, 16 channels = 4 words starting at (tid % 8) * 4): 128-byte runs per pixel
+  const int px = threadIdx.x >> 3, wg = (threadIdx.x & 7) * 4;
   const int64_t pp = p0 + px;
-  if (pp < a.HW && c0 + cg < a.C) {
-    int8_t* dst = a.codes + (b * a.HW + pp) * a.C + c0 + cg;
+  if (pp < a.HW && c0 + wg * 4 < a.C) {
+    uint4 v = make_uint4(tile[px][wg], tile[px][wg + 1], tile[px][wg + 2], tile[px][wg + 3]);
+    int8_t* dst = a.codes + (b * a.HW + pp) * a.C + c0 + wg * 4;
     if ((a.C & 15) == 0) {
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&tile[px][cg]);
+      *reinterpret_cast<uint4*>(dst) = v;
     } else {
-      for (int j = 0; j < 16 && c0 + cg + j < a.C; ++j) dst[j] = tile[px][cg + j];
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+      for (int j = 0; j < 16 && c0 + wg * 4 + j < a.C; ++j) dst[j] = (int8_t)((w4[j >> 2] >> (8 * (j & 3))) & 0xff);
     }
   }
   if (a.overflow) {
@@ -513,24 +542,6 @@ struct ExpandArgs {
   int out_kind;
   int64_t ld_out;
 };
-
-__device__ __forceinline__ float packed_value(const ExpandArgs& a, const uint8_t* pr, int64_t c) {
-  if (a.mode == QT_W_SIGN || (a.mode == QT_W_DOREFA && a.bit_width == 1)) {
-    uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c >> 5));
-    return ((w >> (c & 31)) & 1u) ? 1.f : -1.f;
-  }
-  if (a.mode == QT_W_TERNARY || a.mode == QT_W_XNOR) {
-    uint32_t nz = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c >> 5));
-    uint32_t sg = __ldg(reinterpret_cast<const uint32_t*>(pr + a.n * a.ld_packed) + (c >> 5));
-    if (!((nz >> (c & 31)) & 1u)) return 0.f;
-    return ((sg >> (c & 31)) & 1u) ? 1.f : -1.f;
-  }
-  const int per_word = 32 / a.lane_bits;
-  uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(pr) + c / per_word);
-  uint32_t code = (w >> ((c % per_word) * a.lane_bits)) & ((1u << a.lane_bits) - 1u);
-  if (a.out_kind == 2) return (float)code;                       // raw unsigned code
-  return 2.f * (float)code - (float)((1 << a.bit_width) - 1);    // centred 2c - n
-}
 
 // Each thread produces 16 consecutive output columns of one row; the packed bits/codes those 16 columns need are
 // fetched once (1, 2 or 4 words) and unpacked in registers.
@@ -871,9 +882,11 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   if (p->codes_kind >= 3) vec = vec && (p->ld_codes % 4 == 0) && aligned(p->codes, 8) && ((p->rows * p->ld_codes) % 4 == 0);
 
   // split long rows into chunks when there are too few rows to fill the machine
+  // warp tasks of <= 2048 columns: many small tasks keep the last wave short (8192 x 4096 -> 16384 tasks, ~3.5 waves of
+  // 4 CTAs/SM instead of 1.7); the XNOR row mean needs the whole row in one warp
   a.chunk = p->cols; a.nchunks = 1;
-  if (p->mode != QT_Q_XNOR_ROW && p->cols > 8192 && p->rows < 4096) {
-    a.chunk = 4096;
+  if (p->mode != QT_Q_XNOR_ROW && p->cols >= 4096) {
+    a.chunk = 2048;
     a.nchunks = (int)ceil_div(p->cols, a.chunk);
   }
   if (a.nchunks > 1 && p->row_sum) QT_CUDA_OK(cudaMemsetAsync(p->row_sum, 0, sizeof(int32_t) * p->rows, stream));
