@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QT_VERSION 100
+#define QT_VERSION 101
 
 enum {
   QT_OK = 0,
@@ -75,8 +75,10 @@ typedef struct QtActQuant {
   void* codes;          /* optional low-bit operand, [rows, ld_codes] of int8/uint8 or bf16 (see codes_kind);
                            columns cols..ld_codes-1 are zero-filled */
   int codes_kind;       /* 0 = none, 1 = int8, 2 = uint8, 3 = bf16, 4 = bf16 hi/lo planes (plane stride = rows*ld_codes),
-                           5 = fp16, 6 = bf16 hi/mid/lo planes (24 significant bits: the fp32-faithful split) */
-  int64_t ld_codes;
+                           5 = fp16, 6 = bf16 hi/mid/lo planes (24 significant bits: the fp32-faithful split),
+                           7 = fp4 (e2m1) codes, two per byte, element 2j in the low nibble of byte j; integer codes in
+                               [-4, 4] only (QT_Q_SIGN, QT_Q_TERNARY, QT_Q_DOREFA k = 2); ld_codes % 32 == 0 */
+  int64_t ld_codes;     /* in ELEMENTS (codes_kind 7: two elements per byte) */
   uint32_t* bits;       /* optional bit-packed sign rows [rows, ld_bits] (QT_Q_SIGN only) */
   int64_t ld_bits;
   int32_t* row_sum;     /* optional [rows]: sum over columns of the integer codes */
@@ -143,6 +145,8 @@ int qt_col_absmean(const float* w, int64_t n, int64_t k, int64_t ld_w, float* al
  *   kind 5: fp16 alpha[k] * sign, one plane (XnorNet fast route; pass alpha pre-normalised to max 1 so that the
  *           values sit in fp16's normal range, and put the max back through the epilogue's col_scale)
  *   kind 6: fp16 exact values of kind 1 (integers up to 255 are exact in fp16)
+ *   kind 7: fp4 (e2m1) centred codes, two per byte (sign: +-1, ternary: -1/0/1, DoReFa k<=2: 2c-n in {-3,-1,1,3});
+ *           ld_out % 32 == 0.  The operand of qt_gemm_f4.
  */
 typedef struct QtWeightExpand {
   int mode, bit_width;
@@ -223,6 +227,16 @@ int qt_gemm_b1t2(const uint32_t* a_bits, int64_t lda_words, const uint32_t* w_nz
 int qt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* w, int w_signed, int64_t ldw,
                int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, int backend, void* stream);
 
+/* fp4 (e2m1) codes x fp4 (e2m1) codes -> exact integer accumulators, on tcgen05.mma kind::mxf4.block_scale with unit
+ * scale factors (twice the MAC rate of kind::i8).  This is the 1-bit / ternary / 2-bit contraction of
+ *   LinearBin / BinConv2d    binary_layers.py:42-46,103-106      (+-1 x +-1  ==  K - 2 popc(a ^ w))
+ *   LinearTer / TerConv2d    terner_layers.py:47-51,89-92        ({-1,0,1} weights)
+ *   LinearDorefa k <= 2      dorefa_layers.py:41-45
+ * a: [M, lda] codes, w: [N, ldw] codes (two per byte; lda, ldw in ELEMENTS, multiples of 32; columns K.. zero).
+ * Same integer epilogue as qt_gemm_i8.  tcgen05 only: QT_EUNSUPPORTED on anything but sm_100. */
+int qt_gemm_f4(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,
+               const QtEpilogue* ep, void* stream);
+
 /* Implicit-GEMM convolution (F.conv2d at binary_layers.py:105-106, terner_layers.py:91-92, dorefa_layers.py:79,81) on
  * channels-last 8-bit activation codes x_nhwc[B, H, W, C]: the A operand is fetched by TMA in im2col mode (no im2col
  * matrix is ever materialised; padding taps are zero-filled by the hardware), K runs over (kh, kw, c) with the channel
@@ -255,6 +269,10 @@ int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, const void* 
  * ragged first layers; same epilogue. */
 int qt_gemm_f32(const float* a, int64_t lda, const float* w, int64_t ldw,
                 int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, void* stream);
+
+/* Tuning / test knobs (process-wide).  "f4_tile_n": qt_gemm_f4 tile width, 0 = auto, or 64 / 128 / 240.
+ * Unknown names or values return QT_EINVAL. */
+int qt_set_option(const char* name, int value);
 
 /* Number of kernel launches issued by this library on the calling thread since the last reset
  * (bench.py's gpu_launches). */

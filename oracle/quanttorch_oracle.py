@@ -246,6 +246,19 @@ def dorefa_weight_codes(w: torch.Tensor, k: int) -> np.ndarray:
     return torch.round(n * t).to(torch.int64).numpy()
 
 
+def e2m1_pack(codes: np.ndarray, ld: int) -> np.ndarray:
+    """Integer codes in [-4, 4] -> fp4 (e2m1) nibbles, two per byte (element 2j in the low nibble), rows zero-padded to
+    `ld` elements.  e2m1 magnitudes: 0, 0.5, 1, 1.5, 2, 3, 4, 6 <-> 0..7, sign in bit 3 -- the operand format of the
+    tcgen05 kind::mxf4 contraction (the reference has no packed format: binary_layers.py:42-46 feeds fp32 +-1)."""
+    mag = np.array([0, 2, 4, 5, 6], np.uint8)
+    c = np.asarray(codes, np.int64)
+    assert np.abs(c).max(initial=0) <= 4
+    rows, cols = c.shape
+    nib = np.zeros((rows, ld), np.uint8)
+    nib[:, :cols] = mag[np.abs(c)] | ((c < 0).astype(np.uint8) << 3)
+    return (nib[:, 0::2] | (nib[:, 1::2] << 4)).astype(np.uint8)
+
+
 def int_acc(codes_a: np.ndarray, codes_w: np.ndarray) -> np.ndarray:
     """Exact accumulator: A[M,K] . W[N,K]^T in int64."""
     return codes_a.astype(np.int64) @ codes_w.astype(np.int64).T

@@ -40,6 +40,21 @@ def xnor_codes_kind():
 
 
 _code_only = [False]
+# 1-bit / ternary / 2-bit operands as fp4 (e2m1) codes on tcgen05 kind::mxf4 with unit block scales: exact, and twice the
+# MAC rate of kind::i8.  QTB200_FP4=0 (or set_fp4(False)) keeps every integer operand in 8-bit lanes.
+_fp4 = [os.environ.get("QTB200_FP4", "1") != "0"]
+
+
+def set_fp4(flag):
+    _fp4[0] = bool(flag)
+
+
+def int_codes_kind(x, bit_width=1):
+    """Operand format an activation quantizer should emit for integer codes of `bit_width` bits: fp4 (e2m1) for 2-D
+    inputs whose codes fit {-4..4} (sign, ternary, DoReFa-2), 8-bit lanes otherwise (conv inputs use channels-last int8)."""
+    if _fp4[0] and x.dim() == 2 and bit_width <= 2:
+        return L.CODES_F4
+    return L.CODES_I8
 
 
 class code_only_activations:
@@ -133,12 +148,30 @@ def _a_from_tag(tag):
     a.t, a.ld = tag.codes, tag.ld
     if tag.codes_kind in (L.CODES_I8, L.CODES_U8):
         a.form, a.signed, a.planes = "i8", tag.codes_kind == L.CODES_I8, 1
+    elif tag.codes_kind == L.CODES_F4:
+        a.form, a.signed, a.planes = "f4", True, 1
     elif tag.codes_kind == L.CODES_F16:
         a.form, a.signed, a.planes = "fp16", True, 1
     else:
         a.form, a.signed = "bf16", True
         a.planes = {L.CODES_BF16X2: 2, L.CODES_BF16X3: 3}.get(tag.codes_kind, 1)
     return a
+
+
+def _f4_weight_ok(pack):
+    return (_force_backend["i8"] != L.BACKEND_SIMT
+            and (pack.kind in ("sign", "ternary") or (pack.kind == "dorefa" and pack.bit_width <= 2)))
+
+
+def _requant_i8(x2d, tag):
+    """int8 codes of an already quantized fp32 tensor (quantizing twice is idempotent for sign / ternary / DoReFa)."""
+    mode = {"sign": L.Q_SIGN, "ternary": L.Q_TERNARY, "dorefa": L.Q_DOREFA}[tag.kind]
+    # DoReFa: y = fl(1/n) c  ->  rint(n y) = c
+    _, t2 = ops.quant_act(x2d, mode, bit_width=tag.bit_width if tag.kind == "dorefa" else 0, want_y=False,
+                          codes_kind=L.CODES_I8, want_bits=(tag.kind == "sign"), want_row_sum=(tag.kind == "dorefa"),
+                          kind=tag.kind)
+    t2.scale = tag.scale
+    return _a_from_tag(t2)
 
 
 def _a_split(x2d):
@@ -154,7 +187,7 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
     col_scale = None if pack.col_scale is None else pack.col_scale[w_row0:w_row0 + N]
     int_w = pack.kind in ("sign", "ternary", "dorefa")
 
-    if a.form == "i8" and int_w:
+    if a.form in ("i8", "f4") and int_w:
         use_pop = (a.bits is not None and pack.kind in ("sign", "ternary") and a.scale == 1.0 and out_mode == 0
                    and (_force_popcount[0] or (M <= POPCOUNT_MAX_M and _force_backend["i8"] == L.BACKEND_AUTO)))
         if use_pop:
@@ -165,6 +198,13 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
                 ops.gemm_b1b1(a.bits, a.ld_bits, wbits[0, w_row0:], ldw, M, N, K, epi)
             else:
                 ops.gemm_b1t2(a.bits, a.ld_bits, wbits[0, w_row0:], wbits[1, w_row0:], ldw, M, N, K, epi)
+            return
+        if a.form == "f4":
+            # e2m1 codes x e2m1 centred weight codes: tcgen05 kind::mxf4, unit scales, exact integer accumulators
+            w, ldw = ops.expand_weight(pack, L.CODES_F4)
+            epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
+                               scale=a.scale, acc_out=acc_out, out_offset=out_offset)
+            ops.gemm_f4(a.t, a.ld, w[w_row0:], ldw, M, N, K, epi)
             return
         if pack.kind == "dorefa" and pack.bit_width == 8:
             # raw unsigned codes c, W_q = (2c - 255)/255:  sum a (2c - 255) = 2 sum a c - 255 sum a
@@ -235,8 +275,12 @@ def linear(x, pack, bias):
     a = None
     if tag is not None:
         a = _a_from_tag(tag)
-        if (a.form == "i8" and not int_w) or (a.form == "fp16" and pack.kind == "real"):
+        if (a.form in ("i8", "f4") and not int_w) or (a.form == "fp16" and pack.kind == "real"):
             a = None
+        elif a.form == "f4" and not _f4_weight_ok(pack):
+            # e2m1 activation codes met weights that need 8-bit lanes (DoReFa k >= 3, or the CUDA-core backend was forced):
+            # re-emit the codes as int8 from the fp32 fake-quant tensor (not available in code-only mode)
+            a = None if x2d is None else _requant_i8(x2d, tag)
     if a is None:
         if x2d is None:
             raise RuntimeError("pytorch_quantize_impls_b200: this layer cannot consume the code-only activation it was "

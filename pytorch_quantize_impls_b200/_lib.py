@@ -15,6 +15,7 @@ Q_SIGN, Q_TERNARY, Q_DOREFA, Q_XNOR_ROW, Q_LOG, Q_LIN, Q_SPLIT = range(7)
 W_SIGN, W_TERNARY, W_DOREFA, W_XNOR = range(4)
 CODES_NONE, CODES_I8, CODES_U8, CODES_BF16, CODES_BF16X2, CODES_F16, CODES_BF16X3 = range(7)
 CODES_F16_EXACT = 6      # qt_expand_weight out_kind 6 (fp16 exact integer codes)
+CODES_F4 = 7             # fp4 (e2m1) codes, two per byte: the operand of qt_gemm_f4 (tcgen05 kind::mxf4)
 FMT_BF16, FMT_FP16 = 0, 1
 BACKEND_AUTO, BACKEND_TCGEN05, BACKEND_SIMT = 0, 1, 2
 
@@ -76,11 +77,13 @@ SYMBOLS = {
     "qt_gemm_b1b1": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_gemm_b1t2": (i32, [vp, i64, vp, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_gemm_i8": (i32, [vp, i32, i64, vp, i32, i64, i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
+    "qt_gemm_f4": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_conv_i8": (i32, [vp, i32, C.POINTER(QtConvGeom), vp, i32, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_patch_rowsum": (i32, [vp, i32, C.POINTER(QtConvGeom), vp, vp, vp]),
     "qt_gemm_f16": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, C.POINTER(i32), C.POINTER(i32),
                           i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
     "qt_gemm_f32": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
+    "qt_set_option": (i32, [C.c_char_p, i32]),
     "qt_launch_count": (i64, [i32]),
 }
 
@@ -113,6 +116,10 @@ def check(rc, what):
     if rc != 0:
         msg = lib().qt_last_error().decode("utf-8", "replace")
         raise QtError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def set_option(name, value):
+    check(lib().qt_set_option(name.encode(), int(value)), "qt_set_option")
 
 
 def launch_count(reset=False):

@@ -45,7 +45,7 @@ class ActCodes:
     """Low-bit activation operand produced by an activation quantizer and consumed by the next layer.
 
     kind        'sign' | 'ternary' | 'dorefa' | 'xnor'
-    codes       int8/uint8 [rows, ld] or bf16 [rows, ld] tensor (K-major, zero padded)
+    codes       int8/uint8 [rows, ld], bf16/fp16 [rows, ld] or fp4 (e2m1, uint8 [rows, ld/2]) tensor (K-major, zero padded)
     scale       value = scale * code  (DoReFa: fl(1/n); others 1.0)
     row_sum     int32 [rows] sum of codes (for unsigned-weight zero points), or None
     row_scale   fp32 [rows] (XnorNet row mean), or None
@@ -97,6 +97,10 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
     elif codes_kind in (L.CODES_I8, L.CODES_U8):
         ld = round_up(max(cols, 1), 16)
         codes = torch.empty((rows, ld), dtype=torch.int8 if codes_kind == L.CODES_I8 else torch.uint8, device=dev)
+        overflow = torch.zeros(1, dtype=torch.int32, device=dev) if mode == L.Q_DOREFA else None
+    elif codes_kind == L.CODES_F4:
+        ld = round_up(max(cols, 1), 32)        # elements; two e2m1 codes per byte -> 16-byte rows
+        codes = torch.empty((rows, ld // 2), dtype=torch.uint8, device=dev)
         overflow = torch.zeros(1, dtype=torch.int32, device=dev) if mode == L.Q_DOREFA else None
     elif codes_kind == L.CODES_BF16:
         ld = round_up(max(cols, 1), 8)
@@ -218,7 +222,10 @@ def expand_weight(p, out_kind):
     """Packed k-bit weights -> transient tensor-core operand (lives in L2 between the two kernels)."""
     dev = p.packed.device
     ld = round_up(p.k, 16)
-    if out_kind == L.CODES_I8:
+    if out_kind == L.CODES_F4:
+        ld = round_up(p.k, 32)
+        out = torch.empty((p.n, ld // 2), dtype=torch.uint8, device=dev)
+    elif out_kind == L.CODES_I8:
         out = torch.empty((p.n, ld), dtype=torch.int8, device=dev)
     elif out_kind == L.CODES_U8:
         out = torch.empty((p.n, ld), dtype=torch.uint8, device=dev)
@@ -284,6 +291,11 @@ def gemm_b1t2(a_bits, lda, w_nz, w_sign, ldw, M, N, K, epi):
 def gemm_i8(a, a_signed, lda, w, w_signed, ldw, M, N, K, epi, backend=L.BACKEND_AUTO):
     L.check(L.lib().qt_gemm_i8(_p(a), int(a_signed), lda, _p(w), int(w_signed), ldw, M, N, K, C.byref(epi),
                                backend, _stream()), "qt_gemm_i8")
+
+
+def gemm_f4(a, lda, w, ldw, M, N, K, epi):
+    """e2m1 codes x e2m1 codes on tcgen05 kind::mxf4 (unit block scales): exact integer accumulators."""
+    L.check(L.lib().qt_gemm_f4(_p(a), lda, _p(w), ldw, M, N, K, C.byref(epi), _stream()), "qt_gemm_f4")
 
 
 def gemm_f16(a, lda, a_plane_stride, w, ldw, w_plane_stride, passes, M, N, K, epi, backend=L.BACKEND_AUTO,

@@ -3,14 +3,20 @@
 //   * operands are K-major byte matrices in HBM/L2 (int8/uint8 codes, or bf16 planes), fetched by TMA
 //     (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage shared-memory ring guarded by
 //     full/empty mbarriers;
-//   * one elected thread issues tcgen05.mma (kind::i8 -> s32, kind::f16/bf16 -> f32), 128 x BN x 32 B per
-//     instruction, accumulators live in TMEM (2 x BN columns: double buffered across output tiles);
+//   * one elected thread issues tcgen05.mma (kind::i8 -> s32, kind::f16/bf16 -> f32, kind::mxf4 -> f32), 128 x BN x 32 B
+//     per instruction, accumulators live in TMEM (2 x BN columns: double buffered across output tiles);
+//   * kind::mxf4.block_scale (e2m1 operands, 64 K-elements per 32 B: twice the MAC rate of kind::i8) is run with UNIT
+//     scale factors: the ue8m0 value 0x7F (2^0) is written once into 16 spare TMEM columns with tcgen05.st and every MMA
+//     points its SFA / SFB operands there, so +-1 / {-1,0,1} / 2-bit codes are multiplied exactly and the fp32
+//     accumulators hold exact integers (tile width 240 instead of 256 leaves room for those columns);
 //   * eight epilogue warps drain TMEM with tcgen05.ld (32x32b.x32), apply the integer-exact affine +
 //     scale/bias epilogue and write fp32 through 128B-swizzled smem tiles + cp.async.bulk.tensor stores
 //     (row-major output) or coalesced per-column stores (NCHW output), overlapping the next tile's main loop;
 //   * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule with M fastest so that
 //     concurrently running CTAs share the same weight tile in L2.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include <mutex>
 #include "qt_common.cuh"
 
@@ -19,6 +25,7 @@ namespace qt {
 constexpr int TC_BM = 128;
 constexpr int TC_BK_BYTES = 128;          // one 128B swizzle row of K per stage
 constexpr int TC_THREADS = 320;           // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..9 epilogue
+constexpr uint32_t TC_SF_COL = 496;       // kind::mxf4: TMEM columns 496..511 hold the unit scale factors
 
 struct TcArgs {
   int64_t M, N;
@@ -108,8 +115,16 @@ __device__ __forceinline__ void tile_coords(const TcArgs& g, int tile, int& tm, 
 }
 
 template <int KIND>
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if (KIND == 0) {
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                       uint32_t sf_tmem) {
+  if (KIND == 2) {
+    // SFA at sf_tmem (4 columns), SFB at sf_tmem + 4 (<= 8 columns for N <= 256): all bytes there are 0x7F (ue8m0 1.0)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sf_tmem), "r"(sf_tmem + 4u)
+        : "memory");
+  } else if (KIND == 0) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
@@ -156,7 +171,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr uint32_t A_BYTES = TC_BM * BKB;
   constexpr uint32_t W_BYTES = BN * BKB;
   constexpr uint32_t STAGE_BYTES = A_BYTES + W_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
+  // kind::mxf4: 2 x BN accumulator columns (BN <= 240) + 16 columns of unit scale factors at TC_SF_COL
+  constexpr uint32_t TMEM_COLS = (KIND == 2) ? 512u : 2u * BN;
+  static_assert(KIND != 2 || 2 * BN <= TC_SF_COL, "mxf4 tiles must leave the scale-factor columns free");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -196,6 +213,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (KIND == 2) {
+    if (warp >= 2 && warp < 6) {   // four warps, one per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31)
+      const uint32_t taddr = tmem_base + TC_SF_COL + ((uint32_t)((warp & 3) * 32) << 16);
+      const uint32_t one = 0x7F7F7F7Fu;
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(one) : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   const int num_tiles = g.tiles_m * g.tiles_n;
   const int iters = g.npass * g.num_kblocks;
@@ -257,7 +285,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BKB / 32; ++k) {
             // +32 B along K inside the swizzle atom == +2 in the (addr >> 4) field
-            tc_mma<KIND>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), g.idesc, (it > 0 || k > 0) ? 1u : 0u);
+            tc_mma<KIND>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), g.idesc, (it > 0 || k > 0) ? 1u : 0u,
+                         tmem_base + TC_SF_COL);
           }
           tc_commit(empty_bar(stage));     // frees the smem stage once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -273,8 +302,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int ew = warp - 2;
     const int lane_grp = warp & 3;
     const int half = ew >> 2;
-    constexpr int CHUNKS = BN / 32;
-    constexpr int CH_PER_WARP = CHUNKS / 2;
+    constexpr int CHUNKS = (BN + 31) / 32;          // BN = 240 (kind::mxf4): the last chunk holds 16 columns
+    constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
+    constexpr bool INT_ACC = (KIND == 0 || KIND == 2);   // kind::mxf4 accumulators are exact integers held in fp32
     int as = 0;
     uint32_t aphase = 0;
     const Epi& e = g.ep;
@@ -287,6 +317,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tile_coords(g, tile, tm, tn);
       const int64_t m = (int64_t)tm * TC_BM + lane_grp * 32 + lane;
       const int n_tile = tn * BN;
+      const int n_lim = min(N32, n_tile + BN);     // first column past this tile
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const bool row_ok = m < g.M;
@@ -303,11 +334,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
 #pragma unroll 1
       for (int ci = 0; ci < CH_PER_WARP; ++ci) {
-        const int c0 = (half * CH_PER_WARP + ci) * 32;
+        const int cidx = half * CH_PER_WARP + ci;
+        if (cidx >= CHUNKS) break;
+        const int c0 = cidx * 32;
         const int n0 = n_tile + c0;
-        if (n0 >= N32) break;     // warp-uniform
+        if (n0 >= n_lim) break;     // warp-uniform
+        const bool full_chunk = (BN % 32 == 0) || (c0 + 32 <= BN);
         uint32_t r[32];
         tmem_ld32(tmem_base + (uint32_t)(as * BN + c0) + ((uint32_t)(lane_grp * 32) << 16), r);
+        if (KIND == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = (uint32_t)__float2int_rn(__uint_as_float(r[j]));
+        }
         // per-column scale / bias of this chunk: one coalesced load per lane, broadcast by shuffle below
         const int nl = n0 + lane;
         float cs_l = 1.f, b_l = 0.f;
@@ -315,24 +353,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (e.col_scale) cs_l = __ldg(e.col_scale + nl);
           if (e.bias) b_l = __ldg(e.bias + nl);
         }
-        if (KIND == 0 && e.acc_out && row_ok) {
+        if (INT_ACC && e.acc_out && row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + j < N32) e.acc_out[m * g.N + n0 + j] = (int32_t)r[j];
+            if (n0 + j < n_lim) e.acc_out[m * g.N + n0 + j] = (int32_t)r[j];
         }
         if (!e.out) continue;
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float v;
-          if (KIND == 0) v = (float)(e.acc_mul * (int32_t)r[j] + rsum);
+          if (INT_ACC) v = (float)(e.acc_mul * (int32_t)r[j] + rsum);
           else v = __uint_as_float(r[j]);
           // y = acc * (scale * row_scale) * col_scale + bias; with scale = row/col scale = 1 the multiply is exact and
           // float(acc) + bias is one rounding (BinaryNet / Terner bit-exactness)
           const float cs = __shfl_sync(0xffffffffu, cs_l, j), bb = __shfl_sync(0xffffffffu, b_l, j);
           y[j] = (v * mul) * cs + bb;
         }
-        if (g.tma_store) {
+        if (g.tma_store && full_chunk) {
           // registers (one output row per lane) -> 128B-swizzled smem tile -> one bulk tensor store per 32x32 block:
           // every global write is a full 128-byte line; M/N tails are clipped by the tensor map.
           if (lane == 0) tma_store_wait_read0();      // the previous store has finished reading this buffer
@@ -347,20 +385,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         } else if (e.out_mode == 0) {
           if (!row_ok) continue;
           float* o = e.out + m * e.ldo + n0;
-          if (vec_ok && n0 + 32 <= N32) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-          } else {
+          for (int j = 0; j < 32; j += 4) {
+            if (vec_ok && n0 + j + 4 <= n_lim) {
+              *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < N32) o[j] = y[j];
+              for (int jj = j; jj < j + 4; ++jj)
+                if (n0 + jj < n_lim) o[jj] = y[jj];
+            }
           }
         } else {
           if (!row_ok) continue;
           float* o = e.out + nchw_base + (int64_t)n0 * e.nchw_inner;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + j < N32) o[(int64_t)j * e.nchw_inner] = y[j];   // lanes = consecutive pixels: coalesced per column
+            if (n0 + j < n_lim) o[(int64_t)j * e.nchw_inner] = y[j];   // lanes = consecutive pixels: coalesced per column
         }
       }
       tc_fence_before();
@@ -479,6 +519,30 @@ static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, 
 
 static int pick_bn(int64_t N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }
 
+// kind::mxf4 tiles: 240 columns (two accumulators + the scale-factor columns fit the 512 TMEM columns) unless 128-wide
+// tiles waste clearly fewer padded columns.  QTB200_F4_BN=64|128|240 overrides (tuning / tests).
+static int g_f4_tile_n = -1;
+static int pick_bn_f4(int64_t N) {
+  if (g_f4_tile_n < 0) {
+    const char* s = getenv("QTB200_F4_BN");
+    int v = s ? atoi(s) : 0;
+    g_f4_tile_n = (v == 64 || v == 128 || v == 240) ? v : 0;
+  }
+  if (g_f4_tile_n) return g_f4_tile_n;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  const int64_t pad240 = ceil_div(N, 240) * 240, pad128 = ceil_div(N, 128) * 128;
+  return (double)pad128 < 0.9 * (double)pad240 ? 128 : 240;
+}
+
+static int dispatch_f4(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream);
+
+static int dispatch_f4(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream) {
+  if (bn == 64) return launch_tc<64, 2, 8>(ma, mw, g, stream);
+  if (bn == 128) return launch_tc<128, 2, 6>(ma, mw, g, stream);
+  return launch_tc<240, 2, 4>(ma, mw, g, stream);
+}
+
 static bool tc_available() {
   static int ok = -1;
   if (ok < 0) {
@@ -527,6 +591,45 @@ extern "C" int qt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* 
   g.idesc = (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((w_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) |
             ((uint32_t)(TC_BM >> 4) << 24);
   return dispatch_tc<0>(ma, mw, g, bn, stream);
+}
+
+extern "C" int qt_set_option(const char* name, int value) {
+  QT_REQUIRE(name != nullptr, "qt_set_option: null name");
+  if (strcmp(name, "f4_tile_n") == 0) {
+    QT_REQUIRE(value == 0 || value == 64 || value == 128 || value == 240, "qt_set_option: f4_tile_n must be 0, 64, 128 or 240");
+    g_f4_tile_n = value;
+    return QT_OK;
+  }
+  set_error("qt_set_option: unknown option '%s'", name);
+  return QT_EINVAL;
+}
+
+extern "C" int qt_gemm_f4(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                          const QtEpilogue* ep, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(a && w, "qt_gemm_f4: null operand");
+  QT_REQUIRE(M >= 0 && N >= 0 && K > 0 && lda >= K && ldw >= K, "qt_gemm_f4: bad shape");
+  QT_REQUIRE(lda % 32 == 0 && ldw % 32 == 0 && al16(a) && al16(w),
+             "qt_gemm_f4: e2m1 rows must be 16-byte aligned (lda, ldw multiples of 32 elements)");
+  QT_REQUIRE(K < (1ll << 22), "qt_gemm_f4: K too large for exact fp32 accumulation of 2-bit codes");
+  if (int rc = check_epi(ep, M, N)) return rc;
+  if (M == 0 || N == 0) return QT_OK;
+  if (!tc_available() || M >= (1ll << 31) || N >= (1ll << 31)) {
+    set_error("qt_gemm_f4: needs an sm_100 device (tcgen05 kind::mxf4); there is no CUDA-core route for e2m1 operands");
+    return QT_EUNSUPPORTED;
+  }
+  const int bn = pick_bn_f4(N);
+  CUtensorMap ma, mw;
+  // byte matrices: two e2m1 codes per byte, K/2 bytes per row (zero OOB fill = +0.0 codes)
+  if (int rc = make_map(&ma, a, (uint64_t)M, (uint64_t)((K + 1) / 2), (uint64_t)(lda / 2), TC_BM)) return rc;
+  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)((K + 1) / 2), (uint64_t)(ldw / 2), (uint32_t)bn)) return rc;
+  TcArgs g{};
+  g.M = M; g.N = N; g.num_kblocks = (int)ceil_div((K + 1) / 2, TC_BK_BYTES); g.npass = 1; g.pa[0] = g.pw[0] = 0;
+  g.a_plane_rows = g.w_plane_rows = 0; g.is_int = 1; g.ep = make_epi(ep, M, N);
+  // block-scaled instruction descriptor: A/B = e2m1 (1) at bits 7 / 10, K-major, N >> 3 at 17, scale format ue8m0 (1) at 23,
+  // M >> 4 at 24, scale-factor ids 0, K = 64 per instruction
+  g.idesc = (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | (1u << 23) | ((uint32_t)(TC_BM >> 4) << 24);
+  return dispatch_f4(ma, mw, g, bn, stream);
 }
 
 extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,

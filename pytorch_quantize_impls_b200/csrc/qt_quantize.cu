@@ -124,6 +124,21 @@ __device__ __forceinline__ int code_to_lane(float c, int kind, bool& ovf) {
   return (int)c;
 }
 
+// integer code in [-4, 4] -> e2m1 nibble (sign | magnitude code: 0->0, 1->2, 2->4, 3->5, 4->6); `k` receives the integer
+__device__ __forceinline__ uint32_t code_to_f4(float c, int& k, bool& ovf) {
+  if (!(c >= -4.f && c <= 4.f)) {
+    ovf = true;
+    c = (c != c) ? 0.f : fminf(fmaxf(c, -4.f), 4.f);
+  }
+  k = (int)c;
+  const int m = k < 0 ? -k : k;
+  return ((0x65420u >> (4 * m)) & 0xFu) | (k < 0 ? 8u : 0u);
+}
+__device__ __forceinline__ uint32_t f4_nibble(float v) {   // exact small integers only (weights)
+  int k; bool o = false;
+  return code_to_f4(v, k, o);
+}
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -179,7 +194,8 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
   bool ovf = false;
   float* yr = a.y ? a.y + row * a.ld_y : nullptr;
   int8_t* c8 = (a.codes_kind == 1 || a.codes_kind == 2) ? reinterpret_cast<int8_t*>(a.codes) + row * a.ld_codes : nullptr;
-  __nv_bfloat16* cb = (a.codes_kind >= 3) ? reinterpret_cast<__nv_bfloat16*>(a.codes) + row * a.ld_codes : nullptr;
+  __nv_bfloat16* cb = (a.codes_kind >= 3 && a.codes_kind <= 6) ? reinterpret_cast<__nv_bfloat16*>(a.codes) + row * a.ld_codes : nullptr;
+  uint8_t* c4 = (a.codes_kind == 7) ? reinterpret_cast<uint8_t*>(a.codes) + row * (a.ld_codes >> 1) : nullptr;   // e2m1 pairs
   const bool f16 = a.codes_kind == 5;   // same 2-byte lanes, IEEE half encoding
   __nv_bfloat16* cb_lo = (a.codes_kind == 4 || a.codes_kind == 6) ? cb + a.rows * a.ld_codes : nullptr;
   __nv_bfloat16* cb_lo2 = (a.codes_kind == 6) ? cb_lo + a.rows * a.ld_codes : nullptr;
@@ -249,6 +265,17 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
           isum += (int)o0.code + (int)o1.code + (int)o2.code + (int)o3.code;
         }
       }
+      if (c4) {  // 4 nibbles per lane; lane pairs merge into one 32-bit store (8 codes)
+        uint32_t h = 0;
+        if (valid) {
+          int k0, k1, k2, k3;
+          h = code_to_f4(o0.code, k0, ovf) | (code_to_f4(o1.code, k1, ovf) << 4) | (code_to_f4(o2.code, k2, ovf) << 8) |
+              (code_to_f4(o3.code, k3, ovf) << 12);
+          isum += k0 + k1 + k2 + k3;
+        }
+        const uint32_t hi = __shfl_down_sync(0xffffffffu, h, 1);
+        if (valid && !(lane & 1)) *reinterpret_cast<uint32_t*>(c4 + (c >> 1)) = h | (hi << 16);
+      }
       if (br) {  // 4 bits per lane -> 4 words per 128-column step
         uint32_t nib = 0;
         if (valid) nib = (uint32_t)(o0.code > 0.f) | ((uint32_t)(o1.code > 0.f) << 1) |
@@ -289,6 +316,16 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
           isum += (int)o.code;
         }
       }
+      if (c4) {
+        uint32_t nib = 0;
+        if (valid) {
+          int k;
+          nib = code_to_f4(o.code, k, ovf);
+          isum += k;
+        }
+        const uint32_t hi = __shfl_down_sync(0xffffffffu, nib, 1);
+        if (valid && !(lane & 1)) c4[c >> 1] = (uint8_t)(nib | (hi << 4));
+      }
       if (br) {
         uint32_t w = __ballot_sync(0xffffffffu, valid && o.code > 0.f);
         if (lane == 0) br[base >> 5] = w;
@@ -304,6 +341,7 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
       if (cb_lo) cb_lo[c] = __float2bfloat16_rn(0.f);
       if (cb_lo2) cb_lo2[c] = __float2bfloat16_rn(0.f);
     }
+    if (c4) for (int64_t b = ((a.cols + 1) >> 1) + lane; b < (a.ld_codes >> 1); b += 32) c4[b] = 0;
     if (br) for (int64_t w = ((a.cols + 31) >> 5) + lane; w < a.ld_bits; w += 32) br[w] = 0u;
   }
   if (a.row_sum) {
@@ -581,7 +619,15 @@ __global__ void __launch_bounds__(256) weight_expand_kernel(ExpandArgs a) {
       v[j] = (c0 + j < a.k) ? x : 0.f;
     }
   }
-  if (a.out_kind == 1 || a.out_kind == 2) {
+  if (a.out_kind == 7) {   // e2m1 nibbles: 16 columns -> 8 bytes
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      lo |= f4_nibble(v[j]) << (4 * j);
+      hi |= f4_nibble(v[8 + j]) << (4 * j);
+    }
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.out) + row * (a.ld_out >> 1) + (c0 >> 1)) = make_uint2(lo, hi);
+  } else if (a.out_kind == 1 || a.out_kind == 2) {
     uint32_t w[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -852,7 +898,12 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   if (p->mode == QT_Q_SPLIT) QT_REQUIRE(p->codes_kind == 4 || p->codes_kind == 6, "qt_quant_act: QT_Q_SPLIT needs codes_kind 4 or 6");
   if (p->mode == QT_Q_LOG || p->mode == QT_Q_LIN)
     QT_REQUIRE(p->codes_kind == 0 && !p->bits, "qt_quant_act: Log/Lin quantizers produce fp32 only");
-  QT_REQUIRE(p->codes_kind >= 0 && p->codes_kind <= 6, "qt_quant_act: bad codes_kind");
+  QT_REQUIRE(p->codes_kind >= 0 && p->codes_kind <= 7, "qt_quant_act: bad codes_kind");
+  if (p->codes_kind == 7) {
+    QT_REQUIRE(p->mode == QT_Q_SIGN || p->mode == QT_Q_TERNARY || (p->mode == QT_Q_DOREFA && p->bit_width == 2),
+               "qt_quant_act: fp4 codes hold SIGN / TERNARY / DoReFa-2 codes only");
+    QT_REQUIRE(p->ld_codes % 32 == 0 && p->nhwc_c == 0, "qt_quant_act: fp4 code rows must be multiples of 32 elements (row-major only)");
+  }
   if (p->codes_kind) QT_REQUIRE(p->codes && p->ld_codes >= p->cols, "qt_quant_act: bad codes buffer");
   if (p->bits) QT_REQUIRE(p->mode == QT_Q_SIGN && p->ld_bits * 32 >= p->cols, "qt_quant_act: bits need QT_Q_SIGN and ld_bits*32 >= cols");
   if (p->y) QT_REQUIRE(p->ld_y >= p->cols, "qt_quant_act: ld_y < cols");
@@ -879,7 +930,8 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   bool vec = (p->cols % 4 == 0) && (p->ld_x % 4 == 0) && aligned(p->x, 16);
   if (p->y) vec = vec && (p->ld_y % 4 == 0) && aligned(p->y, 16);
   if (p->codes_kind == 1 || p->codes_kind == 2) vec = vec && (p->ld_codes % 4 == 0) && aligned(p->codes, 4);
-  if (p->codes_kind >= 3) vec = vec && (p->ld_codes % 4 == 0) && aligned(p->codes, 8) && ((p->rows * p->ld_codes) % 4 == 0);
+  if (p->codes_kind >= 3 && p->codes_kind <= 6) vec = vec && (p->ld_codes % 4 == 0) && aligned(p->codes, 8) && ((p->rows * p->ld_codes) % 4 == 0);
+  if (p->codes_kind == 7) vec = vec && aligned(p->codes, 4);
 
   // split long rows into chunks when there are too few rows to fill the machine
   // warp tasks of <= 2048 columns: many small tasks keep the last wave short (8192 x 4096 -> 16384 tasks, ~3.5 waves of
@@ -966,7 +1018,12 @@ extern "C" int qt_expand_weight(const QtWeightExpand* p, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   QT_REQUIRE(p && p->packed && p->out, "qt_expand_weight: null argument");
   QT_REQUIRE(p->mode >= QT_W_SIGN && p->mode <= QT_W_XNOR, "qt_expand_weight: bad mode");
-  QT_REQUIRE(p->out_kind >= 1 && p->out_kind <= 6, "qt_expand_weight: bad out_kind");
+  QT_REQUIRE(p->out_kind >= 1 && p->out_kind <= 7, "qt_expand_weight: bad out_kind");
+  if (p->out_kind == 7) {
+    QT_REQUIRE(p->mode == QT_W_SIGN || p->mode == QT_W_TERNARY || (p->mode == QT_W_DOREFA && p->bit_width <= 2),
+               "qt_expand_weight: fp4 operands hold sign / ternary / DoReFa k<=2 weights only");
+    QT_REQUIRE(p->ld_out % 32 == 0, "qt_expand_weight: fp4 rows must be multiples of 32 elements");
+  }
   QT_REQUIRE(p->ld_out % 16 == 0 && p->ld_out >= p->k, "qt_expand_weight: ld_out must be a multiple of 16 and >= k");
   QT_REQUIRE(aligned(p->out, 16), "qt_expand_weight: out must be 16-byte aligned");
   if (p->out_kind == 4 || p->out_kind == 5) QT_REQUIRE(p->alpha && p->mode == QT_W_XNOR, "qt_expand_weight: kinds 4/5 need XNOR alpha");

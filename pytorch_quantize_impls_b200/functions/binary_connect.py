@@ -19,7 +19,7 @@ class BinaryConnectDeterministic(TaggingFunction):
     def forward(ctx, input):
         ctx.save_for_backward(input)
         full = eng.want_fp32_result(input)
-        y, tag = ops.quant_act(input, L.Q_SIGN, want_y=full, codes_kind=L.CODES_I8,
+        y, tag = ops.quant_act(input, L.Q_SIGN, want_y=full, codes_kind=eng.int_codes_kind(input),
                                want_bits=(input.dim() == 2), kind="sign")
         TaggingFunction._leave(tag)
         return y if full else eng.placeholder_like(input)

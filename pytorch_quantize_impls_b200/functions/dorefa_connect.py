@@ -17,7 +17,7 @@ def _quantize_with_codes(x, bit_width, pre=None):
     their row sums."""
     full = eng.want_fp32_result(x)
     if bit_width == 1:
-        y, tag = ops.quant_act(x, L.Q_SIGN, want_y=full, codes_kind=L.CODES_I8, want_bits=(x.dim() == 2), kind="sign",
+        y, tag = ops.quant_act(x, L.Q_SIGN, want_y=full, codes_kind=eng.int_codes_kind(x), want_bits=(x.dim() == 2), kind="sign",
                                pre=pre)
         return (y if full else eng.placeholder_like(x)), tag
     if bit_width == 32:
@@ -25,6 +25,8 @@ def _quantize_with_codes(x, bit_width, pre=None):
         return x, None
     if 2 <= bit_width <= 8:
         kind = L.CODES_I8 if bit_width <= 7 else L.CODES_U8
+        if bit_width == 2:
+            kind = eng.int_codes_kind(x, 2)      # codes 0..3 are exact e2m1 values
         y, tag = ops.quant_act(x, L.Q_DOREFA, bit_width=bit_width, want_y=full, codes_kind=kind,
                                want_row_sum=(x.dim() == 2), kind="dorefa", pre=pre)
         tag.scale = _f32(1.0) / _f32(2 ** bit_width - 1)

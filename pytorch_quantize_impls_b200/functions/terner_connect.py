@@ -17,7 +17,7 @@ class TernaryConnectDeterministic(TaggingFunction):
     def forward(ctx, input):
         ctx.save_for_backward(input)
         full = eng.want_fp32_result(input)
-        y, tag = ops.quant_act(input, L.Q_TERNARY, want_y=full, codes_kind=L.CODES_I8, kind="ternary")
+        y, tag = ops.quant_act(input, L.Q_TERNARY, want_y=full, codes_kind=eng.int_codes_kind(input), kind="ternary")
         TaggingFunction._leave(tag)
         return y if full else eng.placeholder_like(input)
 

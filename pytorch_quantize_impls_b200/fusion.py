@@ -90,10 +90,10 @@ class FusedBNActQuant(nn.Module):
         if kind == "dorefa":
             y, tag = _quantize_with_codes(x, arg, pre=pre)
         elif kind == "sign":
-            y, tag = ops.quant_act(x, L.Q_SIGN, want_y=full, codes_kind=L.CODES_I8, want_bits=(x.dim() == 2), kind="sign", pre=pre)
+            y, tag = ops.quant_act(x, L.Q_SIGN, want_y=full, codes_kind=eng.int_codes_kind(x), want_bits=(x.dim() == 2), kind="sign", pre=pre)
             y = y if full else eng.placeholder_like(x)
         elif kind == "ternary":
-            y, tag = ops.quant_act(x, L.Q_TERNARY, want_y=full, codes_kind=L.CODES_I8, kind="ternary", pre=pre)
+            y, tag = ops.quant_act(x, L.Q_TERNARY, want_y=full, codes_kind=eng.int_codes_kind(x), kind="ternary", pre=pre)
             y = y if full else eng.placeholder_like(x)
         elif kind == "xnor" and x.dim() == 2:
             y, tag = ops.quant_act(x, L.Q_XNOR_ROW, want_y=full, codes_kind=eng.xnor_codes_kind(), want_row_scale=True,

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(Q):
     h = _lib.lib()
     for name in declared:
         assert hasattr(h, name), name
-    assert h.qt_version() == 100
+    assert h.qt_version() >= 101
     assert h.qt_launch_count(0) == 0
 
 
