@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QT_VERSION 101
+#define QT_VERSION 102
 
 enum {
   QT_OK = 0,
@@ -200,6 +200,37 @@ int qt_im2col(const QtIm2col* p, void* stream);
  *                              output channels (a conv group writes at out + group_offset * P)
  * acc_out (optional, integer kernels) receives the raw int32 accumulators [M, N] row major.
  * ---------------------------------------------------------------------- */
+/* Optional fused re-quantisation of the layer output (the inter-layer pattern every reference net repeats:
+ *   quantized linear/conv -> [BatchNorm (eval)] -> [Hardtanh / ReLU] -> activation quantizer -> next quantized layer,
+ * benchmark/BinaryNet/MLPBin.py:42-53, AlexNetBin.py:13-48, models/samples/AlexNet_Dorefa.py:46-84).  The tcgen05 epilogue
+ * applies  y' = clamp(y, lo, hi)  (the caller folds the BatchNorm affine into col_scale / bias) and the quantizer `mode`
+ * to the fp32 value y it just produced, and writes the NEXT layer's low-bit operand instead of (or besides) the fp32
+ * tensor: the hidden activation never exists in fp32 in HBM.
+ *   codes[m, n]  row-major [M, ld_codes]: for a linear layer that is the next layer's [rows, K] operand, for a conv layer
+ *                (m = (b, oh, ow), n = output channel) it is the channels-last [B, OH, OW, C] code tensor qt_conv_i8 reads.
+ *   QT_Q_XNOR_ROW needs the mean of y' over the whole row, which no single tile sees: the epilogue writes partial row
+ *   sums  row_part[p * M + m]  (p = index of the 32-column chunk group that produced it, row_parts of them in total; the
+ *   library stores the count in row_parts) and the consumer sums them in a fixed order (QtEpilogue.row_scale_parts /
+ *   row_scale_mul = 1/N): deterministic, no atomics.  row_sum_part does the same for the integer code sums the unsigned
+ *   DoReFa-8 weight zero point needs.
+ * Only the tcgen05 kernels implement it; other routes return QT_EUNSUPPORTED when `requant` is set. */
+typedef struct QtRequant {
+  int mode;             /* QT_Q_SIGN, QT_Q_TERNARY, QT_Q_DOREFA or QT_Q_XNOR_ROW */
+  int bit_width;        /* DoReFa k (2..8) */
+  void* codes;          /* [M, ld_codes] */
+  int codes_kind;       /* 1 int8, 2 uint8, 3 bf16, 5 fp16, 7 fp4 (e2m1, two per byte) -- as QtActQuant.codes_kind */
+  int64_t ld_codes;     /* ELEMENTS; multiple of 32 and >= N rounded up to 32; columns N..round_up(N,32)-1 are zero-filled */
+  int clamp;            /* 1: y' = min(max(y, lo), hi) before the quantizer */
+  float lo, hi;
+  float* row_part;      /* QT_Q_XNOR_ROW: [>= qt_requant_max_parts(N), M] partial sums of y' */
+  int32_t* row_sum_part;/* optional: [>= qt_requant_max_parts(N), M] partial sums of the integer codes */
+  int row_parts;        /* OUT: number of partial rows written */
+  int32_t* overflow;    /* optional sticky device flag (a DoReFa code left its lane) */
+} QtRequant;
+
+/* upper bound on QtRequant.row_parts for an N-column output */
+int qt_requant_max_parts(int64_t N);
+
 typedef struct QtEpilogue {
   const float* bias;      /* [N] or NULL */
   const float* row_scale; /* [M] or NULL */
@@ -212,6 +243,12 @@ typedef struct QtEpilogue {
   int out_mode;
   int64_t nchw_inner;
   int32_t* acc_out;
+  /* ---- fused inter-layer chain (all optional; zero-initialise when unused) ---- */
+  QtRequant* requant;     /* NULL: none.  With a requant, `out` may be NULL (code-only chain) */
+  int row_scale_parts;    /* > 0: row_scale is [row_scale_parts, M] partial sums written by a previous layer's requant;
+                             the effective row scale is row_scale_mul * sum_p row_scale[p * M + m] */
+  float row_scale_mul;
+  int row_sum_parts;      /* > 0: row_sum is [row_sum_parts, M] partial sums, summed the same way */
 } QtEpilogue;
 
 /* 1-bit x 1-bit: acc = K - 2 popc(a ^ w).  CUDA-core XNOR + popcount. */

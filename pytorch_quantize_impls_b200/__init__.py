@@ -11,7 +11,7 @@ from . import functions, layers  # noqa: F401
 from . import BinaryNet, DorefaNet, LogLinNet, TernerNet, XnorNet  # noqa: F401
 from ._engine import code_only_activations, set_backend, set_implicit_conv, set_xnor_mode  # noqa: F401
 from ._ops import device_caps, set_strict  # noqa: F401
-from .fusion import FusedBNActQuant, fuse_inference  # noqa: F401
+from .fusion import FusedBNActQuant, FusedLayerQuant, fuse_inference  # noqa: F401
 from .device import device  # noqa: F401
 
 __version__ = '0.1'

@@ -139,12 +139,14 @@ def attach_tag(y, tag):
 
 class _A:
     """Activation operand handed to the contraction."""
-    __slots__ = ("form", "t", "ld", "signed", "scale", "row_sum", "row_scale", "planes", "bits", "ld_bits")
+    __slots__ = ("form", "t", "ld", "signed", "scale", "row_sum", "row_scale", "planes", "bits", "ld_bits",
+                 "row_parts", "row_mul")
 
 
 def _a_from_tag(tag):
     a = _A()
     a.scale, a.row_sum, a.row_scale, a.bits, a.ld_bits = tag.scale, tag.row_sum, tag.row_scale, tag.bits, tag.ld_bits
+    a.row_parts, a.row_mul = tag.row_parts, tag.row_mul
     a.t, a.ld = tag.codes, tag.ld
     if tag.codes_kind in (L.CODES_I8, L.CODES_U8):
         a.form, a.signed, a.planes = "i8", tag.codes_kind == L.CODES_I8, 1
@@ -180,15 +182,108 @@ def _a_split(x2d):
     return _a_from_tag(tag)
 
 
+class RequantUnsupported(RuntimeError):
+    """The fused requant epilogue cannot serve this call (shape / backend); callers run the unfused composition."""
+
+
+class RequantSpec:
+    """What a fused `layer -> [BatchNorm] -> [clamp] -> activation quantizer` chain asks of the layer's epilogue.
+
+    mode, bit_width, kind   the quantizer (L.Q_*, DoReFa k, ActCodes.kind)
+    lo, hi                  clamp in front of it (None: none)
+    col_mul, col_add        folded BatchNorm affine per output column: y' = y * col_mul + col_add (None: identity)
+    """
+
+    def __init__(self, mode, kind, bit_width=0, lo=None, hi=None, col_mul=None, col_add=None):
+        self.mode, self.kind, self.bit_width, self.lo, self.hi = mode, kind, bit_width, lo, hi
+        self.col_mul, self.col_add = col_mul, col_add
+        self.force_8bit = False      # the consumer of the codes cannot read e2m1 operands
+        self._fold = {}
+
+    def fold(self, col_scale, bias, n0, n):
+        """(col_scale', bias') with the BatchNorm affine folded in: y*m + a = acc*(cs*m) + (b*m + a).  Cached per operand."""
+        if self.col_mul is None:
+            return col_scale, bias
+        key = tuple(None if t is None else (t.data_ptr(), t._version) for t in (col_scale, bias, self.col_mul, self.col_add)) + (n0, n)
+        hit = self._fold.get(key)
+        if hit is None:
+            m, ad = self.col_mul[n0:n0 + n], self.col_add[n0:n0 + n]
+            cs = m.contiguous() if col_scale is None else (col_scale * m).contiguous()
+            b = ad.contiguous() if bias is None else (bias * m + ad).contiguous()
+            if len(self._fold) > 8:
+                self._fold.clear()
+            hit = self._fold[key] = (cs, b, col_scale, bias)     # keep the sources alive: the key holds their pointers
+        return hit[0], hit[1]
+
+    def codes_kind(self, two_d):
+        if self.mode == L.Q_XNOR_ROW:
+            return xnor_codes_kind()
+        f4 = _fp4[0] and two_d and not self.force_8bit and _force_backend["i8"] != L.BACKEND_SIMT
+        if self.mode == L.Q_DOREFA:
+            if f4 and self.bit_width <= 2:
+                return L.CODES_F4
+            return L.CODES_U8 if self.bit_width == 8 else L.CODES_I8
+        return L.CODES_F4 if f4 else L.CODES_I8
+
+
+def _requant_tag(spec, rq, shape, layout="rows"):
+    """ActCodes describing what a requant epilogue wrote."""
+    tag = ops.ActCodes()
+    tag.kind, tag.bit_width = spec.kind, spec.bit_width
+    tag.codes, tag.codes_kind, tag.rows, tag.cols, tag.ld = rq.codes, rq.codes_kind, rq.rows, rq.cols, rq.ld
+    tag.scale = 1.0
+    if spec.mode == L.Q_DOREFA:
+        import numpy as np
+        tag.scale = float(np.float32(1.0) / np.float32(2 ** spec.bit_width - 1))
+    tag.row_sum, tag.row_scale, tag.bits, tag.ld_bits = rq.row_sum_part, rq.row_part, None, 0
+    tag.row_parts = rq.row_parts if (rq.row_sum_part is not None or rq.row_part is not None) else 0
+    tag.row_mul = 1.0 / max(rq.cols, 1)
+    tag.overflow, tag.shape, tag.version, tag.layout = rq.overflow, tuple(shape), None, layout
+    return tag
+
+
 def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=None, nchw_inner=1, out_offset=0,
-              acc_out=None):
-    """One GEMM launch (plus the transient weight expansion) for N output columns starting at weight row w_row0."""
+              acc_out=None, requant=None, rq_spec=None):
+    """One GEMM launch (plus the transient weight expansion) for N output columns starting at weight row w_row0.
+    requant: ops.RequantOut receiving the next layer's operand (rq_spec: its RequantSpec, for the BatchNorm fold)."""
+    try:
+        return _contract_impl(a, pack, M, N, K, out, w_row0=w_row0, bias=bias, out_mode=out_mode, ldo=ldo,
+                              nchw_inner=nchw_inner, out_offset=out_offset, acc_out=acc_out, requant=requant, rq_spec=rq_spec)
+    except L.QtError as err:
+        if "(code -3)" not in str(err):
+            raise
+        if requant is not None:
+            raise RequantUnsupported(str(err))
+        if a.row_parts == 0:
+            raise
+    # the operand came from a requant epilogue (partial row sums) but this contraction runs on a CUDA-core route (tiny or
+    # unaligned shape): collapse the partial sums into plain row vectors and run again
+    b = _A()
+    for f in _A.__slots__:
+        if hasattr(a, f):
+            setattr(b, f, getattr(a, f))
+    if a.row_scale is not None:
+        b.row_scale = (a.row_scale[:a.row_parts].sum(0) * a.row_mul).contiguous()
+    if a.row_sum is not None:
+        b.row_sum = a.row_sum[:a.row_parts].sum(0).to(torch.int32).contiguous()
+    b.row_parts, b.row_mul = 0, 1.0
+    return _contract_impl(b, pack, M, N, K, out, w_row0=w_row0, bias=bias, out_mode=out_mode, ldo=ldo,
+                          nchw_inner=nchw_inner, out_offset=out_offset, acc_out=acc_out)
+
+
+def _contract_impl(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=None, nchw_inner=1, out_offset=0,
+                   acc_out=None, requant=None, rq_spec=None):
     ldo = N if ldo is None else ldo
     col_scale = None if pack.col_scale is None else pack.col_scale[w_row0:w_row0 + N]
     int_w = pack.kind in ("sign", "ternary", "dorefa")
+    rp = dict(row_parts=a.row_parts, row_mul=a.row_mul, requant=requant)
+
+    def folded(cs, b):
+        return rq_spec.fold(cs, b, w_row0, N) if rq_spec is not None else (cs, b)
 
     if a.form in ("i8", "f4") and int_w:
         use_pop = (a.bits is not None and pack.kind in ("sign", "ternary") and a.scale == 1.0 and out_mode == 0
+                   and requant is None and a.row_parts == 0
                    and (_force_popcount[0] or (M <= POPCOUNT_MAX_M and _force_backend["i8"] == L.BACKEND_AUTO)))
         if use_pop:
             epi = ops.make_epi(out, ldo=ldo, bias=bias, scale=1.0, acc_out=acc_out, out_offset=out_offset)
@@ -202,8 +297,9 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
         if a.form == "f4":
             # e2m1 codes x e2m1 centred weight codes: tcgen05 kind::mxf4, unit scales, exact integer accumulators
             w, ldw = ops.expand_weight(pack, L.CODES_F4)
-            epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
-                               scale=a.scale, acc_out=acc_out, out_offset=out_offset)
+            cs, b = folded(col_scale, bias)
+            epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=b, col_scale=cs,
+                               scale=a.scale, acc_out=acc_out, out_offset=out_offset, **rp)
             ops.gemm_f4(a.t, a.ld, w[w_row0:], ldw, M, N, K, epi)
             return
         if pack.kind == "dorefa" and pack.bit_width == 8:
@@ -211,14 +307,16 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
             w, ldw = ops.expand_weight(pack, L.CODES_U8)
             if a.row_sum is None:
                 raise RuntimeError("internal: 8-bit DoReFa weights need activation row sums")
-            epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
+            cs, b = folded(col_scale, bias)
+            epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=b, col_scale=cs,
                                row_sum=a.row_sum, scale=a.scale, acc_mul=2, rs_mul=-255, acc_out=acc_out,
-                               out_offset=out_offset)
+                               out_offset=out_offset, **rp)
             ops.gemm_i8(a.t, a.signed, a.ld, w[w_row0:], False, ldw, M, N, K, epi, _force_backend["i8"])
             return
         w, ldw = ops.expand_weight(pack, L.CODES_I8)
-        epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
-                           scale=a.scale, acc_out=acc_out, out_offset=out_offset)
+        cs, b = folded(col_scale, bias)
+        epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=b, col_scale=cs,
+                           scale=a.scale, acc_out=acc_out, out_offset=out_offset, **rp)
         ops.gemm_i8(a.t, a.signed, a.ld, w[w_row0:], True, ldw, M, N, K, epi, _force_backend["i8"])
         return
 
@@ -231,8 +329,9 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
             col_scale = pack.alpha_max[w_row0:w_row0 + N]
         else:
             raise RuntimeError("internal: fp16 activation codes cannot meet a real-valued weight operand")
-        epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
-                           row_scale=a.row_scale, scale=a.scale, out_offset=out_offset)
+        cs, b = folded(col_scale, bias)
+        epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=b, col_scale=cs,
+                           row_scale=a.row_scale, scale=a.scale, out_offset=out_offset, **rp)
         ops.gemm_f16(a.t, a.ld, 0, w[0, w_row0:], ldw, w.stride(0), [(0, 0)], M, N, K, epi, _force_backend["bf16"],
                      fmt=L.FMT_FP16)
         return
@@ -253,13 +352,16 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
         passes += [(i, 1) for i in range(min(a.planes, 2))]
     a_stride = a.t.stride(0) if a.t.dim() == 3 else 0
     w_stride = w.stride(0)
-    epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=bias, col_scale=col_scale,
-                       row_scale=a.row_scale, scale=a.scale, out_offset=out_offset)
+    cs, b = folded(col_scale, bias)
+    epi = ops.make_epi(out, ldo=ldo, out_mode=out_mode, nchw_inner=nchw_inner, bias=b, col_scale=cs,
+                       row_scale=a.row_scale, scale=a.scale, out_offset=out_offset, **rp)
     ops.gemm_f16(a.t, a.ld, a_stride, w[0, w_row0:], ldw, w_stride, passes, M, N, K, epi, _force_backend["bf16"])
 
 
-def linear(x, pack, bias):
-    """F.linear(x, W_q, bias) with W_q given as a WeightPack.  x: [..., K] fp32 CUDA tensor."""
+def linear(x, pack, bias, requant=None):
+    """F.linear(x, W_q, bias) with W_q given as a WeightPack.  x: [..., K] fp32 CUDA tensor.
+    requant (RequantSpec): fused inference chain -- the epilogue writes the next layer's low-bit operand and the
+    fp32 output is never materialised; returns a code-only placeholder carrying that operand."""
     dev = tagged_input_device(x)
     K, N = pack.k, pack.n
     if x.shape[-1] != K:
@@ -268,7 +370,9 @@ def linear(x, pack, bias):
     tag = get_tag(x) if x.dim() == 2 else None
     x2d = None if x.is_meta else ops.as_f32c(x).reshape(-1, K)
     M = x.numel() // K
-    out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    if requant is not None and (x.dim() != 2 or M == 0):
+        raise RequantUnsupported("fused requant needs a non-empty 2-D input")
+    out = None if requant is not None else torch.empty((M, N), dtype=torch.float32, device=dev)
     if M == 0:
         return out.reshape(*lead, N)
     int_w = pack.kind in ("sign", "ternary", "dorefa")
@@ -289,6 +393,12 @@ def linear(x, pack, bias):
         a = _a_split(x2d)
     if bias is not None:
         bias = ops.as_f32c(bias)
+    if requant is not None:
+        rq = ops.RequantOut(requant.mode, requant.bit_width, requant.codes_kind(True), M, N, dev, lo=requant.lo,
+                            hi=requant.hi, want_row_sum=(requant.mode == L.Q_DOREFA))
+        _contract(a, pack, M, N, K, None, bias=bias, requant=rq, rq_spec=requant)
+        y = torch.empty((M, N), dtype=torch.float32, device="meta")
+        return attach_tag(y, _requant_tag(requant, rq, (M, N)))
     _contract(a, pack, M, N, K, out, bias=bias)
     return out.reshape(*lead, N)
 
@@ -297,8 +407,10 @@ def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
 
-def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
-    """F.conv2d(x, W_q, bias, stride, padding, dilation, groups) via im2col gather + GEMM with an NCHW epilogue."""
+def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requant=None):
+    """F.conv2d(x, W_q, bias, stride, padding, dilation, groups) via im2col gather + GEMM with an NCHW epilogue.
+    requant (RequantSpec): the implicit-GEMM epilogue writes the next conv's channels-last codes [B, OH, OW, O] instead of
+    the fp32 NCHW tensor (raises RequantUnsupported when the call cannot take the implicit-GEMM route)."""
     dev = tagged_input_device(x)
     if x.dim() != 4:
         raise RuntimeError("expected a 4-D NCHW input, got %d-D" % x.dim())
@@ -320,7 +432,9 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
         ph, pw = _pair(padding)
     OH = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
     OW = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
-    out = torch.empty((B, O, max(OH, 0), max(OW, 0)), dtype=torch.float32, device=dev)
+    if requant is not None and (B == 0 or OH <= 0 or OW <= 0 or groups != 1 or O % 32 != 0 or requant.mode == L.Q_XNOR_ROW):
+        raise RequantUnsupported("fused conv requant needs groups == 1, out_channels % 32 == 0 and a non-empty output")
+    out = None if requant is not None else torch.empty((B, O, max(OH, 0), max(OW, 0)), dtype=torch.float32, device=dev)
     if B == 0 or OH <= 0 or OW <= 0:
         return out
     Ng, Kg, P = O // groups, Cg * kh * kw, OH * OW
@@ -343,17 +457,31 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
         w, ldw = ops.expand_weight(pack, L.CODES_U8 if need_rs else L.CODES_I8)
         col_scale = pack.col_scale
         done = True
+        rq = None
+        if requant is not None:
+            rq = ops.RequantOut(requant.mode, requant.bit_width, requant.codes_kind(False), B * P, O, dev, lo=requant.lo,
+                                hi=requant.hi, ld=O,
+                                codes=torch.empty((B, OH, OW, O), device=dev,
+                                                  dtype=torch.uint8 if requant.codes_kind(False) == L.CODES_U8 else torch.int8))
         for g in range(groups):
             rs = ops.patch_rowsum(tag.codes, not a_signed, geom, g) if need_rs else None
-            epi = ops.make_epi(out, ldo=O, out_mode=1, nchw_inner=P, bias=None if bias is None else bias[g * Ng:(g + 1) * Ng],
-                               col_scale=None if col_scale is None else col_scale[g * Ng:(g + 1) * Ng],
+            cs = None if col_scale is None else col_scale[g * Ng:(g + 1) * Ng]
+            bg = None if bias is None else bias[g * Ng:(g + 1) * Ng]
+            if requant is not None:
+                cs, bg = requant.fold(cs, bg, g * Ng, Ng)
+            epi = ops.make_epi(out, ldo=O, out_mode=1, nchw_inner=P, bias=bg, col_scale=cs,
                                row_sum=rs, acc_mul=2 if need_rs else 1, rs_mul=-255 if need_rs else 0,
-                               scale=tag.scale, out_offset=g * Ng * P)
+                               scale=tag.scale, out_offset=g * Ng * P, requant=rq)
             if not ops.conv_i8(tag.codes, a_signed, geom, g, w[g * Ng:], not need_rs, ldw, Ng, epi):
                 done = False
                 break
         if done:
+            if requant is not None:
+                y = torch.empty((B, O, OH, OW), dtype=torch.float32, device="meta")
+                return attach_tag(y, _requant_tag(requant, rq, (B, O, OH, OW), layout="nhwc"))
             return out
+    if requant is not None:
+        raise RequantUnsupported("fused conv requant needs the implicit-GEMM route (channels-last 8-bit codes in, C/groups % 32 == 0)")
 
     xf = None
     if tag is not None:
@@ -375,6 +503,7 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups):
         for g in range(groups):
             a = _A()
             a.bits, a.ld_bits, a.row_scale, a.row_sum = None, 0, None, None
+            a.row_parts, a.row_mul = 0, 1.0
             a.ld = ld
             buf = torch.empty((nplanes, M, ld), dtype=dtype, device=dev)
             if tag is not None:

@@ -58,16 +58,25 @@ class QtConvGeom(C.Structure):
                 ("dil_h", i32), ("dil_w", i32), ("groups", i32), ("group", i32), ("OH", i64), ("OW", i64)]
 
 
+class QtRequant(C.Structure):
+    _fields_ = [("mode", i32), ("bit_width", i32), ("codes", vp), ("codes_kind", i32), ("ld_codes", i64),
+                ("clamp", i32), ("lo", f32), ("hi", f32), ("row_part", vp), ("row_sum_part", vp),
+                ("row_parts", i32), ("overflow", vp)]
+
+
 class QtEpilogue(C.Structure):
     _fields_ = [("bias", vp), ("row_scale", vp), ("col_scale", vp), ("row_sum", vp),
                 ("scale", f32), ("acc_mul", C.c_int32), ("rs_mul", C.c_int32),
-                ("out", vp), ("ldo", i64), ("out_mode", i32), ("nchw_inner", i64), ("acc_out", vp)]
+                ("out", vp), ("ldo", i64), ("out_mode", i32), ("nchw_inner", i64), ("acc_out", vp),
+                ("requant", C.POINTER(QtRequant)), ("row_scale_parts", i32), ("row_scale_mul", f32),
+                ("row_sum_parts", i32)]
 
 
 # every symbol include/qtb200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qt_version": (i32, []),
     "qt_last_error": (C.c_char_p, []),
+    "qt_requant_max_parts": (i32, [i64]),
     "qt_device_caps": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "qt_quant_act": (i32, [C.POINTER(QtActQuant), vp]),
     "qt_pack_weight": (i32, [C.POINTER(QtWeightPack), vp]),

@@ -53,7 +53,9 @@ class ActCodes:
     shape       shape of the fp32 tensor the codes describe (e.g. NCHW)
     """
     __slots__ = ("kind", "bit_width", "codes", "codes_kind", "rows", "cols", "ld", "scale", "row_sum",
-                 "row_scale", "bits", "ld_bits", "overflow", "shape", "version", "layout")
+                 "row_scale", "bits", "ld_bits", "overflow", "shape", "version", "layout", "row_parts", "row_mul")
+    # row_parts > 0: the operand was written by a fused requant epilogue; row_scale / row_sum are [row_parts, rows]
+    # partial sums and the consumer epilogue uses  row_mul * sum_p row_scale[p]  /  sum_p row_sum[p]
 
     def check(self):
         if self.overflow is not None and int(self.overflow.item()) != 0:
@@ -131,6 +133,7 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
         tag.scale = 1.0
         tag.row_sum, tag.row_scale, tag.bits, tag.ld_bits = row_sum, row_scale, bits, ldb
         tag.overflow, tag.shape, tag.version, tag.layout = overflow, shape, None, layout
+        tag.row_parts, tag.row_mul = 0, 1.0
         if _strict:
             tag.check()
     return y, tag
@@ -269,14 +272,66 @@ def im2col(x4d, elem_bytes, geom, group, out, ld_out, row_sum=None, is_unsigned=
 
 
 def make_epi(out, *, ldo, out_mode=0, nchw_inner=1, bias=None, row_scale=None, col_scale=None, row_sum=None,
-             scale=1.0, acc_mul=1, rs_mul=0, acc_out=None, out_offset=0):
+             scale=1.0, acc_mul=1, rs_mul=0, acc_out=None, out_offset=0, row_parts=0, row_mul=1.0, requant=None):
+    """requant: a RequantOut (fused re-quantisation of the output); row_parts > 0: row_scale / row_sum are partial sums
+    left by a previous layer's requant epilogue."""
     e = L.QtEpilogue()
     e.bias, e.row_scale, e.col_scale, e.row_sum = _p(bias), _p(row_scale), _p(col_scale), _p(row_sum)
     e.scale, e.acc_mul, e.rs_mul = float(scale), int(acc_mul), int(rs_mul)
     e.out = None if out is None else C.c_void_p(out.data_ptr() + 4 * out_offset)
     e.ldo, e.out_mode, e.nchw_inner = ldo, out_mode, nchw_inner
     e.acc_out = _p(acc_out)
+    if row_parts > 0:
+        if row_scale is not None:
+            e.row_scale_parts, e.row_scale_mul = int(row_parts), float(row_mul)
+        if row_sum is not None:
+            e.row_sum_parts = int(row_parts)
+    if requant is not None:
+        e.requant = C.pointer(requant.c)
+        e._keep = requant        # keep the ctypes struct alive as long as the epilogue
     return e
+
+
+class RequantOut:
+    """Output operand of a fused requant epilogue (include/qtb200.h QtRequant): the next layer's low-bit codes,
+    written by the tcgen05 epilogue instead of the fp32 activation.
+
+    mode/bit_width/codes_kind as qt_quant_act; lo/hi: clamp in front of the quantizer (None: no clamp);
+    rows x cols: logical shape of the codes ([M, N] of the producing GEMM); `codes` may be passed in (conv groups write
+    column slices of one channels-last tensor)."""
+
+    def __init__(self, mode, bit_width, codes_kind, rows, cols, dev, lo=None, hi=None, want_row_sum=False, codes=None,
+                 ld=None, col_offset=0):
+        self.mode, self.bit_width, self.codes_kind, self.rows, self.cols = mode, bit_width, codes_kind, rows, cols
+        self.ld = round_up(max(cols, 1), 32) if ld is None else ld
+        if codes is None:
+            if codes_kind == L.CODES_F4:
+                codes = torch.empty((rows, self.ld // 2), dtype=torch.uint8, device=dev)
+            elif codes_kind in (L.CODES_I8, L.CODES_U8):
+                codes = torch.empty((rows, self.ld), dtype=torch.int8 if codes_kind == L.CODES_I8 else torch.uint8, device=dev)
+            elif codes_kind == L.CODES_F16:
+                codes = torch.empty((rows, self.ld), dtype=torch.float16, device=dev)
+            elif codes_kind == L.CODES_BF16:
+                codes = torch.empty((rows, self.ld), dtype=torch.bfloat16, device=dev)
+            else:
+                raise ValueError("RequantOut: unsupported codes_kind %r" % (codes_kind,))
+        self.codes = codes
+        cap = int(L.lib().qt_requant_max_parts(cols))
+        self.row_part = torch.empty((cap, rows), dtype=torch.float32, device=dev) if mode == L.Q_XNOR_ROW else None
+        self.row_sum_part = torch.empty((cap, rows), dtype=torch.int32, device=dev) if want_row_sum else None
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev) if mode == L.Q_DOREFA else None
+        c = L.QtRequant()
+        c.mode, c.bit_width, c.codes_kind, c.ld_codes = mode, bit_width, codes_kind, self.ld
+        elem_num, elem_den = {L.CODES_F4: (1, 2), L.CODES_I8: (1, 1), L.CODES_U8: (1, 1)}.get(codes_kind, (2, 1))
+        c.codes = C.c_void_p(codes.data_ptr() + col_offset * elem_num // elem_den)
+        c.clamp = 0 if lo is None else 1
+        c.lo, c.hi = (0.0, 0.0) if lo is None else (float(lo), float(hi))
+        c.row_part, c.row_sum_part, c.overflow = _p(self.row_part), _p(self.row_sum_part), _p(self.overflow)
+        self.c = c
+
+    @property
+    def row_parts(self):
+        return int(self.c.row_parts)
 
 
 def gemm_b1b1(a_bits, lda, w_bits, ldw, M, N, K, epi):

@@ -17,7 +17,23 @@ void count_launch(int n) { g_launches += n; }
 
 int check_epi(const QtEpilogue* e, int64_t M, int64_t N) {
   QT_REQUIRE(e != nullptr, "epilogue is NULL");
-  QT_REQUIRE(e->out != nullptr || e->acc_out != nullptr, "epilogue: neither out nor acc_out given");
+  QT_REQUIRE(e->out != nullptr || e->acc_out != nullptr || e->requant != nullptr, "epilogue: neither out, acc_out nor requant given");
+  QT_REQUIRE(e->row_scale_parts >= 0 && e->row_sum_parts >= 0, "epilogue: negative partial-sum count");
+  QT_REQUIRE(e->row_scale_parts == 0 || e->row_scale != nullptr, "epilogue: row_scale_parts without row_scale");
+  QT_REQUIRE(e->row_sum_parts == 0 || e->row_sum != nullptr, "epilogue: row_sum_parts without row_sum");
+  if (const QtRequant* r = e->requant) {
+    QT_REQUIRE(r->mode == QT_Q_SIGN || r->mode == QT_Q_TERNARY || r->mode == QT_Q_DOREFA || r->mode == QT_Q_XNOR_ROW,
+               "requant: mode must be QT_Q_SIGN, QT_Q_TERNARY, QT_Q_DOREFA or QT_Q_XNOR_ROW");
+    QT_REQUIRE(r->mode != QT_Q_DOREFA || (r->bit_width >= 2 && r->bit_width <= 8), "requant: DoReFa bit width must be 2..8");
+    QT_REQUIRE(r->codes != nullptr, "requant: codes is NULL");
+    QT_REQUIRE(r->codes_kind == 1 || r->codes_kind == 2 || r->codes_kind == 3 || r->codes_kind == 5 || r->codes_kind == 7,
+               "requant: codes_kind must be 1 (int8), 2 (uint8), 3 (bf16), 5 (fp16) or 7 (fp4)");
+    QT_REQUIRE(r->codes_kind != 7 || r->mode == QT_Q_SIGN || r->mode == QT_Q_TERNARY || (r->mode == QT_Q_DOREFA && r->bit_width == 2) ||
+               r->mode == QT_Q_XNOR_ROW, "requant: fp4 codes hold integers in [-4, 4] only");
+    QT_REQUIRE(r->ld_codes % 32 == 0 && r->ld_codes >= (N + 31) / 32 * 32, "requant: ld_codes must be a multiple of 32 and >= N rounded up to 32");
+    QT_REQUIRE((reinterpret_cast<uintptr_t>(r->codes) & 15) == 0, "requant: codes must be 16-byte aligned");
+    QT_REQUIRE(r->mode != QT_Q_XNOR_ROW || r->row_part != nullptr, "requant: QT_Q_XNOR_ROW needs row_part");
+  }
   QT_REQUIRE(e->out_mode == 0 || e->out_mode == 1, "epilogue: out_mode must be 0 or 1");
   if (e->out && e->out_mode == 0) QT_REQUIRE(e->ldo >= N, "epilogue: ldo (%lld) < N (%lld)", (long long)e->ldo, (long long)N);
   if (e->out && e->out_mode == 1)
@@ -30,6 +46,8 @@ int check_epi(const QtEpilogue* e, int64_t M, int64_t N) {
 extern "C" {
 
 int qt_version(void) { return QT_VERSION; }
+
+int qt_requant_max_parts(int64_t N) { return (int)(2 * ((N + 127) / 128) + 2); }
 
 const char* qt_last_error(void) { return qt::g_err; }
 

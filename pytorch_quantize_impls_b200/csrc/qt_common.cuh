@@ -55,6 +55,18 @@ struct Epi {
   int64_t nchw_inner;
   int32_t* acc_out;
   int64_t M, N;
+  // fused re-quantisation of the output (QtRequant) and partial-sum row operands (tcgen05 kernels only)
+  int rq_mode;            // -1: none, else QT_Q_SIGN / QT_Q_TERNARY / QT_Q_DOREFA / QT_Q_XNOR_ROW
+  int rq_codes_kind;
+  void* rq_codes;
+  int64_t rq_ld;
+  int rq_clamp;
+  float rq_lo, rq_hi, rq_n;
+  float* rq_row_part;
+  int32_t* rq_row_sum_part;
+  int32_t* rq_overflow;
+  int row_scale_parts, row_sum_parts;
+  float row_scale_mul;
 };
 
 static inline Epi make_epi(const QtEpilogue* e, int64_t M, int64_t N) {
@@ -63,10 +75,21 @@ static inline Epi make_epi(const QtEpilogue* e, int64_t M, int64_t N) {
   d.scale = e->scale; d.acc_mul = e->acc_mul; d.rs_mul = e->rs_mul;
   d.out = e->out; d.ldo = e->ldo; d.out_mode = e->out_mode; d.nchw_inner = e->nchw_inner;
   d.acc_out = e->acc_out; d.M = M; d.N = N;
+  d.rq_mode = -1; d.rq_codes_kind = 0; d.rq_codes = nullptr; d.rq_ld = 0; d.rq_clamp = 0; d.rq_lo = d.rq_hi = 0.f; d.rq_n = 1.f;
+  d.rq_row_part = nullptr; d.rq_row_sum_part = nullptr; d.rq_overflow = nullptr;
+  if (const QtRequant* r = e->requant) {
+    d.rq_mode = r->mode; d.rq_codes_kind = r->codes_kind; d.rq_codes = r->codes; d.rq_ld = r->ld_codes;
+    d.rq_clamp = r->clamp; d.rq_lo = r->lo; d.rq_hi = r->hi;
+    d.rq_n = (r->mode == QT_Q_DOREFA) ? (float)((1u << r->bit_width) - 1u) : 1.f;
+    d.rq_row_part = r->row_part; d.rq_row_sum_part = r->row_sum_part; d.rq_overflow = r->overflow;
+  }
+  d.row_scale_parts = e->row_scale_parts; d.row_sum_parts = e->row_sum_parts; d.row_scale_mul = e->row_scale_mul;
   return d;
 }
 
 int check_epi(const QtEpilogue* e, int64_t M, int64_t N);
+// true when the epilogue asks for something only the tcgen05 kernels implement (requant, partial-sum row operands)
+static inline bool epi_needs_tc(const Epi& e) { return e.rq_mode >= 0 || e.row_scale_parts > 0 || e.row_sum_parts > 0; }
 
 // y = float(acc_mul*acc + rs_mul*row_sum[m]) * scale * row_scale[m] * col_scale[n] + bias[n]
 // The integer part is exact; float(t) * 1.0f + bias is a single rounding, which is what makes the

@@ -193,6 +193,10 @@ __global__ void __launch_bounds__(NTHREADS) simt_gemm_kernel(SimtArgs g) {
 template <typename Op>
 static int launch_simt(SimtArgs& g, cudaStream_t stream) {
   if (g.M == 0 || g.N == 0) return QT_OK;
+  if (epi_needs_tc(g.ep)) {
+    set_error("fused requant / partial-sum row operands are implemented by the tcgen05 kernels only");
+    return QT_EUNSUPPORTED;
+  }
   dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM));
   QT_REQUIRE(grid.y <= 65535, "simt gemm: M too large for grid.y");
   simt_gemm_kernel<Op><<<grid, NTHREADS, 0, stream>>>(g);

@@ -164,6 +164,108 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- fused re-quantisation of one 32-column chunk of an output row (QtRequant) ------------------------------------
+// Semantics are those of act_quant_kernel (qt_quantize.cu): safeSign / ternary thresholds / rint(n y) / torch.sign.
+__device__ __forceinline__ float rq_quant(const Epi& e, float v) {
+  switch (e.rq_mode) {
+    case QT_Q_SIGN: return (v < 0.f) ? -1.f : 1.f;
+    case QT_Q_TERNARY: {
+      const float s = (v < 0.f) ? -1.f : 1.f;
+      const float t = v - 0.5f * s;
+      return (s + ((t < 0.f) ? -1.f : 1.f)) * 0.5f;
+    }
+    case QT_Q_DOREFA: return rintf(e.rq_n * v);
+    default: return (float)((v > 0.f) - (v < 0.f));   // QT_Q_XNOR_ROW
+  }
+}
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_global_v2(void* p, uint32_t a, uint32_t b) {
+  asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+// y[0..31]: fp32 outputs of row m, columns n0..n0+31 (valid while n < n_lim).  Writes the codes of columns n0..n0+ncols-1
+// (zeros past n_lim), accumulates the row partial sums.
+__device__ __forceinline__ void rq_store_chunk(const Epi& e, const float (&y)[32], int64_t m, int n0, int n_lim, int ncols,
+                                               float& psum, int& isum, bool& ovf) {
+  float c[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float v = y[j];
+    if (e.rq_clamp) v = fminf(fmaxf(v, e.rq_lo), e.rq_hi);
+    const bool ok = n0 + j < n_lim;
+    float q = rq_quant(e, v);
+    if (e.rq_mode == QT_Q_XNOR_ROW && ok) psum += v;
+    c[j] = ok ? q : 0.f;
+  }
+  const int kind = e.rq_codes_kind;
+  if (kind == 3 || kind == 5) {          // bf16 / fp16 lanes: 64 bytes per row chunk
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (kind == 5) {
+        __half2 h = __floats2half2_rn(c[2 * j], c[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(c[2 * j], c[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    }
+    uint8_t* dst = reinterpret_cast<uint8_t*>(e.rq_codes) + (m * e.rq_ld + n0) * 2;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (8 * q < ncols && n0 + 8 * q < e.rq_ld) st_global_v4(dst + 16 * q, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    return;
+  }
+  // integer lanes
+  int k[32];
+  if (kind == 7) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float v = c[j];
+      if (!(v >= -4.f && v <= 4.f)) { ovf = true; v = (v != v) ? 0.f : fminf(fmaxf(v, -4.f), 4.f); }
+      k[j] = (int)v;
+    }
+  } else {
+    const float lo = (kind == 1) ? -128.f : 0.f, hi = (kind == 1) ? 127.f : 255.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float v = c[j];
+      if (!(v >= lo && v <= hi)) { ovf = true; v = (v != v) ? 0.f : fminf(fmaxf(v, lo), hi); }
+      k[j] = (int)v;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) isum += k[j];
+  if (kind == 7) {                       // e2m1 nibbles: 16 bytes per row chunk, element 2j in the low nibble of byte j
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int v = k[8 * q + j];
+        const int mag = v < 0 ? -v : v;
+        const uint32_t nib = ((0x65420u >> (4 * mag)) & 0xFu) | (v < 0 ? 8u : 0u);
+        acc |= nib << (4 * j);
+      }
+      w[q] = acc;
+    }
+    uint8_t* dst = reinterpret_cast<uint8_t*>(e.rq_codes) + ((m * e.rq_ld + n0) >> 1);
+    if (n0 < e.rq_ld) st_global_v2(dst, w[0], w[1]);
+    if (16 < ncols && n0 + 16 < e.rq_ld) st_global_v2(dst + 8, w[2], w[3]);
+  } else {                               // int8 / uint8 lanes: 32 bytes per row chunk
+    uint32_t w[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      w[q] = (uint32_t)(k[4 * q] & 0xff) | ((uint32_t)(k[4 * q + 1] & 0xff) << 8) | ((uint32_t)(k[4 * q + 2] & 0xff) << 16) |
+             ((uint32_t)(k[4 * q + 3] & 0xff) << 24);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(e.rq_codes) + (m * e.rq_ld + n0);
+    if (n0 < e.rq_ld) st_global_v4(dst, w[0], w[1], w[2], w[3]);
+    if (16 < ncols && n0 + 16 < e.rq_ld) st_global_v4(dst + 16, w[4], w[5], w[6], w[7]);
+  }
+}
+
 template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -325,13 +427,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int32_t rsum = 0;
       int64_t nchw_base = 0;
       if (row_ok) {
-        if (e.row_scale) mul *= __ldg(e.row_scale + m);
-        if (e.row_sum) rsum = e.rs_mul * __ldg(e.row_sum + m);
+        if (e.row_scale) {
+          if (e.row_scale_parts > 0) {     // partial row sums left by the previous layer's requant epilogue, fixed order
+            float rs = 0.f;
+            for (int p = 0; p < e.row_scale_parts; ++p) rs += __ldg(e.row_scale + (int64_t)p * g.M + m);
+            mul *= rs * e.row_scale_mul;
+          } else {
+            mul *= __ldg(e.row_scale + m);
+          }
+        }
+        if (e.row_sum) {
+          int32_t rs = 0;
+          if (e.row_sum_parts > 0) {
+            for (int p = 0; p < e.row_sum_parts; ++p) rs += __ldg(e.row_sum + (int64_t)p * g.M + m);
+          } else {
+            rs = __ldg(e.row_sum + m);
+          }
+          rsum = e.rs_mul * rs;
+        }
         if (e.out_mode == 1) {
           int64_t img = m / e.nchw_inner, r = m - img * e.nchw_inner;
           nchw_base = img * e.ldo * e.nchw_inner + r;
         }
       }
+      float rq_psum = 0.f;
+      int rq_isum = 0;
+      bool rq_ovf = false;
 #pragma unroll 1
       for (int ci = 0; ci < CH_PER_WARP; ++ci) {
         const int cidx = half * CH_PER_WARP + ci;
@@ -358,7 +479,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 0; j < 32; ++j)
             if (n0 + j < n_lim) e.acc_out[m * g.N + n0 + j] = (int32_t)r[j];
         }
-        if (!e.out) continue;
+        if (!e.out && e.rq_mode < 0) continue;
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -370,6 +491,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const float cs = __shfl_sync(0xffffffffu, cs_l, j), bb = __shfl_sync(0xffffffffu, b_l, j);
           y[j] = (v * mul) * cs + bb;
         }
+        if (e.rq_mode >= 0 && row_ok)
+          rq_store_chunk(e, y, m, n0, n_lim, full_chunk ? 32 : (BN - c0), rq_psum, rq_isum, rq_ovf);
+        if (!e.out) continue;
         if (g.tma_store && full_chunk) {
           // registers (one output row per lane) -> 128B-swizzled smem tile -> one bulk tensor store per 32x32 block:
           // every global write is a full 128-byte line; M/N tails are clipped by the tensor map.
@@ -402,6 +526,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 0; j < 32; ++j)
             if (n0 + j < n_lim) o[(int64_t)j * e.nchw_inner] = y[j];   // lanes = consecutive pixels: coalesced per column
         }
+      }
+      if (e.rq_mode >= 0) {
+        // one partial per (N tile, column half): summed in index order by the consumer (deterministic)
+        const int64_t part = (int64_t)(tn * 2 + half) * g.M + m;
+        if (row_ok && e.rq_row_part) e.rq_row_part[part] = rq_psum;
+        if (row_ok && e.rq_row_sum_part) e.rq_row_sum_part[part] = rq_isum;
+        if (rq_ovf && e.rq_overflow) atomicOr(e.rq_overflow, 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -590,6 +721,7 @@ extern "C" int qt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* 
   // instruction descriptor: D = s32 (2 << 4), A/B = s8 (1) or u8 (0) at bits 7 / 10, K-major both, N >> 3 at 17, M >> 4 at 24
   g.idesc = (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((w_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) |
             ((uint32_t)(TC_BM >> 4) << 24);
+  if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
   return dispatch_tc<0>(ma, mw, g, bn, stream);
 }
 
@@ -629,6 +761,7 @@ extern "C" int qt_gemm_f4(const void* a, int64_t lda, const void* w, int64_t ldw
   // block-scaled instruction descriptor: A/B = e2m1 (1) at bits 7 / 10, K-major, N >> 3 at 17, scale format ue8m0 (1) at 23,
   // M >> 4 at 24, scale-factor ids 0, K = 64 per instruction
   g.idesc = (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | (1u << 23) | ((uint32_t)(TC_BM >> 4) << 24);
+  if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
   return dispatch_f4(ma, mw, g, bn, stream);
 }
 
@@ -641,7 +774,7 @@ extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, c
   QT_REQUIRE(fmt == 0 || fmt == 1, "qt_gemm_f16: fmt must be 0 (bf16) or 1 (fp16)");
   QT_REQUIRE(M >= 0 && N >= 0 && K > 0 && lda >= K && ldw >= K, "qt_gemm_f16: bad shape");
   if (int rc = check_epi(ep, M, N)) return rc;
-  QT_REQUIRE(ep->out, "qt_gemm_f16: needs ep->out");
+  QT_REQUIRE(ep->out || ep->requant, "qt_gemm_f16: needs ep->out (or a requant output)");
   if (M == 0 || N == 0) return QT_OK;
   int max_pa = 0, max_pw = 0;
   for (int i = 0; i < npass; ++i) { max_pa = std::max(max_pa, pa[i]); max_pw = std::max(max_pw, pw[i]); }
@@ -666,6 +799,7 @@ extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, c
   // D = f32 (1 << 4), A/B = bf16 (1) or fp16 (0) at bits 7 / 10
   const uint32_t f = fmt == 0 ? 1u : 0u;
   g.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
   return dispatch_tc<1>(ma, mw, g, bn, stream);
 }
 
@@ -724,6 +858,7 @@ extern "C" int qt_conv_i8(const void* x_nhwc, int a_signed, const QtConvGeom* cg
   g.cv_dh = cg->dil_h; g.cv_dw = cg->dil_w; g.cv_kw = cg->kw; g.cv_c0 = (int)(Cg * cg->group);
   g.idesc = (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((w_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) |
             ((uint32_t)(TC_BM >> 4) << 24);
+  if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
   if (bkb == 128) return dispatch_conv<128>(ma, mw, g, bn, stream);
   if (bkb == 64) return dispatch_conv<64>(ma, mw, g, bn, stream);
   return dispatch_conv<32>(ma, mw, g, bn, stream);

@@ -581,82 +581,99 @@ struct ExpandArgs {
   int64_t ld_out;
 };
 
-// Each thread produces 16 consecutive output columns of one row; the packed bits/codes those 16 columns need are
-// fetched once (1, 2 or 4 words) and unpacked in registers.
+// One thread per 16-byte output vector (CPV = 8 columns of a 16-bit operand, 16 of an 8-bit one, 32 e2m1 nibbles), so that
+// consecutive threads write consecutive 16-byte vectors (every store instruction of a warp covers 512 contiguous bytes).
+// The packed bits / codes of those columns are 1..4 words fetched once (neighbouring threads share them: broadcast loads).
+template <int CPV>
 __global__ void __launch_bounds__(256) weight_expand_kernel(ExpandArgs a) {
-  const int64_t groups_per_row = a.ld_out / 16;
+  const int64_t vec_per_row = a.ld_out / CPV;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= a.n * groups_per_row) return;
-  const int64_t row = gid / groups_per_row, c0 = (gid - row * groups_per_row) * 16;
+  if (gid >= a.n * vec_per_row) return;
+  const int64_t row = gid / vec_per_row, c0 = (gid - row * vec_per_row) * CPV;
   const uint8_t* pr = a.packed + row * a.ld_packed;
-  float v[16];
+  float v[CPV];
   const bool one_bit = a.mode == QT_W_SIGN || (a.mode == QT_W_DOREFA && a.bit_width == 1);
   if (c0 >= a.k) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    for (int j = 0; j < CPV; ++j) v[j] = 0.f;
   } else if (one_bit) {
     const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c0 >> 5)) >> (c0 & 31);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = (c0 + j < a.k) ? (((w >> j) & 1u) ? 1.f : -1.f) : 0.f;
+    for (int j = 0; j < CPV; ++j) v[j] = (c0 + j < a.k) ? (((w >> j) & 1u) ? 1.f : -1.f) : 0.f;
   } else if (a.mode == QT_W_TERNARY || a.mode == QT_W_XNOR) {
     const uint32_t nz = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c0 >> 5)) >> (c0 & 31);
     const uint32_t sg = __ldg(reinterpret_cast<const uint32_t*>(pr + a.n * a.ld_packed) + (c0 >> 5)) >> (c0 & 31);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = (c0 + j < a.k && ((nz >> j) & 1u)) ? (((sg >> j) & 1u) ? 1.f : -1.f) : 0.f;
+    for (int j = 0; j < CPV; ++j) v[j] = (c0 + j < a.k && ((nz >> j) & 1u)) ? (((sg >> j) & 1u) ? 1.f : -1.f) : 0.f;
   } else {
-    const int lb = a.lane_bits;                      // 2, 4 or 8 -> 16 columns span 1, 2 or 4 words
-    const int nwords = lb / 2;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(pr) + (c0 * lb) / 32;
+    const int lb = a.lane_bits;                      // 2, 4 or 8: CPV columns span at most 4 words (CPV * lb <= 128 bits)
+    const int64_t bit0 = c0 * lb;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(pr) + (bit0 >> 5);
+    const int nwords = (int)(((bit0 & 31) + (int64_t)CPV * lb + 31) >> 5);
+    const int64_t words_left = (a.ld_packed >> 2) - (bit0 >> 5);
     uint32_t wds[4] = {0, 0, 0, 0};
-    for (int i = 0; i < nwords; ++i) wds[i] = __ldg(wp + i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nwords && i < words_left) wds[i] = __ldg(wp + i);
     const uint32_t mask = (1u << lb) - 1u;
     const float n = (float)((1 << a.bit_width) - 1);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int bit = j * lb;
-      const uint32_t code = (wds[bit >> 5] >> (bit & 31)) & mask;
+    for (int j = 0; j < CPV; ++j) {
+      const int bit = (int)(bit0 & 31) + j * lb;
+      const uint32_t code = (wds[(bit >> 5) & 3] >> (bit & 31)) & mask;
       float x = (a.out_kind == 2) ? (float)code : 2.f * (float)code - n;
       v[j] = (c0 + j < a.k) ? x : 0.f;
     }
   }
-  if (a.out_kind == 7) {   // e2m1 nibbles: 16 columns -> 8 bytes
-    uint32_t lo = 0, hi = 0;
+  if (CPV == 32) {          // e2m1 nibbles: 32 columns -> 16 bytes
+    uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      lo |= f4_nibble(v[j]) << (4 * j);
-      hi |= f4_nibble(v[8 + j]) << (4 * j);
+    for (int q = 0; q < 4; ++q) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc |= f4_nibble(v[(8 * q + j) % CPV]) << (4 * j);
+      w[q] = acc;
     }
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.out) + row * (a.ld_out >> 1) + (c0 >> 1)) = make_uint2(lo, hi);
-  } else if (a.out_kind == 1 || a.out_kind == 2) {
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out) + row * (a.ld_out >> 1) + (c0 >> 1)) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else if (CPV == 16) {   // int8 / uint8 codes
     uint32_t w[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      w[q] = ((uint32_t)((int)v[4 * q] & 0xff)) | ((uint32_t)((int)v[4 * q + 1] & 0xff) << 8) |
-             ((uint32_t)((int)v[4 * q + 2] & 0xff) << 16) | ((uint32_t)((int)v[4 * q + 3] & 0xff) << 24);
+      w[q] = ((uint32_t)((int)v[(4 * q) % CPV] & 0xff)) | ((uint32_t)((int)v[(4 * q + 1) % CPV] & 0xff) << 8) |
+             ((uint32_t)((int)v[(4 * q + 2) % CPV] & 0xff) << 16) | ((uint32_t)((int)v[(4 * q + 3) % CPV] & 0xff) << 24);
     *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out) + row * a.ld_out + c0) = make_uint4(w[0], w[1], w[2], w[3]);
-  } else {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ld_out + c0;
-    __nv_bfloat16* o2 = o + a.n * a.ld_out;
-    __align__(16) __nv_bfloat16 h[16], l[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float x = v[j];
-      if (a.out_kind == 4 || a.out_kind == 5) x *= (c0 + j < a.k) ? __ldg(a.alpha + c0 + j) : 0.f;
-      if (a.out_kind >= 5) {
-        __half hh = __float2half_rn(x);
-        h[j] = *reinterpret_cast<__nv_bfloat16*>(&hh);
-        l[j] = h[j];
+  } else {                  // 16-bit planes
+    if (a.out_kind == 4 || a.out_kind == 5) {     // XnorNet: alpha[k] * sign
+      float al[8];
+      if (c0 + 8 <= a.k && (c0 & 3) == 0) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(a.alpha + c0)), a1 = __ldg(reinterpret_cast<const float4*>(a.alpha + c0 + 4));
+        al[0] = a0.x; al[1] = a0.y; al[2] = a0.z; al[3] = a0.w; al[4] = a1.x; al[5] = a1.y; al[6] = a1.z; al[7] = a1.w;
       } else {
-        h[j] = __float2bfloat16_rn(x);
-        l[j] = __float2bfloat16_rn(x - __bfloat162float(h[j]));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) al[j] = (c0 + j < a.k) ? __ldg(a.alpha + c0 + j) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j % CPV] *= al[j];
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x0 = v[(2 * q) % CPV], x1 = v[(2 * q + 1) % CPV];
+      if (a.out_kind >= 5) {
+        __half2 hh = __floats2half2_rn(x0, x1);
+        h[q] = *reinterpret_cast<uint32_t*>(&hh);
+        l[q] = 0;
+      } else {
+        const __nv_bfloat16 b0 = __float2bfloat16_rn(x0), b1 = __float2bfloat16_rn(x1);
+        __nv_bfloat162 hh(b0, b1);
+        __nv_bfloat162 ll(__float2bfloat16_rn(x0 - __bfloat162float(b0)), __float2bfloat16_rn(x1 - __bfloat162float(b1)));
+        h[q] = *reinterpret_cast<uint32_t*>(&hh);
+        l[q] = *reinterpret_cast<uint32_t*>(&ll);
       }
     }
-    reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(h)[0];
-    reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(h)[1];
-    if (a.out_kind == 4) {
-      reinterpret_cast<uint4*>(o2)[0] = reinterpret_cast<uint4*>(l)[0];
-      reinterpret_cast<uint4*>(o2)[1] = reinterpret_cast<uint4*>(l)[1];
-    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ld_out + c0;
+    *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (a.out_kind == 4) *reinterpret_cast<uint4*>(o + a.n * a.ld_out) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -1034,8 +1051,12 @@ extern "C" int qt_expand_weight(const QtWeightExpand* p, void* stream_) {
   a.lane_bits = (p->mode == QT_W_DOREFA) ? lane_bits_for(p->bit_width) : 1;
   a.packed = (const uint8_t*)p->packed; a.n = p->n; a.k = p->k; a.ld_packed = p->ld_packed; a.alpha = p->alpha;
   a.out = p->out; a.out_kind = p->out_kind; a.ld_out = p->ld_out;
-  int64_t threads = p->n * (p->ld_out / 16);
-  weight_expand_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, stream>>>(a);
+  const int cpv = (p->out_kind == 7) ? 32 : ((p->out_kind == 1 || p->out_kind == 2) ? 16 : 8);
+  const int64_t threads = p->n * (p->ld_out / cpv);
+  const unsigned blocks = (unsigned)ceil_div(threads, 256);
+  if (cpv == 32) weight_expand_kernel<32><<<blocks, 256, 0, stream>>>(a);
+  else if (cpv == 16) weight_expand_kernel<16><<<blocks, 256, 0, stream>>>(a);
+  else weight_expand_kernel<8><<<blocks, 256, 0, stream>>>(a);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }

@@ -107,6 +107,101 @@ class FusedBNActQuant(nn.Module):
         return "fused"
 
 
+def _bn_affine(bn):
+    with torch.no_grad():
+        s = torch.rsqrt(bn.running_var.float() + bn.eps)
+        if bn.weight is not None:
+            s = s * bn.weight.float()
+        t = -bn.running_mean.float() * s
+        if bn.bias is not None:
+            t = t + bn.bias.float()
+    return s.contiguous(), t.contiguous()
+
+
+class FusedLayerQuant(nn.Module):
+    """quantized Linear / Conv2d -> [BatchNorm (eval)] -> [Hardtanh | ReLU | ReLU6] -> activation quantizer with the
+    quantizer running INSIDE the layer's tcgen05 epilogue (include/qtb200.h QtRequant): under
+    `code_only_activations()` with autograd off, the epilogue writes the next layer's low-bit operand and the fp32
+    activation never reaches HBM (bytes_module -> bytes_chained).  The BatchNorm affine is folded into the
+    epilogue's per-column scale / bias.  Everywhere else (training, autograd, drop-in mode where the caller wants the
+    fp32 tensor, shapes the tensor-core kernels decline) it is exactly the plain composition of its children."""
+
+    def __init__(self, layer, bn, act, quant, consumer=None):
+        super().__init__()
+        self.layer = layer
+        # the tail on its own is the one-pass BatchNorm+clamp+quantizer kernel: used whenever the epilogue fusion does not apply
+        self.tail = FusedBNActQuant(bn, act, quant) if (bn is not None or act is not None) else quant
+        self._consumer_needs_i8 = _needs_8bit_lanes(consumer)
+        self._spec = None
+
+    @property
+    def bn(self):
+        return self.tail.bn if isinstance(self.tail, FusedBNActQuant) else None
+
+    @property
+    def act(self):
+        return self.tail.act if isinstance(self.tail, FusedBNActQuant) else None
+
+    @property
+    def quant(self):
+        return self.tail.quant if isinstance(self.tail, FusedBNActQuant) else self.tail
+
+    def _compose(self, x):
+        return self.tail(self.layer(x))
+
+    def _make_spec(self):
+        kind, arg = self.quant._qt_spec
+        lo, hi = _clamp_range(self.act)
+        bn = self.bn
+        key = None
+        if bn is not None:
+            params = [t for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None]
+            key = tuple((t.data_ptr(), t._version) for t in params)
+        if self._spec is not None and self._spec[0] == key:
+            return self._spec[1]
+        mul = add = None
+        if bn is not None:
+            mul, add = _bn_affine(bn)
+        if kind == "dorefa" and arg == 1:
+            kind = "sign"
+        mode = {"sign": L.Q_SIGN, "ternary": L.Q_TERNARY, "dorefa": L.Q_DOREFA, "xnor": L.Q_XNOR_ROW}[kind]
+        spec = eng.RequantSpec(mode, kind, bit_width=arg if kind == "dorefa" else 0, lo=lo, hi=hi, col_mul=mul, col_add=add)
+        spec.force_8bit = self._consumer_needs_i8
+        self._spec = (key, spec)
+        return spec
+
+    def forward(self, x):
+        bn = self.bn
+        fusable = (eng._code_only[0] and not torch.is_grad_enabled() and (x.is_cuda or x.is_meta)
+                   and x.dim() == (4 if self.layer._is_conv else 2)
+                   and (bn is None or (not bn.training and bn.track_running_stats and bn.running_mean is not None)))
+        if fusable:
+            try:
+                return self.layer._forward_requant(x, self._make_spec())
+            except eng.RequantUnsupported:
+                pass
+        return self._compose(x)
+
+    def extra_repr(self):
+        return "fused epilogue requant"
+
+
+def _needs_8bit_lanes(consumer):
+    """True when the layer that will read the codes cannot take e2m1 operands (DoReFa k >= 3 weights, convs, unknown)."""
+    from .layers.common import QuantLayerMixin
+    if consumer is None or not isinstance(consumer, QuantLayerMixin):
+        return True
+    if consumer._is_conv:
+        return True
+    bw = getattr(consumer, "bit_width", None)
+    return bw is not None and bw > 2
+
+
+def _is_quant_layer(m):
+    from .layers.common import QuantLayerMixin
+    return isinstance(m, QuantLayerMixin) and isinstance(m, (nn.Linear, nn.Conv2d))
+
+
 def fuse_inference(module):
     """Rewrite, in place and recursively, every `[BatchNorm] -> [Hardtanh|ReLU|ReLU6] -> activation quantizer` run found
     inside nn.Sequential containers into a FusedBNActQuant.  Call it after loading weights (the fused module keeps
@@ -117,6 +212,22 @@ def fuse_inference(module):
         mods = list(module.children())
         out, i = [], 0
         while i < len(mods):
+            # quantized layer -> [BN] -> [clamp] -> quantizer: the quantizer moves into the layer's epilogue
+            if _is_quant_layer(mods[i]) and not (mods[i]._is_conv and mods[i].groups != 1):
+                j = i + 1
+                bn = act = None
+                want_bn = nn.BatchNorm2d if mods[i]._is_conv else nn.BatchNorm1d
+                if j < len(mods) and isinstance(mods[j], want_bn):
+                    bn = mods[j]
+                    j += 1
+                if j < len(mods) and isinstance(mods[j], (nn.Hardtanh, nn.ReLU, nn.ReLU6)) and not _is_quantizer(mods[j]):
+                    act = mods[j]
+                    j += 1
+                if j < len(mods) and _is_quantizer(mods[j]) and (mods[j]._qt_spec[0] != "xnor" or not mods[i]._is_conv):
+                    consumer = mods[j + 1] if j + 1 < len(mods) else None
+                    out.append(FusedLayerQuant(mods[i], bn, act, mods[j], consumer))
+                    i = j + 1
+                    continue
             j = i
             bn = act = None
             if isinstance(mods[j], _BN):

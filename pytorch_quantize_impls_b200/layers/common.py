@@ -138,6 +138,15 @@ class QuantLayerMixin(QLayer):
                               self.dilation, self.groups)
         return eng.linear(input, pack, self.bias)
 
+    def _forward_requant(self, input, spec):
+        """Inference chain: contraction with the next activation quantizer fused into the epilogue (fusion.FusedLayerQuant)."""
+        eng.tagged_input_device(input)
+        pack = self._current_pack()
+        if self._is_conv:
+            return eng.conv2d(input, pack, self.bias, tuple(self.weight.shape), self.stride, self.padding,
+                              self.dilation, self.groups, requant=spec)
+        return eng.linear(input, pack, self.bias, requant=spec)
+
     def forward(self, input):
         eng.tagged_input_device(input)
         needs_grad = torch.is_grad_enabled() and (

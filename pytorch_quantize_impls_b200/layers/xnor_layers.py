@@ -22,6 +22,13 @@ class _XnorMixin(QuantLayerMixin):
         op = self.conv_op if self._is_conv else self.lin_op
         return op.apply(input, self.weight, self.bias, pack)
 
+    def _current_pack(self):
+        st = self._eval_state
+        if (not self.training and st is not None and st.version == self.weight._version
+                and st.ptr == self.weight.data_ptr()):
+            return st.pack
+        return self._make_pack(self.weight)
+
     def train(self, mode=True):
         if self.training == mode:
             return self
