@@ -162,7 +162,11 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
   const float* xr = a.x + row * a.ld_x;
 
   float row_mean = 0.f;
-  if (MODE == QT_Q_XNOR_ROW) {  // never chunked: the whole row is reduced by this warp
+  // XnorNet: the codes sign(x) do not depend on the row mean; only the fp32 fake-quant tensor sign(x) * mean does.  Without
+  // a `y` output (code-only chains) the row is therefore read ONCE: the sum is accumulated inside the main loop below.
+  const bool xnor_one_pass = (MODE == QT_Q_XNOR_ROW) && a.y == nullptr;
+  double xsum = 0.0;
+  if (MODE == QT_Q_XNOR_ROW && !xnor_one_pass) {  // never chunked: the whole row is reduced by this warp
     double s = 0.0;
     if (VEC) {
       // 8 independent 16-byte loads in flight per lane (the reduction is latency-bound otherwise); fp32 partial sums of 4
@@ -218,8 +222,11 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
       const int64_t c = base + 4 * lane;
       const bool valid = c < c1;
       const float4 v = vv[u];
-      QOut o0 = quant_elem<MODE>(a.q, pre_col<PRE>(a.q, v.x, c), row_mean), o1 = quant_elem<MODE>(a.q, pre_col<PRE>(a.q, v.y, c + 1), row_mean);
-      QOut o2 = quant_elem<MODE>(a.q, pre_col<PRE>(a.q, v.z, c + 2), row_mean), o3 = quant_elem<MODE>(a.q, pre_col<PRE>(a.q, v.w, c + 3), row_mean);
+      const float p0 = pre_col<PRE>(a.q, v.x, c), p1 = pre_col<PRE>(a.q, v.y, c + 1);
+      const float p2 = pre_col<PRE>(a.q, v.z, c + 2), p3 = pre_col<PRE>(a.q, v.w, c + 3);
+      if (MODE == QT_Q_XNOR_ROW && xnor_one_pass && valid) xsum += ((double)p0 + (double)p1) + ((double)p2 + (double)p3);
+      QOut o0 = quant_elem<MODE>(a.q, p0, row_mean), o1 = quant_elem<MODE>(a.q, p1, row_mean);
+      QOut o2 = quant_elem<MODE>(a.q, p2, row_mean), o3 = quant_elem<MODE>(a.q, p3, row_mean);
       if (valid) {
         if (yr) __stcs(reinterpret_cast<float4*>(yr + c), make_float4(o0.y, o1.y, o2.y, o3.y));   // streamed: never re-read here
         if (c8) {
@@ -294,6 +301,7 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
       const int64_t c = base + lane;
       const bool valid = c < c1;
       float v = valid ? pre_col<PRE>(a.q, __ldg(xr + c), c) : 0.f;
+      if (MODE == QT_Q_XNOR_ROW && xnor_one_pass && valid) xsum += (double)v;
       QOut o = quant_elem<MODE>(a.q, v, row_mean);
       if (valid) {
         if (yr) yr[c] = o.y;
@@ -333,6 +341,10 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
     }
   }
 
+  if (MODE == QT_Q_XNOR_ROW && xnor_one_pass) {
+    xsum = warp_sum_d(xsum);
+    if (a.row_scale && lane == 0) a.row_scale[row] = (float)(xsum / (double)a.cols);
+  }
   // zero-fill the padding columns / words (last chunk only)
   if (chunk_id == a.nchunks - 1) {
     if (c8) for (int64_t c = a.cols + lane; c < a.ld_codes; c += 32) c8[c] = 0;
