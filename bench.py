@@ -339,7 +339,8 @@ def run_ours(args):
     achieved = flops / (avg_ms * 1e-3) / 1e12
     peak = pk["bf16_tflops_sustained"]
     gemm_ms_per_step = sum(sum(v) for v in summ.values()) / args.steps
-    roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<BN=256, kind::f16 (fp16 operands, fp32 accumulate), 4 stages> M=%d N=%d K=%d" % (M, N, K),
+    roofline = {"bound": "tensor", "kernel": "tc_gemm2_kernel<BN=256, kind::f16 (fp16 operands, fp32 accumulate), 6 stages>: CTA pairs (tcgen05 cta_group::2, "
+                          "256x256 tiles), requant epilogue, M=%d N=%d K=%d" % (M, N, K),
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk["src"] == "measured" else "fallback",
                 "avg_launch_ms": round(avg_ms, 4), "gemm_share_of_step": round(gemm_ms_per_step / ms_step, 3),

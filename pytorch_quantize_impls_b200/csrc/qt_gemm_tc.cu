@@ -83,6 +83,37 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
       ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
+// cta_group::2 variants: the destination is this CTA's shared memory, the mbarrier may be the peer (leader) CTA's.
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the variable at shared::cta address `addr` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// commit of cta_group::2 MMAs: arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_cg2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                "r"(c1)
@@ -105,18 +136,44 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 // run concurrently share a handful of weight tiles AND a band of activation rows small enough to stay L2-resident
 // while the fp32 output streams through (without bands the A operand is re-fetched from HBM once per ~2 weight tiles).
 constexpr int TC_BAND_M = 16;
+template <int CG = 1>
 __device__ __forceinline__ void tile_coords(const TcArgs& g, int tile, int& tm, int& tn) {
-  const int band_tiles = TC_BAND_M * g.tiles_n;
+  constexpr int BAND = TC_BAND_M / CG;                            // the band is 2048 rows either way
+  const int band_tiles = BAND * g.tiles_n;
   const int band = tile / band_tiles;
   const int t = tile - band * band_tiles;
-  const int bm = min(TC_BAND_M, g.tiles_m - band * TC_BAND_M);   // last band may be shorter
+  const int bm = min(BAND, g.tiles_m - band * BAND);             // last band may be shorter
   tn = t / bm;
-  tm = band * TC_BAND_M + (t - tn * bm);
+  tm = band * BAND + (t - tn * bm);
 }
 
-template <int KIND>
+template <int KIND, int CG = 1>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
                                        uint32_t sf_tmem) {
+  if (CG == 2) {
+    // one instruction drives the tensor cores of both SMs of the pair: M = 256 (128 rows per CTA), each CTA's shared memory
+    // holds its own A rows and half of the B rows at the same offsets
+    if (KIND == 2) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d_tmem),
+          "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sf_tmem), "r"(sf_tmem + 4u)
+          : "memory");
+    } else if (KIND == 0) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+          "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+          "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+          : "memory");
+    }
+    return;
+  }
   if (KIND == 2) {
     // SFA at sf_tmem (4 columns), SFB at sf_tmem + 4 (<= 8 columns for N <= 256): all bytes there are 0x7F (ue8m0 1.0)
     asm volatile(
@@ -266,13 +323,20 @@ __device__ __forceinline__ void rq_store_chunk(const Epi& e, const float (&y)[32
   }
 }
 
-template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_out, TcArgs g) {
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile -- each CTA
+// stages its own 128 A rows and HALF of the B rows, the leader CTA (cluster rank 0) issues every MMA for both SMs, so the
+// shared-memory traffic per SM and MMA drops from 12 KB to 8 KB (at cta_group::1 the operand reads + TMA fills of a
+// 128 x 256 tile ask for ~190 B/clk of the 128 B/clk shared memory: that, not the tensor pipe, was the limit).
+template <int BN, int KIND, int STAGES, int BKB, bool IM2COL, int CG>
+__device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUtensorMap& map_w, const CUtensorMap& map_out,
+                                             const TcArgs& g) {
+  static_assert(CG == 1 || BN % 16 == 0, "cta_group::2 needs N % 16 == 0");
+  static_assert(CG == 1 || !IM2COL, "the implicit-GEMM conv kernels run at cta_group::1");
   constexpr uint32_t A_BYTES = TC_BM * BKB;
-  constexpr uint32_t W_BYTES = BN * BKB;
+  constexpr uint32_t W_BYTES = (BN / CG) * BKB;         // this CTA's share of the B tile
   constexpr uint32_t STAGE_BYTES = A_BYTES + W_BYTES;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   // kind::mxf4: 2 x BN accumulator columns (BN <= 240) + 16 columns of unit scale factors at TC_SF_COL
   constexpr uint32_t TMEM_COLS = (KIND == 2) ? 512u : 2u * BN;
   static_assert(KIND != 2 || 2 * BN <= TC_SF_COL, "mxf4 tiles must leave the scale-factor columns free");
@@ -303,16 +367,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);
+      mbar_init(tempty_bar(s), 8 * CG);     // the epilogue warps of BOTH CTAs release the leader's accumulator stage
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {      // one warp of EACH CTA of the pair performs the (collective) cta_group::2 allocation
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (KIND == 2) {
@@ -324,22 +394,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's scale-factor columns are in place before the leader issues MMAs
     tc_fence_after();
   }
 
-  const int num_tiles = g.tiles_m * g.tiles_n;
+  const int num_tiles = g.tiles_m * g.tiles_n;      // tiles of (128 * CG) x BN
   const int iters = g.npass * g.num_kblocks;
+  const int worker = (int)blockIdx.x / CG, num_workers = (int)gridDim.x / CG;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         int tm, tn;
-      tile_coords(g, tile, tm, tn);
+      tile_coords<CG>(g, tile, tm, tn);
         for (int pass = 0; pass < g.npass; ++pass) {
-          const int a_row = (int)(g.pa[pass] * g.a_plane_rows) + tm * TC_BM;
-          const int w_row = (int)(g.pw[pass] * g.w_plane_rows) + tn * BN;
+          const int a_row = (int)(g.pa[pass] * g.a_plane_rows) + (tm * CG + (int)cta_rank) * TC_BM;
+          const int w_row = (int)(g.pw[pass] * g.w_plane_rows) + tn * BN + (int)cta_rank * (BN / CG);
           int cv_n = 0, cv_h = 0, cv_w = 0;
           if (IM2COL) {   // first output pixel of this M tile -> base position of its filter window
             const int m0 = tm * TC_BM;
@@ -351,8 +423,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           for (int kb = 0; kb < g.num_kblocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            // cta_group::2: the MMA issuer waits on the LEADER's full barrier, which counts the bytes of both CTAs' loads
+            if (leader) mbar_expect_tx(full_bar(stage), CG * STAGE_BYTES);
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            if (CG == 2) {
+              const uint32_t lbar = mapa_shared(full_bar(stage), 0);
+              tma_load_2d_cg2(sa, &map_a, lbar, kb * BKB, a_row);
+              tma_load_2d_cg2(sa + A_BYTES, &map_w, lbar, kb * BKB, w_row);
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+              continue;
+            }
             if (IM2COL) {
               const int tap = kb / g.cv_cblocks, cb = kb - tap * g.cv_cblocks;
               const int ky = tap / g.cv_kw, kx = tap - ky * g.cv_kw;
@@ -369,12 +449,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -387,13 +467,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BKB / 32; ++k) {
             // +32 B along K inside the swizzle atom == +2 in the (addr >> 4) field
-            tc_mma<KIND>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), g.idesc, (it > 0 || k > 0) ? 1u : 0u,
-                         tmem_base + TC_SF_COL);
+            tc_mma<KIND, CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), g.idesc, (it > 0 || k > 0) ? 1u : 0u,
+                             tmem_base + TC_SF_COL);
           }
-          tc_commit(empty_bar(stage));     // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (CG == 2) tc_commit_cg2(empty_bar(stage)); else tc_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tfull_bar(as));          // accumulator complete -> epilogue
+        if (CG == 2) tc_commit_cg2(tfull_bar(as)); else tc_commit(tfull_bar(as));   // accumulator complete -> epilogue(s)
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -414,10 +495,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         ((reinterpret_cast<uintptr_t>(e.out) & 15) == 0);
     const uint32_t my_buf = epi_base + (uint32_t)ew * 4096u;   // this warp's 32 x 128 B staging tile
     const int N32 = (int)g.N;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int tm, tn;
-      tile_coords(g, tile, tm, tn);
-      const int64_t m = (int64_t)tm * TC_BM + lane_grp * 32 + lane;
+      tile_coords<CG>(g, tile, tm, tn);
+      const int64_t m = (int64_t)(tm * CG + (int)cta_rank) * TC_BM + lane_grp * 32 + lane;
       const int n_tile = tn * BN;
       const int n_lim = min(N32, n_tile + BN);     // first column past this tile
       mbar_wait(tfull_bar(as), aphase);
@@ -505,7 +586,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             st_shared_v4(rowaddr + (uint32_t)((j ^ (lane & 7)) << 4), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) tma_store_2d(&map_out, my_buf, n0, tm * TC_BM + lane_grp * 32);
+          if (lane == 0) tma_store_2d(&map_out, my_buf, n0, (tm * CG + (int)cta_rank) * TC_BM + lane_grp * 32);
         } else if (e.out_mode == 0) {
           if (!row_ok) continue;
           float* o = e.out + m * e.ldo + n0;
@@ -536,7 +617,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));   // the leader issues the MMAs of both CTAs
+        else mbar_arrive(tempty_bar(as));
+      }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
     if (g.tma_store && lane == 0) tma_store_wait_all();   // all bulk stores of this warp have completed
@@ -544,10 +628,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();     // neither CTA leaves (or frees TMEM) while its peer may still signal / read it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_out, TcArgs g) {
+  tc_gemm_body<BN, KIND, STAGES, BKB, IM2COL, 1>(map_a, map_w, map_out, g);
+}
+
+// CTA-pair variant: 256 x BN tiles, cluster of two CTAs on the two SMs of a TPC.
+template <int BN, int KIND, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_out, TcArgs g) {
+  tc_gemm_body<BN, KIND, STAGES, TC_BK_BYTES, false, 2>(map_a, map_w, map_out, g);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -641,8 +742,46 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
   return QT_OK;
 }
 
+// CTA-pair launch: tiles of 256 x BN, grid = 2 x min(#tiles, #SMs / 2); `mw` must have been built with BN / 2 box rows and
+// g.idesc with M = 256.
+template <int BN, int KIND, int STAGES>
+static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK_BYTES + (BN / 2) * TC_BK_BYTES) + 4 * 2 * 4096 + 1024 + 256;
+  CUtensorMap mo = ma;
+  g.tma_store = 0;
+  if (g.ep.out && g.ep.out_mode == 0 && g.ep.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(g.ep.out) & 15) == 0) {
+    if (int rc = make_map(&mo, g.ep.out, (uint64_t)g.M, (uint64_t)g.N * 4, (uint64_t)g.ep.ldo * 4, 32, true)) return rc;
+    g.tma_store = 1;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm2_kernel<BN, KIND, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  g.tiles_m = (int)ceil_div(g.M, 2 * TC_BM);
+  g.tiles_n = (int)ceil_div(g.N, BN);
+  const int grid = 2 * std::min(g.tiles_m * g.tiles_n, num_sms() / 2);
+  tc_gemm2_kernel<BN, KIND, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+// 0 = auto (CTA pairs for large tiles), 1 = always cta_group::1, 2 = cta_group::2 whenever the tile shape allows
+static int g_cta_group = -1;
+static bool use_cta_pair(int64_t M, int bn) {
+  if (g_cta_group < 0) {
+    const char* s = getenv("QTB200_CTA_GROUP");
+    const int v = s ? atoi(s) : 0;
+    g_cta_group = (v == 1 || v == 2) ? v : 0;
+  }
+  if (g_cta_group == 1 || bn < 240) return false;
+  if (g_cta_group == 2) return true;
+  return M >= 1024;      // enough 256-row tiles to keep the 74 pairs busy
+}
+
 template <int KIND>
-static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream) {
+static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream, bool pair = false) {
+  if (pair) return launch_tc2<256, KIND, 6>(ma, mw, g, stream);
   if (bn == 64) return launch_tc<64, KIND, 8>(ma, mw, g, stream);
   if (bn == 128) return launch_tc<128, KIND, 6>(ma, mw, g, stream);
   return launch_tc<256, KIND, 4>(ma, mw, g, stream);
@@ -666,9 +805,8 @@ static int pick_bn_f4(int64_t N) {
   return (double)pad128 < 0.9 * (double)pad240 ? 128 : 240;
 }
 
-static int dispatch_f4(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream);
-
-static int dispatch_f4(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream) {
+static int dispatch_f4(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream, bool pair = false) {
+  if (pair) return launch_tc2<240, 2, 6>(ma, mw, g, stream);
   if (bn == 64) return launch_tc<64, 2, 8>(ma, mw, g, stream);
   if (bn == 128) return launch_tc<128, 2, 6>(ma, mw, g, stream);
   return launch_tc<240, 2, 4>(ma, mw, g, stream);
@@ -712,17 +850,20 @@ extern "C" int qt_gemm_i8(const void* a, int a_signed, int64_t lda, const void* 
   if (!use_tc) return simt_gemm_i8(a, a_signed, lda, w, w_signed, ldw, M, N, K, ep, stream);
 
   const int bn = pick_bn(N);
+  const bool pair = use_cta_pair(M, bn);
+  const int cg = pair ? 2 : 1;
   CUtensorMap ma, mw;
   if (int rc = make_map(&ma, a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, TC_BM)) return rc;
-  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn)) return rc;
+  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(bn / cg))) return rc;
   TcArgs g{};
   g.M = M; g.N = N; g.num_kblocks = (int)ceil_div(K, TC_BK_BYTES); g.npass = 1; g.pa[0] = g.pw[0] = 0;
   g.a_plane_rows = g.w_plane_rows = 0; g.is_int = 1; g.ep = make_epi(ep, M, N);
   // instruction descriptor: D = s32 (2 << 4), A/B = s8 (1) or u8 (0) at bits 7 / 10, K-major both, N >> 3 at 17, M >> 4 at 24
+  // (M = 256 for a CTA pair)
   g.idesc = (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((w_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) |
-            ((uint32_t)(TC_BM >> 4) << 24);
+            ((uint32_t)((TC_BM * cg) >> 4) << 24);
   if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
-  return dispatch_tc<0>(ma, mw, g, bn, stream);
+  return dispatch_tc<0>(ma, mw, g, bn, stream, pair);
 }
 
 extern "C" int qt_set_option(const char* name, int value) {
@@ -730,6 +871,11 @@ extern "C" int qt_set_option(const char* name, int value) {
   if (strcmp(name, "f4_tile_n") == 0) {
     QT_REQUIRE(value == 0 || value == 64 || value == 128 || value == 240, "qt_set_option: f4_tile_n must be 0, 64, 128 or 240");
     g_f4_tile_n = value;
+    return QT_OK;
+  }
+  if (strcmp(name, "cta_group") == 0) {
+    QT_REQUIRE(value >= 0 && value <= 2, "qt_set_option: cta_group must be 0 (auto), 1 or 2");
+    g_cta_group = value;
     return QT_OK;
   }
   set_error("qt_set_option: unknown option '%s'", name);
@@ -751,18 +897,20 @@ extern "C" int qt_gemm_f4(const void* a, int64_t lda, const void* w, int64_t ldw
     return QT_EUNSUPPORTED;
   }
   const int bn = pick_bn_f4(N);
+  const bool pair = use_cta_pair(M, bn);
+  const int cg = pair ? 2 : 1;
   CUtensorMap ma, mw;
   // byte matrices: two e2m1 codes per byte, K/2 bytes per row (zero OOB fill = +0.0 codes)
   if (int rc = make_map(&ma, a, (uint64_t)M, (uint64_t)((K + 1) / 2), (uint64_t)(lda / 2), TC_BM)) return rc;
-  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)((K + 1) / 2), (uint64_t)(ldw / 2), (uint32_t)bn)) return rc;
+  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)((K + 1) / 2), (uint64_t)(ldw / 2), (uint32_t)(bn / cg))) return rc;
   TcArgs g{};
   g.M = M; g.N = N; g.num_kblocks = (int)ceil_div((K + 1) / 2, TC_BK_BYTES); g.npass = 1; g.pa[0] = g.pw[0] = 0;
   g.a_plane_rows = g.w_plane_rows = 0; g.is_int = 1; g.ep = make_epi(ep, M, N);
   // block-scaled instruction descriptor: A/B = e2m1 (1) at bits 7 / 10, K-major, N >> 3 at 17, scale format ue8m0 (1) at 23,
   // M >> 4 at 24, scale-factor ids 0, K = 64 per instruction
-  g.idesc = (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | (1u << 23) | ((uint32_t)(TC_BM >> 4) << 24);
+  g.idesc = (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | (1u << 23) | ((uint32_t)((TC_BM * cg) >> 4) << 24);
   if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
-  return dispatch_f4(ma, mw, g, bn, stream);
+  return dispatch_f4(ma, mw, g, bn, stream, pair);
 }
 
 extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, const void* w, int64_t ldw,
@@ -786,21 +934,23 @@ extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, c
   if (!use_tc) return simt_gemm_f16(a, lda, a_plane_stride, w, ldw, w_plane_stride, fmt, npass, pa, pw, M, N, K, ep, stream);
 
   const int bn = pick_bn(N);
+  const bool pair = use_cta_pair(M, bn);
+  const int cg = pair ? 2 : 1;
   TcArgs g{};
   g.a_plane_rows = max_pa > 0 ? a_plane_stride / lda : 0;
   g.w_plane_rows = max_pw > 0 ? w_plane_stride / ldw : 0;
   const uint64_t a_rows = (uint64_t)(max_pa * g.a_plane_rows + M), w_rows = (uint64_t)(max_pw * g.w_plane_rows + N);
   CUtensorMap ma, mw;
   if (int rc = make_map(&ma, a, a_rows, (uint64_t)K * 2, (uint64_t)lda * 2, TC_BM)) return rc;
-  if (int rc = make_map(&mw, w, w_rows, (uint64_t)K * 2, (uint64_t)ldw * 2, (uint32_t)bn)) return rc;
+  if (int rc = make_map(&mw, w, w_rows, (uint64_t)K * 2, (uint64_t)ldw * 2, (uint32_t)(bn / cg))) return rc;
   g.M = M; g.N = N; g.num_kblocks = (int)ceil_div(K * 2, TC_BK_BYTES); g.npass = npass;
   for (int i = 0; i < npass; ++i) { g.pa[i] = pa[i]; g.pw[i] = pw[i]; }
   g.is_int = 0; g.ep = make_epi(ep, M, N);
   // D = f32 (1 << 4), A/B = bf16 (1) or fp16 (0) at bits 7 / 10
   const uint32_t f = fmt == 0 ? 1u : 0u;
-  g.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  g.idesc = (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((TC_BM * cg) >> 4) << 24);
   if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
-  return dispatch_tc<1>(ma, mw, g, bn, stream);
+  return dispatch_tc<1>(ma, mw, g, bn, stream, pair);
 }
 
 // ---------------------------------------------------------------------------------------------
