@@ -163,14 +163,16 @@ class GemmTimer:
     """CUDA-event timing of every tensor-core GEMM launch inside the timed region (current stream)."""
 
     def __init__(self, torch, ops):
-        self.torch, self.ops, self.ev, self.on = torch, ops, [], False
+        self.torch, self.ops, self.ev, self.on, self.external = torch, ops, [], False, False
         self._orig_bf16, self._orig_i8 = ops.gemm_f16, ops.gemm_i8
 
     def _wrap(self, fn, kind):
         def inner(*a, **k):
-            if not self.on:
+            if not self.on or (self.external and not self.torch.cuda.is_current_stream_capturing()):
                 return fn(*a, **k)
-            s, e = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            # external=True: inside a CUDA-graph capture the records become event-record nodes, re-recorded by every replay
+            s = self.torch.cuda.Event(enable_timing=True, external=self.external)
+            e = self.torch.cuda.Event(enable_timing=True, external=self.external)
             s.record()
             fn(*a, **k)
             e.record()
@@ -213,19 +215,54 @@ def run_ours(args):
     x_host = [torch.randn(BATCH, DIMS[0], generator=g).pin_memory() for _ in range(NBUF)]
     x_dev = [t.to(dev) for t in x_host]
     gathered = torch.empty(world * BATCH, DIMS[-1], device=dev) if world > 1 else None
+    from pytorch_quantize_impls_b200.sharding import PipelinedGather
+    # N > 1: the logits all-gather (the only collective) of step i runs on its own stream beside the kernels of
+    # step i+1; QTB200_BENCH_SYNC_GATHER=1 issues it on the compute stream instead (extra.sync_gather_ms_per_step)
+    gather_mode = os.environ.get("QTB200_GATHER", "ce")      # ce | nccl | sync  (sharding.PipelinedGather)
+    pgather = PipelinedGather(depth=2, mode=gather_mode, pull_streams=int(os.environ.get("QTB200_GATHER_STREAMS", "0")) or None)
+    sync_gather = False
     timer = GemmTimer(torch, _ops)
     timer.install()
 
-    def step(i, x=None):
+    def fwd(x):
         # public nn.Sequential forward; the activation quantizers hand only their low-bit operand to the next layer
-        # (Q.code_only_activations: bit-identical logits, no fp32 fake-quant tensors are written)
+        # (Q.code_only_activations: no fp32 fake-quant tensors are written)
         with Q.code_only_activations():
-            y = net(x_dev[i % NBUF] if x is None else x)
+            return net(x)
+
+    # the forward of each of the NBUF device input buffers is captured once in a CUDA graph and replayed (one launch per
+    # step instead of 7 ctypes launches + torch allocations); QTB200_BENCH_GRAPH=0 times the eager path
+    graph_mode = os.environ.get("QTB200_BENCH_GRAPH", "1") == "1"
+    graphs = None
+    if graph_mode:
+        from pytorch_quantize_impls_b200.pipeline import GraphedModule
+        with torch.no_grad():
+            timer.on, timer.external = True, True
+            graphs = []
+            for xb in x_dev:
+                gm = GraphedModule(fwd, xb)          # 3 eager warm-up forwards, then the capture
+                graphs.append(gm)
+            timer.on, timer.external = False, False
+            # kernels per captured forward: count the library launches of one eager forward (the capture issues the same ones)
+            _lib.launch_count(reset=True)
+            fwd(x_dev[0])
+            launches_per_forward = _lib.launch_count(reset=True)
+
+    def step(i, x=None, eager=False):
+        gm = None
+        if x is None and graphs is not None and not eager:
+            gm = graphs[i % NBUF]
+            y = gm()
+        else:
+            y = fwd(x_dev[i % NBUF] if x is None else x)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, y)      # the only collective: logits
+            _, done = pgather.submit(y)                   # the only collective: logits
+            if gm is not None:
+                gm.wait_for(done)                         # the static logits buffer is re-written by this graph's next replay
         return y
 
     def barrier():
+        pgather.drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -238,27 +275,37 @@ def run_ours(args):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        timer.on = True
+        timer.on = not graph_mode         # graph mode: the GEMM events were captured with the graphs (external event nodes)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
             step(i)
+        pgather.drain()            # the last gathers finish inside the timed region
         e1.record()
         barrier()
         timer.on = False
         launches = _lib.launch_count(reset=True)
+        if graph_mode:
+            launches = launches_per_forward * args.steps      # replays launch the captured kernels without the host path
         ms_total = e0.elapsed_time(e1)
         t = torch.tensor([ms_total], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item()) / args.steps
+        if os.environ.get("QTB200_BENCH_QUICK", "0") == "1":      # development aid: device-resident timing only
+            if rank == 0:
+                print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": round(ms_step, 4), "gather": pgather.mode,
+                                  "gops": round(2.0 * BATCH * MACS_PER_ROW * world / (ms_step * 1e-3) / 1e9, 1)}), flush=True)
+            if world > 1:
+                dist.destroy_process_group()
+            return
 
         # end-to-end through the public API with HOST buffers: every step copies its batch from pinned host memory and
         # returns its logits to pinned host memory, inside the timed region.  pipeline.HostPipeline overlaps the H2D of
         # step i+1 and the D2H of step i-1 with the kernels of step i (separate streams).
         from pytorch_quantize_impls_b200.pipeline import HostPipeline
         outs_host = [torch.empty(BATCH, DIMS[-1]).pin_memory() for _ in range(2)]
-        pipe = HostPipeline(lambda xb: step(0, xb), depth=2)
+        pipe = HostPipeline(lambda xb: step(0, xb), depth=2, graphs=graph_mode and world == 1)
         ins = [x_host[i % NBUF] for i in range(args.steps)]
         outs = [outs_host[i % 2] for i in range(args.steps)]
         pipe.run(ins[:2], outs[:2])
@@ -266,6 +313,7 @@ def run_ours(args):
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
         pipe.run(ins, outs)
+        pgather.drain()
         e3.record()
         barrier()
         t = torch.tensor([e2.elapsed_time(e3)], device=dev)
@@ -279,6 +327,7 @@ def run_ours(args):
         for i in range(args.steps):
             xe.copy_(x_host[i % NBUF], non_blocking=True)
             outs_host[0].copy_(step(i, xe), non_blocking=True)
+        pgather.drain()
         e7.record()
         barrier()
         ms_e2e_serial = e6.elapsed_time(e7) / args.steps
@@ -294,6 +343,7 @@ def run_ours(args):
             ea.record()
             for i in range(args.steps):
                 fn(i)
+            pgather.drain()
             eb.record()
             barrier()
             return ea.elapsed_time(eb) / args.steps
@@ -301,19 +351,29 @@ def run_ours(args):
         def step_default(i):
             y = net_plain(x_dev[i % NBUF])
             if world > 1:
-                dist.all_gather_into_tensor(gathered, y)
+                pgather.submit(y)
 
         def step_code_only(i):
             with Q.code_only_activations():
                 y = net_plain(x_dev[i % NBUF])
             if world > 1:
-                dist.all_gather_into_tensor(gathered, y)
+                pgather.submit(y)
         ms_default = timed(step_default)
         ms_code_only = timed(step_code_only)
         # parity inside the run: fused chain vs the one-kernel-per-module graph on the same batch
         y_f = step(0)
         y_p = net_plain(x_dev[0])
         chain_rel = float((y_f - y_p).abs().max() / y_p.abs().max())
+        gather_ok = None
+        if world > 1:
+            # the pipelined gather against a plain NCCL all_gather of the same logits
+            g_out, _ = pgather.submit(y_f)
+            pgather.drain()
+            dist.all_gather_into_tensor(gathered, y_f)
+            torch.cuda.synchronize()
+            ok = torch.tensor([1 if torch.equal(g_out, gathered) else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            gather_ok = bool(ok.item())
 
         extra = {}
         if rank == 0:
@@ -321,6 +381,8 @@ def run_ours(args):
             extra["xnor_mlp_default_mode_ms_per_step"] = round(ms_default, 4)
             extra["xnor_mlp_code_only_unfused_ms_per_step"] = round(ms_code_only, 4)
             extra["xnor_mlp_fused_vs_unfused_max_rel_diff"] = chain_rel
+            if gather_ok is not None:
+                extra["gathered_logits_equal_nccl_all_gather_on_every_rank"] = gather_ok
 
     if rank != 0:
         if world > 1:
@@ -338,12 +400,16 @@ def run_ours(args):
     flops = 2.0 * M * N * K                         # algorithmic: the logical 1-bit contraction, once
     achieved = flops / (avg_ms * 1e-3) / 1e12
     peak = pk["bf16_tflops_sustained"]
-    gemm_ms_per_step = sum(sum(v) for v in summ.values()) / args.steps
+    # graph mode: one (last-replay) sample per GEMM and graph; eager mode: one sample per GEMM and step
+    gemm_ms_per_step = sum(sum(v) for v in summ.values()) / (NBUF if graph_mode else args.steps)
     roofline = {"bound": "tensor", "kernel": "tc_gemm2_kernel<BN=256, kind::f16 (fp16 operands, fp32 accumulate), 6 stages>: CTA pairs (tcgen05 cta_group::2, "
                           "256x256 tiles), requant epilogue, M=%d N=%d K=%d" % (M, N, K),
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk["src"] == "measured" else "fallback",
                 "avg_launch_ms": round(avg_ms, 4), "gemm_share_of_step": round(gemm_ms_per_step / ms_step, 3),
+                "timing": ("CUDA events recorded as external event nodes inside the captured step graphs; mean over the last replay of "
+                           "each of the %d graphs within the timed region" % NBUF) if graph_mode else
+                          "CUDA events around every launch of the timed region",
                 "traffic": None}
 
     cb = cpu_reference_gops(2048, reps=3, warmup=1)
@@ -360,8 +426,14 @@ def run_ours(args):
                    "(logits within extra.xnor_mlp_fused_vs_unfused_max_rel_diff of the one-kernel-per-module drop-in graph, "
                    "whose time is extra.xnor_mlp_default_mode_ms_per_step)",
                    "l2": "inputs rotate over 3 device buffers of 134 MB each (> 126 MB L2)",
+                   "launch": "each step = one replay of a CUDA graph holding the 7 kernels of the forward" if graph_mode else "eager",
                    "images_per_sec": round(BATCH * world / (ms_step * 1e-3), 1),
-                   "collective": "all_gather of fp32 logits" if world > 1 else "none"},
+                   "collective": {"ce": "one all-gather of the fp32 logits per step by the copy engines over NVLink (symmetric "
+                                        "memory, signal-pad barriers) on a communication stream, overlapped with the next step's "
+                                        "kernels; all complete inside the timed region",
+                                  "nccl": "one NCCL all_gather of the fp32 logits per step on a communication stream",
+                                  "sync": "one NCCL all_gather of the fp32 logits per step on the compute stream"}[pgather.mode]
+                   if world > 1 else "none"},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": round(e2e, 1), "unit": "GOPS", "ms_per_step": round(ms_e2e, 4),
                 "api": "pipeline.HostPipeline(net).run(pinned inputs, pinned outputs): H2D / kernels / D2H on 3 streams",

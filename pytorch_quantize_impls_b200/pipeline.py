@@ -8,16 +8,24 @@ import torch
 
 
 class HostPipeline:
-    def __init__(self, fn, depth=2):
-        """fn: callable mapping a device batch to a device result (e.g. an nn.Module in eval mode)."""
-        self.fn, self.depth = fn, depth
+    def __init__(self, fn, depth=2, graphs=False):
+        """fn: callable mapping a device batch to a device result (e.g. an nn.Module in eval mode).
+        graphs=True: the forward of each of the `depth` device input buffers is captured once in a CUDA graph
+        (GraphedModule) and replayed, one launch per step."""
+        self.fn, self.depth, self.graphs = fn, depth, graphs
         self.h2d = torch.cuda.Stream()
         self.d2h = torch.cuda.Stream()
         self._bufs = None
+        self._graphed = None
 
     def _buffers(self, like, dev):
         if self._bufs is None or self._bufs[0].shape != like.shape or self._bufs[0].device != dev:
             self._bufs = [torch.empty(like.shape, dtype=like.dtype, device=dev) for _ in range(self.depth)]
+            self._graphed = None
+            if self.graphs:
+                for b in self._bufs:
+                    b.zero_()
+                self._graphed = [GraphedModule(self.fn, b) for b in self._bufs]
         return self._bufs
 
     @torch.no_grad()
@@ -43,7 +51,7 @@ class HostPipeline:
                 ready = torch.cuda.Event()
                 ready.record(self.h2d)
             comp.wait_event(ready)
-            y = self.fn(bufs[slot])
+            y = self._graphed[slot]() if self._graphed is not None else self.fn(bufs[slot])
             done = torch.cuda.Event()
             done.record(comp)
             free[slot] = done
@@ -53,6 +61,48 @@ class HostPipeline:
                 y.record_stream(self.d2h)
                 last = torch.cuda.Event()
                 last.record(self.d2h)
+            if self._graphed is not None:
+                self._graphed[slot].wait_for(last)     # the static output is overwritten by this slot's next replay
         if last is not None:
             comp.wait_event(last)
         return host_outputs
+
+
+class GraphedModule:
+    """fn(x) for ONE fixed input buffer captured in a CUDA graph: a whole quantized forward (quantizer, weight expansion and
+    tcgen05 contraction kernels of every layer) is replayed with a single launch, so short steps are not bound by the
+    Python / ctypes launch path (7 kernels in 0.5 ms for BASELINE configs[1]).
+
+    The kernels are launched through the C ABI on torch's current stream, which is the capture stream inside
+    `torch.cuda.graph`; scratch tensors come from the graph's private memory pool.  `fn` must be free of host
+    synchronisation (true of every forward path of this package unless `set_strict(True)`).  The returned tensor is a
+    static buffer that the next replay overwrites: `wait_for(event)` makes the next replay wait for a consumer on another
+    stream (e.g. the pipelined logits gather)."""
+
+    def __init__(self, fn, static_input, warmup=3, pool=None):
+        self.x = static_input
+        self._busy = None
+        side = torch.cuda.Stream(device=static_input.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):               # warm up off the capture: attribute setting, tensor-map entry points, caches
+            for _ in range(warmup):
+                fn(self.x)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, pool=pool):
+            self.y = fn(self.x)
+
+    def pool(self):
+        return self.graph.pool()
+
+    def wait_for(self, event):
+        self._busy = event
+
+    def __call__(self, x=None):
+        if x is not None and x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x, non_blocking=True)
+        if self._busy is not None:
+            torch.cuda.current_stream().wait_event(self._busy)
+            self._busy = None
+        self.graph.replay()
+        return self.y

@@ -29,6 +29,13 @@ def _worker(rank, world, port, batch, q):
         def forward(self, t):
             return O.linear_xnor(O.xnor_act(t, 1), w, b)
     y = sharding.ShardedInference(Net())(x)
+    if batch % world == 0:
+        # the pipelined gather (communication stream on CUDA, synchronous on CPU tensors) returns the same rows
+        pg = sharding.PipelinedGather(depth=2)
+        for _ in range(3):          # rotate through the buffers
+            g, ev = pg.submit(Net()(sharding.shard_batch(x)))
+        pg.drain()
+        assert ev is None and torch.equal(g, y)
     if rank == 0:
         q.put(y)
     dist.barrier()
