@@ -96,9 +96,15 @@ typedef struct QtActQuant {
   int64_t nhwc_c;       /* 0: codes are row-major [rows, ld_codes].  C > 0: x (and y) are NCHW with rows = B images of
                            C channels x (cols / C) pixels, and the int8/uint8 codes are written channels-last
                            [B, H*W, C] (dense) -- the layout the conv gather / TMA im2col reads with 16-byte vectors */
+  int row_parts;        /* QT_Q_XNOR_ROW: capacity of row_scale in [rows]-sized parts (0 or 1: one vector holding the mean).
+                           With P = qt_quant_xnor_parts(cols, y != NULL, row_parts) > 1 the rows are processed in P column
+                           chunks and row_scale[p * rows + r] receives the partial SUM of chunk p (mean = sum_p / cols; the
+                           contraction epilogue adds them in order: QtEpilogue.row_scale_parts / row_scale_mul) */
 } QtActQuant;
 
 int qt_quant_act(const QtActQuant* p, void* stream);
+/* Number of row_scale parts qt_quant_act writes for a QT_Q_XNOR_ROW call (1 = the mean itself). */
+int qt_quant_xnor_parts(int64_t cols, int has_y, int capacity);
 
 /* ------------------------------------------------------------------------
  * Weight quantizers / packers: fp32 master weights [n, k] -> k-bit HBM format.

@@ -30,7 +30,7 @@ class QtActQuant(C.Structure):
                 ("bits", vp), ("ld_bits", i64),
                 ("row_sum", vp), ("row_scale", vp), ("overflow", vp),
                 ("pre_scale", vp), ("pre_shift", vp), ("pre_channels", i64), ("pre_hw", i64), ("pre_clamp", i32),
-                ("pre_lo", f32), ("pre_hi", f32), ("nhwc_c", i64)]
+                ("pre_lo", f32), ("pre_hi", f32), ("nhwc_c", i64), ("row_parts", i32)]
 
 
 class QtWeightPack(C.Structure):
@@ -79,6 +79,7 @@ SYMBOLS = {
     "qt_requant_max_parts": (i32, [i64]),
     "qt_device_caps": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "qt_quant_act": (i32, [C.POINTER(QtActQuant), vp]),
+    "qt_quant_xnor_parts": (i32, [i64, i32, i32]),
     "qt_pack_weight": (i32, [C.POINTER(QtWeightPack), vp]),
     "qt_col_absmean": (i32, [vp, i64, i64, i64, vp, vp]),
     "qt_expand_weight": (i32, [C.POINTER(QtWeightExpand), vp]),

@@ -118,8 +118,17 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
         bits = torch.empty((rows, ldb), dtype=torch.int32, device=dev)
     if want_row_sum:
         row_sum = torch.empty(rows, dtype=torch.int32, device=dev)
+    row_parts = 0
     if want_row_scale:
-        row_scale = torch.empty(rows, dtype=torch.float32, device=dev)
+        if mode == L.Q_XNOR_ROW and not want_y and x.dim() == 2:
+            # one-pass form: long rows are cut into 1024-column chunks that each leave a partial row sum
+            row_parts = int(L.lib().qt_quant_xnor_parts(cols, 0, (cols + 1023) // 1024))
+        if row_parts > 1:
+            row_scale = torch.empty((row_parts, rows), dtype=torch.float32, device=dev)
+            a.row_parts = row_parts
+        else:
+            row_parts = 0
+            row_scale = torch.empty(rows, dtype=torch.float32, device=dev)
     a.codes, a.codes_kind, a.ld_codes = _p(codes), codes_kind, ld
     a.bits, a.ld_bits = _p(bits), ldb
     a.row_sum, a.row_scale, a.overflow = _p(row_sum), _p(row_scale), _p(overflow)
@@ -133,7 +142,7 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
         tag.scale = 1.0
         tag.row_sum, tag.row_scale, tag.bits, tag.ld_bits = row_sum, row_scale, bits, ldb
         tag.overflow, tag.shape, tag.version, tag.layout = overflow, shape, None, layout
-        tag.row_parts, tag.row_mul = 0, 1.0
+        tag.row_parts, tag.row_mul = row_parts, (1.0 / max(cols, 1) if row_parts else 1.0)
         if _strict:
             tag.check()
     return y, tag

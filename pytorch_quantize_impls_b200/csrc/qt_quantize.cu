@@ -3,6 +3,7 @@
 // warp-shuffle reductions, and every derived output (fp32 fake-quant value, low-bit codes, packed bits,
 // row sums) produced from a single read of the fp32 source.
 #include <math.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include "qt_common.cuh"
 
@@ -151,7 +152,7 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 }
 
 template <int MODE, bool VEC, bool PRE>
-__global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
+__global__ void __launch_bounds__(256, (MODE == QT_Q_XNOR_ROW) ? 3 : 4) act_quant_kernel(ActArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t task = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (task >= a.rows * a.nchunks) return;
@@ -178,13 +179,15 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
           const int64_t c = c0r + u * 128;
           v[u] = (c < a.cols) ? __ldg(reinterpret_cast<const float4*>(xr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        float part = 0.f;      // fp32 over 32 values, folded into the fp64 accumulator once per batch
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int64_t c = c0r + u * 128;
           if (c < a.cols)
-            s += (double)pre_col<PRE>(a.q, v[u].x, c) + (double)pre_col<PRE>(a.q, v[u].y, c + 1) +
-                 (double)pre_col<PRE>(a.q, v[u].z, c + 2) + (double)pre_col<PRE>(a.q, v[u].w, c + 3);
+            part += (pre_col<PRE>(a.q, v[u].x, c) + pre_col<PRE>(a.q, v[u].y, c + 1)) +
+                    (pre_col<PRE>(a.q, v[u].z, c + 2) + pre_col<PRE>(a.q, v[u].w, c + 3));
         }
+        s += (double)part;
       }
     } else {
       for (int64_t c = lane; c < a.cols; c += 32) s += (double)pre_col<PRE>(a.q, __ldg(xr + c), c);
@@ -209,6 +212,7 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
     constexpr int U = 4;   // 4 independent 16-byte loads in flight per lane (2 KB per warp) before any use
     for (int64_t base0 = c0; base0 < c1; base0 += 128 * U) {
      float4 vv[U];
+     float xpart = 0.f;     // XnorNet one-pass: fp32 sum of this batch (U x 4 values per lane), then one fp64 add
 #pragma unroll
      for (int u = 0; u < U; ++u) {
        const int64_t cu = base0 + u * 128 + 4 * lane;
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
       const float4 v = vv[u];
       const float p0 = pre_col<PRE>(a.q, v.x, c), p1 = pre_col<PRE>(a.q, v.y, c + 1);
       const float p2 = pre_col<PRE>(a.q, v.z, c + 2), p3 = pre_col<PRE>(a.q, v.w, c + 3);
-      if (MODE == QT_Q_XNOR_ROW && xnor_one_pass && valid) xsum += ((double)p0 + (double)p1) + ((double)p2 + (double)p3);
+      if (MODE == QT_Q_XNOR_ROW && xnor_one_pass && valid) xpart += (p0 + p1) + (p2 + p3);   // fp32 over <= 16 values
       QOut o0 = quant_elem<MODE>(a.q, p0, row_mean), o1 = quant_elem<MODE>(a.q, p1, row_mean);
       QOut o2 = quant_elem<MODE>(a.q, p2, row_mean), o3 = quant_elem<MODE>(a.q, p3, row_mean);
       if (valid) {
@@ -295,6 +299,7 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
         if ((lane & 7) == 0 && widx * 32 < c1) br[widx] = w;
       }
      }
+     if (MODE == QT_Q_XNOR_ROW && xnor_one_pass) xsum += (double)xpart;
     }
   } else {
     for (int64_t base = c0; base < c1; base += 32) {
@@ -343,7 +348,10 @@ __global__ void __launch_bounds__(256, 4) act_quant_kernel(ActArgs a) {
 
   if (MODE == QT_Q_XNOR_ROW && xnor_one_pass) {
     xsum = warp_sum_d(xsum);
-    if (a.row_scale && lane == 0) a.row_scale[row] = (float)(xsum / (double)a.cols);
+    if (a.row_scale && lane == 0) {
+      if (a.nchunks == 1) a.row_scale[row] = (float)(xsum / (double)a.cols);
+      else a.row_scale[(int64_t)chunk_id * a.rows + row] = (float)xsum;     // partial sums: the consumer adds them in order
+    }
   }
   // zero-fill the padding columns / words (last chunk only)
   if (chunk_id == a.nchunks - 1) {
@@ -596,43 +604,132 @@ struct ExpandArgs {
 // One thread per 16-byte output vector (CPV = 8 columns of a 16-bit operand, 16 of an 8-bit one, 32 e2m1 nibbles), so that
 // consecutive threads write consecutive 16-byte vectors (every store instruction of a warp covers 512 contiguous bytes).
 // The packed bits / codes of those columns are 1..4 words fetched once (neighbouring threads share them: broadcast loads).
+// packed words one output vector needs (fetched up front for several vectors per thread: the kernel is latency-bound)
+struct ExpandWords { uint32_t w[4]; };
+
 template <int CPV>
-__global__ void __launch_bounds__(256) weight_expand_kernel(ExpandArgs a) {
-  const int64_t vec_per_row = a.ld_out / CPV;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= a.n * vec_per_row) return;
-  const int64_t row = gid / vec_per_row, c0 = (gid - row * vec_per_row) * CPV;
+__device__ __forceinline__ ExpandWords expand_fetch(const ExpandArgs& a, int64_t row, int64_t c0, bool one_bit) {
+  ExpandWords e;
+  e.w[0] = e.w[1] = e.w[2] = e.w[3] = 0u;
+  if (c0 >= a.k) return e;
   const uint8_t* pr = a.packed + row * a.ld_packed;
-  float v[CPV];
-  const bool one_bit = a.mode == QT_W_SIGN || (a.mode == QT_W_DOREFA && a.bit_width == 1);
-  if (c0 >= a.k) {
-#pragma unroll
-    for (int j = 0; j < CPV; ++j) v[j] = 0.f;
-  } else if (one_bit) {
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c0 >> 5)) >> (c0 & 31);
-#pragma unroll
-    for (int j = 0; j < CPV; ++j) v[j] = (c0 + j < a.k) ? (((w >> j) & 1u) ? 1.f : -1.f) : 0.f;
+  if (one_bit) {
+    e.w[0] = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c0 >> 5));
   } else if (a.mode == QT_W_TERNARY || a.mode == QT_W_XNOR) {
-    const uint32_t nz = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c0 >> 5)) >> (c0 & 31);
-    const uint32_t sg = __ldg(reinterpret_cast<const uint32_t*>(pr + a.n * a.ld_packed) + (c0 >> 5)) >> (c0 & 31);
-#pragma unroll
-    for (int j = 0; j < CPV; ++j) v[j] = (c0 + j < a.k && ((nz >> j) & 1u)) ? (((sg >> j) & 1u) ? 1.f : -1.f) : 0.f;
+    e.w[0] = __ldg(reinterpret_cast<const uint32_t*>(pr) + (c0 >> 5));
+    e.w[1] = __ldg(reinterpret_cast<const uint32_t*>(pr + a.n * a.ld_packed) + (c0 >> 5));
   } else {
     const int lb = a.lane_bits;                      // 2, 4 or 8: CPV columns span at most 4 words (CPV * lb <= 128 bits)
     const int64_t bit0 = c0 * lb;
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(pr) + (bit0 >> 5);
     const int nwords = (int)(((bit0 & 31) + (int64_t)CPV * lb + 31) >> 5);
     const int64_t words_left = (a.ld_packed >> 2) - (bit0 >> 5);
-    uint32_t wds[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (i < nwords && i < words_left) wds[i] = __ldg(wp + i);
+      if (i < nwords && i < words_left) e.w[i] = __ldg(wp + i);
+  }
+  return e;
+}
+
+// bit i of the low byte of b -> bit 4 i (one bit per nibble)
+__device__ __forceinline__ uint32_t spread8_nibbles(uint32_t b) {
+  uint32_t x = b & 0xFFu;
+  x = (x | (x << 12)) & 0x000F000Fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x;
+}
+// bit i of the low nibble of b -> bit 8 i (one bit per byte)
+__device__ __forceinline__ uint32_t spread4_bytes(uint32_t b) { return ((b & 0xFu) * 0x00204081u) & 0x01010101u; }
+
+// Sign / ternary / XnorNet weights straight from their bit planes with integer operations (no per-element float work):
+//   e2m1 nibble  +1 = 0x2, -1 = 0xA;   int8  +1 = 0x01, -1 = 0xFF;   fp16  +-alpha[k] = half(alpha[k]) ^ (neg << 15).
+// Returns false when the (mode, out_kind) pair needs the generic path.
+template <int CPV>
+__device__ __forceinline__ bool expand_emit_bits(const ExpandArgs& a, int64_t row, int64_t c0, bool one_bit, const ExpandWords& e) {
+  const bool planes2 = a.mode == QT_W_TERNARY || a.mode == QT_W_XNOR;
+  if (!one_bit && !planes2) return false;
+  const int sh = (int)(c0 & 31);
+  const int64_t left = a.k - c0;                                   // valid columns from c0 on (may be <= 0 or > CPV)
+  const uint32_t vm = left <= 0 ? 0u : (left >= 32 ? 0xFFFFFFFFu : ((1u << (int)left) - 1u));
+  // nz: element is non-zero; neg: element is negative (bit planes: 1 <-> +1 in the sign plane)
+  const uint32_t nz = (one_bit ? 0xFFFFFFFFu : (e.w[0] >> sh)) & vm;
+  const uint32_t neg = ~((one_bit ? e.w[0] : e.w[1]) >> sh) & nz;
+  if (CPV == 32 && a.out_kind == 7) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = (spread8_nibbles(nz >> (8 * q)) << 1) | (spread8_nibbles(neg >> (8 * q)) << 3);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out) + row * (a.ld_out >> 1) + (c0 >> 1)) = make_uint4(w[0], w[1], w[2], w[3]);
+    return true;
+  }
+  if (CPV == 16 && a.out_kind == 1) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = spread4_bytes(nz >> (4 * q)) | (spread4_bytes(neg >> (4 * q)) * 0xFEu);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out) + row * a.ld_out + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    return true;
+  }
+  if (CPV == 8 && (a.out_kind == 5 || a.out_kind == 6)) {
+    // fp16: kind 5 = alpha[k] * sign (XnorNet), kind 6 = exact +-1 / 0
+    uint32_t h[4];
+    if (a.out_kind == 5) {
+      float al[8];
+      if (left >= 8 && (c0 & 3) == 0) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(a.alpha + c0)), a1 = __ldg(reinterpret_cast<const float4*>(a.alpha + c0 + 4));
+        al[0] = a0.x; al[1] = a0.y; al[2] = a0.z; al[3] = a0.w; al[4] = a1.x; al[5] = a1.y; al[6] = a1.z; al[7] = a1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) al[j] = (j < left) ? __ldg(a.alpha + c0 + j) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __half2 hh = __floats2half2_rn(al[2 * q], al[2 * q + 1]);
+        h[q] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h[q] = 0x3C003C00u;      // half(1.0) twice
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t n2 = (nz >> (2 * q)) & 3u, g2 = (neg >> (2 * q)) & 3u;
+      const uint32_t keep = ((n2 & 1u) ? 0x0000FFFFu : 0u) | ((n2 & 2u) ? 0xFFFF0000u : 0u);
+      const uint32_t flip = ((g2 & 1u) << 15) | ((g2 & 2u) << 30);
+      h[q] = (h[q] ^ flip) & keep;
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ld_out + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+    return true;
+  }
+  return false;
+}
+
+template <int CPV>
+__device__ __forceinline__ void expand_emit(const ExpandArgs& a, int64_t row, int64_t c0, bool one_bit, const ExpandWords& e) {
+  if (expand_emit_bits<CPV>(a, row, c0, one_bit, e)) return;
+  float v[CPV];
+  if (c0 >= a.k) {
+#pragma unroll
+    for (int j = 0; j < CPV; ++j) v[j] = 0.f;
+  } else if (one_bit) {
+    const uint32_t w = e.w[0] >> (c0 & 31);
+#pragma unroll
+    for (int j = 0; j < CPV; ++j) v[j] = (c0 + j < a.k) ? (((w >> j) & 1u) ? 1.f : -1.f) : 0.f;
+  } else if (a.mode == QT_W_TERNARY || a.mode == QT_W_XNOR) {
+    const uint32_t nz = e.w[0] >> (c0 & 31);
+    const uint32_t sg = e.w[1] >> (c0 & 31);
+#pragma unroll
+    for (int j = 0; j < CPV; ++j) v[j] = (c0 + j < a.k && ((nz >> j) & 1u)) ? (((sg >> j) & 1u) ? 1.f : -1.f) : 0.f;
+  } else {
+    const int lb = a.lane_bits;
+    const int64_t bit0 = c0 * lb;
     const uint32_t mask = (1u << lb) - 1u;
     const float n = (float)((1 << a.bit_width) - 1);
 #pragma unroll
     for (int j = 0; j < CPV; ++j) {
       const int bit = (int)(bit0 & 31) + j * lb;
-      const uint32_t code = (wds[(bit >> 5) & 3] >> (bit & 31)) & mask;
+      const int wi = bit >> 5;                 // selects, not an indexed array: the words stay in registers
+      const uint32_t word = (wi == 0) ? e.w[0] : ((wi == 1) ? e.w[1] : ((wi == 2) ? e.w[2] : e.w[3]));
+      const uint32_t code = (word >> (bit & 31)) & mask;
       float x = (a.out_kind == 2) ? (float)code : 2.f * (float)code - n;
       v[j] = (c0 + j < a.k) ? x : 0.f;
     }
@@ -687,6 +784,32 @@ __global__ void __launch_bounds__(256) weight_expand_kernel(ExpandArgs a) {
     *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
     if (a.out_kind == 4) *reinterpret_cast<uint4*>(o + a.n * a.ld_out) = make_uint4(l[0], l[1], l[2], l[3]);
   }
+}
+
+// One thread per FOUR 16-byte output vectors (CPV = 8 columns of a 16-bit operand, 16 of an 8-bit one, 32 e2m1 nibbles), 256
+// vectors apart, so that every store instruction of a warp covers 512 contiguous bytes and the packed words of all four are
+// in flight before the first is unpacked (with one vector per thread the kernel ran 7 latency-bound waves).
+template <int CPV>
+__global__ void __launch_bounds__(256) weight_expand_kernel(ExpandArgs a) {
+  constexpr int U = 4;
+  // 32-bit index arithmetic (the launcher checks n * vec_per_row < 2^31): a 64-bit division per vector costs more than
+  // the unpacking itself
+  const uint32_t vec_per_row = (uint32_t)(a.ld_out / CPV);
+  const uint32_t total = (uint32_t)a.n * vec_per_row;
+  const uint32_t base = blockIdx.x * (256u * U) + threadIdx.x;
+  const bool one_bit = a.mode == QT_W_SIGN || (a.mode == QT_W_DOREFA && a.bit_width == 1);
+  uint32_t row[U], c0[U];
+  ExpandWords e[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint32_t gid = base + u * 256u;
+    row[u] = gid / vec_per_row;
+    c0[u] = (gid - row[u] * vec_per_row) * CPV;
+    if (gid < total) e[u] = expand_fetch<CPV>(a, row[u], c0[u], one_bit);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (base + u * 256u < total) expand_emit<CPV>(a, row[u], c0[u], one_bit, e[u]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -894,6 +1017,12 @@ extern "C" int qt_patch_rowsum(const void* x_nhwc, int is_unsigned, const QtConv
   return QT_OK;
 }
 
+extern "C" int qt_quant_xnor_parts(int64_t cols, int has_y, int capacity) {
+  if (has_y || cols < 2048) return 1;
+  const int parts = (int)((cols + 1023) / 1024);
+  return capacity >= parts ? parts : 1;
+}
+
 extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   QT_REQUIRE(p && p->x, "qt_quant_act: null argument");
@@ -966,9 +1095,20 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   // warp tasks of <= 2048 columns: many small tasks keep the last wave short (8192 x 4096 -> 16384 tasks, ~3.5 waves of
   // 4 CTAs/SM instead of 1.7); the XNOR row mean needs the whole row in one warp
   a.chunk = p->cols; a.nchunks = 1;
-  if (p->mode != QT_Q_XNOR_ROW && p->cols >= 4096) {
-    a.chunk = 2048;
+  if (p->mode != QT_Q_XNOR_ROW && p->cols >= 2048) {
+    static int qchunk = 0;
+    if (qchunk == 0) {
+      const char* e = getenv("QTB200_QCHUNK");
+      qchunk = e ? atoi(e) : 2048;
+      if (qchunk < 128 || qchunk % 128) qchunk = 2048;
+    }
+    a.chunk = qchunk;
     a.nchunks = (int)ceil_div(p->cols, a.chunk);
+  }
+  if (p->mode == QT_Q_XNOR_ROW) {
+    // one-pass form (no fp32 output): chunks of 1024 columns, each writing a partial row SUM (qt_quant_xnor_parts)
+    a.nchunks = qt_quant_xnor_parts(p->cols, p->y != nullptr, p->row_parts);
+    if (a.nchunks > 1) a.chunk = 1024;
   }
   if (a.nchunks > 1 && p->row_sum) QT_CUDA_OK(cudaMemsetAsync(p->row_sum, 0, sizeof(int32_t) * p->rows, stream));
   const int warps_per_block = 8;
@@ -1065,7 +1205,8 @@ extern "C" int qt_expand_weight(const QtWeightExpand* p, void* stream_) {
   a.out = p->out; a.out_kind = p->out_kind; a.ld_out = p->ld_out;
   const int cpv = (p->out_kind == 7) ? 32 : ((p->out_kind == 1 || p->out_kind == 2) ? 16 : 8);
   const int64_t threads = p->n * (p->ld_out / cpv);
-  const unsigned blocks = (unsigned)ceil_div(threads, 256);
+  QT_REQUIRE(threads < (1ll << 31), "qt_expand_weight: weight matrix too large (n * ld_out / %d >= 2^31)", cpv);
+  const unsigned blocks = (unsigned)ceil_div(threads, 256 * 4);     // four vectors per thread
   if (cpv == 32) weight_expand_kernel<32><<<blocks, 256, 0, stream>>>(a);
   else if (cpv == 16) weight_expand_kernel<16><<<blocks, 256, 0, stream>>>(a);
   else weight_expand_kernel<8><<<blocks, 256, 0, stream>>>(a);

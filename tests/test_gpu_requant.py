@@ -224,3 +224,27 @@ def test_fused_module_is_plain_composition_outside_code_only_mode(Q):
     out = fused(xg)
     out.sum().backward()
     assert xg.grad is not None
+
+
+def test_one_pass_xnor_quantizer_partial_sums(Q):
+    """Code-only XnorNet quantizer on long rows: ONE read of x, 1024-column chunks each leaving a partial row sum that the
+    consumer epilogue adds in order; codes = torch.sign(x), mean within fp32 rounding of the fp64-accumulated mean, and the
+    layer output within 1e-6 of the drop-in (two-pass) mode."""
+    torch.manual_seed(21)
+    x = torch.randn(200, 4096).cuda()
+    x[3, :7] = 0.0
+    lay = Q.layers.LinearXNOR(4096, 264).cuda().eval()
+    q = Q.functions.nnQuantXnor(1)
+    with torch.no_grad():
+        full = q(x)
+        y_ref = lay(full)
+        with Q.code_only_activations():
+            ph = q(x)
+            tag = ph._qt_codes
+            y = lay(ph)
+    assert ph.is_meta and tag.row_parts == 4 and tuple(tag.row_scale.shape) == (4, 200)
+    assert torch.equal(tag.codes[:, :4096].float(), torch.sign(x))
+    mean = tag.row_scale.sum(0) * tag.row_mul
+    ref_mean = x.double().mean(1).float()
+    assert float((mean - ref_mean).abs().max()) <= 1e-6 * float(ref_mean.abs().max()) + 1e-9
+    assert float((y - y_ref).abs().max() / y_ref.abs().max()) < 1e-6
