@@ -140,6 +140,26 @@ __device__ __forceinline__ uint32_t f4_nibble(float v) {   // exact small intege
   return code_to_f4(v, k, o);
 }
 
+// Mode-aware variants: the codes of the sign / ternary / XnorNet quantizers are in {-1, 0, +1}, so the integer comes from
+// two predicates (no float->int conversion on the quarter-rate pipe, no range check).
+template <int MODE>
+__device__ __forceinline__ int code_lane_m(float c, int kind, bool& ovf) {
+  if (MODE == QT_Q_SIGN || MODE == QT_Q_TERNARY || MODE == QT_Q_XNOR_ROW) {
+    const int k = (int)(c > 0.f) - (int)(c < 0.f);
+    return (kind == 2 && k < 0) ? (ovf = true, 0) : k;
+  }
+  return code_to_lane(c, kind, ovf);
+}
+template <int MODE>
+__device__ __forceinline__ uint32_t code_f4_m(float c, int& k, bool& ovf) {
+  if (MODE == QT_Q_SIGN || MODE == QT_Q_TERNARY || MODE == QT_Q_XNOR_ROW) {
+    const bool pos = c > 0.f, neg = c < 0.f;
+    k = (int)pos - (int)neg;
+    return (pos ? 0x2u : 0u) | (neg ? 0xAu : 0u);
+  }
+  return code_to_f4(c, k, ovf);
+}
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -234,8 +254,8 @@ __global__ void __launch_bounds__(256, (MODE == QT_Q_XNOR_ROW) ? 3 : 4) act_quan
       if (valid) {
         if (yr) __stcs(reinterpret_cast<float4*>(yr + c), make_float4(o0.y, o1.y, o2.y, o3.y));   // streamed: never re-read here
         if (c8) {
-          int k0 = code_to_lane(o0.code, a.codes_kind, ovf), k1 = code_to_lane(o1.code, a.codes_kind, ovf);
-          int k2 = code_to_lane(o2.code, a.codes_kind, ovf), k3 = code_to_lane(o3.code, a.codes_kind, ovf);
+          int k0 = code_lane_m<MODE>(o0.code, a.codes_kind, ovf), k1 = code_lane_m<MODE>(o1.code, a.codes_kind, ovf);
+          int k2 = code_lane_m<MODE>(o2.code, a.codes_kind, ovf), k3 = code_lane_m<MODE>(o3.code, a.codes_kind, ovf);
           isum += k0 + k1 + k2 + k3;
           uint32_t w = (uint32_t)(k0 & 0xff) | ((uint32_t)(k1 & 0xff) << 8) | ((uint32_t)(k2 & 0xff) << 16) |
                        ((uint32_t)(k3 & 0xff) << 24);
@@ -273,15 +293,15 @@ __global__ void __launch_bounds__(256, (MODE == QT_Q_XNOR_ROW) ? 3 : 4) act_quan
               *reinterpret_cast<uint2*>(cb_lo2 + c) = l2;
             }
           }
-          isum += (int)o0.code + (int)o1.code + (int)o2.code + (int)o3.code;
+          if (a.row_sum) isum += (int)o0.code + (int)o1.code + (int)o2.code + (int)o3.code;
         }
       }
       if (c4) {  // 4 nibbles per lane; lane pairs merge into one 32-bit store (8 codes)
         uint32_t h = 0;
         if (valid) {
           int k0, k1, k2, k3;
-          h = code_to_f4(o0.code, k0, ovf) | (code_to_f4(o1.code, k1, ovf) << 4) | (code_to_f4(o2.code, k2, ovf) << 8) |
-              (code_to_f4(o3.code, k3, ovf) << 12);
+          h = code_f4_m<MODE>(o0.code, k0, ovf) | (code_f4_m<MODE>(o1.code, k1, ovf) << 4) | (code_f4_m<MODE>(o2.code, k2, ovf) << 8) |
+              (code_f4_m<MODE>(o3.code, k3, ovf) << 12);
           isum += k0 + k1 + k2 + k3;
         }
         const uint32_t hi = __shfl_down_sync(0xffffffffu, h, 1);
@@ -311,7 +331,7 @@ __global__ void __launch_bounds__(256, (MODE == QT_Q_XNOR_ROW) ? 3 : 4) act_quan
       if (valid) {
         if (yr) yr[c] = o.y;
         if (c8) {
-          int k = code_to_lane(o.code, a.codes_kind, ovf);
+          int k = code_lane_m<MODE>(o.code, a.codes_kind, ovf);
           isum += k;
           c8[c] = (int8_t)k;
         } else if (cb) {
@@ -326,14 +346,14 @@ __global__ void __launch_bounds__(256, (MODE == QT_Q_XNOR_ROW) ? 3 : 4) act_quan
             cb_lo[c] = m;
             if (cb_lo2) cb_lo2[c] = __float2bfloat16_rn(o.code - __bfloat162float(h) - __bfloat162float(m));
           }
-          isum += (int)o.code;
+          if (a.row_sum) isum += (int)o.code;
         }
       }
       if (c4) {
         uint32_t nib = 0;
         if (valid) {
           int k;
-          nib = code_to_f4(o.code, k, ovf);
+          nib = code_f4_m<MODE>(o.code, k, ovf);
           isum += k;
         }
         const uint32_t hi = __shfl_down_sync(0xffffffffu, nib, 1);
@@ -423,7 +443,7 @@ __global__ void __launch_bounds__(256) act_quant_nhwc_kernel(NhwcArgs a) {
         if (a.q.pre_scale) v = pre_apply(a.q, v, c % a.q.pre_channels);
         QOut o = quant_elem<MODE>(a.q, v, 0.f);
         if (yb) __stcs(yb + c * a.HW + p, o.y);
-        code = code_to_lane(o.code, a.codes_kind, ovf);
+        code = code_lane_m<MODE>(o.code, a.codes_kind, ovf);
       }
       word |= (uint32_t)(code & 0xff) << (8 * j);
     }
@@ -1023,6 +1043,172 @@ extern "C" int qt_quant_xnor_parts(int64_t cols, int has_y, int capacity) {
   return capacity >= parts ? parts : 1;
 }
 
+namespace qt {
+// ---------------------------------------------------------------------------------------------
+// Lean code-only quantizers (inference chains: no fp32 output, no bit plane, no pre-transform, cols % 1024 == 0).
+// Same per-element semantics as quant_elem; the generic kernel above spends ~100 instructions per 16-byte load on output
+// dispatch and 64-bit indexing and becomes issue-bound at ~4 TB/s, this one stays at the HBM rate (scratch/quant_probe.cu).
+// One warp per 1024-column chunk of a row; 4 x 16-byte loads in flight per lane, two batches.
+// ---------------------------------------------------------------------------------------------
+struct LeanArgs {
+  const float* x;
+  void* codes;
+  int32_t* row_sum;      // DoReFa: atomically accumulated (pre-zeroed by the launcher) when nchunks > 1
+  float* row_scale;      // XnorNet: [nchunks, rows] partial sums, or [rows] means when nchunks == 1
+  int32_t* overflow;
+  uint32_t rows, nchunks;
+  int64_t ld_x, ld_codes;   // elements
+  float n;               // DoReFa levels
+  float inv_cols;
+};
+
+template <int MODE, int CK>
+__global__ void __launch_bounds__(256) act_quant_lean_kernel(LeanArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t task = blockIdx.x * 8u + (threadIdx.x >> 5);
+  if (task >= a.rows * a.nchunks) return;
+  const uint32_t row = task / a.nchunks, ch = task - row * a.nchunks;
+  const float* xr = a.x + (int64_t)row * a.ld_x + ch * 1024u + 4u * lane;
+  float psum = 0.f;
+  int isum = 0;
+  bool ovf = false;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(xr + it * 512 + u * 128));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      const uint32_t col = ch * 1024u + (uint32_t)(it * 512 + u * 128) + 4u * lane;     // first of this lane's 4 columns
+      if (CK == 5 || CK == 3) {           // 16-bit float codes of {-1, 0, +1}
+        float c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (MODE == QT_Q_XNOR_ROW) c[j] = (float)((xs[j] > 0.f) - (xs[j] < 0.f));
+          else if (MODE == QT_Q_SIGN) c[j] = (xs[j] < 0.f) ? -1.f : 1.f;
+          else { const float sg = (xs[j] < 0.f) ? -1.f : 1.f; c[j] = (sg + ((xs[j] - 0.5f * sg < 0.f) ? -1.f : 1.f)) * 0.5f; }
+        }
+        if (MODE == QT_Q_XNOR_ROW) psum += (xs[0] + xs[1]) + (xs[2] + xs[3]);
+        uint2 o;
+        if (CK == 5) {
+          __half2 h0 = __floats2half2_rn(c[0], c[1]), h1 = __floats2half2_rn(c[2], c[3]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        } else {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(c[0], c[1]), h1 = __floats2bfloat162_rn(c[2], c[3]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.codes) + (int64_t)row * a.ld_codes + col) = o;
+      } else {
+        int k[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (MODE == QT_Q_SIGN) k[j] = (xs[j] < 0.f) ? -1 : 1;
+          else if (MODE == QT_Q_TERNARY) { const float sg = (xs[j] < 0.f) ? -1.f : 1.f; k[j] = ((xs[j] < 0.f) ? -1 : 1) + ((xs[j] - 0.5f * sg < 0.f) ? -1 : 1); k[j] >>= 1; }
+          else {                          // DoReFa: rint(n x), saturating to the lane with a sticky flag (NaN -> 0 + flag)
+            float c = rintf(a.n * xs[j]);
+            const float lo = (CK == 7) ? -4.f : ((CK == 1) ? -128.f : 0.f), hi = (CK == 7) ? 4.f : ((CK == 1) ? 127.f : 255.f);
+            if (!(c >= lo && c <= hi)) { ovf = true; c = (c != c) ? 0.f : fminf(fmaxf(c, lo), hi); }
+            k[j] = (int)c;
+          }
+          isum += k[j];
+        }
+        if (CK == 7) {                    // e2m1 nibbles; lane pairs merge into one 32-bit store
+          uint32_t h = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int m = k[j] < 0 ? -k[j] : k[j];
+            const uint32_t nib = (MODE == QT_Q_DOREFA) ? (((0x65420u >> (4 * m)) & 0xFu) | (k[j] < 0 ? 8u : 0u))
+                                                       : ((k[j] > 0 ? 0x2u : 0u) | (k[j] < 0 ? 0xAu : 0u));
+            h |= nib << (4 * j);
+          }
+          const uint32_t hi2 = __shfl_down_sync(0xffffffffu, h, 1);
+          if (!(lane & 1u)) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.codes) + (((int64_t)row * a.ld_codes + col) >> 1)) = h | (hi2 << 16);
+        } else {
+          const uint32_t w = (uint32_t)(k[0] & 0xff) | ((uint32_t)(k[1] & 0xff) << 8) | ((uint32_t)(k[2] & 0xff) << 16) | ((uint32_t)(k[3] & 0xff) << 24);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.codes) + (int64_t)row * a.ld_codes + col) = w;
+        }
+      }
+    }
+  }
+  if (MODE == QT_Q_XNOR_ROW && a.row_scale) {
+    double s = warp_sum_d((double)psum);
+    if (lane == 0) {
+      if (a.nchunks == 1) a.row_scale[row] = (float)(s / 1024.0);
+      else a.row_scale[(int64_t)ch * a.rows + row] = (float)s;
+    }
+  }
+  if (a.row_sum) {
+    isum = warp_sum_i(isum);
+    if (lane == 0) {
+      if (a.nchunks == 1) a.row_sum[row] = isum;
+      else atomicAdd(a.row_sum + row, isum);
+    }
+  }
+  if (MODE == QT_Q_DOREFA && a.overflow) {
+    const unsigned any = __ballot_sync(0xffffffffu, ovf);
+    if (any && lane == 0) atomicOr(a.overflow, 1);
+  }
+}
+
+template <int MODE, int CK>
+static int launch_lean(const LeanArgs& a, cudaStream_t stream) {
+  const uint32_t tasks = a.rows * a.nchunks;
+  act_quant_lean_kernel<MODE, CK><<<(tasks + 7u) / 8u, 256, 0, stream>>>(a);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+// Returns 1 when the call was served by a lean kernel, 0 when the generic kernel must run, < 0 on error.
+static int try_lean_quant(const QtActQuant* p, cudaStream_t stream) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("QTB200_LEAN_QUANT"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  if (!enabled) return 0;
+  if (p->y || p->bits || p->pre_scale || p->nhwc_c || !p->codes) return 0;
+  if (p->cols % 1024 != 0 || p->ld_x % 4 != 0 || !aligned(p->x, 16) || p->ld_codes != p->cols) return 0;
+  if (p->rows * (p->cols / 1024) >= (1ll << 31) || p->cols >= (1ll << 31)) return 0;
+  const int ck = p->codes_kind;
+  if (!(ck == 1 || ck == 2 || ck == 3 || ck == 5 || ck == 7)) return 0;
+  if ((ck == 3 || ck == 5) && (p->ld_codes % 4 != 0 || !aligned(p->codes, 8))) return 0;
+  if ((ck == 1 || ck == 2) && (p->ld_codes % 4 != 0 || !aligned(p->codes, 4))) return 0;
+  if (ck == 7 && (p->ld_codes % 8 != 0 || !aligned(p->codes, 4))) return 0;
+  LeanArgs a;
+  a.x = p->x; a.codes = p->codes; a.row_sum = p->row_sum; a.row_scale = p->row_scale; a.overflow = p->overflow;
+  a.rows = (uint32_t)p->rows; a.nchunks = (uint32_t)(p->cols / 1024); a.ld_x = p->ld_x; a.ld_codes = p->ld_codes;
+  a.n = 1.f; a.inv_cols = 1.f / (float)p->cols;
+  if (p->mode == QT_Q_XNOR_ROW) {
+    if (!(ck == 3 || ck == 5)) return 0;
+    // the partial-sum contract of qt_quant_xnor_parts: chunks of 1024 columns only when the caller provided room for them
+    const int parts = qt_quant_xnor_parts(p->cols, 0, p->row_parts);
+    if (p->row_scale && (uint32_t)parts != a.nchunks) return 0;
+    return (ck == 5 ? launch_lean<QT_Q_XNOR_ROW, 5>(a, stream) : launch_lean<QT_Q_XNOR_ROW, 3>(a, stream)) == QT_OK ? 1 : QT_ECUDA;
+  }
+  if (a.nchunks > 1 && p->row_sum) {
+    if (cudaMemsetAsync(p->row_sum, 0, sizeof(int32_t) * p->rows, stream) != cudaSuccess) return 0;
+  }
+  int rc = 0;
+  if (p->mode == QT_Q_SIGN) {
+    if (ck == 7) rc = launch_lean<QT_Q_SIGN, 7>(a, stream);
+    else if (ck == 1) rc = launch_lean<QT_Q_SIGN, 1>(a, stream);
+    else return 0;
+  } else if (p->mode == QT_Q_TERNARY) {
+    if (ck == 7) rc = launch_lean<QT_Q_TERNARY, 7>(a, stream);
+    else if (ck == 1) rc = launch_lean<QT_Q_TERNARY, 1>(a, stream);
+    else return 0;
+  } else if (p->mode == QT_Q_DOREFA) {
+    if (p->bit_width < 2 || p->bit_width > 8) return 0;
+    a.n = (float)((1 << p->bit_width) - 1);
+    if (ck == 7 && p->bit_width == 2) rc = launch_lean<QT_Q_DOREFA, 7>(a, stream);
+    else if (ck == 1) rc = launch_lean<QT_Q_DOREFA, 1>(a, stream);
+    else if (ck == 2) rc = launch_lean<QT_Q_DOREFA, 2>(a, stream);
+    else return 0;
+  } else {
+    return 0;
+  }
+  return rc == QT_OK ? 1 : rc;
+}
+}  // namespace qt
+
 extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   QT_REQUIRE(p && p->x, "qt_quant_act: null argument");
@@ -1068,6 +1254,8 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   a.x = p->x; a.rows = p->rows; a.cols = p->cols; a.ld_x = p->ld_x;
   a.y = p->y; a.ld_y = p->ld_y; a.codes = p->codes; a.codes_kind = p->codes_kind; a.ld_codes = p->ld_codes;
   a.bits = p->bits; a.ld_bits = p->ld_bits; a.row_sum = p->row_sum; a.row_scale = p->row_scale; a.overflow = p->overflow;
+
+  if (int lean = try_lean_quant(p, stream)) return lean > 0 ? QT_OK : lean;
 
   if (p->nhwc_c > 0) {
     QT_REQUIRE(p->codes && (p->codes_kind == 1 || p->codes_kind == 2), "qt_quant_act: NHWC output needs int8/uint8 codes");

@@ -248,3 +248,33 @@ def test_one_pass_xnor_quantizer_partial_sums(Q):
     ref_mean = x.double().mean(1).float()
     assert float((mean - ref_mean).abs().max()) <= 1e-6 * float(ref_mean.abs().max()) + 1e-9
     assert float((y - y_ref).abs().max() / y_ref.abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("qname", ["sign", "ternary", "dorefa2", "dorefa4", "dorefa8", "xnor"])
+def test_lean_code_only_quantizers_match_generic_kernel(Q, qname):
+    """cols % 1024 == 0 in code-only mode takes the lean streaming kernels (act_quant_lean_kernel); their operand must be
+    bit-identical to what the generic kernel emits in drop-in mode (codes, row sums, overflow flag), including edge values."""
+    torch.manual_seed(31)
+    M, K = 70, 2048
+    x = _input(qname, M, K).cuda()
+    if qname.startswith("dorefa"):
+        x[0, :8] = torch.tensor([0.0, 1.0, 0.5, 1 / 6, 0.1667, 0.8333, 1.2, -0.3]).cuda()     # ties, out-of-range (unclamped)
+    else:
+        x[0, :8] = torch.tensor([0.0, -0.0, 0.5, -0.5, 0.4999, -0.5001, 1e-45, float("nan")]).cuda()
+    q = _quantizer(Q, qname)
+    with torch.no_grad():
+        ref = q(x)._qt_codes                     # generic kernel (also writes the fp32 tensor)
+        with Q.code_only_activations():
+            got = q(x)._qt_codes                 # lean kernel
+    assert got.codes_kind == ref.codes_kind
+    if qname == "xnor":
+        assert torch.equal(got.codes.float(), ref.codes.float())
+        mean = got.row_scale.sum(0) * got.row_mul if got.row_parts else got.row_scale
+        ok = torch.isfinite(ref.row_scale)
+        assert float((mean[ok] - ref.row_scale[ok]).abs().max()) <= 2e-7 * float(ref.row_scale[ok].abs().max()) + 1e-9
+    else:
+        assert torch.equal(_codes_as_int(got), _codes_as_int(ref))
+        if ref.row_sum is not None:
+            assert torch.equal(got.row_sum, ref.row_sum)
+        if ref.overflow is not None:
+            assert int(got.overflow.item()) == int(ref.overflow.item())
