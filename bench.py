@@ -410,7 +410,11 @@ def run_ours(args):
                 "timing": ("CUDA events recorded as external event nodes inside the captured step graphs; mean over the last replay of "
                            "each of the %d graphs within the timed region" % NBUF) if graph_mode else
                           "CUDA events around every launch of the timed region",
-                "traffic": None}
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` launch
+                # (profiles/r1i_ncu_full_summary.json: 157.9 MB read + 46.5 MB written; algorithmic 100.7 MB of operands +
+                # 67.1 MB of fp16 codes, part of which is still in L2 when the kernel ends)
+                "traffic": 204.3e6, "traffic_unit": "bytes per launch (ncu, profiles/r1i_ncu_full_summary.json)",
+                "algorithmic_bytes": float(2 * M * K + 2 * N * K + 2 * M * N + 4 * N)}
 
     cb = cpu_reference_gops(2048, reps=3, warmup=1)
     cpu_baseline = {"value": round(cb["gops_best"], 2), "unit": "GOPS", "cores": cb["cores"], "kind": "port",
@@ -485,6 +489,15 @@ def extra_layers(Q, torch, dev, pk, _ops):
             "hbm_gbs_algorithmic": round(bytes_module / ms / 1e6, 1),
             "hbm_frac": round(bytes_module / ms / 1e6 / pk["hbm_gbs"], 4)}
         Q.set_backend(i8="auto", popcount=False)
+    # same layer with the activation quantizer in code-only mode (inference chains: no fp32 sign tensor is written)
+    def fc():
+        i[0] += 1
+        with Q.code_only_activations():
+            return lay(act(xs[i[0] % 2]))
+    ms = time_fn(torch, fc, iters=20)
+    out["linearbin_4096x4096_b8192_code_only_quantizer"] = {
+        "ms": round(ms, 4), "gops": round(ops_ / ms / 1e6, 1), "hbm_gbs_algorithmic": round(bytes_module / ms / 1e6, 1),
+        "hbm_frac": round(bytes_module / ms / 1e6 / pk["hbm_gbs"], 4)}
     # contraction kernel alone on pre-quantized operands
     xq = act(xs[0])
     ms = time_fn(torch, lambda: lay(xq), iters=20)
