@@ -38,6 +38,8 @@ enum {
 };
 
 int qt_version(void);
+/* sizeof() of a struct of this header by name ("QtEpilogue", ...), -1 if unknown: lets a binding check its mirror. */
+int qt_sizeof(const char* struct_name);
 const char* qt_last_error(void);
 /* sm major/minor, SM count, 1 if tcgen05 kernels can run on `device`. */
 int qt_device_caps(int device, int* sm_major, int* sm_minor, int* num_sms, int* has_tcgen05);

@@ -75,6 +75,7 @@ class QtEpilogue(C.Structure):
 # every symbol include/qtb200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qt_version": (i32, []),
+    "qt_sizeof": (i32, [C.c_char_p]),
     "qt_last_error": (C.c_char_p, []),
     "qt_requant_max_parts": (i32, [i64]),
     "qt_device_caps": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),

@@ -47,6 +47,14 @@ extern "C" {
 
 int qt_version(void) { return QT_VERSION; }
 
+int qt_sizeof(const char* name) {
+  if (!name) return -1;
+#define QT_SZ(T) if (strcmp(name, #T) == 0) return (int)sizeof(T);
+  QT_SZ(QtActQuant) QT_SZ(QtWeightPack) QT_SZ(QtWeightExpand) QT_SZ(QtIm2col) QT_SZ(QtRequant) QT_SZ(QtEpilogue) QT_SZ(QtConvGeom)
+#undef QT_SZ
+  return -1;
+}
+
 int qt_requant_max_parts(int64_t N) { return (int)(2 * ((N + 127) / 128) + 2); }
 
 const char* qt_last_error(void) { return qt::g_err; }

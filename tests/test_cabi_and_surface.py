@@ -119,3 +119,13 @@ def test_no_cpu_fallback(Q):
             if f.endswith(".py"):
                 txt = open(os.path.join(root, f)).read()
                 assert "quanttorch_oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_ctypes_mirrors_have_the_c_struct_sizes():
+    """Every ctypes.Structure in _lib.py must have the size the compiler gives the struct of include/qtb200.h."""
+    import ctypes
+    from pytorch_quantize_impls_b200 import _lib as L
+    lib = L.lib()
+    for name in ("QtActQuant", "QtWeightPack", "QtWeightExpand", "QtIm2col", "QtRequant", "QtEpilogue", "QtConvGeom"):
+        assert lib.qt_sizeof(name.encode()) == ctypes.sizeof(getattr(L, name)), name
+    assert lib.qt_sizeof(b"nope") == -1
