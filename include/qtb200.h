@@ -189,9 +189,10 @@ typedef struct QtIm2col {
   void* out;                   /* [B*OH*OW, ld_out] */
   int64_t ld_out;              /* elements; columns beyond (C/groups)*kh*kw zero-filled */
   int32_t* row_sum;            /* optional */
-  int split3;                  /* 1: x is fp32 (elem_bytes 4) and `out` receives THREE bf16 planes hi/mid/lo of the gathered
-                                  values, plane stride = B*OH*OW*ld_out elements (fused gather + fp32-faithful split for
-                                  first layers that see real-valued images) */
+  int split3;                  /* != 0: x is fp32 (elem_bytes 4) and `out` receives bf16 planes of the gathered values, plane
+                                  stride = B*OH*OW*ld_out elements (fused gather + split for first layers that see real-valued
+                                  images): 1 or 3 = THREE planes hi/mid/lo (24 significant bits, fp32-faithful), 2 = TWO planes
+                                  hi/lo (16 significant bits, relative error <= 2^-17) */
 } QtIm2col;
 
 int qt_im2col(const QtIm2col* p, void* stream);

@@ -102,6 +102,16 @@ def tagged_input_device(x):
     return x.device
 
 
+_first_layer_planes = [int(os.environ.get("QTB200_FIRST_LAYER_PLANES", "2"))]
+
+
+def set_first_layer_planes(n):
+    """bf16 planes of a conv layer's real-valued (fp32 image) input: 2 (default, 16 significant bits) or 3 (24 bits)."""
+    if n not in (2, 3):
+        raise ValueError("first-layer planes must be 2 or 3")
+    _first_layer_planes[0] = n
+
+
 def set_implicit_conv(flag):
     """True (default): conv layers on channels-last codes use the TMA-im2col implicit GEMM; False: explicit gather."""
     _implicit_conv[0] = bool(flag)
@@ -268,7 +278,7 @@ def _contract(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=Non
         b.row_sum = a.row_sum[:a.row_parts].sum(0).to(torch.int32).contiguous()
     b.row_parts, b.row_mul = 0, 1.0
     return _contract_impl(b, pack, M, N, K, out, w_row0=w_row0, bias=bias, out_mode=out_mode, ldo=ldo,
-                          nchw_inner=nchw_inner, out_offset=out_offset, acc_out=acc_out)
+                          nchw_inner=nchw_inner, out_offset=out_offset, acc_out=acc_out, rq_spec=rq_spec)
 
 
 def _contract_impl(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ldo=None, nchw_inner=1, out_offset=0,
@@ -283,7 +293,7 @@ def _contract_impl(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ld
 
     if a.form in ("i8", "f4") and int_w:
         use_pop = (a.bits is not None and pack.kind in ("sign", "ternary") and a.scale == 1.0 and out_mode == 0
-                   and requant is None and a.row_parts == 0
+                   and requant is None and rq_spec is None and a.row_parts == 0
                    and (_force_popcount[0] or (M <= POPCOUNT_MAX_M and _force_backend["i8"] == L.BACKEND_AUTO)))
         if use_pop:
             epi = ops.make_epi(out, ldo=ldo, bias=bias, scale=1.0, acc_out=acc_out, out_offset=out_offset)
@@ -358,7 +368,7 @@ def _contract_impl(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ld
     ops.gemm_f16(a.t, a.ld, a_stride, w[0, w_row0:], ldw, w_stride, passes, M, N, K, epi, _force_backend["bf16"])
 
 
-def linear(x, pack, bias, requant=None):
+def linear(x, pack, bias, requant=None, affine=None):
     """F.linear(x, W_q, bias) with W_q given as a WeightPack.  x: [..., K] fp32 CUDA tensor.
     requant (RequantSpec): fused inference chain -- the epilogue writes the next layer's low-bit operand and the
     fp32 output is never materialised; returns a code-only placeholder carrying that operand."""
@@ -399,7 +409,7 @@ def linear(x, pack, bias, requant=None):
         _contract(a, pack, M, N, K, None, bias=bias, requant=rq, rq_spec=requant)
         y = torch.empty((M, N), dtype=torch.float32, device="meta")
         return attach_tag(y, _requant_tag(requant, rq, (M, N)))
-    _contract(a, pack, M, N, K, out, bias=bias)
+    _contract(a, pack, M, N, K, out, bias=bias, rq_spec=affine)     # affine: folded BatchNorm (RequantSpec.fold), fp32 output
     return out.reshape(*lead, N)
 
 
@@ -407,7 +417,7 @@ def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
 
-def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requant=None):
+def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requant=None, affine=None):
     """F.conv2d(x, W_q, bias, stride, padding, dilation, groups) via im2col gather + GEMM with an NCHW epilogue.
     requant (RequantSpec): the implicit-GEMM epilogue writes the next conv's channels-last codes [B, OH, OW, O] instead of
     the fp32 NCHW tensor (raises RequantUnsupported when the call cannot take the implicit-GEMM route)."""
@@ -467,8 +477,8 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
             rs = ops.patch_rowsum(tag.codes, not a_signed, geom, g) if need_rs else None
             cs = None if col_scale is None else col_scale[g * Ng:(g + 1) * Ng]
             bg = None if bias is None else bias[g * Ng:(g + 1) * Ng]
-            if requant is not None:
-                cs, bg = requant.fold(cs, bg, g * Ng, Ng)
+            if requant is not None or affine is not None:
+                cs, bg = (requant or affine).fold(cs, bg, g * Ng, Ng)
             epi = ops.make_epi(out, ldo=O, out_mode=1, nchw_inner=P, bias=bg, col_scale=cs,
                                row_sum=rs, acc_mul=2 if need_rs else 1, rs_mul=-255 if need_rs else 0,
                                scale=tag.scale, out_offset=g * Ng * P, requant=rq)
@@ -488,8 +498,11 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
         elem, ld, nplanes = 1, ops.round_up(Kg, 16), 1
         dtype = tag.codes.dtype
     else:
-        # real-valued input (first layers): fused gather + bf16 hi/mid/lo split straight from the fp32 NCHW tensor
-        elem, ld, nplanes = 2, ops.round_up(Kg, 8), 3
+        # real-valued input (first layers): fused gather + bf16 split straight from the fp32 NCHW tensor.  Two planes (hi/lo,
+        # 16 significant bits: relative error <= 2^-17 per element, two orders of magnitude inside the 1e-3 tolerance) by
+        # default -- the im2col planes of a 224x224 first conv are GBs, a third plane costs 50 % more traffic and MMA passes;
+        # set_first_layer_planes(3) restores the fp32-faithful hi/mid/lo split
+        elem, ld, nplanes = 2, ops.round_up(Kg, 8), _first_layer_planes[0]
         xf = ops.as_f32c(x)
         dtype = torch.bfloat16
 
@@ -513,8 +526,8 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
                            is_unsigned=(dtype == torch.uint8), nhwc=True)
                 a.form, a.t, a.signed, a.scale, a.planes = "i8", buf[0], dtype == torch.int8, tag.scale, 1
             else:
-                ops.im2col(xf[b0:b1], 4, geom, g, buf, ld, split3=True)
-                a.form, a.t, a.signed, a.scale, a.planes = "bf16", buf, True, 1.0, 3
+                ops.im2col(xf[b0:b1], 4, geom, g, buf, ld, split3=nplanes)
+                a.form, a.t, a.signed, a.scale, a.planes = "bf16", buf, True, 1.0, nplanes
             _contract(a, pack, M, Ng, Kg, out, w_row0=g * Ng, bias=None if bias is None else bias[g * Ng:(g + 1) * Ng],
-                      out_mode=1, ldo=O, nchw_inner=P, out_offset=(b0 * O + g * Ng) * P)
+                      out_mode=1, ldo=O, nchw_inner=P, out_offset=(b0 * O + g * Ng) * P, rq_spec=affine)
     return out

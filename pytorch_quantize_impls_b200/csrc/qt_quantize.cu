@@ -907,6 +907,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
 // First-layer gather: fp32 NCHW image -> three bf16 planes (hi/mid/lo) of the im2col matrix in one pass.
 // The column -> (input offset, dy, dx) decomposition is tabulated once per CTA in shared memory, so the inner loop is
 // table lookups + L1-resident gathers; each thread emits 8 consecutive columns (one 16-byte store per plane).
+template <int NPLANES>
 __global__ void __launch_bounds__(256) im2col_split3_kernel(Im2colArgs a, int64_t plane_stride) {
   extern __shared__ int tab[];                 // [kcols] offset, [kcols] (dy << 16 | dx)
   int* toff = tab;
@@ -947,7 +948,7 @@ __global__ void __launch_bounds__(256) im2col_split3_kernel(Im2colArgs a, int64_
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + m * a.ld_out + col0;
     *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
     *reinterpret_cast<uint4*>(o + plane_stride) = *reinterpret_cast<uint4*>(mi);
-    *reinterpret_cast<uint4*>(o + 2 * plane_stride) = *reinterpret_cast<uint4*>(lo);
+    if (NPLANES == 3) *reinterpret_cast<uint4*>(o + 2 * plane_stride) = *reinterpret_cast<uint4*>(lo);
   }
 }
 
@@ -1419,12 +1420,14 @@ extern "C" int qt_im2col(const QtIm2col* p, void* stream_) {
   const int64_t M = p->B * p->OH * p->OW;
   if (M == 0) return QT_OK;
   if (p->split3) {
+    QT_REQUIRE(p->split3 == 1 || p->split3 == 2 || p->split3 == 3, "qt_im2col: split3 must be 0, 1 (= 3 planes), 2 or 3");
     QT_REQUIRE(p->elem_bytes == 4 && !p->nhwc && !p->row_sum, "qt_im2col: split3 needs fp32 NCHW input and no row sums");
     QT_REQUIRE(p->ld_out % 8 == 0 && aligned(p->out, 16) && (M * p->ld_out) % 8 == 0, "qt_im2col: split3 needs ld_out % 8 == 0");
     QT_REQUIRE(a.kcols <= 4096 && p->C * p->H * p->W < (1ll << 31), "qt_im2col: split3 supports up to 4096 gathered columns");
     int64_t vecs = M * (p->ld_out / 8);
     unsigned nb = (unsigned)std::min<int64_t>(ceil_div(vecs, 256), 148 * 16);
-    im2col_split3_kernel<<<nb, 256, 2 * a.kcols * sizeof(int), stream>>>(a, M * p->ld_out);
+    if (p->split3 == 2) im2col_split3_kernel<2><<<nb, 256, 2 * a.kcols * sizeof(int), stream>>>(a, M * p->ld_out);
+    else im2col_split3_kernel<3><<<nb, 256, 2 * a.kcols * sizeof(int), stream>>>(a, M * p->ld_out);
     QT_LAUNCH_CHECK();
     return QT_OK;
   }

@@ -186,6 +186,36 @@ class FusedLayerQuant(nn.Module):
         return "fused epilogue requant"
 
 
+class FusedLayerBN(nn.Module):
+    """quantized Linear / Conv2d -> BatchNorm (eval): the BatchNorm affine is folded into the per-column scale / bias of the
+    layer's epilogue (y*s + t = acc*(cs*s) + (b*s + t)), so the normalisation costs no pass over the activation.  Applies
+    with autograd off and the BatchNorm in eval mode; otherwise the plain composition runs."""
+
+    def __init__(self, layer, bn):
+        super().__init__()
+        self.layer, self.bn = layer, bn
+        self._spec = None
+
+    def _make_spec(self):
+        bn = self.bn
+        params = [t for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None]
+        key = tuple((t.data_ptr(), t._version) for t in params)
+        if self._spec is None or self._spec[0] != key:
+            mul, add = _bn_affine(bn)
+            self._spec = (key, eng.RequantSpec(-1, None, col_mul=mul, col_add=add))
+        return self._spec[1]
+
+    def forward(self, x):
+        bn = self.bn
+        if (not torch.is_grad_enabled() and (x.is_cuda or x.is_meta) and not bn.training and bn.track_running_stats
+                and bn.running_mean is not None):
+            return self.layer._forward_affine(x, self._make_spec())
+        return bn(self.layer(x))
+
+    def extra_repr(self):
+        return "BatchNorm folded into the epilogue"
+
+
 def _needs_8bit_lanes(consumer):
     """True when the layer that will read the codes cannot take e2m1 operands (DoReFa k >= 3 weights, convs, unknown)."""
     from .layers.common import QuantLayerMixin
@@ -227,6 +257,12 @@ def fuse_inference(module):
                     consumer = mods[j + 1] if j + 1 < len(mods) else None
                     out.append(FusedLayerQuant(mods[i], bn, act, mods[j], consumer))
                     i = j + 1
+                    continue
+                if bn is not None:
+                    # layer -> BatchNorm with no quantizer behind it (pool / residual add / plain activation follows):
+                    # fold the normalisation into the layer's epilogue
+                    out.append(FusedLayerBN(mods[i], bn))
+                    i += 2
                     continue
             j = i
             bn = act = None

@@ -147,6 +147,15 @@ class QuantLayerMixin(QLayer):
                               self.dilation, self.groups, requant=spec)
         return eng.linear(input, pack, self.bias, requant=spec)
 
+    def _forward_affine(self, input, spec):
+        """Inference: contraction with a per-output-channel affine (folded eval-mode BatchNorm) in the epilogue."""
+        eng.tagged_input_device(input)
+        pack = self._current_pack()
+        if self._is_conv:
+            return eng.conv2d(input, pack, self.bias, tuple(self.weight.shape), self.stride, self.padding,
+                              self.dilation, self.groups, affine=spec)
+        return eng.linear(input, pack, self.bias, affine=spec)
+
     def forward(self, input):
         eng.tagged_input_device(input)
         needs_grad = torch.is_grad_enabled() and (

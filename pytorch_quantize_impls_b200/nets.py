@@ -88,11 +88,13 @@ class TerBasicBlock(nn.Module):
     def __init__(self, lib, in_planes, planes, stride, act_bits):
         super().__init__()
         self.q_in = lib.nnDorefaQuant(act_bits)
-        self.conv1 = lib.TerConv2d(in_planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
-        # BN -> clamp -> quantizer kept as one Sequential so that fusion.fuse_inference can turn it into a single pass
-        self.post1 = nn.Sequential(nn.BatchNorm2d(planes), nn.Hardtanh(0.0, 1.0), lib.nnDorefaQuant(act_bits))
-        self.conv2 = lib.TerConv2d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        # conv -> BN -> clamp -> quantizer kept as one Sequential so that fusion.fuse_inference can move BN, clamp and the
+        # quantizer into the conv epilogue (the codes go straight to conv2's TMA im2col)
+        self.branch1 = nn.Sequential(lib.TerConv2d(in_planes, planes, kernel_size=3, stride=stride, padding=1, bias=False),
+                                     nn.BatchNorm2d(planes), nn.Hardtanh(0.0, 1.0), lib.nnDorefaQuant(act_bits))
+        # conv -> BN pairs are Sequentials so that fuse_inference folds the BatchNorm into the conv epilogue (FusedLayerBN)
+        self.branch2 = nn.Sequential(lib.TerConv2d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False),
+                                     nn.BatchNorm2d(planes))
         self.clip = nn.Hardtanh(0.0, 1.0)
         self.shortcut = None
         if stride != 1 or in_planes != planes:
@@ -101,8 +103,8 @@ class TerBasicBlock(nn.Module):
 
     def forward(self, x):                      # x in [0, 1]
         xq = self.q_in(x)
-        out = self.post1(self.conv1(xq))
-        out = self.bn2(self.conv2(out))
+        out = self.branch1(xq)
+        out = self.branch2(out)
         out = out + (x if self.shortcut is None else self.shortcut(xq))
         return self.clip(out)
 
@@ -112,8 +114,7 @@ class ResNetTer(nn.Module):
         super().__init__()
         self.in_planes = 64
         # ImageNet stem (7x7 s2 + max-pool): the reference's CIFAR stem at 224x224 would cost 27 GMAC/img
-        self.conv1 = lib.TerConv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
-        self.bn1 = nn.BatchNorm2d(64)
+        self.stem = nn.Sequential(lib.TerConv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False), nn.BatchNorm2d(64))
         self.clip = nn.Hardtanh(0.0, 1.0)
         self.pool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
         cfg = [(64, 1), (128, 2), (256, 2), (512, 2)]
@@ -127,7 +128,7 @@ class ResNetTer(nn.Module):
         self.linear = nn.Linear(512, num_classes)
 
     def forward(self, x):
-        out = self.pool(self.clip(self.bn1(self.conv1(x))))
+        out = self.pool(self.clip(self.stem(x)))
         out = self.layers(out)
         return self.linear(self.avg(out).flatten(1))
 
