@@ -258,6 +258,9 @@ typedef struct QtEpilogue {
                              the effective row scale is row_scale_mul * sum_p row_scale[p * M + m] */
   float row_scale_mul;
   int row_sum_parts;      /* > 0: row_sum is [row_sum_parts, M] partial sums, summed the same way */
+  int out_clamp;          /* 1: y = min(max(y, out_lo), out_hi) before it is written (a Hardtanh / ReLU / ReLU6 that follows the
+                             layer, e.g. models/Resnet/Resnet_bin.py:27-31, costs no pass over the activation) */
+  float out_lo, out_hi;
 } QtEpilogue;
 
 /* 1-bit x 1-bit: acc = K - 2 popc(a ^ w).  CUDA-core XNOR + popcount. */

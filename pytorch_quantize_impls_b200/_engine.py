@@ -287,6 +287,8 @@ def _contract_impl(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ld
     col_scale = None if pack.col_scale is None else pack.col_scale[w_row0:w_row0 + N]
     int_w = pack.kind in ("sign", "ternary", "dorefa")
     rp = dict(row_parts=a.row_parts, row_mul=a.row_mul, requant=requant)
+    if requant is None and rq_spec is not None and rq_spec.lo is not None:
+        rp["out_clamp"] = (rq_spec.lo, rq_spec.hi)       # a clamp activation folded behind the (BatchNorm-folded) layer
 
     def folded(cs, b):
         return rq_spec.fold(cs, b, w_row0, N) if rq_spec is not None else (cs, b)
@@ -481,7 +483,8 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
                 cs, bg = (requant or affine).fold(cs, bg, g * Ng, Ng)
             epi = ops.make_epi(out, ldo=O, out_mode=1, nchw_inner=P, bias=bg, col_scale=cs,
                                row_sum=rs, acc_mul=2 if need_rs else 1, rs_mul=-255 if need_rs else 0,
-                               scale=tag.scale, out_offset=g * Ng * P, requant=rq)
+                               scale=tag.scale, out_offset=g * Ng * P, requant=rq,
+                               out_clamp=(affine.lo, affine.hi) if (affine is not None and affine.lo is not None) else None)
             if not ops.conv_i8(tag.codes, a_signed, geom, g, w[g * Ng:], not need_rs, ldw, Ng, epi):
                 done = False
                 break

@@ -69,7 +69,7 @@ class QtEpilogue(C.Structure):
                 ("scale", f32), ("acc_mul", C.c_int32), ("rs_mul", C.c_int32),
                 ("out", vp), ("ldo", i64), ("out_mode", i32), ("nchw_inner", i64), ("acc_out", vp),
                 ("requant", C.POINTER(QtRequant)), ("row_scale_parts", i32), ("row_scale_mul", f32),
-                ("row_sum_parts", i32)]
+                ("row_sum_parts", i32), ("out_clamp", i32), ("out_lo", f32), ("out_hi", f32)]
 
 
 # every symbol include/qtb200.h declares: name -> (restype, argtypes)

@@ -281,7 +281,8 @@ def im2col(x4d, elem_bytes, geom, group, out, ld_out, row_sum=None, is_unsigned=
 
 
 def make_epi(out, *, ldo, out_mode=0, nchw_inner=1, bias=None, row_scale=None, col_scale=None, row_sum=None,
-             scale=1.0, acc_mul=1, rs_mul=0, acc_out=None, out_offset=0, row_parts=0, row_mul=1.0, requant=None):
+             scale=1.0, acc_mul=1, rs_mul=0, acc_out=None, out_offset=0, row_parts=0, row_mul=1.0, requant=None,
+             out_clamp=None):
     """requant: a RequantOut (fused re-quantisation of the output); row_parts > 0: row_scale / row_sum are partial sums
     left by a previous layer's requant epilogue."""
     e = L.QtEpilogue()
@@ -295,6 +296,8 @@ def make_epi(out, *, ldo, out_mode=0, nchw_inner=1, bias=None, row_scale=None, c
             e.row_scale_parts, e.row_scale_mul = int(row_parts), float(row_mul)
         if row_sum is not None:
             e.row_sum_parts = int(row_parts)
+    if out_clamp is not None:
+        e.out_clamp, e.out_lo, e.out_hi = 1, float(out_clamp[0]), float(out_clamp[1])
     if requant is not None:
         e.requant = C.pointer(requant.c)
         e._keep = requant        # keep the ctypes struct alive as long as the epilogue

@@ -67,6 +67,8 @@ struct Epi {
   int32_t* rq_overflow;
   int row_scale_parts, row_sum_parts;
   float row_scale_mul;
+  int out_clamp;
+  float out_lo, out_hi;
 };
 
 static inline Epi make_epi(const QtEpilogue* e, int64_t M, int64_t N) {
@@ -84,6 +86,7 @@ static inline Epi make_epi(const QtEpilogue* e, int64_t M, int64_t N) {
     d.rq_row_part = r->row_part; d.rq_row_sum_part = r->row_sum_part; d.rq_overflow = r->overflow;
   }
   d.row_scale_parts = e->row_scale_parts; d.row_sum_parts = e->row_sum_parts; d.row_scale_mul = e->row_scale_mul;
+  d.out_clamp = e->out_clamp; d.out_lo = e->out_lo; d.out_hi = e->out_hi;
   return d;
 }
 
@@ -101,6 +104,7 @@ __device__ __forceinline__ float epi_int(const Epi& e, int64_t m, int64_t n, int
   if (e.row_scale) y *= __ldg(e.row_scale + m);
   if (e.col_scale) y *= __ldg(e.col_scale + n);
   if (e.bias) y += __ldg(e.bias + n);
+  if (e.out_clamp) y = fminf(fmaxf(y, e.out_lo), e.out_hi);
   return y;
 }
 __device__ __forceinline__ float epi_f32(const Epi& e, int64_t m, int64_t n, float acc) {
@@ -108,6 +112,7 @@ __device__ __forceinline__ float epi_f32(const Epi& e, int64_t m, int64_t n, flo
   if (e.row_scale) y *= __ldg(e.row_scale + m);
   if (e.col_scale) y *= __ldg(e.col_scale + n);
   if (e.bias) y += __ldg(e.bias + n);
+  if (e.out_clamp) y = fminf(fmaxf(y, e.out_lo), e.out_hi);
   return y;
 }
 __device__ __forceinline__ int64_t epi_addr(const Epi& e, int64_t m, int64_t n) {

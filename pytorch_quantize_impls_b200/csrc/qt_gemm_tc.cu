@@ -571,6 +571,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
           // float(acc) + bias is one rounding (BinaryNet / Terner bit-exactness)
           const float cs = __shfl_sync(0xffffffffu, cs_l, j), bb = __shfl_sync(0xffffffffu, b_l, j);
           y[j] = (v * mul) * cs + bb;
+          if (e.out_clamp) y[j] = fminf(fmaxf(y[j], e.out_lo), e.out_hi);
         }
         if (e.rq_mode >= 0 && row_ok)
           rq_store_chunk(e, y, m, n0, n_lim, full_chunk ? 32 : (BN - c0), rq_psum, rq_isum, rq_ovf);

@@ -191,29 +191,35 @@ class FusedLayerBN(nn.Module):
     layer's epilogue (y*s + t = acc*(cs*s) + (b*s + t)), so the normalisation costs no pass over the activation.  Applies
     with autograd off and the BatchNorm in eval mode; otherwise the plain composition runs."""
 
-    def __init__(self, layer, bn):
+    def __init__(self, layer, bn, act=None):
         super().__init__()
-        self.layer, self.bn = layer, bn
+        self.layer, self.bn, self.act = layer, bn, act        # bn and / or act (Hardtanh / ReLU / ReLU6) may be None
         self._spec = None
 
     def _make_spec(self):
         bn = self.bn
-        params = [t for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None]
-        key = tuple((t.data_ptr(), t._version) for t in params)
+        key = None
+        if bn is not None:
+            params = [t for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None]
+            key = tuple((t.data_ptr(), t._version) for t in params)
         if self._spec is None or self._spec[0] != key:
-            mul, add = _bn_affine(bn)
-            self._spec = (key, eng.RequantSpec(-1, None, col_mul=mul, col_add=add))
+            mul, add = _bn_affine(bn) if bn is not None else (None, None)
+            lo, hi = _clamp_range(self.act)
+            self._spec = (key, eng.RequantSpec(-1, None, lo=lo, hi=hi, col_mul=mul, col_add=add))
         return self._spec[1]
 
     def forward(self, x):
         bn = self.bn
-        if (not torch.is_grad_enabled() and (x.is_cuda or x.is_meta) and not bn.training and bn.track_running_stats
-                and bn.running_mean is not None):
+        if (not torch.is_grad_enabled() and (x.is_cuda or x.is_meta)
+                and (bn is None or (not bn.training and bn.track_running_stats and bn.running_mean is not None))):
             return self.layer._forward_affine(x, self._make_spec())
-        return bn(self.layer(x))
+        y = self.layer(x)
+        if bn is not None:
+            y = bn(y)
+        return self.act(y) if self.act is not None else y
 
     def extra_repr(self):
-        return "BatchNorm folded into the epilogue"
+        return "BatchNorm / clamp folded into the epilogue"
 
 
 def _needs_8bit_lanes(consumer):
@@ -258,11 +264,11 @@ def fuse_inference(module):
                     out.append(FusedLayerQuant(mods[i], bn, act, mods[j], consumer))
                     i = j + 1
                     continue
-                if bn is not None:
-                    # layer -> BatchNorm with no quantizer behind it (pool / residual add / plain activation follows):
-                    # fold the normalisation into the layer's epilogue
-                    out.append(FusedLayerBN(mods[i], bn))
-                    i += 2
+                if bn is not None or act is not None:
+                    # layer -> [BatchNorm] -> [clamp] with no quantizer behind it (pool / residual add follows): fold the
+                    # normalisation and the clamp into the layer's epilogue
+                    out.append(FusedLayerBN(mods[i], bn, act))
+                    i += 1 + (bn is not None) + (act is not None)
                     continue
             j = i
             bn = act = None

@@ -114,8 +114,8 @@ class ResNetTer(nn.Module):
         super().__init__()
         self.in_planes = 64
         # ImageNet stem (7x7 s2 + max-pool): the reference's CIFAR stem at 224x224 would cost 27 GMAC/img
-        self.stem = nn.Sequential(lib.TerConv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False), nn.BatchNorm2d(64))
-        self.clip = nn.Hardtanh(0.0, 1.0)
+        self.stem = nn.Sequential(lib.TerConv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False), nn.BatchNorm2d(64),
+                                  nn.Hardtanh(0.0, 1.0))
         self.pool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
         cfg = [(64, 1), (128, 2), (256, 2), (512, 2)]
         layers = []
@@ -128,7 +128,7 @@ class ResNetTer(nn.Module):
         self.linear = nn.Linear(512, num_classes)
 
     def forward(self, x):
-        out = self.pool(self.clip(self.stem(x)))
+        out = self.pool(self.stem(x))
         out = self.layers(out)
         return self.linear(self.avg(out).flatten(1))
 

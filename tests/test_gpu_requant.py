@@ -278,3 +278,32 @@ def test_lean_code_only_quantizers_match_generic_kernel(Q, qname):
             assert torch.equal(got.row_sum, ref.row_sum)
         if ref.overflow is not None:
             assert int(got.overflow.item()) == int(ref.overflow.item())
+
+
+@pytest.mark.parametrize("conv", [False, True])
+@pytest.mark.parametrize("with_act", [False, True])
+def test_batchnorm_and_clamp_folded_into_fp32_epilogue(Q, conv, with_act):
+    """layer -> BatchNorm (eval) -> [Hardtanh] with no quantizer behind it: FusedLayerBN folds the affine (and the clamp) into
+    the epilogue; the fp32 result matches the three-module composition to fp32 rounding."""
+    torch.manual_seed(17)
+    if conv:
+        lay = Q.layers.TerConv2d(64, 96, kernel_size=3, padding=1, bias=True)
+        bn = nn.BatchNorm2d(96)
+        q, x = Q.functions.nnDorefaQuant(8), torch.rand(4, 64, 10, 10)
+    else:
+        lay = Q.layers.LinearDorefa(512, 264, bit_width=4)
+        bn = nn.BatchNorm1d(264)
+        q, x = Q.functions.nnDorefaQuant(4), torch.rand(130, 512)
+    bn.running_mean.uniform_(-0.2, 0.2); bn.running_var.uniform_(0.5, 1.5)
+    bn.weight.data.uniform_(0.3, 0.9); bn.bias.data.uniform_(-0.3, 0.6)
+    mods = [q, lay, bn] + ([nn.Hardtanh(0.0, 1.0)] if with_act else [])
+    net = nn.Sequential(*mods).cuda().eval()
+    with torch.no_grad():
+        ref = net(x.cuda())
+        fused = Q.fuse_inference(net)
+        assert isinstance(fused[1], Q.FusedLayerBN) and len(fused) == 2
+        y = fused(x.cuda())
+    assert y.shape == ref.shape
+    assert float((y - ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max()))
+    if with_act:
+        assert float(y.min()) >= 0.0 and float(y.max()) <= 1.0
