@@ -14,5 +14,6 @@ from ._engine import (code_only_activations, set_backend, set_first_layer_planes
 from ._ops import device_caps, set_strict  # noqa: F401
 from .fusion import FusedBNActQuant, FusedLayerBN, FusedLayerQuant, fuse_inference  # noqa: F401
 from .device import device  # noqa: F401
+from .checkpoint import load_packed, packed_state, save_packed  # noqa: F401
 
 __version__ = '0.1'

@@ -75,6 +75,20 @@ class _Contraction(torch.autograd.Function):
 class QuantLayerMixin(QLayer):
     _is_conv = False
     _eval_state = None
+    _packed_only = None       # (WeightPack, weight shape) installed by checkpoint.load_packed: no fp32 master weights
+
+    def _wshape(self):
+        return self._packed_only[1] if self._packed_only is not None else tuple(self.weight.shape)
+
+    def _install_packed(self, pack, weight_shape, drop_master=True):
+        """Make the layer packed-only (inference): the kernels read `pack`; the fp32 weights are released."""
+        self._packed_only = (pack, tuple(weight_shape))
+        self._eval_state = None
+        self.training = False
+        if drop_master:
+            if hasattr(self.weight, "org"):
+                del self.weight.org
+            self.weight = torch.nn.Parameter(torch.empty(0, device=self.weight.device), requires_grad=False)
 
     # ---- hooks -------------------------------------------------------------------------
     def _weight_op(self, w):
@@ -85,6 +99,11 @@ class QuantLayerMixin(QLayer):
 
     # ---- weight-swap train()/eval(), e.g. binary_layers.py:30-40 --------------------------
     def train(self, mode=True):
+        if self._packed_only is not None:
+            if mode:
+                raise RuntimeError("this layer holds packed k-bit weights only (checkpoint.load_packed): load fp32 master "
+                                   "weights before training")
+            return self
         if self.training == mode:
             return self
         self.training = mode
@@ -104,6 +123,8 @@ class QuantLayerMixin(QLayer):
         return self
 
     def _current_pack(self):
+        if self._packed_only is not None:
+            return self._packed_only[0]
         if self.training:
             return self._make_pack(self.weight)               # the reference re-quantizes W on every call
         st = self._eval_state
@@ -134,7 +155,7 @@ class QuantLayerMixin(QLayer):
     def _run_kernels(self, input):
         pack = self._current_pack()
         if self._is_conv:
-            return eng.conv2d(input, pack, self.bias, tuple(self.weight.shape), self.stride, self.padding,
+            return eng.conv2d(input, pack, self.bias, self._wshape(), self.stride, self.padding,
                               self.dilation, self.groups)
         return eng.linear(input, pack, self.bias)
 
@@ -143,7 +164,7 @@ class QuantLayerMixin(QLayer):
         eng.tagged_input_device(input)
         pack = self._current_pack()
         if self._is_conv:
-            return eng.conv2d(input, pack, self.bias, tuple(self.weight.shape), self.stride, self.padding,
+            return eng.conv2d(input, pack, self.bias, self._wshape(), self.stride, self.padding,
                               self.dilation, self.groups, requant=spec)
         return eng.linear(input, pack, self.bias, requant=spec)
 
@@ -152,12 +173,14 @@ class QuantLayerMixin(QLayer):
         eng.tagged_input_device(input)
         pack = self._current_pack()
         if self._is_conv:
-            return eng.conv2d(input, pack, self.bias, tuple(self.weight.shape), self.stride, self.padding,
+            return eng.conv2d(input, pack, self.bias, self._wshape(), self.stride, self.padding,
                               self.dilation, self.groups, affine=spec)
         return eng.linear(input, pack, self.bias, affine=spec)
 
     def forward(self, input):
         eng.tagged_input_device(input)
+        if self._packed_only is not None:
+            return self._run_kernels(input)
         needs_grad = torch.is_grad_enabled() and (
             input.requires_grad or self.weight.requires_grad or (self.bias is not None and self.bias.requires_grad))
         if needs_grad:

@@ -14,6 +14,8 @@ from .common import QuantLayerMixin, _EvalState, check_convert
 class _XnorMixin(QuantLayerMixin):
     def forward(self, input):
         eng.tagged_input_device(input)
+        if self._packed_only is not None:
+            return self._run_kernels(input)
         pack = None
         st = self._eval_state
         if (not self.training and st is not None and st.version == self.weight._version
@@ -23,6 +25,8 @@ class _XnorMixin(QuantLayerMixin):
         return op.apply(input, self.weight, self.bias, pack)
 
     def _current_pack(self):
+        if self._packed_only is not None:
+            return self._packed_only[0]
         st = self._eval_state
         if (not self.training and st is not None and st.version == self.weight._version
                 and st.ptr == self.weight.data_ptr()):
@@ -30,6 +34,8 @@ class _XnorMixin(QuantLayerMixin):
         return self._make_pack(self.weight)
 
     def train(self, mode=True):
+        if self._packed_only is not None:
+            return QuantLayerMixin.train(self, mode)
         if self.training == mode:
             return self
         self.training = mode
