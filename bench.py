@@ -502,6 +502,24 @@ def extra_layers(Q, torch, dev, pk, _ops):
     xq = act(xs[0])
     ms = time_fn(torch, lambda: lay(xq), iters=20)
     out["linearbin_4096x4096_b8192_contraction_only"] = {"ms": round(ms, 4), "tops": round(ops_ / ms / 1e9, 1)}
+    # training step of the same layer (fwd on the low-bit kernels, STE backward): gradient contractions on the bf16
+    # tensor-core route (engine.grad_*) vs fp32 torch.matmul
+    lay_t = Q.layers.LinearBin(K, N).to(dev)
+    go = torch.randn(M, N, generator=g).to(dev)
+
+    def train_step():
+        i[0] += 1
+        xin = xs[i[0] % 2].detach().requires_grad_(True)
+        lay_t.zero_grad(set_to_none=True)
+        y = lay_t(act(xin))
+        y.backward(go)
+    with torch.enable_grad():
+        for backend in ("tcgen05", "torch"):
+            Q.set_grad_backend(backend)
+            ms = time_fn(torch, train_step, iters=5, warm=2)
+            out["linearbin_4096x4096_b8192_train_step_grad_" + backend] = {"ms": round(ms, 3)}
+        Q.set_grad_backend("tcgen05")
+    del lay_t, go
     xu = [torch.rand(M, K, generator=g).to(dev) for _ in range(2)]
     ld = Q.layers.LinearDorefa(K, N, bit_width=4).to(dev)
     ld.eval()

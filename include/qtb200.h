@@ -319,6 +319,21 @@ int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, const void* 
 int qt_gemm_f32(const float* a, int64_t lda, const float* w, int64_t ldw,
                 int64_t M, int64_t N, int64_t K, const QtEpilogue* ep, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Backward (straight-through estimators), SURVEY 8f-2.  The gradient contractions of the dense layers
+ *   grad_x = g . W_q            (binary_connect.py:104-105, terner_connect.py:96-98, dorefa_connect.py:139-146, xnor_connect.py:121-122)
+ *   grad_W = g^T . x  (+ STE)   (binary_connect.py:106-107, xnor_connect.py:123-126)
+ * run on qt_gemm_f16 with bf16 hi/lo planes (relative error <= 2^-17); the operand contracted along its LEADING dimension
+ * is transposed and split in one pass by qt_transpose_split:
+ *   x fp32 [rows, ld_x] -> out bf16 [planes][cols, ld_out]  (out[p][c][r]; ld_out >= rows, multiple of 8 for the tensor path;
+ *   columns rows..ld_out-1 zero-filled; plane stride = cols * ld_out).
+ * qt_ste_clip: out = |x| <= thresh ? g : 0 -- the clip-mask STE of BinaryConnect / TernaryConnect
+ * (binary_connect.py:30-38, terner_connect.py:29-34) in one pass.
+ * ---------------------------------------------------------------------- */
+int qt_transpose_split(const float* x, int64_t rows, int64_t cols, int64_t ld_x, void* out, int64_t ld_out, int planes,
+                       void* stream);
+int qt_ste_clip(const float* g, const float* x, float thresh, float* out, int64_t n, void* stream);
+
 /* Tuning / test knobs (process-wide).  "f4_tile_n": qt_gemm_f4 tile width, 0 = auto, or 64 / 128 / 240.
  * Unknown names or values return QT_EINVAL. */
 int qt_set_option(const char* name, int value);

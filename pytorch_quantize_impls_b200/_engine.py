@@ -534,3 +534,56 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
             _contract(a, pack, M, Ng, Kg, out, w_row0=g * Ng, bias=None if bias is None else bias[g * Ng:(g + 1) * Ng],
                       out_mode=1, ldo=O, nchw_inner=P, out_offset=(b0 * O + g * Ng) * P, rq_spec=affine)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backward: gradient contractions of the dense layers on the bf16 tensor-core route
+# ---------------------------------------------------------------------------------------------------------------------
+_grad_backend = [os.environ.get("QTB200_GRAD_GEMM", "tcgen05")]
+
+
+def set_grad_backend(name):
+    """'tcgen05' (default): grad_x / grad_W of the dense layers run as bf16 hi/lo plane products on qt_gemm_f16 (relative error
+    <= 2^-16, inside the 1e-4 the gradient parity tests ask for); 'torch': fp32 torch.matmul."""
+    if name not in ("tcgen05", "torch"):
+        raise ValueError("grad backend must be 'tcgen05' or 'torch'")
+    _grad_backend[0] = name
+
+
+_GRAD_PASSES = [(0, 0), (1, 0), (0, 1)]        # hi*hi + lo*hi + hi*lo  (lo*lo is below 2^-32 of the leading term)
+
+
+def grad_input_linear(g2d, wq2d):
+    """grad_x[m, k] = sum_n g[m, n] * W_q[n, k]   (g . W_q, e.g. binary_connect.py:104-105).  fp32 in, fp32 out."""
+    if _grad_backend[0] != "tcgen05" or not g2d.is_cuda:
+        return g2d @ wq2d
+    g2d, wq2d = ops.as_f32c(g2d), ops.as_f32c(wq2d)
+    M, N = g2d.shape
+    K = wq2d.shape[1]
+    out = torch.empty((M, K), dtype=torch.float32, device=g2d.device)
+    if M == 0 or K == 0 or N == 0:
+        return out.zero_()
+    _, tag = ops.quant_act(g2d, L.Q_SPLIT, want_y=False, codes_kind=L.CODES_BF16X2, kind="real")     # [2, M, ld]
+    wT, ldw = ops.transpose_split(wq2d, planes=2)                                                     # [2, K, ld]
+    epi = ops.make_epi(out, ldo=K)
+    ops.gemm_f16(tag.codes, tag.ld, tag.codes.stride(0), wT, ldw, wT.stride(0), _GRAD_PASSES, M, K, N, epi,
+                 _force_backend["bf16"])
+    return out
+
+
+def grad_weight_linear(g2d, x2d):
+    """grad_Wq[n, k] = sum_m g[m, n] * x[m, k]   (g^T . x, e.g. binary_connect.py:106-107): the reduction runs over the batch, so
+    both operands are transposed + split in one pass each."""
+    if _grad_backend[0] != "tcgen05" or not g2d.is_cuda:
+        return g2d.t() @ x2d
+    g2d, x2d = ops.as_f32c(g2d), ops.as_f32c(x2d)
+    M, N = g2d.shape
+    K = x2d.shape[1]
+    out = torch.empty((N, K), dtype=torch.float32, device=g2d.device)
+    if M == 0 or K == 0 or N == 0:
+        return out.zero_()
+    gT, ldg = ops.transpose_split(g2d, planes=2)          # [2, N, ld(M)]
+    xT, ldx = ops.transpose_split(x2d, planes=2)          # [2, K, ld(M)]
+    epi = ops.make_epi(out, ldo=K)
+    ops.gemm_f16(gT, ldg, gT.stride(0), xT, ldx, xT.stride(0), _GRAD_PASSES, N, K, M, epi, _force_backend["bf16"])
+    return out

@@ -404,3 +404,25 @@ def device_caps(device=0):
     maj, mnr, sms, tc = C.c_int(), C.c_int(), C.c_int(), C.c_int()
     L.check(L.lib().qt_device_caps(device, C.byref(maj), C.byref(mnr), C.byref(sms), C.byref(tc)), "qt_device_caps")
     return dict(sm_major=maj.value, sm_minor=mnr.value, num_sms=sms.value, has_tcgen05=bool(tc.value))
+
+
+def transpose_split(x2d, planes=2):
+    """fp32 [R, C] -> bf16 planes of the transpose [planes, C, ld] (ld = R rounded up to 8): the K-major operand of a
+    gradient contraction whose reduction runs over the leading dimension of x2d."""
+    require_cuda(x2d, "tensor")
+    x2d = as_f32c(x2d)
+    R, Cc = x2d.shape
+    ld = round_up(max(R, 1), 8)
+    out = torch.empty((planes, Cc, ld), dtype=torch.bfloat16, device=x2d.device)
+    L.check(L.lib().qt_transpose_split(_p(x2d), R, Cc, Cc, _p(out), ld, planes, _stream()), "qt_transpose_split")
+    return out, ld
+
+
+def ste_clip(grad, x, thresh=1.001):
+    """grad * 1[|x| <= thresh] in one pass (the clip-mask straight-through estimator)."""
+    require_cuda(grad, "grad")
+    g = as_f32c(grad)
+    xx = as_f32c(x)
+    out = torch.empty_like(g)
+    L.check(L.lib().qt_ste_clip(_p(g), _p(xx), float(thresh), _p(out), g.numel(), _stream()), "qt_ste_clip")
+    return out

@@ -952,6 +952,64 @@ __global__ void __launch_bounds__(256) im2col_split3_kernel(Im2colArgs a, int64_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward (STE) helpers
+// ---------------------------------------------------------------------------------------------
+// fp32 [rows, cols] -> bf16 planes of the TRANSPOSE, out[p][c][r] (plane stride = cols * ld_out), p = 0 hi, 1 lo (, 2 lo2).
+// Feeds the tcgen05 bf16 GEMM for the gradient contractions, whose reduction runs over the batch (grad_W = g^T x) or over the
+// output features (grad_x = g W_q): the operand that is contracted along its leading dimension has to be K-major.
+// 64 x 64 tile through shared memory: coalesced fp32 reads, 128-byte bf16 rows on the way out.
+template <int NPLANES>
+__global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_x,
+                                                              __nv_bfloat16* __restrict__ out, int64_t ld_out) {
+  __shared__ float tile[64][65];
+  const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 64;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int idx = threadIdx.x + 256 * i;
+    const int r = idx >> 6, c = idx & 63;
+    float v = 0.f;
+    if (r0 + r < rows && c0 + c < cols) v = __ldg(x + (r0 + r) * ld_x + c0 + c);
+    tile[r][c] = v;
+  }
+  __syncthreads();
+  const int64_t plane = cols * ld_out;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int idx = threadIdx.x + 256 * i;
+    const int c = idx >> 6, r = idx & 63;
+    if (c0 + c < cols && r0 + r < ld_out) {          // columns rows..ld_out-1 of the transposed rows are zero-filled
+      const float v = tile[r][c];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const int64_t o = (c0 + c) * ld_out + r0 + r;
+      out[o] = h;
+      if (NPLANES >= 2) {
+        const float r1 = v - __bfloat162float(h);
+        const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+        out[plane + o] = m;
+        if (NPLANES >= 3) out[2 * plane + o] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+      }
+    }
+  }
+}
+
+// out = (|x| <= thresh) ? g : 0   -- the clip-mask straight-through estimator of BinaryConnect / TernaryConnect
+// (binary_connect.py:30-38, terner_connect.py:29-34: g.clone(); g[abs(x) > 1.001] = 0), one pass instead of four.
+__global__ void __launch_bounds__(256) ste_clip_kernel(const float* __restrict__ g, const float* __restrict__ x, float thresh,
+                                                       float* __restrict__ out, int64_t n) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 4 <= n && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const float4 gv = __ldcs(reinterpret_cast<const float4*>(g + i4)), xv = __ldcs(reinterpret_cast<const float4*>(x + i4));
+    float4 o;
+    o.x = (fabsf(xv.x) > thresh) ? 0.f : gv.x; o.y = (fabsf(xv.y) > thresh) ? 0.f : gv.y;
+    o.z = (fabsf(xv.z) > thresh) ? 0.f : gv.z; o.w = (fabsf(xv.w) > thresh) ? 0.f : gv.w;
+    *reinterpret_cast<float4*>(out + i4) = o;
+  } else {
+    for (int64_t i = i4; i < n && i < i4 + 4; ++i) out[i] = (fabsf(x[i]) > thresh) ? 0.f : g[i];
+  }
+}
+
 template <bool UNSIGNED>
 __global__ void __launch_bounds__(256) rowsum_i8_kernel(const uint8_t* __restrict__ a, int64_t rows, int64_t ld,
                                                         int32_t* __restrict__ out) {
@@ -1399,6 +1457,33 @@ extern "C" int qt_expand_weight(const QtWeightExpand* p, void* stream_) {
   if (cpv == 32) weight_expand_kernel<32><<<blocks, 256, 0, stream>>>(a);
   else if (cpv == 16) weight_expand_kernel<16><<<blocks, 256, 0, stream>>>(a);
   else weight_expand_kernel<8><<<blocks, 256, 0, stream>>>(a);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+
+extern "C" int qt_transpose_split(const float* x, int64_t rows, int64_t cols, int64_t ld_x, void* out, int64_t ld_out, int planes,
+                                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(x && out, "qt_transpose_split: null argument");
+  QT_REQUIRE(rows >= 0 && cols >= 0 && ld_x >= cols && ld_out >= rows, "qt_transpose_split: bad shape");
+  QT_REQUIRE(planes >= 1 && planes <= 3, "qt_transpose_split: planes must be 1, 2 or 3");
+  if (rows == 0 || cols == 0) return QT_OK;
+  dim3 grid((unsigned)ceil_div(cols, 64), (unsigned)ceil_div(ld_out, 64));
+  QT_REQUIRE(grid.y <= 65535, "qt_transpose_split: too many rows");
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (planes == 1) transpose_split_kernel<1><<<grid, 256, 0, stream>>>(x, rows, cols, ld_x, o, ld_out);
+  else if (planes == 2) transpose_split_kernel<2><<<grid, 256, 0, stream>>>(x, rows, cols, ld_x, o, ld_out);
+  else transpose_split_kernel<3><<<grid, 256, 0, stream>>>(x, rows, cols, ld_x, o, ld_out);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+extern "C" int qt_ste_clip(const float* g, const float* x, float thresh, float* out, int64_t n, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(g && x && out && n >= 0, "qt_ste_clip: bad argument");
+  if (n == 0) return QT_OK;
+  ste_clip_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, stream>>>(g, x, thresh, out, n);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }

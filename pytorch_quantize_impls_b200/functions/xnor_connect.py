@@ -118,9 +118,9 @@ def XNORDense(dim=[0, 1]):
             weight_q = torch.sign(weight) * mean
             gi = gw = gb = None
             if ctx.needs_input_grad[0]:
-                gi = grad_output.mm(weight_q)
+                gi = eng.grad_input_linear(grad_output, weight_q)
             if ctx.needs_input_grad[1]:
-                t = grad_output.t().mm(input)
+                t = eng.grad_weight_linear(grad_output, input)
                 gw = mean * t + torch.sign(weight) * torch.mean(t * torch.sign(weight), DIM, keepdim=True)
             if bias is not None and ctx.needs_input_grad[2]:
                 gb = grad_output.sum(0).squeeze(0)

@@ -57,11 +57,12 @@ class _Contraction(torch.autograd.Function):
             if bias is not None and ctx.needs_input_grad[2]:
                 gb = grad_output.sum((0, 2, 3))
         else:
+            # gradient contractions on the bf16 tensor-core route (engine.grad_*: hi/lo planes, ~2^-16 relative error)
             g2 = grad_output.reshape(-1, grad_output.shape[-1])
             if ctx.needs_input_grad[0]:
-                gi = (g2 @ wqd).reshape(input.shape)
+                gi = eng.grad_input_linear(g2, wqd).reshape(input.shape)
             if ctx.needs_input_grad[1]:
-                gwq = g2.t() @ input.reshape(-1, input.shape[-1])
+                gwq = eng.grad_weight_linear(g2, input.reshape(-1, input.shape[-1]))
             if bias is not None and ctx.needs_input_grad[2]:
                 gb = g2.sum(0)
         if ctx.needs_input_grad[1]:
