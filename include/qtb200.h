@@ -60,8 +60,8 @@ enum {
   QT_Q_TERNARY = 1,  /* x>=.5 -> 1, -.5<=x<.5 -> 0, else -1   codes {-1,0,+1}        */
   QT_Q_DOREFA = 2,   /* c = rint((2^k-1) x), y = fl(1/n) c    codes c (unclamped)    */
   QT_Q_XNOR_ROW = 3, /* sign(x) * mean(x,row)  (torch.sign)   codes {-1,0,+1}, row_scale = mean */
-  QT_Q_LOG = 4,      /* sign(x) 2^clamp(round(log2|x|), fsr-2^bw, fsr)   (fp32 only) */
-  QT_Q_LIN = 5,      /* sign(x) clamp(round(|x|/step) step, 0, 2^fsr)    (fp32 only) */
+  QT_Q_LOG = 4,      /* sign(x) 2^clamp(round(log2|x|), fsr-2^bw, fsr)   codes = the value (bf16 lanes)       */
+  QT_Q_LIN = 5,      /* sign(x) clamp(round(|x|/step) step, 0, 2^fsr)    codes = value / step (int8 / uint8 / bf16 lanes) */
   QT_Q_SPLIT = 6     /* no quantisation: bf16 hi/lo (codes_kind 4) or hi/mid/lo (codes_kind 6) split of x */
 };
 
@@ -167,6 +167,14 @@ typedef struct QtWeightExpand {
 } QtWeightExpand;
 
 int qt_expand_weight(const QtWeightExpand* p, void* stream);
+
+/* LogLin layers (log_lin_layers.py:6-93, log_lin_connect.py:9-80) keep their weights as int8 codes in HBM:
+ *   lin: code = sign * round(|w| / step) in [-2^bw, 2^bw], value = code * step, step = 2^(fsr - bw)
+ *        -> with Lin-quantized activations (QT_Q_LIN, int8 codes) the layer is an exact qt_gemm_i8 with scale step_a * step_w;
+ *   log: code = sign * (e - emin + 1), 0 <-> 0, value = sign * 2^e, emin = fsr - 2^bw.
+ * qt_expand_loglin writes the bf16 operand of qt_gemm_f16 (lin: the integer code, log: the power of two; both exact). */
+int qt_expand_loglin(const void* codes, int64_t n, int64_t k, int64_t ld_codes, int is_log, int emin, void* out, int64_t ld_out,
+                     void* stream);
 
 /* ------------------------------------------------------------------------
  * im2col gather for the conv layers (binary_layers.py:103-106, terner_layers.py:89-92,

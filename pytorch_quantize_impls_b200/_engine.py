@@ -192,6 +192,15 @@ def _a_split(x2d):
     return _a_from_tag(tag)
 
 
+def _scaled(a, f):
+    b = _A()
+    for fld in _A.__slots__:
+        if hasattr(a, fld):
+            setattr(b, fld, getattr(a, fld))
+    b.scale = a.scale * f
+    return b
+
+
 class RequantUnsupported(RuntimeError):
     """The fused requant epilogue cannot serve this call (shape / backend); callers run the unfused composition."""
 
@@ -285,7 +294,9 @@ def _contract_impl(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ld
                    acc_out=None, requant=None, rq_spec=None):
     ldo = N if ldo is None else ldo
     col_scale = None if pack.col_scale is None else pack.col_scale[w_row0:w_row0 + N]
-    int_w = pack.kind in ("sign", "ternary", "dorefa")
+    int_w = pack.kind in ("sign", "ternary", "dorefa", "lin")
+    if pack.wscale != 1.0:           # LogLin 'lin' weights: value = code * step
+        a = _scaled(a, pack.wscale)
     rp = dict(row_parts=a.row_parts, row_mul=a.row_mul, requant=requant)
     if requant is None and rq_spec is not None and rq_spec.lo is not None:
         rp["out_clamp"] = (rq_spec.lo, rq_spec.hi)       # a clamp activation folded behind the (BatchNorm-folded) layer
@@ -334,7 +345,7 @@ def _contract_impl(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ld
 
     if a.form == "fp16":
         # XnorNet activations (+-1 / 0 codes in fp16, row_scale = mean): one fp16 tensor pass
-        if int_w:
+        if int_w and pack.kind != "lin":
             w, ldw = ops.expand_weight(pack, L.CODES_F16_EXACT)
         elif pack.kind == "xnor":
             w, ldw = ops.expand_weight(pack, L.CODES_F16)
@@ -350,8 +361,8 @@ def _contract_impl(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ld
     if a.form != "bf16":
         raise RuntimeError("internal: integer activation codes cannot meet a real-valued weight operand")
     # bf16 routes
-    if int_w:
-        w, ldw = ops.expand_weight(pack, L.CODES_BF16)
+    if int_w or pack.kind == "log":
+        w, ldw = ops.expand_weight(pack, L.CODES_BF16)       # exact in one plane
         wplanes = 1
     elif pack.kind == "xnor":
         w, ldw = ops.expand_weight(pack, L.CODES_BF16X2)
@@ -387,11 +398,11 @@ def linear(x, pack, bias, requant=None, affine=None):
     out = None if requant is not None else torch.empty((M, N), dtype=torch.float32, device=dev)
     if M == 0:
         return out.reshape(*lead, N)
-    int_w = pack.kind in ("sign", "ternary", "dorefa")
+    int_w = pack.kind in ("sign", "ternary", "dorefa", "lin")
     a = None
     if tag is not None:
         a = _a_from_tag(tag)
-        if (a.form in ("i8", "f4") and not int_w) or (a.form == "fp16" and pack.kind == "real"):
+        if (a.form in ("i8", "f4") and not int_w) or (a.form == "fp16" and pack.kind in ("real", "lin", "log")):
             a = None
         elif a.form == "f4" and not _f4_weight_ok(pack):
             # e2m1 activation codes met weights that need 8-bit lanes (DoReFa k >= 3, or the CUDA-core backend was forced):
@@ -451,7 +462,7 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
         return out
     Ng, Kg, P = O // groups, Cg * kh * kw, OH * OW
     geom = (kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW)
-    int_w = pack.kind in ("sign", "ternary", "dorefa")
+    int_w = pack.kind in ("sign", "ternary", "dorefa", "lin")
     tag = get_tag(x)
     if tag is not None and not (tag.codes_kind in (L.CODES_I8, L.CODES_U8) and int_w and tag.layout == "nhwc"):
         tag = None
@@ -483,7 +494,7 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
                 cs, bg = (requant or affine).fold(cs, bg, g * Ng, Ng)
             epi = ops.make_epi(out, ldo=O, out_mode=1, nchw_inner=P, bias=bg, col_scale=cs,
                                row_sum=rs, acc_mul=2 if need_rs else 1, rs_mul=-255 if need_rs else 0,
-                               scale=tag.scale, out_offset=g * Ng * P, requant=rq,
+                               scale=tag.scale * pack.wscale, out_offset=g * Ng * P, requant=rq,
                                out_clamp=(affine.lo, affine.hi) if (affine is not None and affine.lo is not None) else None)
             if not ops.conv_i8(tag.codes, a_signed, geom, g, w[g * Ng:], not need_rs, ldw, Ng, epi):
                 done = False

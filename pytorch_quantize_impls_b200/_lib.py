@@ -94,6 +94,7 @@ SYMBOLS = {
     "qt_gemm_f16": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, C.POINTER(i32), C.POINTER(i32),
                           i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
     "qt_gemm_f32": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
+    "qt_expand_loglin": (i32, [vp, i64, i64, i64, i32, i32, vp, i64, vp]),
     "qt_transpose_split": (i32, [vp, i64, i64, i64, vp, i64, i32, vp]),
     "qt_ste_clip": (i32, [vp, vp, f32, vp, i64, vp]),
     "qt_set_option": (i32, [C.c_char_p, i32]),

@@ -151,7 +151,12 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
 class WeightPack:
     """k-bit weight matrix resident in HBM (the persistent format) + what the epilogue needs."""
     __slots__ = ("kind", "bit_width", "n", "k", "packed", "ld_packed", "alpha", "alpha_norm", "alpha_max", "stats",
-                 "col_scale", "planes", "ld_planes", "wq")
+                 "col_scale", "planes", "ld_planes", "wq", "wscale", "emin")
+    # kind 'lin' / 'log' (LogLin layers): packed = int8 codes [1, n, ld]; value = code * wscale (lin) or
+    # sign(code) * 2^(emin + |code| - 1) (log)
+
+    def __init__(self):
+        self.wscale, self.emin = 1.0, 0
 
     def nbytes(self):
         t = self.packed if self.packed is not None else self.planes
@@ -221,6 +226,29 @@ def pack_real_weight(wq2d):
     return p
 
 
+def pack_loglin_weight(wq2d, dtype, fsr, bit_width):
+    """Lin / Log *quantized* weights (the values the reference's weight op returns) -> int8 codes [1, n, ld] (8 bits per weight
+    in HBM instead of 32): lin code = wq / step, log code = sign * (log2|wq| - emin + 1).  bit_width <= 6."""
+    require_cuda(wq2d, "weight")
+    wq2d = as_f32c(wq2d)
+    n, k = wq2d.shape
+    ld = round_up(max(k, 1), 16)
+    p = WeightPack()
+    p.kind, p.bit_width, p.n, p.k = dtype, bit_width, n, k
+    p.alpha = p.alpha_norm = p.alpha_max = p.stats = p.col_scale = p.planes = p.wq = None
+    p.ld_planes = 0
+    codes = torch.zeros((1, n, ld), dtype=torch.int8, device=wq2d.device)
+    if dtype == "lin":
+        p.wscale, p.emin = float(2.0 ** (fsr - bit_width)), 0
+        codes[0, :, :k] = torch.round(wq2d / p.wscale).to(torch.int8)
+    else:
+        p.wscale, p.emin = 1.0, int(fsr - 2 ** bit_width)
+        mag = torch.where(wq2d == 0, torch.zeros_like(wq2d), torch.log2(wq2d.abs().clamp_min(1e-38)) - p.emin + 1)
+        codes[0, :, :k] = (torch.sign(wq2d) * torch.round(mag)).to(torch.int8)
+    p.packed, p.ld_packed = codes, ld
+    return p
+
+
 def col_absmean(w2d):
     require_cuda(w2d, "weight")
     w2d = as_f32c(w2d)
@@ -233,6 +261,16 @@ def col_absmean(w2d):
 def expand_weight(p, out_kind):
     """Packed k-bit weights -> transient tensor-core operand (lives in L2 between the two kernels)."""
     dev = p.packed.device
+    if p.kind in ("lin", "log"):
+        if p.kind == "lin" and out_kind == L.CODES_I8:
+            return p.packed[0], p.ld_packed                  # the HBM format IS the int8 operand
+        if out_kind != L.CODES_BF16:
+            raise RuntimeError("internal: LogLin weights expand to int8 (lin) or bf16 operands only")
+        ld = round_up(p.k, 16)
+        out = torch.empty((1, p.n, ld), dtype=torch.bfloat16, device=dev)
+        L.check(L.lib().qt_expand_loglin(_p(p.packed), p.n, p.k, p.ld_packed, 1 if p.kind == "log" else 0, int(p.emin),
+                                         _p(out), ld, _stream()), "qt_expand_loglin")
+        return out, ld
     ld = round_up(p.k, 16)
     if out_kind == L.CODES_F4:
         ld = round_up(p.k, 32)

@@ -19,7 +19,7 @@ from .layers.common import QuantLayerMixin
 
 FORMAT = "qtb200-packed-v1"
 _TENSORS = ("packed", "alpha", "alpha_norm", "alpha_max", "stats", "col_scale", "planes")
-_SCALARS = ("kind", "bit_width", "n", "k", "ld_packed", "ld_planes")
+_SCALARS = ("kind", "bit_width", "n", "k", "ld_packed", "ld_planes", "wscale", "emin")
 
 
 def _quant_layers(model):

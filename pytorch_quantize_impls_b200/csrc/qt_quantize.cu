@@ -76,7 +76,7 @@ __device__ __forceinline__ QOut quant_elem(const QParams& q, float x, float row_
       float e = fminf(fmaxf(rintf(log2f(fabsf(x))), q.lo_e), q.hi_e);
       float p = exp2f(e);
       o.y = q.with_sign ? sign3(x) * p : p;
-      o.code = 0.f;
+      o.code = o.y;                 // a power of two (or 0): exact in a bf16 lane
       break;
     }
     case QT_Q_LIN: {
@@ -85,7 +85,7 @@ __device__ __forceinline__ QOut quant_elem(const QParams& q, float x, float row_
       } else {
         o.y = fminf(fmaxf(rintf(x / q.step) * q.step, 0.f), q.maxv);
       }
-      o.code = 0.f;
+      o.code = o.y / q.step;        // integer in [-2^bw, 2^bw]: step is a power of two, the division is exact
       break;
     }
     default: {  // QT_Q_SPLIT
@@ -1010,6 +1010,30 @@ __global__ void __launch_bounds__(256) ste_clip_kernel(const float* __restrict__
   }
 }
 
+
+// LogLin weights: int8 codes in HBM -> bf16 operand.
+//   lin: value = code * 2^(fsr - bw)            -> the operand is the integer code itself (exact), the step goes to the epilogue
+//   log: value = sign(code) * 2^(emin + |code| - 1), code 0 <-> 0   -> the operand is the power of two (exact in bf16)
+__global__ void __launch_bounds__(256) loglin_expand_kernel(const int8_t* __restrict__ codes, int64_t n, int64_t k, int64_t ld_codes,
+                                                            int is_log, int emin, __nv_bfloat16* __restrict__ out, int64_t ld_out) {
+  const int64_t vec_per_row = ld_out / 8;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n * vec_per_row) return;
+  const int64_t row = gid / vec_per_row, c0 = (gid - row * vec_per_row) * 8;
+  __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = 0.f;
+    if (c0 + j < k) {
+      const int c = codes[row * ld_codes + c0 + j];
+      if (!is_log) v = (float)c;
+      else if (c != 0) v = ldexpf(c < 0 ? -1.f : 1.f, emin + (c < 0 ? -c : c) - 1);
+    }
+    h[j] = __float2bfloat16_rn(v);
+  }
+  *reinterpret_cast<uint4*>(out + row * ld_out + c0) = *reinterpret_cast<uint4*>(h);
+}
+
 template <bool UNSIGNED>
 __global__ void __launch_bounds__(256) rowsum_i8_kernel(const uint8_t* __restrict__ a, int64_t rows, int64_t ld,
                                                         int32_t* __restrict__ out) {
@@ -1299,8 +1323,14 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
     a.q.maxv = ldexpf(1.f, p->fsr);
   }
   if (p->mode == QT_Q_SPLIT) QT_REQUIRE(p->codes_kind == 4 || p->codes_kind == 6, "qt_quant_act: QT_Q_SPLIT needs codes_kind 4 or 6");
-  if (p->mode == QT_Q_LOG || p->mode == QT_Q_LIN)
-    QT_REQUIRE(p->codes_kind == 0 && !p->bits, "qt_quant_act: Log/Lin quantizers produce fp32 only");
+  if (p->mode == QT_Q_LOG)
+    QT_REQUIRE((p->codes_kind == 0 || p->codes_kind == 3) && !p->bits && !p->row_sum,
+               "qt_quant_act: the Log quantizer emits fp32 and / or bf16 values (codes_kind 3)");
+  if (p->mode == QT_Q_LIN) {
+    QT_REQUIRE((p->codes_kind >= 0 && p->codes_kind <= 3) && !p->bits, "qt_quant_act: the Lin quantizer emits int8 / uint8 / bf16 codes");
+    if (p->codes_kind == 1) QT_REQUIRE(p->bit_width <= 6, "qt_quant_act: int8 Lin codes need bit_width <= 6");
+    if (p->codes_kind == 2) QT_REQUIRE(p->bit_width <= 7 && !p->with_sign, "qt_quant_act: uint8 Lin codes need with_sign = 0, bit_width <= 7");
+  }
   QT_REQUIRE(p->codes_kind >= 0 && p->codes_kind <= 7, "qt_quant_act: bad codes_kind");
   if (p->codes_kind == 7) {
     QT_REQUIRE(p->mode == QT_Q_SIGN || p->mode == QT_Q_TERNARY || (p->mode == QT_Q_DOREFA && p->bit_width == 2),
@@ -1318,7 +1348,8 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
 
   if (p->nhwc_c > 0) {
     QT_REQUIRE(p->codes && (p->codes_kind == 1 || p->codes_kind == 2), "qt_quant_act: NHWC output needs int8/uint8 codes");
-    QT_REQUIRE(p->mode == QT_Q_SIGN || p->mode == QT_Q_TERNARY || p->mode == QT_Q_DOREFA, "qt_quant_act: NHWC output: SIGN/TERNARY/DOREFA only");
+    QT_REQUIRE(p->mode == QT_Q_SIGN || p->mode == QT_Q_TERNARY || p->mode == QT_Q_DOREFA || p->mode == QT_Q_LIN,
+               "qt_quant_act: NHWC output: SIGN / TERNARY / DOREFA / LIN only");
     QT_REQUIRE(p->cols % p->nhwc_c == 0 && p->ld_x == p->cols && (!p->y || p->ld_y == p->cols) && !p->bits && !p->row_sum,
                "qt_quant_act: NHWC output needs dense NCHW input and no bits / row sums");
     NhwcArgs n;
@@ -1328,6 +1359,7 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
     dim3 grid((unsigned)ceil_div(n.HW, 32), (unsigned)ceil_div(n.C, 128), (unsigned)n.B);
     if (p->mode == QT_Q_SIGN) act_quant_nhwc_kernel<QT_Q_SIGN><<<grid, 256, 0, stream>>>(n);
     else if (p->mode == QT_Q_TERNARY) act_quant_nhwc_kernel<QT_Q_TERNARY><<<grid, 256, 0, stream>>>(n);
+    else if (p->mode == QT_Q_LIN) act_quant_nhwc_kernel<QT_Q_LIN><<<grid, 256, 0, stream>>>(n);
     else act_quant_nhwc_kernel<QT_Q_DOREFA><<<grid, 256, 0, stream>>>(n);
     QT_LAUNCH_CHECK();
     return QT_OK;
@@ -1484,6 +1516,20 @@ extern "C" int qt_ste_clip(const float* g, const float* x, float thresh, float* 
   QT_REQUIRE(g && x && out && n >= 0, "qt_ste_clip: bad argument");
   if (n == 0) return QT_OK;
   ste_clip_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, stream>>>(g, x, thresh, out, n);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+
+extern "C" int qt_expand_loglin(const void* codes, int64_t n, int64_t k, int64_t ld_codes, int is_log, int emin, void* out,
+                                int64_t ld_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(codes && out, "qt_expand_loglin: null argument");
+  QT_REQUIRE(n >= 0 && k >= 0 && ld_codes >= k && ld_out >= k && ld_out % 8 == 0 && aligned(out, 16), "qt_expand_loglin: bad shape");
+  if (n == 0 || k == 0) return QT_OK;
+  const int64_t threads = n * (ld_out / 8);
+  loglin_expand_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, stream>>>((const int8_t*)codes, n, k, ld_codes, is_log, emin,
+                                                                              (__nv_bfloat16*)out, ld_out);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }

@@ -16,6 +16,8 @@ class _LogLinMixin(QuantLayerMixin):
     def _make_pack(self, w):
         with torch.no_grad():
             wq = self.weight_op.forward(w.detach())
+        if 1 <= self.bit_width <= 6:      # int8 codes in HBM (8 bits per weight; exact int8 / bf16 operands)
+            return ops.pack_loglin_weight(ops.conv_weight_2d(wq), self._dtype, self.fsr, self.bit_width)
         return ops.pack_real_weight(ops.conv_weight_2d(wq))
 
     def clamp(self):
@@ -41,9 +43,10 @@ class LinearQuant(_LogLinMixin, torch.nn.Linear):
     def __init__(self, in_features, out_features, bias=True, dtype="lin", fsr=7, bit_width=3):
         self.bit_width = bit_width
         self.fsr = fsr
+        self._dtype = dtype
         torch.nn.Linear.__init__(self, in_features, out_features, bias=bias)
         self.weight_op = log_lin_connect.nnQuant(dtype=dtype, fsr=fsr, bit_width=bit_width, with_sign=True,
-                                                 lin_back=True)
+                                                 lin_back=True, _emit_codes=False)
 
     def reset_parameters(self):
         self._reset_loglin()
@@ -64,10 +67,11 @@ class QuantConv2d(_LogLinMixin, torch.nn.Conv2d):
                  fsr=7, bit_width=3, dtype="lin"):
         self.fsr = fsr
         self.bit_width = bit_width
+        self._dtype = dtype
         torch.nn.Conv2d.__init__(self, in_channels, out_channels, kernel_size, stride=stride, padding=padding,
                                  dilation=dilation, groups=groups, bias=bias)
         self.weight_op = log_lin_connect.nnQuant(dtype=dtype, fsr=fsr, bit_width=bit_width, with_sign=True,
-                                                 lin_back=True)
+                                                 lin_back=True, _emit_codes=False)
 
     def reset_parameters(self):
         if self.bit_width == 32:
