@@ -12,7 +12,8 @@ from . import BinaryNet, DorefaNet, LogLinNet, TernerNet, XnorNet  # noqa: F401
 from ._engine import (code_only_activations, set_backend, set_first_layer_planes, set_fp4, set_grad_backend,  # noqa: F401
                       set_implicit_conv, set_xnor_mode)
 from ._ops import device_caps, set_strict  # noqa: F401
-from .fusion import FusedBNActQuant, FusedLayerBN, FusedLayerQuant, fuse_inference  # noqa: F401
+from .fusion import (FusedBNActQuant, FusedLayerBN, FusedLayerQuant, OperandPrefetch, fuse_inference,  # noqa: F401
+                     prefetch_operands)
 from .device import device  # noqa: F401
 from .checkpoint import load_packed, packed_state, save_packed  # noqa: F401
 

@@ -151,12 +151,14 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
 class WeightPack:
     """k-bit weight matrix resident in HBM (the persistent format) + what the epilogue needs."""
     __slots__ = ("kind", "bit_width", "n", "k", "packed", "ld_packed", "alpha", "alpha_norm", "alpha_max", "stats",
-                 "col_scale", "planes", "ld_planes", "wq", "wscale", "emin")
+                 "col_scale", "planes", "ld_planes", "wq", "wscale", "emin", "_prefetch", "_last_kind")
     # kind 'lin' / 'log' (LogLin layers): packed = int8 codes [1, n, ld]; value = code * wscale (lin) or
     # sign(code) * 2^(emin + |code| - 1) (log)
 
     def __init__(self):
         self.wscale, self.emin = 1.0, 0
+        self._prefetch = None        # (out_kind, operand, ld, event): expanded ahead of time on a side stream
+        self._last_kind = None       # operand kind the last contraction asked for (what a prefetch expands)
 
     def nbytes(self):
         t = self.packed if self.packed is not None else self.planes
@@ -260,6 +262,19 @@ def col_absmean(w2d):
 
 def expand_weight(p, out_kind):
     """Packed k-bit weights -> transient tensor-core operand (lives in L2 between the two kernels)."""
+    p._last_kind = out_kind
+    pf = p._prefetch
+    if pf is not None:
+        p._prefetch = None
+        if pf[0] == out_kind:                    # expanded ahead of time (fusion.OperandPrefetch): wait for it, no launch here
+            cur = torch.cuda.current_stream()
+            cur.wait_event(pf[3])
+            pf[1].record_stream(cur)
+            return pf[1], pf[2]
+    return _expand_weight(p, out_kind)
+
+
+def _expand_weight(p, out_kind):
     dev = p.packed.device
     if p.kind in ("lin", "log"):
         if p.kind == "lin" and out_kind == L.CODES_I8:

@@ -291,3 +291,53 @@ def fuse_inference(module):
             for k, m in enumerate(out):
                 module.add_module(str(k), m)
     return module
+
+
+class OperandPrefetch(nn.Module):
+    """Inference wrapper: at the start of every forward the transient tensor-core operands of ALL eval-mode quantized layers
+    of `net` (the weight expansions, 5-15 us each) are launched on a side stream, so that they run beside the first
+    activation quantizer instead of in front of each contraction; every layer then waits for its own operand only.
+    The operand kind expanded for a layer is the one its previous forward asked for (the first forward runs unchanged).
+    Works eagerly and inside CUDA-graph capture (the side stream forks from and re-joins the calling stream)."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+        self._side = None
+
+    def forward(self, x):
+        from .layers.common import QuantLayerMixin
+        if torch.is_grad_enabled() or not (x.is_cuda or x.is_meta):
+            return self.net(x)
+        packs = []
+        for m in self.net.modules():
+            if isinstance(m, QuantLayerMixin) and not m.training:
+                pack = m._current_pack()
+                if pack.packed is not None and pack._last_kind is not None and pack._prefetch is None:
+                    packs.append(pack)
+        if not packs:
+            return self.net(x)
+        dev = packs[0].packed.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        self._side.wait_event(fork)
+        with torch.cuda.stream(self._side):
+            for pack in packs:
+                out, ld = ops._expand_weight(pack, pack._last_kind)
+                done = torch.cuda.Event()
+                done.record(self._side)
+                pack._prefetch = (pack._last_kind, out, ld, done)
+        try:
+            return self.net(x)
+        finally:
+            cur.wait_stream(self._side)          # re-join (also covers operands nobody consumed)
+            for pack in packs:
+                pack._prefetch = None
+
+
+def prefetch_operands(net):
+    """Wrap `net` (typically after fuse_inference) in an OperandPrefetch."""
+    return OperandPrefetch(net)

@@ -307,3 +307,25 @@ def test_batchnorm_and_clamp_folded_into_fp32_epilogue(Q, conv, with_act):
     assert float((y - ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max()))
     if with_act:
         assert float(y.min()) >= 0.0 and float(y.max()) <= 1.0
+
+
+def test_operand_prefetch_is_transparent(Q):
+    """fusion.OperandPrefetch launches the weight expansions of all layers on a side stream at the start of the forward: same
+    results bit for bit, eagerly and under CUDA-graph replay."""
+    from pytorch_quantize_impls_b200.pipeline import GraphedModule
+    torch.manual_seed(23)
+    lays = [Q.layers.LinearXNOR(512, 384), Q.layers.LinearXNOR(384, 256), Q.layers.LinearBin(256, 64)]
+    net = nn.Sequential(Q.functions.nnQuantXnor(1), lays[0], Q.functions.nnQuantXnor(1), lays[1], Q.functions.BinaryConnect(),
+                        lays[2]).cuda().eval()
+    x = torch.randn(300, 512).cuda()
+    with torch.no_grad():
+        ref = net(x)
+        pf = Q.prefetch_operands(net)
+        y0 = pf(x)                      # first call: nothing to prefetch yet (kinds unknown) or kinds learnt from `ref`
+        y1 = pf(x)
+        assert torch.equal(y0, ref) and torch.equal(y1, ref)
+        assert all(l._current_pack()._prefetch is None for l in lays)
+        gm = GraphedModule(lambda t: pf(t), x.clone())
+        for _ in range(3):
+            yg = gm()
+        assert torch.equal(yg, ref)
