@@ -9,8 +9,16 @@ batch 8192 per GPU, synthetic N(0,1) inputs (seed 1234), random-init weights.  O
     nnQuantXnor(1) -> LinearXNOR -> nnQuantXnor(1) -> LinearXNOR -> nnQuantXnor(1) -> LinearXNOR
 over one batch.  metric = quantized-GEMM GOPS = 2*B*sum(K_l*N_l) / time (logical low-bit contraction).
 
+How the step runs (all through the public package API): `fuse_inference` moves every hidden nnQuantXnor into the tcgen05
+epilogue of the layer in front of it, `code_only_activations()` keeps hidden activations as fp16 sign codes,
+`prefetch_operands` expands the packed weights on a side stream beside the input quantizer, and each of the three rotating
+input buffers has its forward captured in a CUDA graph (`pipeline.GraphedModule`), replayed once per step.  N > 1: one process
+per GPU, contiguous batch shards, the logits all-gather of step i (copy engines over NVLink) overlaps step i+1.
+
 Prints ONE JSON line (rank 0).  Keys follow the driver contract plus `roofline`, `cpu_baseline`, `e2e`, `clocks`,
-`gpu_launches` and an `extra` object with the north-star LinearBin 4096x4096 batch 8192 layer and a DoReFa-4 layer.
+`gpu_launches` and an `extra` object with the north-star LinearBin 4096x4096 batch 8192 layer (inference and training step)
+and a DoReFa-4 layer.  Environment switches (development): QTB200_BENCH_GRAPH=0, QTB200_BENCH_PREFETCH=0,
+QTB200_GATHER=ce|nccl|sync, QTB200_BENCH_QUICK=1.
 """
 import argparse
 import json

@@ -1,0 +1,55 @@
+"""CPU: `fuse_inference` is a pure module-graph rewrite -- which runs of modules fold into which fused module can be checked
+without a GPU (the fused modules fall back to the plain composition on anything but the inference chain, which is GPU work)."""
+import torch
+from torch import nn
+
+import pytorch_quantize_impls_b200 as Q
+from pytorch_quantize_impls_b200 import nets
+
+F, L = Q.functions, Q.layers
+
+
+def names(seq):
+    return [type(m).__name__ for m in seq]
+
+
+def test_linear_chain_patterns():
+    net = nn.Sequential(F.BinaryConnect(), L.LinearBin(64, 64), nn.BatchNorm1d(64), nn.Hardtanh(), F.BinaryConnect(),
+                        L.LinearTer(64, 64), F.nnDorefaQuant(4), L.LinearDorefa(64, 32, bit_width=4), nn.BatchNorm1d(32),
+                        nn.ReLU(), L.LinearBin(32, 8))
+    fused = Q.fuse_inference(net)
+    assert names(fused) == ["fronteur", "FusedLayerQuant", "FusedLayerQuant", "FusedLayerBN", "LinearBin"]
+    a, b, c = fused[1], fused[2], fused[3]
+    assert isinstance(a.layer, L.LinearBin) and isinstance(a.bn, nn.BatchNorm1d) and isinstance(a.act, nn.Hardtanh)
+    assert isinstance(b.layer, L.LinearTer) and b.bn is None and b.act is None
+    assert isinstance(c.layer, L.LinearDorefa) and isinstance(c.bn, nn.BatchNorm1d) and isinstance(c.act, nn.ReLU)
+    # lane format hint: the sign codes feeding LinearTer may be e2m1, the DoReFa-4 codes feeding LinearDorefa(4) need 8-bit lanes
+    assert a._consumer_needs_i8 is False and b._consumer_needs_i8 is True
+
+
+def test_pool_between_layer_and_batchnorm_keeps_the_one_pass_kernel():
+    net = nn.Sequential(L.DorefaConv2d(3, 32, 3, bit_width=4), nn.MaxPool2d(2), nn.BatchNorm2d(32), nn.Hardtanh(0., 1.),
+                        F.nnDorefaQuant(4), L.DorefaConv2d(32, 64, 3, bit_width=4), nn.BatchNorm2d(64), nn.Hardtanh(0., 1.),
+                        F.nnDorefaQuant(4), L.DorefaConv2d(64, 64, 3, groups=2, bit_width=4), nn.BatchNorm2d(64))
+    fused = Q.fuse_inference(net)
+    assert names(fused) == ["DorefaConv2d", "MaxPool2d", "FusedBNActQuant", "FusedLayerQuant", "DorefaConv2d", "BatchNorm2d"]
+
+
+def test_resnet_blocks_and_unknown_modules_are_left_alone():
+    net = Q.fuse_inference(nets.resnet18_ternary())
+    assert names(net.stem) == ["FusedLayerBN"] and isinstance(net.stem[0].act, nn.Hardtanh)
+    blk = net.layers[2]                       # first down-sampling block
+    assert names(blk.branch1) == ["FusedLayerQuant"] and names(blk.branch2) == ["FusedLayerBN"]
+    assert names(blk.shortcut) == ["FusedLayerBN"] and isinstance(net.linear, nn.Linear)
+    plain = nn.Sequential(nn.Linear(4, 4), nn.BatchNorm1d(4), nn.ReLU())
+    assert names(Q.fuse_inference(plain)) == ["Linear", "BatchNorm1d", "ReLU"]          # not a quantized layer: untouched
+
+
+def test_fused_modules_are_the_plain_composition_in_training_mode():
+    """With autograd on (or BatchNorm in training mode) the fused wrappers must run their children one by one; on the CPU that
+    reaches the first quantized child, which refuses CPU tensors loudly (no CPU fallback)."""
+    import pytest
+    net = Q.fuse_inference(nn.Sequential(L.LinearBin(8, 8), nn.BatchNorm1d(8), nn.Hardtanh(), F.BinaryConnect()))
+    assert names(net) == ["FusedLayerQuant"]
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        net(torch.randn(4, 8))
