@@ -443,9 +443,12 @@ def run_ours(args):
                    "l2": "inputs rotate over 3 device buffers of 134 MB each (> 126 MB L2)",
                    "launch": "each step = one replay of a CUDA graph holding the 7 kernels of the forward" if graph_mode else "eager",
                    "images_per_sec": round(BATCH * world / (ms_step * 1e-3), 1),
-                   "collective": {"ce": "one all-gather of the fp32 logits per step by the copy engines over NVLink (symmetric "
-                                        "memory, signal-pad barriers) on a communication stream, overlapped with the next step's "
-                                        "kernels; all complete inside the timed region",
+                   "collective": {"ce": "one all-gather of the fp32 logits per step by the copy engines over NVLink (every rank "
+                                        "pushes its shard into the peer-mapped gathered buffers of all ranks, one signal-pad "
+                                        "barrier) on a communication stream, overlapped with the next step's kernels; all "
+                                        "complete inside the timed region",
+                                  "ce_pull": "one all-gather of the fp32 logits per step by the copy engines over NVLink (staged "
+                                             "shard, barrier, peer pulls, barrier) on a communication stream",
                                   "nccl": "one NCCL all_gather of the fp32 logits per step on a communication stream",
                                   "sync": "one NCCL all_gather of the fp32 logits per step on the compute stream"}[pgather.mode]
                    if world > 1 else "none"},

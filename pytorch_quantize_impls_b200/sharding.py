@@ -62,8 +62,11 @@ class PipelinedGather:
     parallelism), so the collective of one step runs beside the kernels of the next one.
 
     mode "ce" (default on CUDA): the gather is done by the COPY ENGINES over NVLink through symmetric memory
-        (torch.distributed._symmetric_memory: every rank stages its logits in a peer-mapped buffer, a signal-pad barrier,
-        then each rank pulls the G-1 remote shards with peer-to-peer async copies, a second barrier releases the stage).
+        (torch.distributed._symmetric_memory).  PUSH form: the gathered buffers themselves are peer-mapped; every rank writes
+        its shard straight from the logits tensor into rows [rank*B, (rank+1)*B) of every peer's buffer (posted NVLink
+        writes, spread over up to 4 streams), then ONE signal-pad barrier tells everybody that all shards have landed.
+    mode "ce_pull": every rank stages its logits in a peer-mapped buffer, barrier, each rank pulls the G-1 remote shards,
+        a second barrier releases the stage (one more copy and one more barrier per step than the push form).
         No SM is taken from the compute kernels: the tcgen05 GEMMs are persistent one-CTA-per-SM kernels with ~225 KB of
         shared memory, an NCCL kernel cannot share an SM with them, and running one beside them stalls both (measured:
         2.5 ms/step instead of 0.5 at 2 GPUs).
@@ -72,8 +75,8 @@ class PipelinedGather:
     On CPU tensors (gloo tests) it degrades to the synchronous collective."""
 
     def __init__(self, depth=2, mode="ce", pull_streams=None):
-        if mode not in ("ce", "nccl", "sync"):
-            raise ValueError("mode must be 'ce', 'nccl' or 'sync'")
+        if mode not in ("ce", "ce_pull", "nccl", "sync"):
+            raise ValueError("mode must be 'ce', 'ce_pull', 'nccl' or 'sync'")
         self.depth, self.mode = depth, mode
         # mode "ce": the G-1 peer pulls of one step are spread over this many streams so that several copy engines
         # (and NVLink ports) work at once; 1 = one pull after the other
@@ -91,6 +94,18 @@ class PipelinedGather:
         if o is None or tuple(o.shape) != shape or o.dtype != y.dtype or o.device != y.device:
             o = self._outs[slot] = torch.empty(shape, dtype=y.dtype, device=y.device)
         return o
+
+    def _symmetric_out(self, slot, y, world):
+        """Peer-mapped gathered buffer of `slot` (push form) + its rendezvous handle."""
+        shape = (world * y.shape[0],) + tuple(y.shape[1:])
+        st = self._stage[slot]
+        if st is None or tuple(st[0].shape) != shape or st[0].dtype != y.dtype:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty(*shape, dtype=y.dtype, device=y.device)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            st = self._stage[slot] = (buf, hdl)
+            self._outs[slot] = buf
+        return st
 
     def _symmetric_stage(self, slot, y):
         st = self._stage[slot]
@@ -115,9 +130,12 @@ class PipelinedGather:
             return out, None
         if self._comm is None:
             self._comm = torch.cuda.Stream(device=y_local.device)
-        if self.mode == "ce":
+        if self.mode in ("ce", "ce_pull"):
             try:
-                buf, hdl = self._symmetric_stage(slot, y_local)      # collective on first use of a slot (every rank gets here)
+                if self.mode == "ce":
+                    out, hdl = self._symmetric_out(slot, y_local, world)     # collective on first use of a slot
+                else:
+                    buf, hdl = self._symmetric_stage(slot, y_local)
             except Exception as err:                                 # no peer mapping on this system: NCCL on the side stream
                 import warnings
                 warnings.warn("PipelinedGather: symmetric memory unavailable (%s); using NCCL" % (err,))
@@ -128,6 +146,30 @@ class PipelinedGather:
         self._comm.wait_event(ready)
         with torch.cuda.stream(self._comm):
             if self.mode == "ce":
+                n = y_local.shape[0]
+                nps = self.pull_streams if self.pull_streams else min(4, world)
+                while len(self._pull) < nps - 1:
+                    self._pull.append(torch.cuda.Stream(device=y_local.device))
+                start = torch.cuda.Event()
+                start.record(self._comm)
+                lanes = [self._comm] + self._pull[:nps - 1]
+                full_shape = (world * n,) + tuple(y_local.shape[1:])
+                for step in range(world):
+                    dst = (rank + step) % world                      # my own buffer first, then round the ring
+                    peer_out = out if dst == rank else hdl.get_buffer(dst, full_shape, y_local.dtype)
+                    lane = lanes[step % len(lanes)]
+                    with torch.cuda.stream(lane):
+                        if lane is not self._comm and step < len(lanes):
+                            lane.wait_event(start)
+                        peer_out[rank * n:(rank + 1) * n].copy_(y_local, non_blocking=True)
+                        if lane is not self._comm:
+                            y_local.record_stream(lane)
+                for lane in lanes[1:]:
+                    ev = torch.cuda.Event()
+                    ev.record(lane)
+                    self._comm.wait_event(ev)
+                hdl.barrier(channel=slot)                            # every shard of this step has landed in every buffer
+            elif self.mode == "ce_pull":
                 n = y_local.shape[0]
                 buf.copy_(y_local, non_blocking=True)
                 hdl.barrier(channel=slot)                            # every rank has staged this step
