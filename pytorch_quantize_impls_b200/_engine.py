@@ -49,6 +49,12 @@ def set_fp4(flag):
     _fp4[0] = bool(flag)
 
 
+def want_sign_bits(x):
+    """Packed sign bits are the operand of the CUDA-core XNOR+popcount kernels only, which serve GEMV-like batches
+    (rows <= POPCOUNT_MAX_M) or a forced popcount backend: larger batches skip the bit plane (and its HBM write)."""
+    return x.dim() == 2 and (_force_popcount[0] or x.shape[0] <= POPCOUNT_MAX_M)
+
+
 def int_codes_kind(x, bit_width=1):
     """Operand format an activation quantizer should emit for integer codes of `bit_width` bits: fp4 (e2m1) for 2-D
     inputs whose codes fit {-4..4} (sign, ternary, DoReFa-2), 8-bit lanes otherwise (conv inputs use channels-last int8)."""

@@ -20,7 +20,7 @@ class BinaryConnectDeterministic(TaggingFunction):
         ctx.save_for_backward(input)
         full = eng.want_fp32_result(input)
         y, tag = ops.quant_act(input, L.Q_SIGN, want_y=full, codes_kind=eng.int_codes_kind(input),
-                               want_bits=(input.dim() == 2), kind="sign")
+                               want_bits=eng.want_sign_bits(input), kind="sign")
         TaggingFunction._leave(tag)
         return y if full else eng.placeholder_like(input)
 

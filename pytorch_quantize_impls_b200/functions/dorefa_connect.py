@@ -17,7 +17,7 @@ def _quantize_with_codes(x, bit_width, pre=None):
     their row sums."""
     full = eng.want_fp32_result(x)
     if bit_width == 1:
-        y, tag = ops.quant_act(x, L.Q_SIGN, want_y=full, codes_kind=eng.int_codes_kind(x), want_bits=(x.dim() == 2), kind="sign",
+        y, tag = ops.quant_act(x, L.Q_SIGN, want_y=full, codes_kind=eng.int_codes_kind(x), want_bits=eng.want_sign_bits(x), kind="sign",
                                pre=pre)
         return (y if full else eng.placeholder_like(x)), tag
     if bit_width == 32:

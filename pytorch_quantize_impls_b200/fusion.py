@@ -90,7 +90,7 @@ class FusedBNActQuant(nn.Module):
         if kind == "dorefa":
             y, tag = _quantize_with_codes(x, arg, pre=pre)
         elif kind == "sign":
-            y, tag = ops.quant_act(x, L.Q_SIGN, want_y=full, codes_kind=eng.int_codes_kind(x), want_bits=(x.dim() == 2), kind="sign", pre=pre)
+            y, tag = ops.quant_act(x, L.Q_SIGN, want_y=full, codes_kind=eng.int_codes_kind(x), want_bits=eng.want_sign_bits(x), kind="sign", pre=pre)
             y = y if full else eng.placeholder_like(x)
         elif kind == "ternary":
             y, tag = ops.quant_act(x, L.Q_TERNARY, want_y=full, codes_kind=eng.int_codes_kind(x), kind="ternary", pre=pre)
