@@ -149,6 +149,50 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
+# host placement
+# --------------------------------------------------------------------------------------------
+class gpu_local_numa:
+    """Context manager: pin the calling thread to the CPUs of the NUMA node the GPU hangs off while pinned host buffers are
+    allocated (first touch puts their pages on that node, so the H2D DMA of every rank reads local memory instead of
+    crossing the socket interconnect); the previous affinity is restored on exit.  Does nothing when the topology cannot be
+    read (single node, containers without sysfs, ...)."""
+
+    def __init__(self, torch, index):
+        self.cpus, self.prev = None, None
+        try:
+            pr = torch.cuda.get_device_properties(index)
+            bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+            if node >= 0 and os.path.isdir("/sys/devices/system/node/node1"):      # more than one node
+                cpus = set()
+                for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+                allowed = os.sched_getaffinity(0)
+                if cpus & allowed:
+                    self.cpus = cpus & allowed
+        except Exception:
+            self.cpus = None
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                self.prev = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus)
+            except Exception:
+                self.prev = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            try:
+                os.sched_setaffinity(0, self.prev)
+            except Exception:
+                pass
+        return False
+
+
+# --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
 def build_xnor_mlp(Q, torch, dev, seed=1234):
@@ -223,7 +267,8 @@ def run_ours(args):
         net = Q.prefetch_operands(net)
     g = torch.Generator().manual_seed(1234 + rank)
     NBUF = 3   # rotate over 3 x 134 MB inputs (> 126 MB L2) so no step finds its input in L2
-    x_host = [torch.randn(BATCH, DIMS[0], generator=g).pin_memory() for _ in range(NBUF)]
+    with gpu_local_numa(torch, local):          # pinned host buffers on the GPU's NUMA node
+        x_host = [torch.randn(BATCH, DIMS[0], generator=g).pin_memory() for _ in range(NBUF)]
     x_dev = [t.to(dev) for t in x_host]
     gathered = torch.empty(world * BATCH, DIMS[-1], device=dev) if world > 1 else None
     from pytorch_quantize_impls_b200.sharding import PipelinedGather
@@ -315,7 +360,8 @@ def run_ours(args):
         # returns its logits to pinned host memory, inside the timed region.  pipeline.HostPipeline overlaps the H2D of
         # step i+1 and the D2H of step i-1 with the kernels of step i (separate streams).
         from pytorch_quantize_impls_b200.pipeline import HostPipeline
-        outs_host = [torch.empty(BATCH, DIMS[-1]).pin_memory() for _ in range(2)]
+        with gpu_local_numa(torch, local):
+            outs_host = [torch.empty(BATCH, DIMS[-1]).pin_memory() for _ in range(2)]
         pipe = HostPipeline(lambda xb: step(0, xb), depth=2, graphs=graph_mode and world == 1)
         ins = [x_host[i % NBUF] for i in range(args.steps)]
         outs = [outs_host[i % 2] for i in range(args.steps)]
