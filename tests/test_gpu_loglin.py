@@ -87,3 +87,35 @@ def test_loglin_layers_with_real_and_log_activations(Q, dtype, fsr, bw):
         assert rel(lay(Q.functions.Quant(x.cuda(), "log", 1, 3, True)), ref_log) < 1e-5
         assert rel(conv(Q.functions.Quant(xi.cuda(), "lin", 1, 4, True)), ref_conv) < 1e-5
     assert lay._make_pack(lay.weight).kind == dtype
+
+
+def _golden_loglin_cases():
+    import os, re
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "quanttorch_ref_loglin_v1.npz"))
+    cases = {}
+    for k in z.files:
+        name, field = k.split("/")
+        cases.setdefault(name, {})[field] = torch.from_numpy(z[k].copy()) if z[k].ndim else int(z[k])
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_golden_loglin_cases()))
+def test_loglin_chains_match_live_reference_goldens(Q, name):
+    """LogLin layers fed by Lin / Log quantized activations vs outputs of the LIVE reference (oracle/gen_golden_loglin.py):
+    the activation quantizer is bit-exact, the layer output within 1e-5 (Lin x Lin: exact integers, one fp32 rounding)."""
+    import re
+    c = _golden_loglin_cases()[name]
+    kind, da, fa, ba, dw, fw, bw = re.fullmatch(r"(dense|conv)_(lin|log)(-?\d+)_(\d+)__(lin|log)(-?\d+)_(\d+)", name).groups()
+    fa, ba, fw, bw = int(fa), int(ba), int(fw), int(bw)
+    if kind == "dense":
+        lay = Q.layers.LinearQuant(c["w"].shape[1], c["w"].shape[0], dtype=dw, fsr=fw, bit_width=bw)
+    else:
+        lay = Q.layers.QuantConv2d(c["w"].shape[1], c["w"].shape[0], 3, stride=c["stride"], padding=c["padding"], fsr=fw,
+                                   bit_width=bw, dtype=dw)
+    lay.weight.data.copy_(c["w"]); lay.bias.data.copy_(c["b"])
+    lay = lay.cuda()           # training mode, as the golden conv cases were produced
+    with torch.no_grad():
+        xq = Q.functions.Quant(c["x"].cuda(), da, fa, ba, True)
+        assert torch.equal(xq.cpu(), c["xq"])
+        assert rel(lay(xq), c["out"]) < 1e-5
