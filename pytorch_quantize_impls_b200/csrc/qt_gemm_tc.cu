@@ -730,10 +730,13 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
     if (int rc = make_map(&mo, g.ep.out, (uint64_t)g.M, (uint64_t)g.N * 4, (uint64_t)g.ep.ldo * 4, 32, true)) return rc;
     g.tma_store = 1;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in shared-memory size is a per-device function attribute: remember it per device (one process may drive several)
+  static bool attr_set[64] = {};
+  int dev = 0;
+  QT_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, KIND, STAGES, BKB, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   g.tiles_m = (int)ceil_div(g.M, TC_BM);
   g.tiles_n = (int)ceil_div(g.N, BN);
@@ -754,10 +757,12 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, c
     if (int rc = make_map(&mo, g.ep.out, (uint64_t)g.M, (uint64_t)g.N * 4, (uint64_t)g.ep.ldo * 4, 32, true)) return rc;
     g.tma_store = 1;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  QT_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm2_kernel<BN, KIND, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   g.tiles_m = (int)ceil_div(g.M, 2 * TC_BM);
   g.tiles_n = (int)ceil_div(g.N, BN);
