@@ -1,3 +1,15 @@
-"""Facade, QuantTorch/BinaryNet.py:1-2."""
-from .functions.binary_connect import *  # noqa
-from .layers.binary_layers import *  # noqa
+"""BinaryNet facade -- BinaryNet (Courbariaux et al.): sign activations / weights.
+
+One import gives a model file every op and layer of the family, as `QuantTorch/BinaryNet.py:1-2` does for the reference
+(`from QuantTorch.BinaryNet import LinearX, ...`).  The names are listed explicitly (no star import), so that what a drop-in
+user can rely on is visible here and checked by tests/test_cabi_and_surface.py.
+"""
+from .functions.binary_connect import (  # noqa: F401
+    AP2, BinaryConnect, BinaryConnectDeterministic, BinaryConnectStochastic, BinaryConv2d, BinaryDense,
+    ShiftBatch, TaggingFunction, front, safeSign, ste_clip,
+)
+from .layers.binary_layers import (  # noqa: F401
+    BinConv2d, LinearBin, QuantLayerMixin, ShiftNormBatch1d, ShiftNormBatch2d, check_convert,
+)
+
+__all__ = sorted(n for n in dir() if not n.startswith("_"))
