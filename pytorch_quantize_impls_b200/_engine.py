@@ -1,14 +1,23 @@
 """Contraction routing: (activation operand kind) x (weight pack kind) -> kernel + epilogue.
 
-                      | W sign / ternary / dorefa (integer codes) | W xnor (alpha[k] * sign) / real planes
-  --------------------+-------------------------------------------+-----------------------------------------
-  A int8/uint8 codes  | tcgen05 kind::i8 (or XNOR-popcount for    | falls back to the row below (A re-read
-  (Binary/Ter/DoReFa) | 1-bit x 1-bit/ternary when M is small)    | as real values)
-  A bf16 codes (xnor) | tcgen05 kind::f16, 1 pass, row_scale      | 2 passes (W hi, W lo), row_scale
-  A real (untagged)   | bf16 hi/mid/lo split of A, 3 passes       | 5 passes (3 A planes x W hi, 2 x W lo)
+                        | W sign / ternary / DoReFa / Lin (integer codes)     | W xnor (alpha[k] * sign), log (2^e), real planes
+  ----------------------+------------------------------------------------------+--------------------------------------------------
+  A e2m1 codes          | tcgen05 kind::mxf4, unit block scales (sign, ternary, | re-read as real values (row below); not available
+  (sign/ter/DoReFa-2,   | DoReFa <= 2 weights); other integer weights: codes    | in code-only mode
+   2-D inputs)          | re-emitted as int8                                    |
+  A int8/uint8 codes    | tcgen05 kind::i8 (XNOR-popcount kernels for 1-bit x   | same
+  (DoReFa-k, Lin, conv) | {1-bit, ternary} when M <= 64); conv: TMA im2col      |
+  A fp16 codes (xnor)   | kind::f16 on exact fp16 codes, row_scale = row mean   | xnor: ONE kind::f16 pass on fp16(alpha[k]/alpha_max * s),
+                        |                                                       | alpha_max in the epilogue (bf16x2 mode: 2 passes)
+  A bf16 values (log)   | kind::f16 (bf16), 1 pass                              | log: 1 pass; xnor / real: 2 passes (W hi, W lo)
+  A real (untagged)     | bf16 hi/mid/lo split of A, 3 passes (conv first       | 5 passes (3 A planes x W hi, 2 x W lo); log: 3
+                        | layers: hi/lo gather+split, 2 passes)                 |
 
-Integer accumulators are exact; the real-activation route carries 24 significant bits of the activation
-(fp32-faithful), real-valued weights 16 bits (error ~2^-17), far inside the 1e-3 tolerance of the north star.
+Integer accumulators are exact (kind::i8: s32; kind::mxf4: integers in fp32 for K < 2^22); the real-activation route carries 24
+(16 for first conv layers) significant bits of the activation, real-valued weights 16 bits, far inside the 1e-3 tolerance of
+the north star.  Epilogue options shared by every tcgen05 route: scale / row / column scales, bias, folded BatchNorm, output
+clamp, NCHW addressing, raw accumulators, and the fused re-quantisation that writes the next layer's operand (RequantSpec).
+Large tiles run on CTA pairs (cta_group::2); everything a tensor route declines falls to the CUDA-core kernels.
 """
 import os
 import threading
