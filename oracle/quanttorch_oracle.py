@@ -14,9 +14,10 @@ the same order; that makes it bit-identical to the live reference on CPU
 is present, and against the committed vectors in ``tests/golden/`` everywhere).
 
 Parity pinning: PINNED for BinaryNet / Terner / DoReFa / LogLin by the
-reference's own known-answer tests (ported in ``tests/test_oracle_kat.py``)
-and by golden vectors generated from the live reference
-(``oracle/gen_golden.py``).  XnorNet: the reference's own XNOR tests are empty
+reference's own known-answer tests (ported in
+``tests/test_oracle_golden.py::test_reference_kats``) and by golden vectors
+generated from the live reference (``oracle/gen_golden.py``, ``gen_golden_grads.py``,
+``gen_golden_loglin.py``).  XnorNet: the reference's own XNOR tests are empty
 files (tests/implementations/XNOR/*.py, 0 bytes), so XnorNet parity is pinned
 only by outputs of the reference run here (golden vectors), not by reference
 KATs.
