@@ -16,5 +16,6 @@ from .fusion import (FusedBNActQuant, FusedLayerBN, FusedLayerQuant, OperandPref
                      prefetch_operands)
 from .device import device  # noqa: F401
 from .checkpoint import load_packed, packed_state, save_packed  # noqa: F401
+from . import convertor  # noqa: F401
 
 __version__ = '0.1'
