@@ -76,6 +76,31 @@ def cpu_reference_gops(batch, reps, warmup=1, seed=1234):
                 cores=cores, batch=batch)
 
 
+def cpu_linearbin_gops(batch=1024, reps=3, seed=99):
+    """Reference CPU path of the north-star layer (BinaryConnect -> LinearBin 4096 x 4096: fake-quant ops + fp32 F.linear, the
+    oracle port) on all host threads, on a bounded `batch`-row sample."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import quanttorch_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(seed)
+    K = N = 4096
+    w = torch.empty(N, K).normal_(0, K ** -0.5, generator=g)
+    b = torch.empty(N).uniform_(-1, 1, generator=g)
+    x = torch.randn(batch, K, generator=g)
+    times = []
+    with torch.no_grad():
+        for i in range(reps + 1):
+            t0 = time.perf_counter()
+            O.binary_mlp_layer(x, w, b)
+            if i:
+                times.append(time.perf_counter() - t0)
+    return {"gops": round(2.0 * batch * K * N / min(times) / 1e9, 1), "ms_sample": round(min(times) * 1e3, 2), "cores": cores,
+            "sample": "oracle port of BinaryConnect -> LinearBin (train-mode forward: weights re-binarised every call), %d rows, best of %d"
+                      % (batch, reps)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -435,6 +460,10 @@ def run_ours(args):
         extra = {}
         if rank == 0:
             extra = extra_layers(Q, torch, dev, pk, _ops)
+            try:
+                extra["linearbin_4096x4096_cpu_reference"] = cpu_linearbin_gops()
+            except Exception as err:            # a reporting extra must never cost the bench line
+                extra["linearbin_4096x4096_cpu_reference"] = {"error": str(err)}
             extra["xnor_mlp_default_mode_ms_per_step"] = round(ms_default, 4)
             extra["xnor_mlp_code_only_unfused_ms_per_step"] = round(ms_code_only, 4)
             extra["xnor_mlp_fused_vs_unfused_max_rel_diff"] = chain_rel

@@ -28,3 +28,15 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_cpu_reference_helpers_run():
+    """The CPU legs bench.py reports beside the GPU numbers (oracle port on the host cores) work on a bounded sample."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    r = bench.cpu_linearbin_gops(batch=64, reps=1)
+    assert r["gops"] > 0 and r["cores"] >= 1 and "LinearBin" in r["sample"]
+    m = bench.cpu_reference_gops(32, reps=1, warmup=0)
+    assert m["gops_best"] > 0 and m["batch"] == 32
