@@ -17,7 +17,7 @@ Parity pinning: PINNED for BinaryNet / Terner / DoReFa / LogLin by the
 reference's own known-answer tests (ported in
 ``tests/test_oracle_golden.py::test_reference_kats``) and by golden vectors
 generated from the live reference (``oracle/gen_golden.py``, ``gen_golden_grads.py``,
-``gen_golden_loglin.py``).  XnorNet: the reference's own XNOR tests are empty
+``gen_golden_loglin.py``, ``gen_golden_functional.py``).  XnorNet: the reference's own XNOR tests are empty
 files (tests/implementations/XNOR/*.py, 0 bytes), so XnorNet parity is pinned
 only by outputs of the reference run here (golden vectors), not by reference
 KATs.
@@ -201,6 +201,83 @@ def linear_loglin(x, w, b=None, dtype="lin", fsr=7, bit_width=3):
 def conv_loglin(x, w, b=None, dtype="lin", fsr=7, bit_width=3, **kw):
     """QuantTorch/layers/log_lin_layers.py:87-93 (training-mode branch)."""
     return _conv(x, loglin_weight(w, dtype, fsr, bit_width), b, **kw)
+
+
+# --------------------------------------------------------------------------
+# functional dense / conv ops with hand-written backward (SURVEY.md 8a rows a5, a14, a20)
+# Each returns (output, weight_q); `*_grads` restate the reference's backward formulas.
+# --------------------------------------------------------------------------
+
+def ternary_functional_weight(w: torch.Tensor) -> torch.Tensor:
+    """QuantTorch/functions/terner_connect.py:83-90 (deterministic branch): built on torch.sign, NOT safeSign, so
+    0 -> 0, +0.5 -> +0.5 and -0.5 -> -0.5 -- this differs from the layer path (ternary_det)."""
+    sign = torch.sign(w)
+    return (sign + torch.sign(w - 0.5 * sign)) / 2
+
+
+def dorefa_functional_weight(w: torch.Tensor, bit_width: int, conv: bool) -> torch.Tensor:
+    """QuantDense: dorefa_connect.py:127-133 (normalises by max|tanh W|); QuantConv2d: :166-172 (by tanh(max|W|), the same
+    value up to rounding).  No all-zero guard here (unlike nnQuantWeight)."""
+    if bit_width == 1:
+        return safe_sign(w) * torch.mean(torch.abs(w)).detach()
+    if bit_width == 32:
+        return w
+    m = torch.tanh(torch.max(torch.abs(w))) if conv else torch.max(torch.abs(torch.tanh(w)))
+    return 2 * dorefa_quantize(0.5 + torch.tanh(w) / (2 * m), bit_width) - 1
+
+
+def binary_dense(x, w, b=None):
+    """QuantTorch/functions/binary_connect.py:96-101."""
+    wq = safe_sign(w)
+    return F.linear(x, wq, b), wq
+
+
+def ternary_dense(x, w, b=None):
+    """QuantTorch/functions/terner_connect.py:83-93."""
+    wq = ternary_functional_weight(w)
+    return F.linear(x, wq, b), wq
+
+
+def ternary_conv2d(x, w, b=None, **kw):
+    """QuantTorch/functions/terner_connect.py:122-131."""
+    wq = ternary_functional_weight(w)
+    return _conv(x, wq, b, **kw), wq
+
+
+def quant_dense(x, w, b=None, bit_width=3):
+    """QuantTorch/functions/dorefa_connect.py:125-136."""
+    wq = dorefa_functional_weight(w, bit_width, conv=False)
+    return F.linear(x, wq, b), wq
+
+
+def quant_conv2d(x, w, b=None, bit_width=3, **kw):
+    """QuantTorch/functions/dorefa_connect.py:164-175."""
+    wq = dorefa_functional_weight(w, bit_width, conv=True)
+    return _conv(x, wq, b, **kw), wq
+
+
+def dense_grads(go, x, wq, has_bias=True):
+    """grad_input = g . W_q, grad_weight = g^T . x (no STE mask), grad_bias = sum g: binary_connect.py:103-112,
+    terner_connect.py:95-105, dorefa_connect.py:138-152 (before the tanh factor)."""
+    return go.mm(wq), go.t().mm(x), (go.sum(0) if has_bias else None)
+
+
+def conv_grads(go, x, w_shape, wq, has_bias=True, **kw):
+    """terner_connect.py:133-149 / dorefa_connect.py:177-196 (before the tanh factor)."""
+    gi = torch.nn.grad.conv2d_input(x.shape, wq, go, **kw)
+    gw = torch.nn.grad.conv2d_weight(x, w_shape, go, **kw)
+    # bias gradient: the reference reduces one axis at a time (terner_connect.py:144, dorefa_connect.py:190), which fixes
+    # the fp32 summation order
+    gb = go.sum(0).squeeze(0).sum(1).squeeze(1).sum(-1).squeeze(-1) if has_bias else None
+    return gi, gw, gb
+
+
+def dorefa_functional_grad_weight(gw, w, bit_width, conv):
+    """The tanh chain of the DoReFa functional ops: dorefa_connect.py:146-149 (dense) / :186-187 (conv)."""
+    if bit_width in (1, 32):
+        return gw
+    m = torch.tanh(torch.max(torch.abs(w))) if conv else torch.max(torch.abs(torch.tanh(w)))
+    return gw * (1 - torch.pow(torch.tanh(w), 2)) / m
 
 
 # --------------------------------------------------------------------------

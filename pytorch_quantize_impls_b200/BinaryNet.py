@@ -5,11 +5,11 @@ One import gives a model file every op and layer of the family, as `QuantTorch/B
 user can rely on is visible here and checked by tests/test_cabi_and_surface.py.
 """
 from .functions.binary_connect import (  # noqa: F401
-    AP2, BinaryConnect, BinaryConnectDeterministic, BinaryConnectStochastic, BinaryConv2d, BinaryDense,
-    ShiftBatch, TaggingFunction, front, safeSign, ste_clip,
+    BinaryConnect, BinaryConnectDeterministic, BinaryConnectStochastic, BinaryConv2d, BinaryDense,
+    TaggingFunction, front, safeSign, ste_clip,
 )
 from .layers.binary_layers import (  # noqa: F401
-    BinConv2d, LinearBin, QuantLayerMixin, ShiftNormBatch1d, ShiftNormBatch2d, check_convert,
+    BinConv2d, LinearBin, QuantLayerMixin, check_convert,
 )
 
 __all__ = sorted(n for n in dir() if not n.startswith("_"))

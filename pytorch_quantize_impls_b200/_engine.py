@@ -185,6 +185,18 @@ def _a_from_tag(tag):
     return a
 
 
+def _checked_tag(tag, x):
+    """The operand if its codes are inside their lane (ops.set_strict); None -> the caller contracts with the fp32 tensor on the
+    real-activation route, which is what the reference computes for out-of-range DoReFa inputs."""
+    if tag is None or ops.codes_in_range(tag):
+        return tag
+    if x.is_meta:
+        raise RuntimeError("pytorch_quantize_impls_b200: a k-bit activation code left its lane (inputs of a DoReFa quantizer "
+                           "outside [0, 1]) and code-only mode keeps no fp32 tensor to fall back on; clamp the activations "
+                           "(Hardtanh(0, 1)) or leave code_only_activations()")
+    return None
+
+
 def _f4_weight_ok(pack):
     return (_force_backend["i8"] != L.BACKEND_SIMT
             and (pack.kind in ("sign", "ternary") or (pack.kind == "dorefa" and pack.bit_width <= 2)))
@@ -265,6 +277,7 @@ def _requant_tag(spec, rq, shape, layout="rows"):
     tag = ops.ActCodes()
     tag.kind, tag.bit_width = spec.kind, spec.bit_width
     tag.codes, tag.codes_kind, tag.rows, tag.cols, tag.ld = rq.codes, rq.codes_kind, rq.rows, rq.cols, rq.ld
+    tag.range_ok = rq.overflow is None or ops.clamp_guarantees_lane(rq.codes_kind, spec.bit_width, spec.lo, spec.hi)
     tag.scale = 1.0
     if spec.mode == L.Q_DOREFA:
         import numpy as np
@@ -407,6 +420,7 @@ def linear(x, pack, bias, requant=None, affine=None):
     lead = x.shape[:-1]
     tag = get_tag(x) if x.dim() == 2 else None
     x2d = None if x.is_meta else ops.as_f32c(x).reshape(-1, K)
+    tag = _checked_tag(tag, x)
     M = x.numel() // K
     if requant is not None and (x.dim() != 2 or M == 0):
         raise RequantUnsupported("fused requant needs a non-empty 2-D input")
@@ -481,6 +495,7 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
     tag = get_tag(x)
     if tag is not None and not (tag.codes_kind in (L.CODES_I8, L.CODES_U8) and int_w and tag.layout == "nhwc"):
         tag = None
+    tag = _checked_tag(tag, x)
     if bias is not None:
         bias = ops.as_f32c(bias)
     need_rs = int_w and pack.kind == "dorefa" and pack.bit_width == 8

@@ -8,12 +8,49 @@ from . import _lib as L
 _strict = False
 
 
-def set_strict(flag: bool):
-    """strict=True: after every k-bit activation quantizer, synchronise and raise if a code left its
-    8-bit lane (the reference's _quantize does not clamp, dorefa_connect.py:24-25).  Default False:
-    the sticky device flag is kept on the operand and can be inspected with ActCodes.check()."""
+def set_strict(flag):
+    """Policy for k-bit activation codes that leave their 8-bit (or e2m1) lane -- the reference's _quantize does not clamp
+    (dorefa_connect.py:24-25), so inputs outside [0, 1] produce codes outside [0, 2^k - 1], and far enough outside they no
+    longer fit the lane (int8 for k <= 7, uint8 for k = 8, {-4..4} for the e2m1 lane of k = 2):
+
+      False (default)  the quantizer saturates the code and raises a sticky device flag; the layer that CONSUMES the operand
+                       checks the flag before contracting (one host synchronisation per quantizer whose range is not
+                       guaranteed by a fused clamp) and, when it is set, contracts with the fp32 fake-quant tensor on the
+                       real-activation route instead -- the output then equals the reference's; in code-only mode, where
+                       no fp32 tensor exists, it raises
+      True             synchronise and raise right after every k-bit quantizer
+      "off"            never look at the flag (CUDA-graph capture behaves like this: a capture cannot synchronise); the
+                       caller promises inputs in lane range, e.g. [0, 1] behind a Hardtanh(0, 1)
+    """
     global _strict
-    _strict = bool(flag)
+    if flag not in (True, False, "off"):
+        raise ValueError("set_strict: True, False or 'off'")
+    _strict = flag
+
+
+def codes_in_range(tag):
+    """True when the consumer may contract on `tag`'s codes (see set_strict).  Caches a clean result on the tag."""
+    if tag is None or tag.overflow is None or tag.range_ok or _strict == "off":
+        return True
+    if torch.cuda.is_current_stream_capturing():
+        return True
+    ok = int(tag.overflow.item()) == 0
+    if ok:
+        tag.range_ok = True
+    return ok
+
+
+def _lane_range(codes_kind):
+    return {L.CODES_I8: (-128, 127), L.CODES_U8: (0, 255), L.CODES_F4: (-4, 4)}.get(codes_kind)
+
+
+def clamp_guarantees_lane(codes_kind, bit_width, lo, hi):
+    """A clamp to [lo, hi] in front of a DoReFa-k quantizer keeps round(n x) inside the lane of `codes_kind`."""
+    r = _lane_range(codes_kind)
+    if r is None or lo is None or hi is None:
+        return r is None
+    n = float(2 ** bit_width - 1)
+    return round(n * lo) >= r[0] and round(n * hi) <= r[1]
 
 
 def round_up(a, b):
@@ -53,9 +90,14 @@ class ActCodes:
     shape       shape of the fp32 tensor the codes describe (e.g. NCHW)
     """
     __slots__ = ("kind", "bit_width", "codes", "codes_kind", "rows", "cols", "ld", "scale", "row_sum",
-                 "row_scale", "bits", "ld_bits", "overflow", "shape", "version", "layout", "row_parts", "row_mul")
+                 "row_scale", "bits", "ld_bits", "overflow", "shape", "version", "layout", "row_parts", "row_mul",
+                 "range_ok")
+    # range_ok: the codes are known to sit inside their lane (a clamp in front of the quantizer, or a checked clean flag)
     # row_parts > 0: the operand was written by a fused requant epilogue; row_scale / row_sum are [row_parts, rows]
     # partial sums and the consumer epilogue uses  row_mul * sum_p row_scale[p]  /  sum_p row_sum[p]
+
+    def __init__(self):
+        self.range_ok = False
 
     def check(self):
         if self.overflow is not None and int(self.overflow.item()) != 0:
@@ -143,7 +185,9 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
         tag.row_sum, tag.row_scale, tag.bits, tag.ld_bits = row_sum, row_scale, bits, ldb
         tag.overflow, tag.shape, tag.version, tag.layout = overflow, shape, None, layout
         tag.row_parts, tag.row_mul = row_parts, (1.0 / max(cols, 1) if row_parts else 1.0)
-        if _strict:
+        tag.range_ok = overflow is None or (pre is not None and mode == L.Q_DOREFA
+                                            and clamp_guarantees_lane(codes_kind, bit_width, pre[2], pre[3]))
+        if _strict is True:
             tag.check()
     return y, tag
 

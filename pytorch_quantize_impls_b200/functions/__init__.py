@@ -1,7 +1,7 @@
 """Same export list as QuantTorch/functions/__init__.py:1-51, minus the Elastic/WQR regularisers
 (out of scope: training-time penalties whose forward is a plain fp32 GEMM)."""
-from .binary_connect import (AP2, BinaryConnect, BinaryConnectDeterministic, BinaryConnectStochastic, BinaryConv2d,
-                             BinaryDense, ShiftBatch)
+from .binary_connect import (BinaryConnect, BinaryConnectDeterministic, BinaryConnectStochastic, BinaryConv2d,
+                             BinaryDense)
 from .common import front, front2, safeSign
 from .dorefa_connect import DorefaQuant, QuantConv2d, QuantDense, nnDorefaQuant, nnQuantWeight
 from .log_lin_connect import LinQuant, LogQuant, Quant, nnQuant

@@ -107,34 +107,3 @@ def BinaryConv2d(stride=1, padding=1, dilation=1, groups=1):
             return (gi, gw, gb) if bias is not None else (gi, gw)
 
     return _BinaryConv2d
-
-
-def AP2(x):
-    """sign(x) * 2^round(log2|x|), binary_connect.py:157-169 (shift-BN primitive; torch ops, off the measured path)."""
-    two = torch.ones_like(x) * 2
-    return safeSign(x) * torch.pow(two, torch.round(torch.log2(torch.abs(x))))
-
-
-class ShiftBatch(torch.autograd.Function):
-    """Shift-based batch-norm primitive, binary_connect.py:173-214 (off the measured path; torch ops)."""
-
-    @staticmethod
-    def forward(ctx, input, running_mean, running_var, weight, bias, eps):
-        inputs_mu = input - running_mean
-        sqrtvar = torch.sqrt(running_var + eps)
-        norm_inputs = inputs_mu * AP2(1 / sqrtvar)
-        out = norm_inputs * AP2(weight) + bias
-        ctx.save_for_backward(input, weight, sqrtvar, norm_inputs)
-        return out
-
-    @staticmethod
-    def backward(ctx, grad_output):
-        input, weight, sqrtvar, norm_inputs = ctx.saved_tensors
-        gi = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gi = grad_output * weight / sqrtvar
-        if ctx.needs_input_grad[3]:
-            gw = grad_output * norm_inputs
-        if ctx.needs_input_grad[4]:
-            gb = grad_output.sum(0).squeeze(0)
-        return gi, None, None, gw, gb, None

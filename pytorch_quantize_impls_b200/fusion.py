@@ -210,8 +210,12 @@ class FusedLayerBN(nn.Module):
 
     def forward(self, x):
         bn = self.bn
+        n_out = self.layer.out_channels if self.layer._is_conv else self.layer.out_features
         if (not torch.is_grad_enabled() and (x.is_cuda or x.is_meta)
-                and (bn is None or (not bn.training and bn.track_running_stats and bn.running_mean is not None))):
+                # BatchNorm1d over a 3-D input normalises dim 1, not the layer's output features: only the plain ranks fold
+                and x.dim() == (4 if self.layer._is_conv else 2)
+                and (bn is None or (not bn.training and bn.track_running_stats and bn.running_mean is not None
+                                    and bn.num_features == n_out))):
             return self.layer._forward_affine(x, self._make_spec())
         y = self.layer(x)
         if bn is not None:

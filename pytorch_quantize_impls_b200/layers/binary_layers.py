@@ -21,7 +21,17 @@ class _BinMixin(QuantLayerMixin):
         if self.deterministic:
             return ops.pack_weight(ops.conv_weight_2d(w.detach()), "sign")
         # stochastic binarisation draws new +-1 weights each call; pack the drawn signs
-        return ops.pack_weight(ops.conv_weight_2d(self.bin_op.apply(w.detach())), "sign")
+        return self._make_pack_of_sample(self.bin_op.apply(w.detach()))
+
+    def _make_pack_of_sample(self, wq):
+        return ops.pack_weight(ops.conv_weight_2d(wq.detach()), "sign")      # sign(+-1) = +-1
+
+    def _weight_op_host(self, w):
+        one = torch.ones_like(w)
+        if self.deterministic:
+            return torch.where(w < 0, -one, one)                             # 0, -0.0, NaN -> +1 (functions/common.py:4-7)
+        p = (torch.clamp(w, -1, 1) + 1) / 2                                  # binary_connect.py:57-61
+        return torch.where(torch.rand_like(w) < p, one, -one)
 
 
 class LinearBin(_BinMixin, torch.nn.Linear):
@@ -68,55 +78,3 @@ class BinConv2d(_BinMixin, torch.nn.Conv2d):
     def clamp(self):
         """Clamp real weights to [-1, 1] (weights only, binary_layers.py:81-85)."""
         self.weight.data.clamp_(-1, 1)
-
-
-class ShiftNormBatch1d(torch.nn.Module):
-    """Shift-based batch norm, binary_layers.py:110-129 (off the measured path; torch ops)."""
-    __constants__ = ['momentum', 'eps']
-
-    def __init__(self, in_dim, eps=1e-5, momentum=0.1):
-        super().__init__()
-        self.in_features = in_dim
-        self.weight = torch.nn.Parameter(torch.Tensor(self.in_features))
-        self.bias = torch.nn.Parameter(torch.Tensor(self.in_features))
-        self.register_buffer('running_mean', torch.zeros(self.in_features))
-        self.register_buffer('running_var', torch.ones(self.in_features))
-        self.eps = eps
-        self.momentum = momentum
-
-    def forward(self, x):
-        self.running_mean = (1 - self.momentum) * self.running_mean + self.momentum * torch.mean(x, 0).detach()
-        d = x - self.running_mean
-        self.running_var = (1 - self.momentum) * self.running_var + self.momentum * torch.mean(
-            d * binary_connect.AP2(d), 0).detach()
-        return binary_connect.ShiftBatch.apply(x, self.running_mean, self.running_var, self.weight, self.bias, self.eps)
-
-
-class ShiftNormBatch2d(torch.nn.Module):
-    """2-D shift-based batch norm, binary_layers.py:134-160 (off the measured path; torch ops)."""
-    __constants__ = ['momentum', 'eps']
-
-    def __init__(self, in_channels, eps=1e-5, momentum=0.1):
-        super().__init__()
-        self.in_features = in_channels
-        self.weight = torch.nn.Parameter(torch.Tensor(self.in_features))
-        self.bias = torch.nn.Parameter(torch.Tensor(self.in_features))
-        self.register_buffer('running_mean', torch.zeros(self.in_features))
-        self.register_buffer('running_var', torch.ones(self.in_features))
-        self.eps = eps
-        self.momentum = momentum
-
-    @staticmethod
-    def _tile(tensor, dim):
-        return tensor.repeat(dim[0], dim[1], 1).transpose(2, 0)
-
-    def forward(self, x):
-        dim = x.size()[-2:]
-        self.running_mean = (1 - self.momentum) * self.running_mean + self.momentum * torch.mean(x, [0, 2, 3]).detach()
-        curr_mean = ShiftNormBatch2d._tile(self.running_mean, dim)
-        d = x - curr_mean
-        self.running_var = (1 - self.momentum) * self.running_var + self.momentum * torch.mean(
-            d * binary_connect.AP2(d), [0, 2, 3]).detach()
-        return binary_connect.ShiftBatch.apply(x, curr_mean, ShiftNormBatch2d._tile(self.running_var, dim),
-                                               ShiftNormBatch2d._tile(self.weight, dim),
-                                               ShiftNormBatch2d._tile(self.bias, dim), self.eps)

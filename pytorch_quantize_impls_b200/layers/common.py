@@ -36,8 +36,13 @@ class _Contraction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, input, weight, bias, layer):
         ctx.layer = layer
+        # the mode and (for stochastic layers) the drawn weights of THIS forward are what backward must see: the reference's
+        # autograd graph keeps the sampled tensor, it does not draw again
+        ctx.was_training = layer.training
+        pack, wq_sample = layer._pack_for_forward()
+        ctx.wq_sample = wq_sample
         ctx.save_for_backward(input, weight, bias)
-        return layer._run_kernels(input)
+        return layer._run_kernels(input, pack)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -46,8 +51,9 @@ class _Contraction(torch.autograd.Function):
         gi = gw = gb = None
         with torch.enable_grad():
             w = weight.detach().requires_grad_(True)
-            wq = layer._weight_op(w) if layer.training else w
-        wqd = wq.detach()
+            # stochastic ops: the graph only serves the STE (a function of w alone); the VALUES come from the forward's sample
+            wq = layer._weight_op(w) if ctx.was_training else w
+        wqd = ctx.wq_sample if ctx.wq_sample is not None else wq.detach()
         if layer._is_conv:
             kw = dict(stride=layer.stride, padding=layer.padding, dilation=layer.dilation, groups=layer.groups)
             if ctx.needs_input_grad[0]:
@@ -98,6 +104,28 @@ class QuantLayerMixin(QLayer):
     def _make_pack(self, w):
         raise NotImplementedError
 
+    def _weight_op_host(self, w):
+        """The weight op as plain torch arithmetic, for the train(False) swap of a layer whose weights are not on a CUDA
+        device yet (`model.eval(); model.cuda()`): module state management, not a contraction path -- forward on a CPU
+        tensor still raises."""
+        raise NotImplementedError
+
+    def _is_stochastic(self):
+        return not getattr(self, "deterministic", True)
+
+    def _make_pack_of_sample(self, wq):
+        """Pack of an already drawn stochastic sample (values in the quantizer's own output set)."""
+        raise NotImplementedError
+
+    def _pack_for_forward(self):
+        """(WeightPack, drawn weights or None) for one forward.  Stochastic layers draw ONCE here: the pack the kernels
+        contract with and the tensor backward multiplies the output gradient by are the same sample."""
+        if self._packed_only is None and self.training and self._is_stochastic():
+            with torch.no_grad():
+                wq = self._weight_op(self.weight.detach())
+            return self._make_pack_of_sample(wq), wq
+        return self._current_pack(), None
+
     # ---- weight-swap train()/eval(), e.g. binary_layers.py:30-40 --------------------------
     def train(self, mode=True):
         if self._packed_only is not None:
@@ -107,26 +135,44 @@ class QuantLayerMixin(QLayer):
             return self
         if self.training == mode:
             return self
-        self.training = mode
         if mode:
             self.weight.data.copy_(self.weight.org.data)
             self._eval_state = None
+            self.training = True
+            return self
+        # eval: nothing of the layer's state changes until quantisation and packing have succeeded
+        master = self.weight.data.clone()
+        st = None
+        with torch.no_grad():
+            if self.weight.is_cuda:
+                st = _EvalState()
+                if self._is_stochastic():
+                    wq = self._weight_op(self.weight).detach()        # ONE draw: stored weights and pack agree
+                    st.pack = self._make_pack_of_sample(wq)
+                else:
+                    st.pack = self._make_pack(self.weight)            # packed once, from the fp32 master weights
+                    wq = self._weight_op(self.weight).detach()
+            else:
+                # weights still on the host: swap with torch arithmetic, pack on the first CUDA forward (_current_pack
+                # re-packs from `weight.org` / the stored quantized values)
+                wq = self._weight_op_host(self.weight.detach())
+        if not hasattr(self.weight, 'org'):
+            self.weight.org = master
         else:
-            if not hasattr(self.weight, 'org'):
-                self.weight.org = self.weight.data.clone()
-            self.weight.org.data.copy_(self.weight.data)
-            st = _EvalState()
-            st.pack = self._make_pack(self.weight)            # packed once, from the fp32 master weights
-            with torch.no_grad():
-                self.weight.data.copy_(self._weight_op(self.weight).detach())
+            self.weight.org.data = master
+        self.weight.data.copy_(wq)
+        if st is not None:
             st.version, st.ptr = self.weight._version, self.weight.data_ptr()
-            self._eval_state = st
+        self._eval_state = st
+        self.training = False
         return self
 
     def _current_pack(self):
         if self._packed_only is not None:
             return self._packed_only[0]
         if self.training:
+            if self._is_stochastic():
+                return self._pack_for_forward()[0]
             return self._make_pack(self.weight)               # the reference re-quantizes W on every call
         st = self._eval_state
         if st is not None and st.version == self.weight._version and st.ptr == self.weight.data_ptr():
@@ -141,20 +187,25 @@ class QuantLayerMixin(QLayer):
         w = self.weight.detach()
         org = getattr(self.weight, "org", None)
         with torch.no_grad():
-            if org is not None and org.shape == w.shape:
-                org = org.to(w.device)
-                if torch.equal(self._weight_op(org), w):
-                    st.pack = self._make_pack(org)
-            if st.pack is None and torch.equal(self._weight_op(w), w):
-                st.pack = self._make_pack(w)
+            if self._is_stochastic():
+                # the stored values ARE the sample drawn at train(False); never draw again in eval mode
+                st.pack = self._make_pack_of_sample(w)
+            else:
+                if org is not None and org.shape == w.shape:
+                    org = org.to(w.device)
+                    if torch.equal(self._weight_op(org), w):
+                        st.pack = self._make_pack(org)
+                if st.pack is None and torch.equal(self._weight_op(w), w):
+                    st.pack = self._make_pack(w)
         if st.pack is None:
             st.pack = ops.pack_real_weight(ops.conv_weight_2d(w))
         st.version, st.ptr = self.weight._version, self.weight.data_ptr()
         self._eval_state = st
         return st.pack
 
-    def _run_kernels(self, input):
-        pack = self._current_pack()
+    def _run_kernels(self, input, pack=None):
+        if pack is None:
+            pack = self._pack_for_forward()[0]
         if self._is_conv:
             return eng.conv2d(input, pack, self.bias, self._wshape(), self.stride, self.padding,
                               self.dilation, self.groups)

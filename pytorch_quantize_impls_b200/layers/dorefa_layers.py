@@ -22,6 +22,21 @@ class _DorefaMixin(QuantLayerMixin):
             return ops.pack_real_weight(ops.conv_weight_2d(self.weight_op.forward(w.detach())))
 
 
+    def _weight_op_host(self, w):
+        k = self.bit_width                                                   # dorefa_connect.py:99-111
+        if k == 32:
+            return w.clone()
+        one = torch.ones_like(w)
+        if k == 1:
+            return torch.where(w < 0, -one, one) * torch.mean(torch.abs(w))
+        if torch.max(torch.abs(w)) == 0.0:
+            return torch.zeros_like(w)
+        t = torch.tanh(w)
+        t = t / (2 * torch.max(torch.abs(t))) + 0.5
+        n = torch.pow(one * 2, k) - 1
+        return 2 * ((1 / n) * torch.round(n * t)) - 1
+
+
 class LinearDorefa(_DorefaMixin, torch.nn.Linear):
     """y = x . quantize_w(W)^T + b with k-bit weights (dorefa_layers.py:11-45)."""
 

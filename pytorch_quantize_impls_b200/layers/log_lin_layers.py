@@ -20,6 +20,15 @@ class _LogLinMixin(QuantLayerMixin):
             return ops.pack_loglin_weight(ops.conv_weight_2d(wq), self._dtype, self.fsr, self.bit_width)
         return ops.pack_real_weight(ops.conv_weight_2d(wq))
 
+    def _weight_op_host(self, w):
+        if self._dtype == "lin":                                             # log_lin_connect.py:61-68
+            if self.bit_width == 32:
+                return w.clone()
+            step = 2.0 ** (self.fsr - self.bit_width)
+            return torch.sign(w) * torch.clamp(torch.round(torch.abs(w) / step) * step, 0, 2 ** self.fsr)
+        e = torch.clamp(torch.round(torch.log2(torch.abs(w))), self.fsr - 2 ** self.bit_width, self.fsr)
+        return torch.sign(w) * torch.pow(torch.ones_like(w) * 2, e)         # log_lin_connect.py:29-32
+
     def clamp(self):
         self.weight.data.clamp_(-1 * 2 ** (self.fsr), 2 ** (self.fsr))
 

@@ -22,7 +22,17 @@ class _TerMixin(QuantLayerMixin):
         if self.deterministic:
             return ops.pack_weight(w2, "ternary")
         # stochastic: the drawn values are already in {-1, 0, 1}; the deterministic packer maps them to themselves
-        return ops.pack_weight(ops.conv_weight_2d(self.ter_op.apply(w.detach())), "ternary")
+        return self._make_pack_of_sample(self.ter_op.apply(w.detach()))
+
+    def _make_pack_of_sample(self, wq):
+        return ops.pack_weight(ops.conv_weight_2d(wq.detach()), "ternary")
+
+    def _weight_op_host(self, w):
+        one = torch.ones_like(w)
+        s = torch.where(w < 0, -one, one)
+        if self.deterministic:
+            return (s + torch.where(w - 0.5 * s < 0, -one, one)) / 2        # terner_connect.py:24-27
+        return s - s * (torch.rand_like(w) > torch.abs(w)).to(w.dtype)       # terner_connect.py:50-55
 
 
 class LinearTer(_TerMixin, torch.nn.Linear):

@@ -117,7 +117,12 @@ class PipelinedGather:
         return st
 
     def submit(self, y_local):
-        """Enqueue the gather of `y_local` ([B/G, ...], equal shards).  Returns (gathered tensor, completion event or None)."""
+        """Enqueue the gather of `y_local` ([B/G, ...], equal shards).  Returns (gathered tensor, completion event or None).
+
+        Contract for the returned buffer (it is one of `depth` rotating slots, peer-writable in mode "ce"): whatever reads it
+        must be enqueued -- on the stream that calls `submit`, or on a stream that stream waits for -- BEFORE the submit that
+        re-uses the slot (`depth` submits later).  The push of that later step is ordered after those reads on every rank
+        by a cross-rank release barrier."""
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return y_local, None
         world, rank = dist.get_world_size(), dist.get_rank()
@@ -147,6 +152,12 @@ class PipelinedGather:
         with torch.cuda.stream(self._comm):
             if self.mode == "ce":
                 n = y_local.shape[0]
+                # release barrier: a peer may only overwrite my rows of slot `slot` once I am done with what step i - depth left
+                # there.  Every rank's communication stream reaches this barrier after its own `ready` event, i.e. after all
+                # work its submitting stream had enqueued before this submit -- which is where a consumer of the previous
+                # contents of the slot must have been enqueued (see `submit` docstring).  Without it a faster rank could
+                # write into a buffer a slower rank is still reading (write-after-read across ranks).
+                hdl.barrier(channel=self.depth + slot)
                 nps = self.pull_streams if self.pull_streams else min(4, world)
                 while len(self._pull) < nps - 1:
                     self._pull.append(torch.cuda.Stream(device=y_local.device))

@@ -48,13 +48,13 @@ def test_ctypes_structs_match_header_field_order(Q):
 
 def test_surface_names(Q):
     fn = ["safeSign", "BinaryConnectDeterministic", "BinaryConnectStochastic", "BinaryConnect", "BinaryDense",
-          "BinaryConv2d", "AP2", "ShiftBatch", "nnDorefaQuant", "DorefaQuant", "nnQuantWeight", "QuantDense",
+          "BinaryConv2d", "nnDorefaQuant", "DorefaQuant", "nnQuantWeight", "QuantDense",
           "QuantConv2d", "LogQuant", "LinQuant", "nnQuant", "Quant", "TernaryConnectDeterministic",
           "TernaryConnectStochastic", "TernaryConnect", "TernaryDense", "TernaryConv2d", "nnQuantXnor", "QuantXnor",
           "XNORDense", "XNORConv2d"]
     for n in fn:
         assert hasattr(Q.functions, n), n
-    for n in ["LinearBin", "BinConv2d", "ShiftNormBatch1d", "ShiftNormBatch2d", "LinearDorefa", "DorefaConv2d",
+    for n in ["LinearBin", "BinConv2d", "LinearDorefa", "DorefaConv2d",
               "LinearQuant", "QuantConv2d", "LinearTer", "TerConv2d", "LinearXNOR", "XNORConv2d"]:
         assert hasattr(Q.layers, n), n
     assert Q.BinaryNet.LinearBin is Q.layers.LinearBin and Q.BinaryNet.BinaryConnect is Q.functions.BinaryConnect
