@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QT_VERSION 102
+#define QT_VERSION 103
 
 enum {
   QT_OK = 0,
@@ -102,6 +102,10 @@ typedef struct QtActQuant {
                            With P = qt_quant_xnor_parts(cols, y != NULL, row_parts) > 1 the rows are processed in P column
                            chunks and row_scale[p * rows + r] receives the partial SUM of chunk p (mean = sum_p / cols; the
                            contraction epilogue adds them in order: QtEpilogue.row_scale_parts / row_scale_mul) */
+  int max_ctas;         /* 0: one CTA per 8 row chunks (fastest when the quantizer has the GPU to itself).  > 0: at most this many
+                           CTAs, each looping over row chunks -- a bounded footprint (8 warps, ~8 K registers, no shared memory
+                           per CTA) that shares every SM with a persistent tcgen05 contraction running on another stream
+                           (the quantizer of row band i+1 beside the product of band i).  Code-only calls only (no y / bits) */
 } QtActQuant;
 
 int qt_quant_act(const QtActQuant* p, void* stream);
@@ -269,6 +273,11 @@ typedef struct QtEpilogue {
   int out_clamp;          /* 1: y = min(max(y, out_lo), out_hi) before it is written (a Hardtanh / ReLU / ReLU6 that follows the
                              layer, e.g. models/Resnet/Resnet_bin.py:27-31, costs no pass over the activation) */
   float out_lo, out_hi;
+  const float* residual;  /* optional fp32 [M, ld_res] (row major): y += residual[m, n] after scale / bias and BEFORE out_clamp and the
+                             requant -- the shortcut add of a residual block (models/Resnet/Resnet_bin.py:27-31
+                             `out += self.shortcut(x); out = F.relu(out)`) folded into the second conv's epilogue, with the
+                             channels-last fp32 activation as [pixels, channels] matrix.  out_mode 0 only */
+  int64_t ld_res;
 } QtEpilogue;
 
 /* 1-bit x 1-bit: acc = K - 2 popc(a ^ w).  CUDA-core XNOR + popcount. */
@@ -309,6 +318,47 @@ typedef struct QtConvGeom {
 
 int qt_conv_i8(const void* x_nhwc, int a_signed, const QtConvGeom* g, const void* w, int w_signed, int64_t ldw,
                int64_t N, const QtEpilogue* ep, void* stream);
+
+/* The same implicit GEMM on channels-last bf16 activations x_nhwc[B, H, W, C] and bf16 weights w[N, kh*kw*C/groups]
+ * (tcgen05 kind::f16, fp32 accumulation): the first layer of every reference net, which sees the fp32 image
+ * (models/Alexnet/Alexnet_Bin.py:13, models/Resnet/Resnet_bin.py:68, models/VGG/VGG_LinQuant.py:12 -> F.conv2d of a real
+ * input with quantized weights).  Needs (C/groups) * 2 bytes % 32 == 0: callers feed the "plane pixel" tensor of
+ * qt_image_planes, whose 16 slots per pixel hold the bf16 hi / mid / lo parts of the (<= 5) image channels, against weights
+ * whose integer codes are repeated per part -- one pass, 24 significant bits of the input.  ldw in ELEMENTS. */
+int qt_conv_bf16(const void* x_nhwc, const QtConvGeom* g, const void* w, int64_t ldw, int64_t N, const QtEpilogue* ep, void* stream);
+
+/* fp32 NCHW image x[B, C, H, W] -> channels-last bf16 plane pixels out[B, Hp, Wp, 16] with the conv's zero padding
+ * materialised: out[b, h + pad_h, w + pad_w, p * C + c] = part p of x[b, c, h, w]  (p = 0 hi, 1 mid, 2 lo; hi + mid + lo == x
+ * to 24 significant bits), every other slot / border pixel zero.  planes * C <= 16.  Pixels of the source that fall outside
+ * [Hp, Wp] after the shift are dropped (a strided conv never reads them).  Because consecutive pixels of a row are adjacent
+ * in memory, the caller may view f pixels as one pixel of 16 f slots: a stride-f filter row of kw taps becomes a stride-1
+ * row of floor((kw - 1) / f) + 1 taps (space-to-depth along W), which is how 7x7/2 and 11x11/4 stems keep the number of
+ * TMA stages per tile small. */
+int qt_image_planes(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int planes, int pad_h, int pad_w,
+                    int64_t Hp, int64_t Wp, void* out, void* stream);
+
+/* Max-pool (nn.MaxPool2d, ceil_mode = False, dilation 1; OH = floor((H + 2 pad - k) / stride) + 1) on channels-last tensors.
+ *   qt_pool_codes      8-bit activation codes [B, H, W, C] -> [B, OH, OW, C].  An activation quantizer is monotone, so
+ *                      pool(quantize(clamp(bn(y)))) == quantize(clamp(bn(pool(y)))) whenever the BatchNorm scale of the channel
+ *                      is >= 0, and equals the MIN-pool of the codes when it is negative: use_min[c] (optional, [C] bytes)
+ *                      selects min for those channels.  This lets `conv -> MaxPool -> BatchNorm -> Hardtanh -> quantizer`
+ *                      (models/Alexnet/Alexnet_Bin.py:13-22, benchmark/BinaryNet/AlexNetBin.py:13-24) run as conv with the
+ *                      requant epilogue followed by a pool over 1-byte codes instead of fp32.  C % 16 == 0.
+ *   qt_pool_quant_f32  fp32 [B, H, W, C] -> pooled fp32 (optional) and / or the 8-bit codes of the pooled values
+ *                      (mode QT_Q_SIGN / QT_Q_TERNARY / QT_Q_DOREFA as qt_quant_act; codes_kind 1 int8, 2 uint8).  C % 4 == 0. */
+typedef struct QtPoolGeom {
+  int64_t B, H, W, C;
+  int kh, kw, stride_h, stride_w, pad_h, pad_w;
+  int64_t OH, OW;
+} QtPoolGeom;
+
+/* row_sum[r] = sum of the 8-bit codes of row r of codes[rows, ld] (zero padding included): the activation row sums the unsigned
+ * DoReFa-8 weight zero point needs (see qt_gemm_i8) when a Linear layer reads the flattened codes a conv chain left. */
+int qt_rowsum_codes(const void* codes, int is_unsigned, int64_t rows, int64_t ld, int32_t* row_sum, void* stream);
+
+int qt_pool_codes(const void* x_nhwc, int is_unsigned, const QtPoolGeom* g, const uint8_t* use_min, void* out, void* stream);
+int qt_pool_quant_f32(const float* x_nhwc, const QtPoolGeom* g, float* out, int mode, int bit_width, void* codes, int codes_kind,
+                      int32_t* overflow, void* stream);
 
 /* Per-output-pixel sum of the 8-bit codes under the filter window of conv group `group` (zero padding contributes 0):
  * row_sum[m] = sum_{kh,kw,c} x_nhwc[b, ih, iw, c].  It is the activation row sum the unsigned-weight (DoReFa-8) zero point

@@ -9,11 +9,11 @@ tooling; only the hot path (functions, layers, facades) exists.
 from . import _lib  # noqa: F401  (defines the loud failure when libqtb200.so is missing)
 from . import functions, layers  # noqa: F401
 from . import BinaryNet, DorefaNet, LogLinNet, TernerNet, XnorNet  # noqa: F401
-from ._engine import (code_only_activations, set_backend, set_first_layer_planes, set_fp4, set_grad_backend,  # noqa: F401
-                      set_implicit_conv, set_xnor_mode)
+from ._engine import (code_only_activations, set_backend, set_first_layer_implicit, set_first_layer_planes, set_fp4,  # noqa: F401
+                      set_grad_backend, set_implicit_conv, set_xnor_mode)
 from ._ops import device_caps, set_strict  # noqa: F401
-from .fusion import (FusedBNActQuant, FusedLayerBN, FusedLayerQuant, OperandPrefetch, fuse_inference,  # noqa: F401
-                     prefetch_operands)
+from .fusion import (FlattenCodes, FusedActLayer, FusedBasicBlock, FusedBNActQuant, FusedConvPool, FusedLayerBN,  # noqa: F401
+                     FusedLayerPoolQuant, FusedLayerQuant, OperandPrefetch, fuse_inference, prefetch_operands)
 from .device import device  # noqa: F401
 from .checkpoint import load_packed, packed_state, save_packed  # noqa: F401
 from . import convertor  # noqa: F401

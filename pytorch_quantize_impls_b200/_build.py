@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libqtb200.so")
-SOURCES = ["qt_api.cu", "qt_quantize.cu", "qt_gemm_simt.cu", "qt_gemm_tc.cu"]
+SOURCES = ["qt_api.cu", "qt_quantize.cu", "qt_layers.cu", "qt_gemm_simt.cu", "qt_gemm_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--cudart", "static", "-Xptxas", "-v"]

@@ -455,14 +455,137 @@ def linear(x, pack, bias, requant=None, affine=None):
     return out.reshape(*lead, N)
 
 
+_band_streams = {}
+
+
+def _tag_tensors(tag):
+    return [t for t in (tag.codes, tag.row_sum, tag.row_scale, tag.bits, tag.overflow) if t is not None]
+
+
+def linear_banded(x, quantize, pack, bias, nbands=4, affine=None):
+    """`activation quantizer -> F.linear(., W_q, bias)` on an fp32 [M, K] input as a two-stream pipeline over row bands: the
+    quantizer of band i+1 (a bounded grid: one 8-warp CTA per SM, no shared memory) runs on a side stream BESIDE the persistent
+    tcgen05 contraction of band i, so the HBM-bound pass (read fp32, write codes) hides behind the tensor-bound one instead of
+    preceding it.  The weights are expanded once.  quantize(x_rows, max_ctas) -> ActCodes (code-only).  fp32 result [M, N]."""
+    dev = x.device
+    M, K = x.shape
+    N = pack.n
+    out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    if bias is not None:
+        bias = ops.as_f32c(bias)
+    step = -(-M // nbands)
+    step = -(-step // 256) * 256                      # whole CTA-pair tiles per band
+    bounds = [(b0, min(M, b0 + step)) for b0 in range(0, M, step)]
+    cur = torch.cuda.current_stream(dev)
+    side = _band_streams.get(dev)
+    if side is None:
+        side = _band_streams[dev] = torch.cuda.Stream(device=dev)
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    side.wait_event(fork)
+    tags, evs = [], []
+    sms = ops.device_caps(dev.index if dev.index is not None else torch.cuda.current_device())["num_sms"]
+    with torch.cuda.stream(side):
+        for i, (b0, b1) in enumerate(bounds):
+            # band 0 has the GPU to itself; the others share every SM with a contraction
+            tag = quantize(x[b0:b1], 0 if i == 0 else sms)
+            for t in _tag_tensors(tag):
+                t.record_stream(cur)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            tags.append(tag)
+            evs.append(ev)
+    pack._hold_on = True
+    try:
+        for (b0, b1), tag, ev in zip(bounds, tags, evs):
+            cur.wait_event(ev)
+            a = _a_from_tag(tag)
+            _contract(a, pack, b1 - b0, N, K, out[b0:b1], bias=bias, rq_spec=affine)
+    finally:
+        pack._hold_on, pack._hold = False, None
+        cur.wait_stream(side)
+    return out
+
+
 def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
 
-def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requant=None, affine=None):
-    """F.conv2d(x, W_q, bias, stride, padding, dilation, groups) via im2col gather + GEMM with an NCHW epilogue.
-    requant (RequantSpec): the implicit-GEMM epilogue writes the next conv's channels-last codes [B, OH, OW, O] instead of
-    the fp32 NCHW tensor (raises RequantUnsupported when the call cannot take the implicit-GEMM route)."""
+_first_layer_implicit = [os.environ.get("QTB200_FIRST_LAYER_IMPLICIT", "1") != "0"]
+
+
+def set_first_layer_implicit(flag):
+    """True (default): conv layers on real-valued inputs with <= 8 channels (the image layers) run as an implicit GEMM on bf16
+    plane pixels (qt_image_planes + qt_conv_bf16); False: explicit gather + split (qt_im2col)."""
+    _first_layer_implicit[0] = bool(flag)
+
+
+def _out_clamp(affine, requant, keep_out):
+    """Clamp applied to the fp32 value the epilogue WRITES (the requant path clamps its own copy)."""
+    if affine is not None and affine.lo is not None:
+        return affine.lo, affine.hi
+    if keep_out and requant is not None and requant.lo is not None:
+        return requant.lo, requant.hi
+    return None
+
+
+def _first_layer_weights(pack, O, kh, kw, Cin, P, f, kwf):
+    """bf16 weights of the plane-pixel implicit GEMM: [O, kh, kwf, f, 16] -- the exact integer codes of W_q repeated for each of
+    the P parts (hi / mid / lo) of the input channels, zero in the unused slots and in the taps a folded row adds.
+    Cached on the pack while its packed tensor is unchanged."""
+    key = (pack.packed.data_ptr(), pack.packed._version, kh, kw, Cin, P, f)
+    hit = getattr(pack, "_first", None)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    w, ldw = ops._expand_weight(pack, L.CODES_BF16)             # [1, O, ld]: exact codes, K order (kh, kw, c)
+    wv = w[0, :O, :kh * kw * Cin].reshape(O, kh, kw, Cin)
+    wz = torch.zeros((O, kh, kwf * f, 16), dtype=torch.bfloat16, device=w.device)
+    for p in range(P):
+        wz[:, :, :kw, p * Cin:(p + 1) * Cin] = wv
+    wz = wz.reshape(O, kh * kwf * f * 16)
+    pack._first = (key, wz, wz.shape[1])
+    return wz, wz.shape[1]
+
+
+def _conv_first_layer(xf, pack, geom, O, Cin, epi_kw):
+    """Real-valued NCHW input with few channels: one pass over the image builds zero-padded channels-last bf16 plane pixels
+    (each channel as hi / mid / lo bf16 parts side by side, 32 bytes per pixel), and the conv runs as an implicit GEMM fed by TMA
+    im2col.  A stride-f row of kw taps is read as floor((kw - 1) / f) + 1 taps of f-pixel super pixels.  Returns False when the
+    shape does not fit (the caller gathers explicitly)."""
+    kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW = geom
+    if groups != 1 or Cin > 8 or pack.kind not in ("sign", "ternary", "dorefa", "lin") or pack.packed is None:
+        return False
+    if pack.kind == "dorefa" and not (1 <= pack.bit_width <= 8):
+        return False
+    if sh > 8 or sw > 8:
+        return False
+    B = xf.shape[0]
+    P = 3 if 3 * Cin <= 16 else 2
+    f = sw if (sw in (2, 4) and dw == 1) else 1
+    if f > 1:
+        kwf = (kw - 1) // f + 1
+        Wp = f * (OW + kwf - 1)
+        g_w, g_kw, g_sw, g_dw = Wp // f, kwf, 1, 1
+    else:
+        kwf = kw
+        Wp = (OW - 1) * sw + (kw - 1) * dw + 1
+        g_w, g_kw, g_sw, g_dw = Wp, kw, sw, dw
+    Hp = (OH - 1) * sh + (kh - 1) * dh + 1
+    planes = ops.image_planes(xf, P, ph, pw, Hp, Wp)
+    wz, ldw = _first_layer_weights(pack, O, kh, kw, Cin, P, f, kwf)
+    epi = ops.make_epi(**epi_kw)
+    ops.conv_bf16(planes, (B, 16 * f, Hp, g_w, kh, g_kw, sh, g_sw, 0, 0, dh, g_dw, 1, 0, OH, OW), wz, ldw, O, epi)
+    return True
+
+
+def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requant=None, affine=None, out_format="nchw",
+           residual=None, keep_out=False):
+    """F.conv2d(x, W_q, bias, stride, padding, dilation, groups): implicit GEMM (TMA im2col) on channels-last codes or bf16
+    plane pixels, or an explicit gather + GEMM for the shapes those decline.
+    requant (RequantSpec): the epilogue writes the next conv's channels-last codes [B, OH, OW, O] instead of the fp32 tensor
+    (raises RequantUnsupported when the call cannot take an implicit-GEMM route); keep_out=True writes the fp32 tensor too.
+    out_format "nhwc": the fp32 result is a channels-last tensor (memory [B, OH, OW, O], full-line TMA stores);
+    residual: channels-last fp32 [B, O, OH, OW] added before the clamp / requant (out_format "nhwc" only)."""
     dev = tagged_input_device(x)
     if x.dim() != 4:
         raise RuntimeError("expected a 4-D NCHW input, got %d-D" % x.dim())
@@ -486,9 +609,22 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
     OW = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
     if requant is not None and (B == 0 or OH <= 0 or OW <= 0 or groups != 1 or O % 32 != 0 or requant.mode == L.Q_XNOR_ROW):
         raise RequantUnsupported("fused conv requant needs groups == 1, out_channels % 32 == 0 and a non-empty output")
-    out = None if requant is not None else torch.empty((B, O, max(OH, 0), max(OW, 0)), dtype=torch.float32, device=dev)
+    nhwc_out = out_format == "nhwc"
+    if residual is not None:
+        if not nhwc_out or not ops.is_channels_last(residual) or tuple(residual.shape) != (B, O, OH, OW) \
+                or residual.dtype != torch.float32:
+            raise RuntimeError("internal: the residual must be a channels-last fp32 tensor of the output's shape")
+    want_out = requant is None or keep_out
+    out = None
+    if want_out:
+        out = torch.empty((B, O, max(OH, 0), max(OW, 0)), dtype=torch.float32, device=dev,
+                          memory_format=torch.channels_last if nhwc_out else torch.contiguous_format)
     if B == 0 or OH <= 0 or OW <= 0:
         return out
+    # output addressing of the epilogue: NCHW (per-column coalesced stores) or row-major [pixels, channels] (TMA stores)
+    out_kw = (dict(out_mode=0, ldo=O, nchw_inner=1) if nhwc_out else dict(out_mode=1, ldo=O, nchw_inner=OH * OW))
+    if residual is not None:
+        out_kw.update(residual=residual, ld_res=O)
     Ng, Kg, P = O // groups, Cg * kh * kw, OH * OW
     geom = (kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW)
     int_w = pack.kind in ("sign", "ternary", "dorefa", "lin")
@@ -522,20 +658,53 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
             bg = None if bias is None else bias[g * Ng:(g + 1) * Ng]
             if requant is not None or affine is not None:
                 cs, bg = (requant or affine).fold(cs, bg, g * Ng, Ng)
-            epi = ops.make_epi(out, ldo=O, out_mode=1, nchw_inner=P, bias=bg, col_scale=cs,
+            epi = ops.make_epi(out, bias=bg, col_scale=cs,
                                row_sum=rs, acc_mul=2 if need_rs else 1, rs_mul=-255 if need_rs else 0,
-                               scale=tag.scale * pack.wscale, out_offset=g * Ng * P, requant=rq,
-                               out_clamp=(affine.lo, affine.hi) if (affine is not None and affine.lo is not None) else None)
+                               scale=tag.scale * pack.wscale, out_offset=g * Ng * (1 if nhwc_out else P), requant=rq,
+                               out_clamp=_out_clamp(affine, requant, keep_out),
+                               **out_kw)
             if not ops.conv_i8(tag.codes, a_signed, geom, g, w[g * Ng:], not need_rs, ldw, Ng, epi):
                 done = False
                 break
         if done:
             if requant is not None:
-                y = torch.empty((B, O, OH, OW), dtype=torch.float32, device="meta")
+                y = out if keep_out else torch.empty((B, O, OH, OW), dtype=torch.float32, device="meta")
+                return attach_tag(y, _requant_tag(requant, rq, (B, O, OH, OW), layout="nhwc"))
+            return out
+
+    # real-valued image input (first layers): implicit GEMM on bf16 plane pixels
+    if tag is None and not x.is_meta and int_w and _first_layer_implicit[0] and _force_backend["bf16"] != L.BACKEND_SIMT \
+            and (requant is None or (groups == 1 and O % 32 == 0)):
+        rq = None
+        if requant is not None:
+            ck = requant.codes_kind(False)
+            rq = ops.RequantOut(requant.mode, requant.bit_width, ck, B * P, O, dev, lo=requant.lo, hi=requant.hi, ld=O,
+                                codes=torch.empty((B, OH, OW, O), device=dev,
+                                                  dtype=torch.uint8 if ck == L.CODES_U8 else torch.int8))
+        cs, bg = pack.col_scale, bias
+        if requant is not None or affine is not None:
+            cs, bg = (requant or affine).fold(cs, bg, 0, O)
+        epi_kw = dict(out=out, bias=bg, col_scale=cs, scale=pack.wscale, requant=rq,
+                      out_clamp=_out_clamp(affine, requant, keep_out), **out_kw)
+        if _conv_first_layer(ops.as_f32c(x), pack, geom, O, Cin, epi_kw):
+            if requant is not None:
+                y = out if keep_out else torch.empty((B, O, OH, OW), dtype=torch.float32, device="meta")
                 return attach_tag(y, _requant_tag(requant, rq, (B, O, OH, OW), layout="nhwc"))
             return out
     if requant is not None:
-        raise RequantUnsupported("fused conv requant needs the implicit-GEMM route (channels-last 8-bit codes in, C/groups % 32 == 0)")
+        raise RequantUnsupported("fused conv requant needs an implicit-GEMM route (channels-last 8-bit codes in with C/groups % 32 == 0, "
+                                 "or an image input with <= 8 channels)")
+    if nhwc_out:
+        # the explicit-gather route below writes NCHW: run it and convert (rare shapes only)
+        aff = affine
+        if residual is not None and affine is not None and affine.lo is not None:      # the clamp comes after the add
+            aff = RequantSpec(-1, None, col_mul=affine.col_mul, col_add=affine.col_add)
+        y = conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, affine=aff)
+        if residual is not None:
+            y = y + residual
+            if affine is not None and affine.lo is not None:
+                y = torch.clamp(y, affine.lo, affine.hi)
+        return y.contiguous(memory_format=torch.channels_last)
 
     xf = None
     if tag is not None:

@@ -30,7 +30,7 @@ class QtActQuant(C.Structure):
                 ("bits", vp), ("ld_bits", i64),
                 ("row_sum", vp), ("row_scale", vp), ("overflow", vp),
                 ("pre_scale", vp), ("pre_shift", vp), ("pre_channels", i64), ("pre_hw", i64), ("pre_clamp", i32),
-                ("pre_lo", f32), ("pre_hi", f32), ("nhwc_c", i64), ("row_parts", i32)]
+                ("pre_lo", f32), ("pre_hi", f32), ("nhwc_c", i64), ("row_parts", i32), ("max_ctas", i32)]
 
 
 class QtWeightPack(C.Structure):
@@ -58,6 +58,12 @@ class QtConvGeom(C.Structure):
                 ("dil_h", i32), ("dil_w", i32), ("groups", i32), ("group", i32), ("OH", i64), ("OW", i64)]
 
 
+class QtPoolGeom(C.Structure):
+    _fields_ = [("B", i64), ("H", i64), ("W", i64), ("C", i64),
+                ("kh", i32), ("kw", i32), ("stride_h", i32), ("stride_w", i32), ("pad_h", i32), ("pad_w", i32),
+                ("OH", i64), ("OW", i64)]
+
+
 class QtRequant(C.Structure):
     _fields_ = [("mode", i32), ("bit_width", i32), ("codes", vp), ("codes_kind", i32), ("ld_codes", i64),
                 ("clamp", i32), ("lo", f32), ("hi", f32), ("row_part", vp), ("row_sum_part", vp),
@@ -69,7 +75,8 @@ class QtEpilogue(C.Structure):
                 ("scale", f32), ("acc_mul", C.c_int32), ("rs_mul", C.c_int32),
                 ("out", vp), ("ldo", i64), ("out_mode", i32), ("nchw_inner", i64), ("acc_out", vp),
                 ("requant", C.POINTER(QtRequant)), ("row_scale_parts", i32), ("row_scale_mul", f32),
-                ("row_sum_parts", i32), ("out_clamp", i32), ("out_lo", f32), ("out_hi", f32)]
+                ("row_sum_parts", i32), ("out_clamp", i32), ("out_lo", f32), ("out_hi", f32),
+                ("residual", vp), ("ld_res", i64)]
 
 
 # every symbol include/qtb200.h declares: name -> (restype, argtypes)
@@ -91,6 +98,11 @@ SYMBOLS = {
     "qt_gemm_f4": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_conv_i8": (i32, [vp, i32, C.POINTER(QtConvGeom), vp, i32, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_patch_rowsum": (i32, [vp, i32, C.POINTER(QtConvGeom), vp, vp, vp]),
+    "qt_conv_bf16": (i32, [vp, C.POINTER(QtConvGeom), vp, i64, i64, C.POINTER(QtEpilogue), vp]),
+    "qt_image_planes": (i32, [vp, i64, i64, i64, i64, i32, i32, i32, i64, i64, vp, vp]),
+    "qt_rowsum_codes": (i32, [vp, i32, i64, i64, vp, vp]),
+    "qt_pool_codes": (i32, [vp, i32, C.POINTER(QtPoolGeom), vp, vp, vp]),
+    "qt_pool_quant_f32": (i32, [vp, C.POINTER(QtPoolGeom), vp, i32, i32, vp, i32, vp, vp]),
     "qt_gemm_f16": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, C.POINTER(i32), C.POINTER(i32),
                           i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
     "qt_gemm_f32": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),

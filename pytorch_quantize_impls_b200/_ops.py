@@ -106,7 +106,7 @@ class ActCodes:
 
 
 def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_kind=L.CODES_NONE,
-              want_bits=False, want_row_sum=False, want_row_scale=False, kind=None, pre=None):
+              want_bits=False, want_row_sum=False, want_row_scale=False, kind=None, pre=None, max_ctas=0):
     """Run one activation-quantizer pass.  Returns (y or None, ActCodes or None).
     pre = (scale[C], shift[C], lo, hi) fuses x' = clamp(x*scale[ch] + shift[ch], lo, hi) in front (lo/hi None: no clamp)."""
     require_cuda(x, "input")
@@ -171,6 +171,7 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
         else:
             row_parts = 0
             row_scale = torch.empty(rows, dtype=torch.float32, device=dev)
+    a.max_ctas = int(max_ctas)
     a.codes, a.codes_kind, a.ld_codes = _p(codes), codes_kind, ld
     a.bits, a.ld_bits = _p(bits), ldb
     a.row_sum, a.row_scale, a.overflow = _p(row_sum), _p(row_scale), _p(overflow)
@@ -195,7 +196,8 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
 class WeightPack:
     """k-bit weight matrix resident in HBM (the persistent format) + what the epilogue needs."""
     __slots__ = ("kind", "bit_width", "n", "k", "packed", "ld_packed", "alpha", "alpha_norm", "alpha_max", "stats",
-                 "col_scale", "planes", "ld_planes", "wq", "wscale", "emin", "_prefetch", "_last_kind")
+                 "col_scale", "planes", "ld_planes", "wq", "wscale", "emin", "_prefetch", "_last_kind", "_first", "_hold",
+                 "_hold_on")
     # kind 'lin' / 'log' (LogLin layers): packed = int8 codes [1, n, ld]; value = code * wscale (lin) or
     # sign(code) * 2^(emin + |code| - 1) (log)
 
@@ -203,6 +205,8 @@ class WeightPack:
         self.wscale, self.emin = 1.0, 0
         self._prefetch = None        # (out_kind, operand, ld, event): expanded ahead of time on a side stream
         self._last_kind = None       # operand kind the last contraction asked for (what a prefetch expands)
+        self._first = None           # cached plane-pixel weights of a first conv layer (engine._first_layer_weights)
+        self._hold, self._hold_on = None, False   # one expansion shared by the row bands of engine.linear_banded
 
     def nbytes(self):
         t = self.packed if self.packed is not None else self.planes
@@ -307,6 +311,16 @@ def col_absmean(w2d):
 def expand_weight(p, out_kind):
     """Packed k-bit weights -> transient tensor-core operand (lives in L2 between the two kernels)."""
     p._last_kind = out_kind
+    if p._hold_on and p._hold is not None and p._hold[0] == out_kind:
+        return p._hold[1], p._hold[2]
+    if p._hold_on:
+        w, ld = expand_weight_now(p, out_kind)
+        p._hold = (out_kind, w, ld)
+        return w, ld
+    return expand_weight_now(p, out_kind)
+
+
+def expand_weight_now(p, out_kind):
     pf = p._prefetch
     if pf is not None:
         p._prefetch = None
@@ -379,7 +393,7 @@ def im2col(x4d, elem_bytes, geom, group, out, ld_out, row_sum=None, is_unsigned=
 
 def make_epi(out, *, ldo, out_mode=0, nchw_inner=1, bias=None, row_scale=None, col_scale=None, row_sum=None,
              scale=1.0, acc_mul=1, rs_mul=0, acc_out=None, out_offset=0, row_parts=0, row_mul=1.0, requant=None,
-             out_clamp=None):
+             out_clamp=None, residual=None, ld_res=0):
     """requant: a RequantOut (fused re-quantisation of the output); row_parts > 0: row_scale / row_sum are partial sums
     left by a previous layer's requant epilogue."""
     e = L.QtEpilogue()
@@ -398,6 +412,8 @@ def make_epi(out, *, ldo, out_mode=0, nchw_inner=1, bias=None, row_scale=None, c
     if requant is not None:
         e.requant = C.pointer(requant.c)
         e._keep = requant        # keep the ctypes struct alive as long as the epilogue
+    if residual is not None:
+        e.residual, e.ld_res = _p(residual), int(ld_res)
     return e
 
 
@@ -441,6 +457,81 @@ class RequantOut:
     @property
     def row_parts(self):
         return int(self.c.row_parts)
+
+
+def is_channels_last(x):
+    """4-D tensor whose memory is [B, H, W, C] dense (torch.channels_last), and not also plain-contiguous."""
+    return (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+            and not (x.is_contiguous() and x.shape[1] != 1))
+
+
+def quant_act_nhwc(x_cl, mode, *, bit_width=0, codes_kind=L.CODES_I8, kind=None):
+    """Activation quantizer on a channels-last fp32 tensor [B, C, H, W] (memory [B, H, W, C]): the codes come out channels-last
+    too, with no transpose -- the tensor is one [B*H*W, C] row matrix.  Code-only (no fp32 result).  C % 16 == 0."""
+    require_cuda(x_cl, "input")
+    B, Cn, Hn, Wn = x_cl.shape
+    if not is_channels_last(x_cl) or x_cl.dtype != torch.float32 or Cn % 16:
+        raise RuntimeError("internal: quant_act_nhwc needs a channels-last fp32 tensor with C % 16 == 0")
+    rows = x_cl.permute(0, 2, 3, 1).reshape(B * Hn * Wn, Cn)          # a view: same memory
+    _, tag = quant_act(rows, mode, bit_width=bit_width, want_y=False, codes_kind=codes_kind, kind=kind)
+    tag.codes = tag.codes.view(B, Hn, Wn, Cn)
+    tag.rows, tag.cols, tag.ld, tag.layout, tag.shape = B, Cn * Hn * Wn, Cn * Hn * Wn, "nhwc", (B, Cn, Hn, Wn)
+    return tag
+
+
+def conv_bf16(x_nhwc, geom_args, w, ldw, N, epi):
+    """Implicit-GEMM conv on channels-last bf16 activations (qt_conv_bf16).  geom_args: the 16 QtConvGeom fields."""
+    g = L.QtConvGeom(*geom_args)
+    L.check(L.lib().qt_conv_bf16(_p(x_nhwc), C.byref(g), _p(w), ldw, N, C.byref(epi), _stream()), "qt_conv_bf16")
+
+
+def image_planes(x, planes, pad_h, pad_w, Hp, Wp):
+    """fp32 NCHW image -> zero-padded channels-last bf16 plane pixels [B, Hp, Wp, 16] (qt_image_planes)."""
+    require_cuda(x, "input")
+    x = as_f32c(x)
+    B, Cn, Hn, Wn = x.shape
+    out = torch.empty((B, Hp, Wp, 16), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().qt_image_planes(_p(x), B, Cn, Hn, Wn, planes, pad_h, pad_w, Hp, Wp, _p(out), _stream()), "qt_image_planes")
+    return out
+
+
+def _pool_geom(B, H, W, Cn, k, s, p):
+    (kh, kw), (sh, sw), (ph, pw) = k, s, p
+    OH, OW = (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+    return L.QtPoolGeom(B, H, W, Cn, kh, kw, sh, sw, ph, pw, OH, OW), OH, OW
+
+
+def pool_codes(codes_nhwc, k, s, p, use_min=None):
+    """Max-pool (per-channel min where use_min[c]) of channels-last 8-bit codes [B, H, W, C] (qt_pool_codes)."""
+    B, H, W, Cn = codes_nhwc.shape
+    g, OH, OW = _pool_geom(B, H, W, Cn, k, s, p)
+    out = torch.empty((B, OH, OW, Cn), dtype=codes_nhwc.dtype, device=codes_nhwc.device)
+    L.check(L.lib().qt_pool_codes(_p(codes_nhwc), int(codes_nhwc.dtype == torch.uint8), C.byref(g), _p(use_min), _p(out),
+                                  _stream()), "qt_pool_codes")
+    return out
+
+
+def rowsum_codes(codes2d):
+    """int32 row sums of an 8-bit code matrix [rows, ld] (qt_rowsum_codes)."""
+    rows, ld = codes2d.shape
+    out = torch.empty(rows, dtype=torch.int32, device=codes2d.device)
+    L.check(L.lib().qt_rowsum_codes(_p(codes2d), int(codes2d.dtype == torch.uint8), rows, ld, _p(out), _stream()), "qt_rowsum_codes")
+    return out
+
+
+def pool_quant_f32(x_cl, k, s, p, want_out=True, mode=None, bit_width=0, codes_kind=L.CODES_NONE):
+    """Max-pool of a channels-last fp32 tensor fused with an activation quantizer (qt_pool_quant_f32).
+    Returns (pooled channels-last fp32 tensor or None, codes [B, OH, OW, C] or None, overflow flag or None)."""
+    B, Cn, H, W = x_cl.shape
+    g, OH, OW = _pool_geom(B, H, W, Cn, k, s, p)
+    out = torch.empty((B, Cn, OH, OW), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last) if want_out else None
+    codes = overflow = None
+    if mode is not None:
+        codes = torch.empty((B, OH, OW, Cn), dtype=torch.int8 if codes_kind == L.CODES_I8 else torch.uint8, device=x_cl.device)
+        overflow = torch.zeros(1, dtype=torch.int32, device=x_cl.device) if mode == L.Q_DOREFA else None
+    L.check(L.lib().qt_pool_quant_f32(_p(x_cl), C.byref(g), _p(out), -1 if mode is None else mode, bit_width, _p(codes),
+                                      codes_kind, _p(overflow), _stream()), "qt_pool_quant_f32")
+    return out, codes, overflow
 
 
 def gemm_b1b1(a_bits, lda, w_bits, ldw, M, N, K, epi):

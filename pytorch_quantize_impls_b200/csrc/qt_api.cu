@@ -35,6 +35,7 @@ int check_epi(const QtEpilogue* e, int64_t M, int64_t N) {
     QT_REQUIRE(r->mode != QT_Q_XNOR_ROW || r->row_part != nullptr, "requant: QT_Q_XNOR_ROW needs row_part");
   }
   QT_REQUIRE(e->out_mode == 0 || e->out_mode == 1, "epilogue: out_mode must be 0 or 1");
+  if (e->residual) QT_REQUIRE(e->out_mode == 0 && e->ld_res >= N, "epilogue: residual needs out_mode 0 and ld_res >= N");
   if (e->out && e->out_mode == 0) QT_REQUIRE(e->ldo >= N, "epilogue: ldo (%lld) < N (%lld)", (long long)e->ldo, (long long)N);
   if (e->out && e->out_mode == 1)
     QT_REQUIRE(e->ldo >= N && e->nchw_inner > 0 && M % e->nchw_inner == 0, "epilogue: NCHW inner (%lld) must divide M (%lld)",
@@ -50,7 +51,7 @@ int qt_version(void) { return QT_VERSION; }
 int qt_sizeof(const char* name) {
   if (!name) return -1;
 #define QT_SZ(T) if (strcmp(name, #T) == 0) return (int)sizeof(T);
-  QT_SZ(QtActQuant) QT_SZ(QtWeightPack) QT_SZ(QtWeightExpand) QT_SZ(QtIm2col) QT_SZ(QtRequant) QT_SZ(QtEpilogue) QT_SZ(QtConvGeom)
+  QT_SZ(QtActQuant) QT_SZ(QtWeightPack) QT_SZ(QtWeightExpand) QT_SZ(QtIm2col) QT_SZ(QtRequant) QT_SZ(QtEpilogue) QT_SZ(QtConvGeom) QT_SZ(QtPoolGeom)
 #undef QT_SZ
   return -1;
 }

@@ -69,6 +69,8 @@ struct Epi {
   float row_scale_mul;
   int out_clamp;
   float out_lo, out_hi;
+  const float* residual;   // optional fp32 [M, ld_res] added to y before the clamp (row-major outputs only)
+  int64_t ld_res;
 };
 
 static inline Epi make_epi(const QtEpilogue* e, int64_t M, int64_t N) {
@@ -87,6 +89,7 @@ static inline Epi make_epi(const QtEpilogue* e, int64_t M, int64_t N) {
   }
   d.row_scale_parts = e->row_scale_parts; d.row_sum_parts = e->row_sum_parts; d.row_scale_mul = e->row_scale_mul;
   d.out_clamp = e->out_clamp; d.out_lo = e->out_lo; d.out_hi = e->out_hi;
+  d.residual = e->residual; d.ld_res = e->ld_res;
   return d;
 }
 
@@ -104,6 +107,7 @@ __device__ __forceinline__ float epi_int(const Epi& e, int64_t m, int64_t n, int
   if (e.row_scale) y *= __ldg(e.row_scale + m);
   if (e.col_scale) y *= __ldg(e.col_scale + n);
   if (e.bias) y += __ldg(e.bias + n);
+  if (e.residual) y += __ldg(e.residual + m * e.ld_res + n);
   if (e.out_clamp) y = fminf(fmaxf(y, e.out_lo), e.out_hi);
   return y;
 }
@@ -112,6 +116,7 @@ __device__ __forceinline__ float epi_f32(const Epi& e, int64_t m, int64_t n, flo
   if (e.row_scale) y *= __ldg(e.row_scale + m);
   if (e.col_scale) y *= __ldg(e.col_scale + n);
   if (e.bias) y += __ldg(e.bias + n);
+  if (e.residual) y += __ldg(e.residual + m * e.ld_res + n);
   if (e.out_clamp) y = fminf(fmaxf(y, e.out_lo), e.out_hi);
   return y;
 }

@@ -208,7 +208,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// tcgen05.ld of one 32-column chunk of this warp's 32 TMEM lanes (thread = lane = accumulator row).  Issue and wait are
+// separate so that the load of chunk i+1 is in flight while chunk i is stored; the wait lists the destination registers as
+// read-write operands, which keeps the compiler from touching them between the two statements.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -217,8 +220,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+// 32 per-column epilogue parameters (col_scale / bias) of columns n0..n0+31 into registers.  Every lane reads the SAME
+// addresses (a lane owns one output row and all 32 columns of the chunk): 8 uniform 16-byte loads, one L1 wavefront each.
+__device__ __forceinline__ void load_col32(const float* __restrict__ p, int n0, int n_lim, bool vec, float fill, float (&v)[32]) {
+  if (vec && n0 + 32 <= n_lim) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p + n0) + q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (n0 + j < n_lim) ? __ldg(p + n0 + j) : fill;
+  }
 }
 
 // ---- fused re-quantisation of one 32-column chunk of an output row (QtRequant) ------------------------------------
@@ -242,84 +268,72 @@ __device__ __forceinline__ void st_global_v2(void* p, uint32_t a, uint32_t b) {
   asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
 // y[0..31]: fp32 outputs of row m, columns n0..n0+31 (valid while n < n_lim).  Writes the codes of columns n0..n0+ncols-1
-// (zeros past n_lim), accumulates the row partial sums.
+// (zeros past n_lim), accumulates the row partial sums.  Works through the chunk 8 columns at a time so that only the packed
+// words, not 32 more floats and 32 more integers, are live beside the caller's registers.
 __device__ __forceinline__ void rq_store_chunk(const Epi& e, const float (&y)[32], int64_t m, int n0, int n_lim, int ncols,
                                                float& psum, int& isum, bool& ovf) {
-  float c[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float v = y[j];
-    if (e.rq_clamp) v = fminf(fmaxf(v, e.rq_lo), e.rq_hi);
-    const bool ok = n0 + j < n_lim;
-    float q = rq_quant(e, v);
-    if (e.rq_mode == QT_Q_XNOR_ROW && ok) psum += v;
-    c[j] = ok ? q : 0.f;
-  }
   const int kind = e.rq_codes_kind;
-  if (kind == 3 || kind == 5) {          // bf16 / fp16 lanes: 64 bytes per row chunk
-    uint32_t w[16];
+  const bool f16 = (kind == 3 || kind == 5);
+  const float lo = (kind == 7) ? -4.f : ((kind == 1) ? -128.f : 0.f), hi = (kind == 7) ? 4.f : ((kind == 1) ? 127.f : 255.f);
+  uint8_t* const base = reinterpret_cast<uint8_t*>(e.rq_codes);
+  uint32_t w[4];      // words waiting for their 16-byte (int8) / 8-byte (e2m1) store
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (kind == 5) {
-        __half2 h = __floats2half2_rn(c[2 * j], c[2 * j + 1]);
-        w[j] = *reinterpret_cast<uint32_t*>(&h);
-      } else {
-        __nv_bfloat162 h = __floats2bfloat162_rn(c[2 * j], c[2 * j + 1]);
-        w[j] = *reinterpret_cast<uint32_t*>(&h);
+  for (int q = 0; q < 4; ++q) {
+    float c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = y[8 * q + j];
+      if (e.rq_clamp) v = fminf(fmaxf(v, e.rq_lo), e.rq_hi);
+      const bool ok = n0 + 8 * q + j < n_lim;
+      const float qv = rq_quant(e, v);
+      if (e.rq_mode == QT_Q_XNOR_ROW && ok) psum += v;
+      c[j] = ok ? qv : 0.f;
+    }
+    if (f16) {                           // bf16 / fp16 lanes: 16 bytes per 8 columns
+      uint32_t h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kind == 5) {
+          __half2 t = __floats2half2_rn(c[2 * j], c[2 * j + 1]);
+          h[j] = *reinterpret_cast<uint32_t*>(&t);
+        } else {
+          __nv_bfloat162 t = __floats2bfloat162_rn(c[2 * j], c[2 * j + 1]);
+          h[j] = *reinterpret_cast<uint32_t*>(&t);
+        }
       }
+      if (8 * q < ncols && n0 + 8 * q < e.rq_ld) st_global_v4(base + (m * e.rq_ld + n0) * 2 + 16 * q, h[0], h[1], h[2], h[3]);
+      continue;
     }
-    uint8_t* dst = reinterpret_cast<uint8_t*>(e.rq_codes) + (m * e.rq_ld + n0) * 2;
+    int k[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (8 * q < ncols && n0 + 8 * q < e.rq_ld) st_global_v4(dst + 16 * q, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-    return;
-  }
-  // integer lanes
-  int k[32];
-  if (kind == 7) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float v = c[j];
-      if (!(v >= -4.f && v <= 4.f)) { ovf = true; v = (v != v) ? 0.f : fminf(fmaxf(v, -4.f), 4.f); }
-      k[j] = (int)v;
-    }
-  } else {
-    const float lo = (kind == 1) ? -128.f : 0.f, hi = (kind == 1) ? 127.f : 255.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 8; ++j) {
       float v = c[j];
       if (!(v >= lo && v <= hi)) { ovf = true; v = (v != v) ? 0.f : fminf(fmaxf(v, lo), hi); }
       k[j] = (int)v;
+      isum += k[j];
     }
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) isum += k[j];
-  if (kind == 7) {                       // e2m1 nibbles: 16 bytes per row chunk, element 2j in the low nibble of byte j
-    uint32_t w[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    if (kind == 7) {                     // e2m1 nibbles: 4 bytes per 8 columns, element 2j in the low nibble of byte j
       uint32_t acc = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int v = k[8 * q + j];
-        const int mag = v < 0 ? -v : v;
-        const uint32_t nib = ((0x65420u >> (4 * mag)) & 0xFu) | (v < 0 ? 8u : 0u);
-        acc |= nib << (4 * j);
+        const int mag = k[j] < 0 ? -k[j] : k[j];
+        acc |= (((0x65420u >> (4 * mag)) & 0xFu) | (k[j] < 0 ? 8u : 0u)) << (4 * j);
       }
-      w[q] = acc;
+      w[q & 1] = acc;
+      if (q & 1) {
+        uint8_t* dst = base + ((m * e.rq_ld + n0) >> 1) + 4 * (q - 1);
+        if ((q == 1 && n0 < e.rq_ld) || (q == 3 && 16 < ncols && n0 + 16 < e.rq_ld)) st_global_v2(dst, w[0], w[1]);
+      }
+    } else {                             // int8 / uint8 lanes: 8 bytes per 8 columns
+      w[2 * (q & 1)] = (uint32_t)(k[0] & 0xff) | ((uint32_t)(k[1] & 0xff) << 8) | ((uint32_t)(k[2] & 0xff) << 16) |
+                       ((uint32_t)(k[3] & 0xff) << 24);
+      w[2 * (q & 1) + 1] = (uint32_t)(k[4] & 0xff) | ((uint32_t)(k[5] & 0xff) << 8) | ((uint32_t)(k[6] & 0xff) << 16) |
+                           ((uint32_t)(k[7] & 0xff) << 24);
+      if (q & 1) {
+        uint8_t* dst = base + (m * e.rq_ld + n0) + 8 * (q - 1);
+        if ((q == 1 && n0 < e.rq_ld) || (q == 3 && 16 < ncols && n0 + 16 < e.rq_ld)) st_global_v4(dst, w[0], w[1], w[2], w[3]);
+      }
     }
-    uint8_t* dst = reinterpret_cast<uint8_t*>(e.rq_codes) + ((m * e.rq_ld + n0) >> 1);
-    if (n0 < e.rq_ld) st_global_v2(dst, w[0], w[1]);
-    if (16 < ncols && n0 + 16 < e.rq_ld) st_global_v2(dst + 8, w[2], w[3]);
-  } else {                               // int8 / uint8 lanes: 32 bytes per row chunk
-    uint32_t w[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      w[q] = (uint32_t)(k[4 * q] & 0xff) | ((uint32_t)(k[4 * q + 1] & 0xff) << 8) | ((uint32_t)(k[4 * q + 2] & 0xff) << 16) |
-             ((uint32_t)(k[4 * q + 3] & 0xff) << 24);
-    uint8_t* dst = reinterpret_cast<uint8_t*>(e.rq_codes) + (m * e.rq_ld + n0);
-    if (n0 < e.rq_ld) st_global_v4(dst, w[0], w[1], w[2], w[3]);
-    if (16 < ncols && n0 + 16 < e.rq_ld) st_global_v4(dst + 16, w[4], w[5], w[6], w[7]);
   }
 }
 
@@ -327,7 +341,7 @@ __device__ __forceinline__ void rq_store_chunk(const Epi& e, const float (&y)[32
 // stages its own 128 A rows and HALF of the B rows, the leader CTA (cluster rank 0) issues every MMA for both SMs, so the
 // shared-memory traffic per SM and MMA drops from 12 KB to 8 KB (at cta_group::1 the operand reads + TMA fills of a
 // 128 x 256 tile ask for ~190 B/clk of the 128 B/clk shared memory: that, not the tensor pipe, was the limit).
-template <int BN, int KIND, int STAGES, int BKB, bool IM2COL, int CG>
+template <int BN, int KIND, int STAGES, int BKB, bool IM2COL, int CG, int EPB>
 __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUtensorMap& map_w, const CUtensorMap& map_out,
                                              const TcArgs& g) {
   static_assert(CG == 1 || BN % 16 == 0, "cta_group::2 needs N % 16 == 0");
@@ -343,7 +357,10 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr uint32_t EPI_BYTES = 8 * 4096;         // 8 epilogue warps x (32 rows x 128 B) staging tile
+  // 8 epilogue warps x EPB staging tiles of 32 rows x 128 B.  EPB = 2: a warp fills one tile while the bulk store of the
+  // previous chunk still reads the other (short-K products, where the epilogue and not the MMA loop sets the tile time)
+  static_assert(EPB == 1 || EPB == 2, "one or two staging tiles per epilogue warp");
+  constexpr uint32_t EPI_BYTES = 8 * 4096 * EPB;
   const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;
   const uint32_t bar_base = epi_base + EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -493,21 +510,29 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
     const Epi& e = g.ep;
     const bool vec_ok = (e.out != nullptr) && e.out_mode == 0 && (e.ldo % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(e.out) & 15) == 0);
-    const uint32_t my_buf = epi_base + (uint32_t)ew * 4096u;   // this warp's 32 x 128 B staging tile
+    const uint32_t my_buf = epi_base + (uint32_t)ew * (4096u * EPB);   // this warp's 32 x 128 B staging tile(s)
+    uint32_t buf_sel = 0;
     const int N32 = (int)g.N;
+    const bool cs_vec = (reinterpret_cast<uintptr_t>(e.col_scale) & 15) == 0;
+    const bool b_vec = (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
+    const bool res_vec = (e.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.residual) & 15) == 0);
+    // kind::mxf4 holds exact integers in fp32: with the identity integer affine they are used as they are
+    const bool plain_acc = (KIND == 2) && e.acc_mul == 1 && e.row_sum == nullptr && e.acc_out == nullptr;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int tm, tn;
       tile_coords<CG>(g, tile, tm, tn);
       const int64_t m = (int64_t)(tm * CG + (int)cta_rank) * TC_BM + lane_grp * 32 + lane;
       const int n_tile = tn * BN;
       const int n_lim = min(N32, n_tile + BN);     // first column past this tile
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
+      // chunks of this warp that hold at least one valid column (warp-uniform)
+      const int c_begin = half * CH_PER_WARP;
+      int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
+      while (c_end > c_begin && n_tile + (c_end - 1) * 32 >= n_lim) --c_end;
       const bool row_ok = m < g.M;
       float mul = e.scale;
       int32_t rsum = 0;
       int64_t nchw_base = 0;
-      if (row_ok) {
+      if (row_ok) {          // row operands: fetched before the accumulator is waited for
         if (e.row_scale) {
           if (e.row_scale_parts > 0) {     // partial row sums left by the previous layer's requant epilogue, fixed order
             float rs = 0.f;
@@ -531,74 +556,105 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
           nchw_base = img * e.ldo * e.nchw_inner + r;
         }
       }
+      if (e.residual && row_ok) {     // residual rows come from HBM: pull this warp's 128-byte row pieces into L2 ahead of use
+        for (int c = c_begin; c < c_end; ++c)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(e.residual + m * e.ld_res + n_tile + c * 32));
+      }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
       float rq_psum = 0.f;
       int rq_isum = 0;
       bool rq_ovf = false;
+      uint32_t r[32];
+      const uint32_t t_row = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lane_grp * 32) << 16);
+      if (c_begin < c_end) tmem_ld32_issue(t_row + (uint32_t)(c_begin * 32), r);
 #pragma unroll 1
-      for (int ci = 0; ci < CH_PER_WARP; ++ci) {
-        const int cidx = half * CH_PER_WARP + ci;
-        if (cidx >= CHUNKS) break;
+      for (int cidx = c_begin; cidx < c_end; ++cidx) {
         const int c0 = cidx * 32;
         const int n0 = n_tile + c0;
-        if (n0 >= n_lim) break;     // warp-uniform
         const bool full_chunk = (BN % 32 == 0) || (c0 + 32 <= BN);
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t)(as * BN + c0) + ((uint32_t)(lane_grp * 32) << 16), r);
-        if (KIND == 2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = (uint32_t)__float2int_rn(__uint_as_float(r[j]));
-        }
-        // per-column scale / bias of this chunk: one coalesced load per lane, broadcast by shuffle below
-        const int nl = n0 + lane;
-        float cs_l = 1.f, b_l = 0.f;
-        if (nl < N32) {
-          if (e.col_scale) cs_l = __ldg(e.col_scale + nl);
-          if (e.bias) b_l = __ldg(e.bias + nl);
-        }
+        const bool add_res = e.residual != nullptr && row_ok;
+        tmem_ld_wait(r);
         if (INT_ACC && e.acc_out && row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + j < n_lim) e.acc_out[m * g.N + n0 + j] = (int32_t)r[j];
+            if (n0 + j < n_lim) e.acc_out[m * g.N + n0 + j] = (KIND == 2) ? __float2int_rn(__uint_as_float(r[j])) : (int32_t)r[j];
         }
-        if (!e.out && e.rq_mode < 0) continue;
-        float y[32];
+        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float v;
-          if (INT_ACC) v = (float)(e.acc_mul * (int32_t)r[j] + rsum);
-          else v = __uint_as_float(r[j]);
+          float a;
+          if (!INT_ACC || plain_acc) a = __uint_as_float(r[j]);
+          else if (KIND == 2) a = (float)(e.acc_mul * __float2int_rn(__uint_as_float(r[j])) + rsum);
+          else a = (float)(e.acc_mul * (int32_t)r[j] + rsum);
           // y = acc * (scale * row_scale) * col_scale + bias; with scale = row/col scale = 1 the multiply is exact and
           // float(acc) + bias is one rounding (BinaryNet / Terner bit-exactness)
-          const float cs = __shfl_sync(0xffffffffu, cs_l, j), bb = __shfl_sync(0xffffffffu, b_l, j);
-          y[j] = (v * mul) * cs + bb;
-          if (e.out_clamp) y[j] = fminf(fmaxf(y[j], e.out_lo), e.out_hi);
+          v[j] = a * mul;
+        }
+        // the accumulator chunk is in v: let the next chunk's TMEM read run beside the stores of this one
+        if (cidx + 1 < c_end) tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), r);
+        if (!e.out && e.rq_mode < 0) continue;
+        if (e.col_scale) {
+          float cs[32];
+          load_col32(e.col_scale, n0, N32, cs_vec, 1.f, cs);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= cs[j];
+        }
+        if (e.bias) {
+          float bb[32];
+          load_col32(e.bias, n0, N32, b_vec, 0.f, bb);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += bb[j];
+        }
+        if (add_res) {
+          const float* rp = e.residual + m * e.ld_res + n0;
+          if (res_vec && n0 + 32 <= n_lim) {
+            float4 t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = __ldcs(reinterpret_cast<const float4*>(rp) + q);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { v[4 * q] += t[q].x; v[4 * q + 1] += t[q].y; v[4 * q + 2] += t[q].z; v[4 * q + 3] += t[q].w; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < n_lim) v[j] += __ldg(rp + j);
+          }
+        }
+        if (e.out_clamp) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], e.out_lo), e.out_hi);
         }
         if (e.rq_mode >= 0 && row_ok)
-          rq_store_chunk(e, y, m, n0, n_lim, full_chunk ? 32 : (BN - c0), rq_psum, rq_isum, rq_ovf);
+          rq_store_chunk(e, v, m, n0, n_lim, full_chunk ? 32 : (BN - c0), rq_psum, rq_isum, rq_ovf);
         if (!e.out) continue;
         if (g.tma_store && full_chunk) {
           // registers (one output row per lane) -> 128B-swizzled smem tile -> one bulk tensor store per 32x32 block:
           // every global write is a full 128-byte line; M/N tails are clipped by the tensor map.
-          if (lane == 0) tma_store_wait_read0();      // the previous store has finished reading this buffer
+          if (lane == 0) {      // the store that last used this staging tile has finished reading it
+            if (EPB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else tma_store_wait_read0();
+          }
           __syncwarp();
-          const uint32_t rowaddr = my_buf + (uint32_t)lane * 128u;
+          const uint32_t tile_buf = my_buf + buf_sel * 4096u;
+          const uint32_t rowaddr = tile_buf + (uint32_t)lane * 128u;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            st_shared_v4(rowaddr + (uint32_t)((j ^ (lane & 7)) << 4), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+            st_shared_v4(rowaddr + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) tma_store_2d(&map_out, my_buf, n0, (tm * CG + (int)cta_rank) * TC_BM + lane_grp * 32);
+          if (lane == 0) tma_store_2d(&map_out, tile_buf, n0, (tm * CG + (int)cta_rank) * TC_BM + lane_grp * 32);
+          if (EPB == 2) buf_sel ^= 1u;
         } else if (e.out_mode == 0) {
           if (!row_ok) continue;
           float* o = e.out + m * e.ldo + n0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             if (vec_ok && n0 + j + 4 <= n_lim) {
-              *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
 #pragma unroll
               for (int jj = j; jj < j + 4; ++jj)
-                if (n0 + jj < n_lim) o[jj] = y[jj];
+                if (n0 + jj < n_lim) o[jj] = v[jj];
             }
           }
         } else {
@@ -606,7 +662,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
           float* o = e.out + nchw_base + (int64_t)n0 * e.nchw_inner;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + j < n_lim) o[(int64_t)j * e.nchw_inner] = y[j];   // lanes = consecutive pixels: coalesced per column
+            if (n0 + j < n_lim) o[(int64_t)j * e.nchw_inner] = v[j];   // lanes = consecutive pixels: coalesced per column
         }
       }
       if (e.rq_mode >= 0) {
@@ -637,19 +693,19 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
   }
 }
 
-template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false>
+template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false, int EPB = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_out, TcArgs g) {
-  tc_gemm_body<BN, KIND, STAGES, BKB, IM2COL, 1>(map_a, map_w, map_out, g);
+  tc_gemm_body<BN, KIND, STAGES, BKB, IM2COL, 1, EPB>(map_a, map_w, map_out, g);
 }
 
 // CTA-pair variant: 256 x BN tiles, cluster of two CTAs on the two SMs of a TPC.
-template <int BN, int KIND, int STAGES>
+template <int BN, int KIND, int STAGES, int EPB = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out, TcArgs g) {
-  tc_gemm_body<BN, KIND, STAGES, TC_BK_BYTES, false, 2>(map_a, map_w, map_out, g);
+  tc_gemm_body<BN, KIND, STAGES, TC_BK_BYTES, false, 2, EPB>(map_a, map_w, map_out, g);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -720,9 +776,12 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false>
+constexpr size_t TC_SMEM_MAX = 232448;    // 227 KB opt-in limit per CTA
+
+template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false, int EPB = 1>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (TC_BM * BKB + BN * BKB) + 4 * 2 * 4096 + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * BKB + BN * BKB) + (size_t)EPB * 8 * 4096 + 1024 + 256;
+  static_assert(smem <= TC_SMEM_MAX, "tc_gemm_kernel: shared memory budget");
   // output tensor map (row-major fp32): only when every row pitch / base is 16-byte aligned
   CUtensorMap mo = ma;
   g.tma_store = 0;
@@ -735,22 +794,23 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
   int dev = 0;
   QT_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, KIND, STAGES, BKB, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, KIND, STAGES, BKB, IM2COL, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   g.tiles_m = (int)ceil_div(g.M, TC_BM);
   g.tiles_n = (int)ceil_div(g.N, BN);
   int grid = std::min(g.tiles_m * g.tiles_n, num_sms());
-  tc_gemm_kernel<BN, KIND, STAGES, BKB, IM2COL><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
+  tc_gemm_kernel<BN, KIND, STAGES, BKB, IM2COL, EPB><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }
 
 // CTA-pair launch: tiles of 256 x BN, grid = 2 x min(#tiles, #SMs / 2); `mw` must have been built with BN / 2 box rows and
 // g.idesc with M = 256.
-template <int BN, int KIND, int STAGES>
+template <int BN, int KIND, int STAGES, int EPB = 1>
 static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK_BYTES + (BN / 2) * TC_BK_BYTES) + 4 * 2 * 4096 + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK_BYTES + (BN / 2) * TC_BK_BYTES) + (size_t)EPB * 8 * 4096 + 1024 + 256;
+  static_assert(smem <= TC_SMEM_MAX, "tc_gemm2_kernel: shared memory budget");
   CUtensorMap mo = ma;
   g.tma_store = 0;
   if (g.ep.out && g.ep.out_mode == 0 && g.ep.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(g.ep.out) & 15) == 0) {
@@ -761,13 +821,13 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, c
   int dev = 0;
   QT_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm2_kernel<BN, KIND, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm2_kernel<BN, KIND, STAGES, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   g.tiles_m = (int)ceil_div(g.M, 2 * TC_BM);
   g.tiles_n = (int)ceil_div(g.N, BN);
   const int grid = 2 * std::min(g.tiles_m * g.tiles_n, num_sms() / 2);
-  tc_gemm2_kernel<BN, KIND, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
+  tc_gemm2_kernel<BN, KIND, STAGES, EPB><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }
@@ -785,12 +845,16 @@ static bool use_cta_pair(int64_t M, int bn) {
   return M >= 1024;      // enough 256-row tiles to keep the 74 pairs busy
 }
 
+// Tile / pipeline variants.  Short K loops (a tile's MMAs take less time than draining its accumulator) run with two staging
+// tiles per epilogue warp and one operand stage less; long K loops keep the deeper operand ring.
 template <int KIND>
 static int dispatch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream, bool pair = false) {
-  if (pair) return launch_tc2<256, KIND, 6>(ma, mw, g, stream);
-  if (bn == 64) return launch_tc<64, KIND, 8>(ma, mw, g, stream);
-  if (bn == 128) return launch_tc<128, KIND, 6>(ma, mw, g, stream);
-  return launch_tc<256, KIND, 4>(ma, mw, g, stream);
+  const bool short_k = g.npass * g.num_kblocks <= 24;
+  if (pair) return short_k ? launch_tc2<256, KIND, 5, 2>(ma, mw, g, stream) : launch_tc2<256, KIND, 6, 1>(ma, mw, g, stream);
+  if (bn == 64) return launch_tc<64, KIND, 6, TC_BK_BYTES, false, 2>(ma, mw, g, stream);
+  if (bn == 128) return launch_tc<128, KIND, 5, TC_BK_BYTES, false, 2>(ma, mw, g, stream);
+  return short_k ? launch_tc<256, KIND, 3, TC_BK_BYTES, false, 2>(ma, mw, g, stream)
+                 : launch_tc<256, KIND, 4, TC_BK_BYTES, false, 1>(ma, mw, g, stream);
 }
 
 static int pick_bn(int64_t N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }
@@ -812,10 +876,11 @@ static int pick_bn_f4(int64_t N) {
 }
 
 static int dispatch_f4(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream, bool pair = false) {
-  if (pair) return launch_tc2<240, 2, 6>(ma, mw, g, stream);
-  if (bn == 64) return launch_tc<64, 2, 8>(ma, mw, g, stream);
-  if (bn == 128) return launch_tc<128, 2, 6>(ma, mw, g, stream);
-  return launch_tc<240, 2, 4>(ma, mw, g, stream);
+  // e2m1 operands carry 4x the MACs per byte of fp16: the K loop of a tile is short, the fp32 drain is what has to keep up
+  if (pair) return launch_tc2<240, 2, 5, 2>(ma, mw, g, stream);
+  if (bn == 64) return launch_tc<64, 2, 6, TC_BK_BYTES, false, 2>(ma, mw, g, stream);
+  if (bn == 128) return launch_tc<128, 2, 5, TC_BK_BYTES, false, 2>(ma, mw, g, stream);
+  return launch_tc<240, 2, 3, TC_BK_BYTES, false, 2>(ma, mw, g, stream);
 }
 
 static bool tc_available() {
@@ -960,39 +1025,43 @@ extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// implicit-GEMM convolution on channels-last 8-bit codes (TMA im2col mode feeds the A operand)
+// implicit-GEMM convolution on channels-last activations (TMA im2col mode feeds the A operand):
+// 8-bit codes on kind::i8, bf16 values on kind::f16
 // ---------------------------------------------------------------------------------------------
 namespace qt {
-template <int BKB>
+template <int KIND, int BKB>
 static int dispatch_conv(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream) {
-  // stage = 128 x BKB (pixels) + BN x BKB (filters); keep ~192 KB of operands in flight
-  if (bn == 64) return launch_tc<64, 0, 8, BKB, true>(ma, mw, g, stream);
-  if (bn == 128) return launch_tc<128, 0, (BKB == 128 ? 6 : 8), BKB, true>(ma, mw, g, stream);
-  return launch_tc<256, 0, (BKB == 128 ? 4 : 8), BKB, true>(ma, mw, g, stream);
+  // stage = 128 x BKB (pixels) + BN x BKB (filters)
+  if (bn == 64) return launch_tc<64, KIND, (BKB == 128 ? 6 : 8), BKB, true, 2>(ma, mw, g, stream);
+  if (bn == 128) return launch_tc<128, KIND, (BKB == 128 ? 5 : 8), BKB, true, 2>(ma, mw, g, stream);
+  if constexpr (BKB == 128) return launch_tc<256, KIND, 4, BKB, true, 1>(ma, mw, g, stream);
+  else return launch_tc<256, KIND, (BKB == 64 ? 6 : 8), BKB, true, 2>(ma, mw, g, stream);
 }
-}  // namespace qt
 
-extern "C" int qt_conv_i8(const void* x_nhwc, int a_signed, const QtConvGeom* cg, const void* w, int w_signed, int64_t ldw,
-                          int64_t N, const QtEpilogue* ep, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  QT_REQUIRE(x_nhwc && cg && w, "qt_conv_i8: null argument");
-  QT_REQUIRE(cg->groups >= 1 && cg->C % cg->groups == 0 && cg->group >= 0 && cg->group < cg->groups, "qt_conv_i8: bad groups");
+// elem_bytes 1: int8 / uint8 codes (KIND 0); 2: bf16 (KIND 1).  C, ldw in ELEMENTS.
+static int conv_implicit(const void* x_nhwc, int elem_bytes, int a_signed, const QtConvGeom* cg, const void* w, int w_signed,
+                         int64_t ldw, int64_t N, const QtEpilogue* ep, cudaStream_t stream, const char* who) {
+  QT_REQUIRE(x_nhwc && cg && w, "%s: null argument", who);
+  QT_REQUIRE(cg->groups >= 1 && cg->C % cg->groups == 0 && cg->group >= 0 && cg->group < cg->groups, "%s: bad groups", who);
   const int64_t Cg = cg->C / cg->groups, taps = (int64_t)cg->kh * cg->kw, K = taps * Cg;
   const int64_t P = cg->OH * cg->OW, M = cg->B * P;
   if (int rc = check_epi(ep, M, N)) return rc;
   if (M == 0 || N == 0) return QT_OK;
-  const int bkb = (Cg % 128 == 0) ? 128 : ((Cg % 64 == 0) ? 64 : ((Cg % 32 == 0) ? 32 : 0));
-  const bool ok = tc_available() && bkb != 0 && cg->C % 16 == 0 && al16(x_nhwc) && al16(w) && ldw % 16 == 0 && ldw >= K &&
-                  M < (1ll << 31) && cg->dil_w * (cg->kw - 1) < 65536 && cg->dil_h * (cg->kh - 1) < 65536 &&
+  const int64_t cgb = Cg * elem_bytes;        // bytes of one pixel's channel group
+  const int bkb = (cgb % 128 == 0) ? 128 : ((cgb % 64 == 0) ? 64 : ((cgb % 32 == 0) ? 32 : 0));
+  const bool ok = tc_available() && bkb != 0 && (cg->C * elem_bytes) % 16 == 0 && al16(x_nhwc) && al16(w) && (ldw * elem_bytes) % 16 == 0 &&
+                  ldw >= K && M < (1ll << 31) && cg->dil_w * (cg->kw - 1) < 65536 && cg->dil_h * (cg->kh - 1) < 65536 &&
                   cg->stride_w <= 8 && cg->stride_h <= 8;
-  if (!ok) { set_error("qt_conv_i8: shape not supported by the TMA im2col path (needs sm_100, C/groups %% 32 == 0, 16-byte aligned operands)"); return QT_EUNSUPPORTED; }
+  if (!ok) { set_error("%s: shape not supported by the TMA im2col path (needs sm_100, (C/groups) * element size %% 32 == 0, 16-byte aligned operands)", who); return QT_EUNSUPPORTED; }
   EncodeIm2colFn enc = get_encode_im2col_fn();
   if (!enc) { set_error("cuTensorMapEncodeIm2col entry point not available"); return QT_ECUDA; }
 
   CUtensorMap ma, mw;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)cg->C, (cuuint64_t)cg->W, (cuuint64_t)cg->H, (cuuint64_t)cg->B};
-    cuuint64_t strides[3] = {(cuuint64_t)cg->C, (cuuint64_t)cg->W * cg->C, (cuuint64_t)cg->H * cg->W * cg->C};
+    // byte tensor: the channel axis is counted in bytes so that one map type serves both element sizes
+    const cuuint64_t cb = (cuuint64_t)cg->C * elem_bytes;
+    cuuint64_t dims[4] = {cb, (cuuint64_t)cg->W, (cuuint64_t)cg->H, (cuuint64_t)cg->B};
+    cuuint64_t strides[3] = {cb, (cuuint64_t)cg->W * cb, (cuuint64_t)cg->H * cg->W * cb};
     // bounding box of filter-window base positions: [-pad, (size - 1) + pad - (k - 1) * dil]
     int lower[2] = {-cg->pad_w, -cg->pad_h};
     int upper[2] = {cg->pad_w - (cg->kw - 1) * cg->dil_w, cg->pad_h - (cg->kh - 1) * cg->dil_h};
@@ -1003,19 +1072,37 @@ extern "C" int qt_conv_i8(const void* x_nhwc, int a_signed, const QtConvGeom* cg
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed with CUresult %d", (int)r); return QT_EUNSUPPORTED; }
   }
   const int bn = pick_bn(N);
-  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn, false, bkb)) return rc;
+  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)K * elem_bytes, (uint64_t)ldw * elem_bytes, (uint32_t)bn, false, bkb)) return rc;
   TcArgs g{};
-  g.M = M; g.N = N; g.npass = 1; g.pa[0] = g.pw[0] = 0; g.a_plane_rows = g.w_plane_rows = 0; g.is_int = 1;
+  g.M = M; g.N = N; g.npass = 1; g.pa[0] = g.pw[0] = 0; g.a_plane_rows = g.w_plane_rows = 0; g.is_int = elem_bytes == 1;
   g.ep = make_epi(ep, M, N);
-  g.cv_cblocks = (int)(Cg / bkb);
+  g.cv_cblocks = (int)(cgb / bkb);
   g.num_kblocks = (int)taps * g.cv_cblocks;
   g.cv_OW = (int)cg->OW; g.cv_OHW = (int)P;
   g.cv_sh = cg->stride_h; g.cv_sw = cg->stride_w; g.cv_ph = cg->pad_h; g.cv_pw = cg->pad_w;
-  g.cv_dh = cg->dil_h; g.cv_dw = cg->dil_w; g.cv_kw = cg->kw; g.cv_c0 = (int)(Cg * cg->group);
-  g.idesc = (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((w_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) |
-            ((uint32_t)(TC_BM >> 4) << 24);
+  g.cv_dh = cg->dil_h; g.cv_dw = cg->dil_w; g.cv_kw = cg->kw; g.cv_c0 = (int)(cgb * cg->group);
   if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
-  if (bkb == 128) return dispatch_conv<128>(ma, mw, g, bn, stream);
-  if (bkb == 64) return dispatch_conv<64>(ma, mw, g, bn, stream);
-  return dispatch_conv<32>(ma, mw, g, bn, stream);
+  if (elem_bytes == 1) {
+    g.idesc = (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((w_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) |
+              ((uint32_t)(TC_BM >> 4) << 24);
+    if (bkb == 128) return dispatch_conv<0, 128>(ma, mw, g, bn, stream);
+    if (bkb == 64) return dispatch_conv<0, 64>(ma, mw, g, bn, stream);
+    return dispatch_conv<0, 32>(ma, mw, g, bn, stream);
+  }
+  // D = f32 (1 << 4), A/B = bf16 (1) at bits 7 / 10
+  g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  if (bkb == 128) return dispatch_conv<1, 128>(ma, mw, g, bn, stream);
+  if (bkb == 64) return dispatch_conv<1, 64>(ma, mw, g, bn, stream);
+  return dispatch_conv<1, 32>(ma, mw, g, bn, stream);
+}
+}  // namespace qt
+
+extern "C" int qt_conv_i8(const void* x_nhwc, int a_signed, const QtConvGeom* cg, const void* w, int w_signed, int64_t ldw,
+                          int64_t N, const QtEpilogue* ep, void* stream_) {
+  return conv_implicit(x_nhwc, 1, a_signed, cg, w, w_signed, ldw, N, ep, (cudaStream_t)stream_, "qt_conv_i8");
+}
+
+extern "C" int qt_conv_bf16(const void* x_nhwc, const QtConvGeom* cg, const void* w, int64_t ldw, int64_t N, const QtEpilogue* ep,
+                            void* stream_) {
+  return conv_implicit(x_nhwc, 2, 1, cg, w, 1, ldw, N, ep, (cudaStream_t)stream_, "qt_conv_bf16");
 }

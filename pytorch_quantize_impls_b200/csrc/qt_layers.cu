@@ -1,0 +1,260 @@
+// Channels-last helpers of the conv path (sm_100a): everything here is HBM-bound elementwise / window work.
+//
+//   qt_image_planes   fp32 NCHW image -> zero-padded channels-last bf16 "plane pixel" tensor (hi / mid / lo parts of every
+//                     channel side by side in one 32-byte pixel): the A operand of the first-layer implicit GEMM
+//   qt_pool_codes     max-pool on channels-last 8-bit activation codes (per-channel max or min)
+//   qt_pool_quant_f32 max-pool of a channels-last fp32 activation fused with the next activation quantizer
+#include "qt_common.cuh"
+
+namespace qt {
+
+static bool al(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// image planes.  One thread per output pixel (b, hp, wp): reads its C channel values (coalesced along w for every c),
+// splits each into P bf16 parts, writes 16 slots = 32 bytes (two 16-byte stores; consecutive threads -> consecutive
+// pixels).  Border pixels (the conv's zero padding, materialised) and unused slots are zero.
+// ---------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256) image_planes_kernel(const float* __restrict__ x, int B, int C, int H, int W, int Hp, int Wp,
+                                                           int pad_h, int pad_w, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)B * Hp * Wp;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (int64_t)gridDim.x * blockDim.x) {
+    const int wp = (int)(pix % Wp);
+    const int64_t t = pix / Wp;
+    const int hp = (int)(t % Hp);
+    const int64_t b = t / Hp;
+    const int h = hp - pad_h, w = wp - pad_w;
+    __align__(16) __nv_bfloat16 s[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[j] = __float2bfloat16_rn(0.f);
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const float* xp = x + ((b * C) * H + h) * (int64_t)W + w;
+      for (int c = 0; c < C; ++c) {
+        const float v = __ldg(xp + (int64_t)c * H * W);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        s[c] = hi;
+        if (P >= 2) {
+          const float r1 = v - __bfloat162float(hi);
+          const __nv_bfloat16 mi = __float2bfloat16_rn(r1);
+          s[C + c] = mi;
+          if (P >= 3) s[2 * C + c] = __float2bfloat16_rn(r1 - __bfloat162float(mi));
+        }
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + pix * 16);
+    o[0] = reinterpret_cast<const uint4*>(s)[0];
+    o[1] = reinterpret_cast<const uint4*>(s)[1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooling on codes: one thread per (output pixel, 16-channel vector); window taps outside the image are skipped
+// (-inf padding of nn.MaxPool2d).  use_min[c] != 0 turns channel c into a min-pool: pooling AFTER a per-channel affine
+// with a negative scale (a folded BatchNorm) equals the affine of the min.
+// ---------------------------------------------------------------------------------------------
+struct PoolArgs {
+  const void* x;
+  void* out;
+  const uint8_t* use_min;
+  int B, H, W, C, OH, OW;
+  int kh, kw, sh, sw, ph, pw;
+};
+
+template <bool UNSIGNED>
+__device__ __forceinline__ uint32_t vmax4(uint32_t a, uint32_t b) { return UNSIGNED ? __vmaxu4(a, b) : __vmaxs4(a, b); }
+template <bool UNSIGNED>
+__device__ __forceinline__ uint32_t vmin4(uint32_t a, uint32_t b) { return UNSIGNED ? __vminu4(a, b) : __vmins4(a, b); }
+
+template <bool UNSIGNED, bool HAS_MIN>
+__global__ void __launch_bounds__(256) pool_codes_kernel(PoolArgs a) {
+  const int cv = a.C >> 4;
+  const int64_t total = (int64_t)a.B * a.OH * a.OW * cv;
+  for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(id % cv);
+    int64_t t = id / cv;
+    const int ow = (int)(t % a.OW);
+    t /= a.OW;
+    const int oh = (int)(t % a.OH);
+    const int64_t b = t / a.OH;
+    const uint32_t lo_id = UNSIGNED ? 0u : 0x80808080u, hi_id = UNSIGNED ? 0xFFFFFFFFu : 0x7F7F7F7Fu;
+    uint4 mx = make_uint4(lo_id, lo_id, lo_id, lo_id), mn = make_uint4(hi_id, hi_id, hi_id, hi_id);
+    const int h0 = oh * a.sh - a.ph, w0 = ow * a.sw - a.pw;
+    for (int ky = 0; ky < a.kh; ++ky) {
+      const int h = h0 + ky;
+      if (h < 0 || h >= a.H) continue;
+      for (int kx = 0; kx < a.kw; ++kx) {
+        const int w = w0 + kx;
+        if (w < 0 || w >= a.W) continue;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.x) +
+                                                              (((b * a.H + h) * a.W + w) * (int64_t)a.C)) + v);
+        mx.x = vmax4<UNSIGNED>(mx.x, q.x); mx.y = vmax4<UNSIGNED>(mx.y, q.y);
+        mx.z = vmax4<UNSIGNED>(mx.z, q.z); mx.w = vmax4<UNSIGNED>(mx.w, q.w);
+        if (HAS_MIN) {
+          mn.x = vmin4<UNSIGNED>(mn.x, q.x); mn.y = vmin4<UNSIGNED>(mn.y, q.y);
+          mn.z = vmin4<UNSIGNED>(mn.z, q.z); mn.w = vmin4<UNSIGNED>(mn.w, q.w);
+        }
+      }
+    }
+    if (HAS_MIN) {
+      // byte mask from the per-channel flags (0 / 1 bytes -> 0x00 / 0xFF)
+      const uint4 f = __ldg(reinterpret_cast<const uint4*>(a.use_min) + v);
+      const uint32_t k0 = (f.x & 0x01010101u) * 0xFFu, k1 = (f.y & 0x01010101u) * 0xFFu;
+      const uint32_t k2 = (f.z & 0x01010101u) * 0xFFu, k3 = (f.w & 0x01010101u) * 0xFFu;
+      mx.x = (mx.x & ~k0) | (mn.x & k0); mx.y = (mx.y & ~k1) | (mn.y & k1);
+      mx.z = (mx.z & ~k2) | (mn.z & k2); mx.w = (mx.w & ~k3) | (mn.w & k3);
+    }
+    reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out) + (((b * a.OH + oh) * a.OW + ow) * (int64_t)a.C))[v] = mx;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 channels-last max-pool fused with the activation quantizer that follows it (stem of a residual net:
+// conv -> BN -> clamp [epilogue] -> max-pool -> {fp32 residual stream, 8-bit codes of the first block}).
+// One thread per (output pixel, 4-channel vector).
+// ---------------------------------------------------------------------------------------------
+struct PoolQuantArgs {
+  const float* x;
+  float* out;          // optional pooled fp32 [B, OH, OW, C]
+  void* codes;         // optional [B, OH, OW, C] int8 / uint8
+  int32_t* overflow;
+  int mode, codes_kind;
+  float n;
+  int B, H, W, C, OH, OW;
+  int kh, kw, sh, sw, ph, pw;
+};
+
+__device__ __forceinline__ int pq_code(int mode, float n, float v, float lo, float hi, bool& ovf) {
+  if (mode == QT_Q_SIGN) return (v < 0.f) ? -1 : 1;
+  if (mode == QT_Q_TERNARY) {
+    const float s = (v < 0.f) ? -1.f : 1.f;
+    return (((v < 0.f) ? -1 : 1) + ((v - 0.5f * s < 0.f) ? -1 : 1)) >> 1;
+  }
+  float c = rintf(n * v);
+  if (!(c >= lo && c <= hi)) { ovf = true; c = (c != c) ? 0.f : fminf(fmaxf(c, lo), hi); }
+  return (int)c;
+}
+
+__global__ void __launch_bounds__(256) pool_quant_f32_kernel(PoolQuantArgs a) {
+  const int cv = a.C >> 2;
+  const int64_t total = (int64_t)a.B * a.OH * a.OW * cv;
+  const float lo = (a.codes_kind == 1) ? -128.f : 0.f, hi = (a.codes_kind == 1) ? 127.f : 255.f;
+  bool ovf = false;
+  for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(id % cv);
+    int64_t t = id / cv;
+    const int ow = (int)(t % a.OW);
+    t /= a.OW;
+    const int oh = (int)(t % a.OH);
+    const int64_t b = t / a.OH;
+    const float ninf = -__int_as_float(0x7f800000);
+    float4 m = make_float4(ninf, ninf, ninf, ninf);
+    const int h0 = oh * a.sh - a.ph, w0 = ow * a.sw - a.pw;
+    for (int ky = 0; ky < a.kh; ++ky) {
+      const int h = h0 + ky;
+      if (h < 0 || h >= a.H) continue;
+      for (int kx = 0; kx < a.kw; ++kx) {
+        const int w = w0 + kx;
+        if (w < 0 || w >= a.W) continue;
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(a.x + (((b * a.H + h) * a.W + w) * (int64_t)a.C)) + v);
+        // NaN-propagating like torch's max_pool2d
+        m.x = (q.x > m.x || q.x != q.x) ? q.x : m.x; m.y = (q.y > m.y || q.y != q.y) ? q.y : m.y;
+        m.z = (q.z > m.z || q.z != q.z) ? q.z : m.z; m.w = (q.w > m.w || q.w != q.w) ? q.w : m.w;
+      }
+    }
+    const int64_t o = ((b * a.OH + oh) * a.OW + ow) * (int64_t)a.C;
+    if (a.out) reinterpret_cast<float4*>(a.out + o)[v] = m;
+    if (a.codes) {
+      const int k0 = pq_code(a.mode, a.n, m.x, lo, hi, ovf), k1 = pq_code(a.mode, a.n, m.y, lo, hi, ovf);
+      const int k2 = pq_code(a.mode, a.n, m.z, lo, hi, ovf), k3 = pq_code(a.mode, a.n, m.w, lo, hi, ovf);
+      reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.codes) + o)[v] =
+          (uint32_t)(k0 & 0xff) | ((uint32_t)(k1 & 0xff) << 8) | ((uint32_t)(k2 & 0xff) << 16) | ((uint32_t)(k3 & 0xff) << 24);
+    }
+  }
+  if (a.overflow && ovf) atomicOr(a.overflow, 1);
+}
+
+static unsigned grid_for(int64_t total, int threads) {
+  int64_t blocks = ceil_div(total, threads);
+  const int64_t cap = 148ll * 64;          // grid-stride beyond ~8 resident waves
+  return (unsigned)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+}  // namespace qt
+
+using namespace qt;
+
+extern "C" int qt_image_planes(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int planes, int pad_h, int pad_w,
+                               int64_t Hp, int64_t Wp, void* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(x && out, "qt_image_planes: null argument");
+  QT_REQUIRE(planes >= 1 && planes <= 3 && C >= 1 && planes * C <= 16, "qt_image_planes: planes * C must fit the 16 slots of a pixel");
+  QT_REQUIRE(B >= 0 && H > 0 && W > 0 && Hp > 0 && Wp > 0 && pad_h >= 0 && pad_w >= 0, "qt_image_planes: bad shape");
+  QT_REQUIRE(al(out, 16), "qt_image_planes: out must be 16-byte aligned");
+  QT_REQUIRE(B * Hp * Wp < (1ll << 40) && H * W < (1ll << 31), "qt_image_planes: tensor too large");
+  if (B == 0) return QT_OK;
+  const unsigned grid = grid_for(B * Hp * Wp, 256);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (planes == 1) image_planes_kernel<1><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, o);
+  else if (planes == 2) image_planes_kernel<2><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, o);
+  else image_planes_kernel<3><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, o);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+static int pool_geom_ok(const QtPoolGeom* g, const char* who) {
+  QT_REQUIRE(g, "%s: null geometry", who);
+  QT_REQUIRE(g->B >= 0 && g->H > 0 && g->W > 0 && g->C > 0 && g->kh > 0 && g->kw > 0 && g->stride_h > 0 && g->stride_w > 0 &&
+             g->pad_h >= 0 && g->pad_w >= 0 && 2 * g->pad_h <= g->kh && 2 * g->pad_w <= g->kw, "%s: bad geometry", who);
+  QT_REQUIRE(g->OH == (g->H + 2 * g->pad_h - g->kh) / g->stride_h + 1 && g->OW == (g->W + 2 * g->pad_w - g->kw) / g->stride_w + 1 &&
+             g->OH > 0 && g->OW > 0, "%s: OH / OW do not match floor((size + 2 pad - k) / stride) + 1", who);
+  QT_REQUIRE(g->B < (1ll << 31) && g->H < (1 << 20) && g->W < (1 << 20) && g->C < (1 << 24), "%s: tensor too large", who);
+  return QT_OK;
+}
+
+extern "C" int qt_pool_codes(const void* x_nhwc, int is_unsigned, const QtPoolGeom* g, const uint8_t* use_min, void* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(x_nhwc && out, "qt_pool_codes: null argument");
+  if (int rc = pool_geom_ok(g, "qt_pool_codes")) return rc;
+  QT_REQUIRE(g->C % 16 == 0 && al(x_nhwc, 16) && al(out, 16) && (!use_min || al(use_min, 16)),
+             "qt_pool_codes: needs C %% 16 == 0 and 16-byte aligned buffers");
+  if (g->B == 0) return QT_OK;
+  PoolArgs a;
+  a.x = x_nhwc; a.out = out; a.use_min = use_min;
+  a.B = (int)g->B; a.H = (int)g->H; a.W = (int)g->W; a.C = (int)g->C; a.OH = (int)g->OH; a.OW = (int)g->OW;
+  a.kh = g->kh; a.kw = g->kw; a.sh = g->stride_h; a.sw = g->stride_w; a.ph = g->pad_h; a.pw = g->pad_w;
+  const unsigned grid = grid_for(g->B * g->OH * g->OW * (g->C / 16), 256);
+  if (is_unsigned) {
+    if (use_min) pool_codes_kernel<true, true><<<grid, 256, 0, stream>>>(a);
+    else pool_codes_kernel<true, false><<<grid, 256, 0, stream>>>(a);
+  } else {
+    if (use_min) pool_codes_kernel<false, true><<<grid, 256, 0, stream>>>(a);
+    else pool_codes_kernel<false, false><<<grid, 256, 0, stream>>>(a);
+  }
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+extern "C" int qt_pool_quant_f32(const float* x_nhwc, const QtPoolGeom* g, float* out, int mode, int bit_width, void* codes,
+                                 int codes_kind, int32_t* overflow, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(x_nhwc && (out || codes), "qt_pool_quant_f32: null argument");
+  if (int rc = pool_geom_ok(g, "qt_pool_quant_f32")) return rc;
+  QT_REQUIRE(g->C % 4 == 0 && al(x_nhwc, 16) && (!out || al(out, 16)) && (!codes || al(codes, 4)),
+             "qt_pool_quant_f32: needs C %% 4 == 0 and aligned buffers");
+  if (codes) {
+    QT_REQUIRE(mode == QT_Q_SIGN || mode == QT_Q_TERNARY || mode == QT_Q_DOREFA, "qt_pool_quant_f32: SIGN / TERNARY / DOREFA codes only");
+    QT_REQUIRE(codes_kind == 1 || codes_kind == 2, "qt_pool_quant_f32: int8 / uint8 code lanes only");
+    QT_REQUIRE(mode != QT_Q_DOREFA || (bit_width >= 2 && bit_width <= 8), "qt_pool_quant_f32: DoReFa bit width must be 2..8");
+    QT_REQUIRE(codes_kind == 1 || mode == QT_Q_DOREFA, "qt_pool_quant_f32: sign / ternary codes need the int8 lane");
+  }
+  if (g->B == 0) return QT_OK;
+  PoolQuantArgs a;
+  a.x = x_nhwc; a.out = out; a.codes = codes; a.overflow = overflow; a.mode = mode; a.codes_kind = codes_kind;
+  a.n = (mode == QT_Q_DOREFA) ? (float)((1 << bit_width) - 1) : 1.f;
+  a.B = (int)g->B; a.H = (int)g->H; a.W = (int)g->W; a.C = (int)g->C; a.OH = (int)g->OH; a.OW = (int)g->OW;
+  a.kh = g->kh; a.kw = g->kw; a.sh = g->stride_h; a.sw = g->stride_w; a.ph = g->pad_h; a.pw = g->pad_w;
+  pool_quant_f32_kernel<<<grid_for(g->B * g->OH * g->OW * (g->C / 4), 256), 256, 0, stream>>>(a);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}

@@ -1143,18 +1143,20 @@ struct LeanArgs {
   int64_t ld_x, ld_codes;   // elements
   float n;               // DoReFa levels
   float inv_cols;
+  int max_ctas;          // 0: one CTA per 8 tasks; > 0: grid bound (persistent form)
 };
 
 template <int MODE, int CK>
 __global__ void __launch_bounds__(256) act_quant_lean_kernel(LeanArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t task = blockIdx.x * 8u + (threadIdx.x >> 5);
-  if (task >= a.rows * a.nchunks) return;
+  const uint32_t total = a.rows * a.nchunks;
+  bool ovf = false;
+  // one task per warp when the grid covers them all; a bounded grid (QtActQuant.max_ctas) walks the tasks with a stride
+  for (uint32_t task = blockIdx.x * 8u + (threadIdx.x >> 5); task < total; task += gridDim.x * 8u) {
   const uint32_t row = task / a.nchunks, ch = task - row * a.nchunks;
   const float* xr = a.x + (int64_t)row * a.ld_x + ch * 1024u + 4u * lane;
   float psum = 0.f;
   int isum = 0;
-  bool ovf = false;
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
     float4 v[4];
@@ -1228,6 +1230,7 @@ __global__ void __launch_bounds__(256) act_quant_lean_kernel(LeanArgs a) {
       else atomicAdd(a.row_sum + row, isum);
     }
   }
+  }   // task loop
   if (MODE == QT_Q_DOREFA && a.overflow) {
     const unsigned any = __ballot_sync(0xffffffffu, ovf);
     if (any && lane == 0) atomicOr(a.overflow, 1);
@@ -1237,7 +1240,9 @@ __global__ void __launch_bounds__(256) act_quant_lean_kernel(LeanArgs a) {
 template <int MODE, int CK>
 static int launch_lean(const LeanArgs& a, cudaStream_t stream) {
   const uint32_t tasks = a.rows * a.nchunks;
-  act_quant_lean_kernel<MODE, CK><<<(tasks + 7u) / 8u, 256, 0, stream>>>(a);
+  uint32_t grid = (tasks + 7u) / 8u;
+  if (a.max_ctas > 0 && grid > (uint32_t)a.max_ctas) grid = (uint32_t)a.max_ctas;
+  act_quant_lean_kernel<MODE, CK><<<grid, 256, 0, stream>>>(a);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }
@@ -1258,7 +1263,7 @@ static int try_lean_quant(const QtActQuant* p, cudaStream_t stream) {
   LeanArgs a;
   a.x = p->x; a.codes = p->codes; a.row_sum = p->row_sum; a.row_scale = p->row_scale; a.overflow = p->overflow;
   a.rows = (uint32_t)p->rows; a.nchunks = (uint32_t)(p->cols / 1024); a.ld_x = p->ld_x; a.ld_codes = p->ld_codes;
-  a.n = 1.f; a.inv_cols = 1.f / (float)p->cols;
+  a.n = 1.f; a.inv_cols = 1.f / (float)p->cols; a.max_ctas = p->max_ctas;
   if (p->mode == QT_Q_XNOR_ROW) {
     if (!(ck == 3 || ck == 5)) return 0;
     // the partial-sum contract of qt_quant_xnor_parts: chunks of 1024 columns only when the caller provided room for them
@@ -1530,6 +1535,18 @@ extern "C" int qt_expand_loglin(const void* codes, int64_t n, int64_t k, int64_t
   const int64_t threads = n * (ld_out / 8);
   loglin_expand_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, stream>>>((const int8_t*)codes, n, k, ld_codes, is_log, emin,
                                                                               (__nv_bfloat16*)out, ld_out);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+extern "C" int qt_rowsum_codes(const void* codes, int is_unsigned, int64_t rows, int64_t ld, int32_t* row_sum, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(codes && row_sum, "qt_rowsum_codes: null argument");
+  QT_REQUIRE(rows >= 0 && ld > 0 && ld % 4 == 0 && aligned(codes, 4), "qt_rowsum_codes: rows of 8-bit codes must be 4-byte aligned multiples of 4");
+  if (rows == 0) return QT_OK;
+  const uint8_t* a = reinterpret_cast<const uint8_t*>(codes);
+  if (is_unsigned) rowsum_i8_kernel<true><<<(unsigned)ceil_div(rows, 8), 256, 0, stream>>>(a, rows, ld, row_sum);
+  else rowsum_i8_kernel<false><<<(unsigned)ceil_div(rows, 8), 256, 0, stream>>>(a, rows, ld, row_sum);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }

@@ -226,6 +226,274 @@ class FusedLayerBN(nn.Module):
         return "BatchNorm / clamp folded into the epilogue"
 
 
+def _pool_params(pool):
+    """(kernel, stride, padding) pairs of an nn.MaxPool2d the pooling kernels can run, else None."""
+    if not isinstance(pool, nn.MaxPool2d) or pool.ceil_mode or pool.return_indices:
+        return None
+    two = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+    if two(pool.dilation) != (1, 1):
+        return None
+    k = two(pool.kernel_size)
+    s = two(pool.stride if pool.stride is not None else pool.kernel_size)
+    p = two(pool.padding)
+    if 2 * p[0] > k[0] or 2 * p[1] > k[1]:
+        return None
+    return k, s, p
+
+
+def _bn_ready(bn):
+    return bn is None or (not bn.training and bn.track_running_stats and bn.running_mean is not None)
+
+
+class FusedLayerPoolQuant(FusedLayerQuant):
+    """quantized Conv2d -> MaxPool2d -> [BatchNorm (eval)] -> [clamp] -> activation quantizer (models/Alexnet/Alexnet_Bin.py:13-22,
+    benchmark/BinaryNet/AlexNetBin.py:13-24): the conv's tcgen05 epilogue applies BatchNorm + clamp + quantizer and writes
+    channels-last 8-bit codes, and the pool runs on the codes (qt_pool_codes: 1 byte per element instead of 4 + 4).  An activation
+    quantizer is monotone, so pooling commutes with it; where the folded BatchNorm scale of a channel is negative the pool of that
+    channel is a min-pool.  Falls back to the plain composition wherever FusedLayerQuant would."""
+
+    def __init__(self, layer, pool, bn, act, quant, consumer=None):
+        super().__init__(layer, bn, act, quant, consumer)
+        self.pool = pool
+        self._mask = None
+
+    def _compose(self, x):
+        return self.tail(self.pool(self.layer(x)))
+
+    def _min_mask(self, spec):
+        if spec.col_mul is None:
+            return None
+        key = (spec.col_mul.data_ptr(), spec.col_mul._version)
+        if self._mask is None or self._mask[0] != key:
+            neg = spec.col_mul < 0
+            self._mask = (key, neg.to(torch.uint8).contiguous() if bool(neg.any()) else None)
+        return self._mask[1]
+
+    def forward(self, x):
+        geo = _pool_params(self.pool)
+        fusable = (geo is not None and eng._code_only[0] and not torch.is_grad_enabled() and (x.is_cuda or x.is_meta)
+                   and x.dim() == 4 and self.layer.out_channels % 16 == 0 and _bn_ready(self.bn))
+        if fusable:
+            spec = self._make_spec()
+            try:
+                y = self.layer._forward_requant(x, spec)
+            except eng.RequantUnsupported:
+                return self._compose(x)
+            tag = eng.get_tag(y)
+            pooled = ops.pool_codes(tag.codes, *geo, use_min=self._min_mask(spec))
+            B, PH, PW, Cn = pooled.shape
+            tag.codes, tag.rows, tag.cols, tag.ld = pooled, B, Cn * PH * PW, Cn * PH * PW
+            out = torch.empty((B, Cn, PH, PW), dtype=torch.float32, device="meta")
+            return eng.attach_tag(out, tag)
+        return self._compose(x)
+
+    def extra_repr(self):
+        return "fused epilogue requant + pool on codes"
+
+
+class FusedConvPool(nn.Module):
+    """quantized Conv2d -> [BatchNorm (eval)] -> [clamp] -> MaxPool2d with an fp32 result (the stem of a residual net,
+    models/Resnet/Resnet_bin.py:68-69 + pool): BatchNorm and clamp fold into the conv epilogue, which writes a channels-last
+    fp32 tensor with full-line TMA stores; the pool reads it once (qt_pool_quant_f32) and returns a channels-last tensor."""
+
+    def __init__(self, layer, bn, act, pool):
+        super().__init__()
+        self.inner = FusedLayerBN(layer, bn, act)
+        self.pool = pool
+
+    def forward(self, x):
+        geo = _pool_params(self.pool)
+        lay = self.inner.layer
+        if (geo is not None and not torch.is_grad_enabled() and x.is_cuda and x.dim() == 4 and lay._is_conv
+                and lay.out_channels % 4 == 0 and _bn_ready(self.inner.bn)):
+            y = lay._forward_affine(x, self.inner._make_spec(), out_format="nhwc")
+            return ops.pool_quant_f32(y, *geo)[0]
+        return self.pool(self.inner(x))
+
+
+class FlattenCodes(nn.Module):
+    """Flatten between the conv stack and the classifier of a fused chain.  The conv chain leaves channels-last codes
+    [B, H, W, C]; their flatten is (h, w, c)-ordered, so the Linear that follows is told to permute its weight columns once
+    (QuantLayerMixin._in_perm) and then reads the codes as they are -- no transpose pass, no fp32 detour."""
+
+    def __init__(self, flatten, consumer):
+        super().__init__()
+        self.flatten = flatten
+        self._consumer = [consumer]            # not a registered child: it already lives in the parent container
+
+    def forward(self, x):
+        cons = self._consumer[0]
+        if x.dim() != 4 or torch.is_grad_enabled() or not (x.is_cuda or x.is_meta):
+            if cons._in_perm is not None:
+                raise RuntimeError("this network was re-ordered for inference by fuse_inference (channels-last flatten): run it under "
+                                   "torch.no_grad() on 4-D CUDA inputs")
+            return self.flatten(x)
+        B, Cn, H, W = x.shape
+        if cons._in_perm is None:
+            cons._set_in_perm((Cn, H, W))
+        elif cons._in_perm != (Cn, H, W):
+            raise RuntimeError("FlattenCodes: activation shape changed after the classifier weights were re-ordered")
+        tag = eng.get_tag(x)
+        if x.is_meta:
+            out = torch.empty((B, Cn * H * W), dtype=torch.float32, device="meta")
+        else:
+            out = x.permute(0, 2, 3, 1).reshape(B, -1)
+        if tag is not None and tag.layout == "nhwc" and tag.codes.dim() == 4 and (Cn * H * W) % 16 == 0:
+            t2 = ops.ActCodes()
+            for f in ops.ActCodes.__slots__:
+                if hasattr(tag, f):
+                    setattr(t2, f, getattr(tag, f))
+            t2.codes = tag.codes.view(B, H * W * Cn)
+            t2.rows, t2.cols, t2.ld, t2.layout = B, H * W * Cn, H * W * Cn, "rows"
+            t2.row_sum, t2.row_parts, t2.row_mul = None, 0, 1.0
+            if getattr(cons, "bit_width", None) == 8 and tag.kind == "dorefa":
+                t2.row_sum = ops.rowsum_codes(t2.codes)         # zero point of unsigned 8-bit weights
+            return eng.attach_tag(out, t2)
+        if x.is_meta:
+            raise RuntimeError("FlattenCodes: the code-only activation cannot be flattened for this classifier")
+        return out
+
+
+class FusedActLayer(nn.Module):
+    """activation quantizer -> quantized Linear at the head of a chain, where the input is a real fp32 tensor: under
+    `code_only_activations()` the pair runs as a two-stream pipeline over row bands (engine.linear_banded) -- the HBM-bound
+    quantizer of band i+1 beside the tensor-bound contraction of band i -- instead of one after the other."""
+    MIN_ROWS = 4096
+
+    def __init__(self, quant, inner):
+        super().__init__()
+        self.quant, self.inner = quant, inner
+
+    def _layer(self):
+        return self.inner.layer if isinstance(self.inner, FusedLayerBN) else self.inner
+
+    def forward(self, x):
+        lay = self._layer()
+        kind, arg = self.quant._qt_spec
+        ok = (eng._code_only[0] and not torch.is_grad_enabled() and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+              and x.shape[0] >= self.MIN_ROWS and x.shape[1] % 1024 == 0 and x.is_contiguous() and not lay.training
+              and not (isinstance(self.inner, FusedLayerBN) and not _bn_ready(self.inner.bn)))
+        if not ok:
+            return self.inner(self.quant(x))
+        if kind == "dorefa" and arg == 1:
+            kind = "sign"
+        pack = lay._current_pack()
+        int_w = pack.kind in ("sign", "ternary", "dorefa", "lin")
+        if kind == "xnor":
+            if pack.kind not in ("xnor", "sign", "ternary", "dorefa"):
+                return self.inner(self.quant(x))
+        elif not int_w or not (kind in ("sign", "ternary") or 2 <= arg <= 8):
+            return self.inner(self.quant(x))
+        # 1-bit / ternary / 2-bit codes ride the e2m1 lane when the weights can meet them there, else an 8-bit lane
+        f4 = eng._fp4[0] and eng._f4_weight_ok(pack) and (kind in ("sign", "ternary") or arg == 2)
+        small = L.CODES_F4 if f4 else L.CODES_I8
+
+        def quantize(rows, max_ctas):
+            if kind == "sign":
+                return ops.quant_act(rows, L.Q_SIGN, want_y=False, codes_kind=small, kind="sign", max_ctas=max_ctas)[1]
+            if kind == "ternary":
+                return ops.quant_act(rows, L.Q_TERNARY, want_y=False, codes_kind=small, kind="ternary", max_ctas=max_ctas)[1]
+            if kind == "xnor":
+                return ops.quant_act(rows, L.Q_XNOR_ROW, want_y=False, codes_kind=eng.xnor_codes_kind(), want_row_scale=True,
+                                     kind="xnor", max_ctas=max_ctas)[1]
+            ck = small if arg == 2 else (L.CODES_I8 if arg <= 7 else L.CODES_U8)
+            tag = ops.quant_act(rows, L.Q_DOREFA, bit_width=arg, want_y=False, codes_kind=ck, want_row_sum=True, kind="dorefa",
+                                max_ctas=max_ctas)[1]
+            tag.scale = _f32(_f32(1.0) / _f32(2 ** arg - 1))
+            return tag
+
+        affine = self.inner._make_spec() if isinstance(self.inner, FusedLayerBN) else None
+        return eng.linear_banded(x, quantize, pack, lay.bias, affine=affine)
+
+    def extra_repr(self):
+        return "banded quantizer / contraction pipeline"
+
+
+class FusedBasicBlock(nn.Module):
+    """Residual block (models/Resnet/Resnet_bin.py:7-32 with k-bit activations, nets.TerBasicBlock) for inference chains:
+
+        xq   = q_in(x)                                   codes (left by the previous block's epilogue, else one quantizer pass)
+        c1   = conv1(xq) -> BN -> clamp -> quantizer     requant epilogue, channels-last codes
+        res  = x  |  shortcut conv(xq) -> BN             channels-last fp32
+        out  = clamp(BN(conv2(c1)) + res)                ONE epilogue: residual add + clamp + fp32 channels-last store (TMA)
+                                                         + the NEXT block's q_in codes
+
+    so the residual stream is read once and written once per block (plus 1 byte of codes) instead of the add / clamp / quantizer
+    passes.  Outside code-only inference it is the wrapped block."""
+
+    def __init__(self, block, next_spec=None):
+        super().__init__()
+        self.block = block
+        self._next = next_spec                 # _qt_spec of the next block's input quantizer (None: no codes needed)
+        self._spec2 = None
+
+    def _parts(self):
+        b = self.block
+        f1 = b.branch1[0] if len(b.branch1) == 1 else None
+        f2 = b.branch2[0] if len(b.branch2) == 1 else None
+        fs = None if b.shortcut is None else (b.shortcut[0] if len(b.shortcut) == 1 else NotImplemented)
+        if not isinstance(f1, FusedLayerQuant) or not isinstance(f2, FusedLayerBN) or fs is NotImplemented \
+                or (fs is not None and not isinstance(fs, FusedLayerBN)):
+            return None
+        return f1, f2, fs
+
+    def _make_spec2(self, f2, lo, hi):
+        bn = f2.bn
+        key = None
+        if bn is not None:
+            key = tuple((t.data_ptr(), t._version) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None)
+        if self._spec2 is None or self._spec2[0] != key:
+            mul, add = _bn_affine(bn) if bn is not None else (None, None)
+            plain = eng.RequantSpec(-1, None, lo=lo, hi=hi, col_mul=mul, col_add=add)
+            rq = None
+            if self._next is not None:
+                rq = eng.RequantSpec(L.Q_DOREFA, "dorefa", bit_width=self._next[1], lo=lo, hi=hi, col_mul=mul, col_add=add)
+                rq.force_8bit = True
+            self._spec2 = (key, plain, rq)
+        return self._spec2[1], self._spec2[2]
+
+    def forward(self, x):
+        parts = self._parts()
+        b = self.block
+        spec_in = getattr(b.q_in, "_qt_spec", None)
+        lo, hi = _clamp_range(b.clip)
+        ok = (parts is not None and eng._code_only[0] and not torch.is_grad_enabled() and x.dim() == 4 and x.is_cuda
+              and x.dtype == torch.float32 and spec_in is not None and spec_in[0] == "dorefa" and 2 <= spec_in[1] <= 8
+              and lo is not NotImplemented and x.shape[1] % 16 == 0
+              and (self._next is None or (self._next[0] == "dorefa" and 2 <= self._next[1] <= 8)))
+        if ok:
+            f1, f2, fs = parts
+            ok = _bn_ready(f1.bn) and _bn_ready(f2.bn) and (fs is None or _bn_ready(fs.bn)) and f2.act is None \
+                and f2.layer.out_channels % 32 == 0
+        if not ok:
+            return b(x)
+        abits = spec_in[1]
+        tag = eng.get_tag(x)
+        if not (tag is not None and tag.layout == "nhwc" and tag.kind == "dorefa" and tag.bit_width == abits):
+            if not ops.is_channels_last(x):
+                x = x.contiguous(memory_format=torch.channels_last)
+            tag = ops.quant_act_nhwc(x, L.Q_DOREFA, bit_width=abits, codes_kind=L.CODES_U8 if abits == 8 else L.CODES_I8,
+                                     kind="dorefa")
+            tag.scale = _f32(_f32(1.0) / _f32(2 ** abits - 1))
+        elif not ops.is_channels_last(x):
+            x = x.contiguous(memory_format=torch.channels_last)
+        xq = eng.attach_tag(torch.empty(x.shape, dtype=torch.float32, device="meta"), tag)
+        c1 = f1(xq)
+        if eng.get_tag(c1) is None or not c1.is_meta:
+            return b(x)                        # the first conv declined the fused epilogue: plain block
+        res = x if fs is None else fs.layer._forward_affine(xq, fs._make_spec(), out_format="nhwc")
+        plain, rq = self._make_spec2(f2, lo, hi)
+        if rq is not None:
+            try:
+                return f2.layer._forward_requant(c1, rq, out_format="nhwc", residual=res, keep_out=True)
+            except eng.RequantUnsupported:
+                pass
+        return f2.layer._forward_affine(c1, plain, out_format="nhwc", residual=res)
+
+    def extra_repr(self):
+        return "residual add + clamp + next quantizer in the second conv's epilogue"
+
+
 def _needs_8bit_lanes(consumer):
     """True when the layer that will read the codes cannot take e2m1 operands (DoReFa k >= 3 weights, convs, unknown)."""
     from .layers.common import QuantLayerMixin
@@ -242,59 +510,121 @@ def _is_quant_layer(m):
     return isinstance(m, QuantLayerMixin) and isinstance(m, (nn.Linear, nn.Conv2d))
 
 
+def _is_flatten(m):
+    return isinstance(m, nn.Flatten) and m.start_dim == 1 and m.end_dim == -1 or type(m).__name__ == "Flatten" and not list(m.parameters())
+
+
+def _is_block(m):
+    """Residual block with the attribute layout of nets.TerBasicBlock."""
+    return all(hasattr(m, a) for a in ("q_in", "branch1", "branch2", "clip", "shortcut")) and not isinstance(m, FusedBasicBlock)
+
+
 def fuse_inference(module):
-    """Rewrite, in place and recursively, every `[BatchNorm] -> [Hardtanh|ReLU|ReLU6] -> activation quantizer` run found
-    inside nn.Sequential containers into a FusedBNActQuant.  Call it after loading weights (the fused module keeps
-    the original sub-modules as children `bn`, `act`, `quant`).  Returns `module`."""
+    """Rewrite, in place and recursively, the inter-layer patterns of the reference nets found inside nn.Sequential containers:
+
+        layer -> [BatchNorm] -> [clamp] -> quantizer                 FusedLayerQuant      (quantizer in the layer's epilogue)
+        conv  -> MaxPool -> [BatchNorm] -> [clamp] -> quantizer      FusedLayerPoolQuant  (+ pool on the codes)
+        layer -> [BatchNorm] -> [clamp]                              FusedLayerBN         (affine + clamp in the epilogue)
+        conv  -> [BatchNorm] -> [clamp] -> MaxPool                   FusedConvPool        (channels-last fp32 + one pool pass)
+        [BatchNorm] -> [clamp] -> quantizer                          FusedBNActQuant      (one elementwise pass)
+        Flatten between a conv chain and a quantized Linear          FlattenCodes         (channels-last flatten, weights re-ordered)
+        quantizer -> quantized Linear at the head of a chain         FusedActLayer        (banded quantizer / contraction pipeline)
+        residual blocks (nets.TerBasicBlock)                         FusedBasicBlock      (add + clamp + next quantizer in conv2)
+
+    Call it after loading weights (the fused modules keep the original sub-modules as children).  Returns `module`."""
     for name, child in list(module.named_children()):
         fuse_inference(child)
-    if isinstance(module, nn.Sequential):
-        mods = list(module.children())
-        out, i = [], 0
-        while i < len(mods):
-            # quantized layer -> [BN] -> [clamp] -> quantizer: the quantizer moves into the layer's epilogue
-            if _is_quant_layer(mods[i]) and not (mods[i]._is_conv and mods[i].groups != 1):
-                j = i + 1
-                bn = act = None
-                want_bn = nn.BatchNorm2d if mods[i]._is_conv else nn.BatchNorm1d
-                if j < len(mods) and isinstance(mods[j], want_bn):
-                    bn = mods[j]
-                    j += 1
-                if j < len(mods) and isinstance(mods[j], (nn.Hardtanh, nn.ReLU, nn.ReLU6)) and not _is_quantizer(mods[j]):
-                    act = mods[j]
-                    j += 1
-                if j < len(mods) and _is_quantizer(mods[j]) and (mods[j]._qt_spec[0] != "xnor" or not mods[i]._is_conv):
-                    consumer = mods[j + 1] if j + 1 < len(mods) else None
-                    out.append(FusedLayerQuant(mods[i], bn, act, mods[j], consumer))
-                    i = j + 1
-                    continue
-                if bn is not None or act is not None:
-                    # layer -> [BatchNorm] -> [clamp] with no quantizer behind it (pool / residual add follows): fold the
-                    # normalisation and the clamp into the layer's epilogue
-                    out.append(FusedLayerBN(mods[i], bn, act))
-                    i += 1 + (bn is not None) + (act is not None)
-                    continue
-            j = i
-            bn = act = None
-            if isinstance(mods[j], _BN):
+    if not isinstance(module, nn.Sequential):
+        return module
+    mods = list(module.children())
+    out, i = [], 0
+    clamp_t = (nn.Hardtanh, nn.ReLU, nn.ReLU6)
+    while i < len(mods):
+        m = mods[i]
+        if _is_quant_layer(m) and not (m._is_conv and m.groups != 1):
+            j = i + 1
+            pool = bn = act = None
+            want_bn = nn.BatchNorm2d if m._is_conv else nn.BatchNorm1d
+            if m._is_conv and j < len(mods) and _pool_params(mods[j]) is not None:
+                pool = mods[j]
+                j += 1
+            if j < len(mods) and isinstance(mods[j], want_bn):
                 bn = mods[j]
                 j += 1
-            if j < len(mods) and _clamp_range(mods[j])[0] is not NotImplemented and not _is_quantizer(mods[j]) \
-                    and isinstance(mods[j], (nn.Hardtanh, nn.ReLU, nn.ReLU6)):
+            if j < len(mods) and isinstance(mods[j], clamp_t) and not _is_quantizer(mods[j]):
                 act = mods[j]
                 j += 1
-            if j < len(mods) and _is_quantizer(mods[j]) and (bn is not None or act is not None):
-                out.append(FusedBNActQuant(bn, act, mods[j]))
+            if j < len(mods) and _is_quantizer(mods[j]) and (mods[j]._qt_spec[0] != "xnor" or not m._is_conv):
+                # the quantizer moves into the layer's epilogue (a pool in between runs on the codes)
+                k = j + 1
+                consumer = mods[k] if k < len(mods) else None
+                if consumer is not None and _is_flatten(consumer) and k + 1 < len(mods):
+                    consumer = mods[k + 1]
+                if pool is not None:
+                    out.append(FusedLayerPoolQuant(m, pool, bn, act, mods[j], consumer))
+                else:
+                    out.append(FusedLayerQuant(m, bn, act, mods[j], consumer))
                 i = j + 1
-            else:
-                out.append(mods[i])
+                continue
+            if pool is None and (bn is not None or act is not None):
+                if m._is_conv and j < len(mods) and _pool_params(mods[j]) is not None:
+                    out.append(FusedConvPool(m, bn, act, mods[j]))       # conv -> BN -> clamp -> pool (fp32 result)
+                    i = j + 1
+                    continue
+                # layer -> [BatchNorm] -> [clamp] with no quantizer behind it (pool / residual add follows)
+                out.append(FusedLayerBN(m, bn, act))
+                i = j
+                continue
+        j = i
+        bn = act = None
+        if isinstance(mods[j], _BN):
+            bn = mods[j]
+            j += 1
+        if j < len(mods) and isinstance(mods[j], clamp_t) and not _is_quantizer(mods[j]):
+            act = mods[j]
+            j += 1
+        if j < len(mods) and _is_quantizer(mods[j]) and (bn is not None or act is not None):
+            out.append(FusedBNActQuant(bn, act, mods[j]))
+            i = j + 1
+        else:
+            out.append(mods[i])
+            i += 1
+    # second pass over the rewritten list: flatten on codes, banded head pair, residual blocks
+    res, i = [], 0
+    while i < len(out):
+        m = out[i]
+        nxt = out[i + 1] if i + 1 < len(out) else None
+        if (_is_flatten(m) and res and isinstance(res[-1], (FusedLayerQuant, FusedBNActQuant)) and nxt is not None
+                and _is_quant_layer(_unwrap(nxt)) and not _unwrap(nxt)._is_conv and hasattr(_unwrap(nxt), "_set_in_perm")
+                and type(_unwrap(nxt)).__name__ != "LinearXNOR"):
+            src = res[-1]
+            if isinstance(src, FusedLayerQuant) and src.layer._is_conv:
+                res.append(FlattenCodes(m, _unwrap(nxt)))
                 i += 1
-        if len(out) != len(mods):
-            for k in list(module._modules.keys()):
-                del module._modules[k]
-            for k, m in enumerate(out):
-                module.add_module(str(k), m)
+                continue
+        if (_is_quantizer(m) and not isinstance(m, (FusedBNActQuant,)) and nxt is not None
+                and (_is_quant_layer(nxt) or isinstance(nxt, FusedLayerBN)) and not _unwrap(nxt)._is_conv
+                and not (res and isinstance(res[-1], FlattenCodes))):
+            res.append(FusedActLayer(m, nxt))
+            i += 2
+            continue
+        if _is_block(m):
+            nspec = getattr(nxt.q_in, "_qt_spec", None) if (nxt is not None and _is_block(nxt)) else None
+            res.append(FusedBasicBlock(m, nspec))
+            i += 1
+            continue
+        res.append(m)
+        i += 1
+    if len(res) != len(mods) or any(a is not b for a, b in zip(res, mods)):
+        for k in list(module._modules.keys()):
+            del module._modules[k]
+        for k, m in enumerate(res):
+            module.add_module(str(k), m)
     return module
+
+
+def _unwrap(m):
+    return m.layer if isinstance(m, (FusedLayerQuant, FusedLayerBN)) else m
 
 
 class OperandPrefetch(nn.Module):

@@ -19,12 +19,12 @@ class _BinMixin(QuantLayerMixin):
 
     def _make_pack(self, w):
         if self.deterministic:
-            return ops.pack_weight(ops.conv_weight_2d(w.detach()), "sign")
+            return ops.pack_weight(self._w2d(w.detach()), "sign")
         # stochastic binarisation draws new +-1 weights each call; pack the drawn signs
         return self._make_pack_of_sample(self.bin_op.apply(w.detach()))
 
     def _make_pack_of_sample(self, wq):
-        return ops.pack_weight(ops.conv_weight_2d(wq.detach()), "sign")      # sign(+-1) = +-1
+        return ops.pack_weight(self._w2d(wq.detach()), "sign")      # sign(+-1) = +-1
 
     def _weight_op_host(self, w):
         one = torch.ones_like(w)

@@ -83,6 +83,21 @@ class QuantLayerMixin(QLayer):
     _is_conv = False
     _eval_state = None
     _packed_only = None       # (WeightPack, weight shape) installed by checkpoint.load_packed: no fp32 master weights
+    _in_perm = None           # (C, H, W): this Linear reads a channels-last flatten (fusion.FlattenCodes) of a [C, H, W] activation
+
+    def _w2d(self, w):
+        """[out, K] matrix the packers read: conv weights with the channel fastest (the K order of the im2col kernels); a Linear
+        fed by channels-last flattened codes gets its columns permuted from (c, h, w) to (h, w, c) order."""
+        if self._in_perm is not None and w.dim() == 2:
+            C_, H_, W_ = self._in_perm
+            return w.reshape(w.shape[0], C_, H_, W_).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+        return ops.conv_weight_2d(w)
+
+    def _set_in_perm(self, perm):
+        if self._packed_only is not None:
+            raise RuntimeError("packed-only layers cannot be re-ordered")
+        self._in_perm = perm
+        self._eval_state = None
 
     def _wshape(self):
         return self._packed_only[1] if self._packed_only is not None else tuple(self.weight.shape)
@@ -198,7 +213,7 @@ class QuantLayerMixin(QLayer):
                 if st.pack is None and torch.equal(self._weight_op(w), w):
                     st.pack = self._make_pack(w)
         if st.pack is None:
-            st.pack = ops.pack_real_weight(ops.conv_weight_2d(w))
+            st.pack = ops.pack_real_weight(self._w2d(w))
         st.version, st.ptr = self.weight._version, self.weight.data_ptr()
         self._eval_state = st
         return st.pack
@@ -211,22 +226,22 @@ class QuantLayerMixin(QLayer):
                               self.dilation, self.groups)
         return eng.linear(input, pack, self.bias)
 
-    def _forward_requant(self, input, spec):
+    def _forward_requant(self, input, spec, **conv_kw):
         """Inference chain: contraction with the next activation quantizer fused into the epilogue (fusion.FusedLayerQuant)."""
         eng.tagged_input_device(input)
         pack = self._current_pack()
         if self._is_conv:
             return eng.conv2d(input, pack, self.bias, self._wshape(), self.stride, self.padding,
-                              self.dilation, self.groups, requant=spec)
+                              self.dilation, self.groups, requant=spec, **conv_kw)
         return eng.linear(input, pack, self.bias, requant=spec)
 
-    def _forward_affine(self, input, spec):
+    def _forward_affine(self, input, spec, **conv_kw):
         """Inference: contraction with a per-output-channel affine (folded eval-mode BatchNorm) in the epilogue."""
         eng.tagged_input_device(input)
         pack = self._current_pack()
         if self._is_conv:
             return eng.conv2d(input, pack, self.bias, self._wshape(), self.stride, self.padding,
-                              self.dilation, self.groups, affine=spec)
+                              self.dilation, self.groups, affine=spec, **conv_kw)
         return eng.linear(input, pack, self.bias, affine=spec)
 
     def forward(self, input):

@@ -15,11 +15,11 @@ class _DorefaMixin(QuantLayerMixin):
         return self.weight_op.forward(w)
 
     def _make_pack(self, w):
-        w2 = ops.conv_weight_2d(w.detach())
+        w2 = self._w2d(w.detach())
         if 1 <= self.bit_width <= 8:
             return ops.pack_weight(w2, "dorefa", self.bit_width)     # k-bit codes (+ E / 1/n column scale)
         with torch.no_grad():                                        # k == 32 (or 9..16): real-valued operand
-            return ops.pack_real_weight(ops.conv_weight_2d(self.weight_op.forward(w.detach())))
+            return ops.pack_real_weight(self._w2d(self.weight_op.forward(w.detach())))
 
 
     def _weight_op_host(self, w):

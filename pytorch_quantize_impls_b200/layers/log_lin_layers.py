@@ -17,8 +17,8 @@ class _LogLinMixin(QuantLayerMixin):
         with torch.no_grad():
             wq = self.weight_op.forward(w.detach())
         if 1 <= self.bit_width <= 6:      # int8 codes in HBM (8 bits per weight; exact int8 / bf16 operands)
-            return ops.pack_loglin_weight(ops.conv_weight_2d(wq), self._dtype, self.fsr, self.bit_width)
-        return ops.pack_real_weight(ops.conv_weight_2d(wq))
+            return ops.pack_loglin_weight(self._w2d(wq), self._dtype, self.fsr, self.bit_width)
+        return ops.pack_real_weight(self._w2d(wq))
 
     def _weight_op_host(self, w):
         if self._dtype == "lin":                                             # log_lin_connect.py:61-68

@@ -18,14 +18,14 @@ class _TerMixin(QuantLayerMixin):
         return self.ter_op.apply(w)
 
     def _make_pack(self, w):
-        w2 = ops.conv_weight_2d(w.detach())
+        w2 = self._w2d(w.detach())
         if self.deterministic:
             return ops.pack_weight(w2, "ternary")
         # stochastic: the drawn values are already in {-1, 0, 1}; the deterministic packer maps them to themselves
         return self._make_pack_of_sample(self.ter_op.apply(w.detach()))
 
     def _make_pack_of_sample(self, wq):
-        return ops.pack_weight(ops.conv_weight_2d(wq.detach()), "ternary")
+        return ops.pack_weight(self._w2d(wq.detach()), "ternary")
 
     def _weight_op_host(self, w):
         one = torch.ones_like(w)

@@ -16,11 +16,7 @@ class _XnorMixin(QuantLayerMixin):
         eng.tagged_input_device(input)
         if self._packed_only is not None:
             return self._run_kernels(input)
-        pack = None
-        st = self._eval_state
-        if (not self.training and st is not None and st.version == self.weight._version
-                and st.ptr == self.weight.data_ptr()):
-            pack = st.pack
+        pack = None if self.training else self._current_pack()
         op = self.conv_op if self._is_conv else self.lin_op
         return op.apply(input, self.weight, self.bias, pack)
 
@@ -31,28 +27,35 @@ class _XnorMixin(QuantLayerMixin):
         if (not self.training and st is not None and st.version == self.weight._version
                 and st.ptr == self.weight.data_ptr()):
             return st.pack
-        return self._make_pack(self.weight)
+        pack = self._make_pack(self.weight)
+        if not self.training:
+            # eval mode with a stale / missing cache (module moved with .to(), eval() before .cuda(), state_dict loaded):
+            # forward re-applies the op to the stored weights in both modes (reference behaviour), so pack those once
+            st = _EvalState()
+            st.pack, st.version, st.ptr = pack, self.weight._version, self.weight.data_ptr()
+            self._eval_state = st
+        return pack
 
     def train(self, mode=True):
         if self._packed_only is not None:
             return QuantLayerMixin.train(self, mode)
         if self.training == mode:
             return self
-        self.training = mode
         if mode:
             self.weight.data.copy_(self.weight.org.data)
             self._eval_state = None
+            self.training = True
+            return self
+        master = self.weight.data.clone()
+        with torch.no_grad():
+            wq = self._weight_op(self.weight).detach()          # torch arithmetic: works wherever the weights live
+        if not hasattr(self.weight, 'org'):
+            self.weight.org = master
         else:
-            if not hasattr(self.weight, 'org'):
-                self.weight.org = self.weight.data.clone()
-            self.weight.org.data.copy_(self.weight.data)
-            with torch.no_grad():
-                self.weight.data.copy_(self._weight_op(self.weight).detach())
-            # forward re-applies the op to the swapped weights (reference behaviour); pack those once
-            st = _EvalState()
-            st.pack = self._make_pack(self.weight)
-            st.version, st.ptr = self.weight._version, self.weight.data_ptr()
-            self._eval_state = st
+            self.weight.org.data = master
+        self.weight.data.copy_(wq)
+        self._eval_state = None                                  # packed on the first eval-mode forward (_current_pack)
+        self.training = False
         return self
 
 

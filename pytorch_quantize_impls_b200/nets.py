@@ -69,10 +69,12 @@ def alexnet_dorefa(bit_width=4, act_bits=None, num_classes=10, coef=3, lib=None)
         lib.DorefaConv2d(192 * coef, 384 * coef, kernel_size=3, padding=1, bit_width=k), *act(384 * coef),
         lib.DorefaConv2d(384 * coef, 256 * coef, kernel_size=3, padding=1, bit_width=k), *act(256 * coef),
         lib.DorefaConv2d(256 * coef, 256, kernel_size=3, padding=1, bit_width=k),
-        nn.MaxPool2d(kernel_size=3, stride=2), nn.BatchNorm2d(256), nn.Hardtanh(0.0, 1.0),
+        nn.MaxPool2d(kernel_size=3, stride=2), *act(256),
     ]
+    # the quantizer sits in front of Flatten (elementwise: the same values either way), so that the conv chain hands its
+    # channels-last codes straight to the classifier (fusion.FlattenCodes)
     classifier = [
-        Flatten(), lib.nnDorefaQuant(a),
+        Flatten(),
         lib.LinearDorefa(256 * 6 * 6, 4096, bit_width=k), *act(4096, False),
         lib.LinearDorefa(4096, 4096, bit_width=k), *act(4096, False),
         lib.LinearDorefa(4096, num_classes, bit_width=k),
@@ -115,8 +117,7 @@ class ResNetTer(nn.Module):
         self.in_planes = 64
         # ImageNet stem (7x7 s2 + max-pool): the reference's CIFAR stem at 224x224 would cost 27 GMAC/img
         self.stem = nn.Sequential(lib.TerConv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False), nn.BatchNorm2d(64),
-                                  nn.Hardtanh(0.0, 1.0))
-        self.pool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+                                  nn.Hardtanh(0.0, 1.0), nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
         cfg = [(64, 1), (128, 2), (256, 2), (512, 2)]
         layers = []
         for (planes, stride), n in zip(cfg, num_blocks):
@@ -128,8 +129,7 @@ class ResNetTer(nn.Module):
         self.linear = nn.Linear(512, num_classes)
 
     def forward(self, x):
-        out = self.pool(self.stem(x))
-        out = self.layers(out)
+        out = self.layers(self.stem(x))
         return self.linear(self.avg(out).flatten(1))
 
 
@@ -156,8 +156,8 @@ def vgg_dorefa(bit_width=8, num_classes=10, lib=None):
         return m
 
     features = [*block(3, 64, False), *block(64, 64, True), *block(64, 128, False), *block(128, 128, True),
-                *block(128, 256, False), *block(256, 256, True, quant=False)]
-    classifier = [Flatten(), lib.nnDorefaQuant(k),
+                *block(128, 256, False), *block(256, 256, True)]
+    classifier = [Flatten(),                  # quantizer in front of Flatten: see alexnet_dorefa
                   lib.LinearDorefa(4096, 1024, bit_width=k), nn.BatchNorm1d(1024), nn.Hardtanh(0.0, 1.0), lib.nnDorefaQuant(k),
                   lib.LinearDorefa(1024, 1024, bit_width=k), nn.BatchNorm1d(1024), nn.Hardtanh(0.0, 1.0), lib.nnDorefaQuant(k),
                   lib.LinearDorefa(1024, num_classes, bit_width=k)]

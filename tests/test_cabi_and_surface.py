@@ -129,3 +129,36 @@ def test_ctypes_mirrors_have_the_c_struct_sizes():
     for name in ("QtActQuant", "QtWeightPack", "QtWeightExpand", "QtIm2col", "QtRequant", "QtEpilogue", "QtConvGeom"):
         assert lib.qt_sizeof(name.encode()) == ctypes.sizeof(getattr(L, name)), name
     assert lib.qt_sizeof(b"nope") == -1
+
+
+@pytest.mark.parametrize("mk", [
+    lambda Q: Q.layers.LinearBin(8, 4), lambda Q: Q.layers.LinearBin(8, 4, deterministic=False),
+    lambda Q: Q.layers.LinearTer(8, 4), lambda Q: Q.layers.TerConv2d(2, 4, 3, deterministic=False),
+    lambda Q: Q.layers.LinearDorefa(8, 4, bit_width=3), lambda Q: Q.layers.DorefaConv2d(2, 4, 3, bit_width=1),
+    lambda Q: Q.layers.LinearQuant(8, 4, dtype="log"), lambda Q: Q.layers.LinearQuant(8, 4, dtype="lin"),
+    lambda Q: Q.layers.LinearXNOR(8, 4)])
+def test_eval_swap_before_moving_to_the_gpu(mk):
+    """`model.eval(); model.cuda()` is a common drop-in order and the reference supports eval() on CPU weights
+    (binary_layers.py:30-40): the swap happens with host arithmetic, packing waits for the first CUDA forward, and a failed
+    swap never leaves the layer half-switched."""
+    import pytorch_quantize_impls_b200 as Q
+    import quanttorch_oracle as O
+    torch.manual_seed(5)
+    lay = mk(Q)
+    w0 = lay.weight.data.clone()
+    lay.eval()
+    assert lay.training is False and torch.equal(lay.weight.org, w0)
+    wq = lay.weight.data
+    name = type(lay).__name__
+    if getattr(lay, "deterministic", True):
+        ref = {"LinearBin": lambda: O.binary_det(w0), "LinearTer": lambda: O.ternary_det(w0),
+               "LinearDorefa": lambda: O.dorefa_weight(w0, 3), "DorefaConv2d": lambda: O.dorefa_weight(w0, 1),
+               "LinearQuant": lambda: O.loglin_weight(w0, lay._dtype, lay.fsr, lay.bit_width),
+               "LinearXNOR": lambda: O.xnor_weight(w0)}[name]()
+        assert torch.equal(wq, ref)
+    else:
+        assert set(wq.unique().tolist()) <= {-1.0, 0.0, 1.0}
+    lay.eval()                                   # idempotent
+    assert torch.equal(lay.weight.data, wq)
+    lay.train()
+    assert lay.training is True and torch.equal(lay.weight.data, w0)

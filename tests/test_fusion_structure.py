@@ -27,18 +27,22 @@ def test_linear_chain_patterns():
     assert a._consumer_needs_i8 is False and b._consumer_needs_i8 is True
 
 
-def test_pool_between_layer_and_batchnorm_keeps_the_one_pass_kernel():
+def test_pool_between_layer_and_quantizer_runs_on_codes():
     net = nn.Sequential(L.DorefaConv2d(3, 32, 3, bit_width=4), nn.MaxPool2d(2), nn.BatchNorm2d(32), nn.Hardtanh(0., 1.),
                         F.nnDorefaQuant(4), L.DorefaConv2d(32, 64, 3, bit_width=4), nn.BatchNorm2d(64), nn.Hardtanh(0., 1.),
                         F.nnDorefaQuant(4), L.DorefaConv2d(64, 64, 3, groups=2, bit_width=4), nn.BatchNorm2d(64))
     fused = Q.fuse_inference(net)
-    assert names(fused) == ["DorefaConv2d", "MaxPool2d", "FusedBNActQuant", "FusedLayerQuant", "DorefaConv2d", "BatchNorm2d"]
+    # conv -> pool -> BN -> clamp -> quantizer: the quantizer runs in the conv epilogue, the pool on the codes
+    assert names(fused) == ["FusedLayerPoolQuant", "FusedLayerQuant", "DorefaConv2d", "BatchNorm2d"]
+    assert isinstance(fused[0].pool, nn.MaxPool2d) and isinstance(fused[0].bn, nn.BatchNorm2d)
 
 
 def test_resnet_blocks_and_unknown_modules_are_left_alone():
     net = Q.fuse_inference(nets.resnet18_ternary())
-    assert names(net.stem) == ["FusedLayerBN"] and isinstance(net.stem[0].act, nn.Hardtanh)
-    blk = net.layers[2]                       # first down-sampling block
+    assert names(net.stem) == ["FusedConvPool"] and isinstance(net.stem[0].inner.act, nn.Hardtanh)
+    assert set(names(net.layers)) == {"FusedBasicBlock"}
+    assert net.layers[0]._next == ("dorefa", 8) and net.layers[-1]._next is None
+    blk = net.layers[2].block                 # first down-sampling block
     assert names(blk.branch1) == ["FusedLayerQuant"] and names(blk.branch2) == ["FusedLayerBN"]
     assert names(blk.shortcut) == ["FusedLayerBN"] and isinstance(net.linear, nn.Linear)
     plain = nn.Sequential(nn.Linear(4, 4), nn.BatchNorm1d(4), nn.ReLU())
@@ -53,3 +57,14 @@ def test_fused_modules_are_the_plain_composition_in_training_mode():
     assert names(net) == ["FusedLayerQuant"]
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         net(torch.randn(4, 8))
+
+
+def test_network_configs_fuse_into_code_chains():
+    """BASELINE configs 3 and 5: every conv block folds its BatchNorm + clamp + quantizer (and pool) into the conv, the classifier
+    reads the channels-last flatten of the codes, no stand-alone BatchNorm / pool / quantizer is left."""
+    for net in (nets.alexnet_dorefa(bit_width=4), nets.vgg_dorefa(bit_width=8)):
+        fused = names(Q.fuse_inference(net))
+        assert not ({"BatchNorm2d", "BatchNorm1d", "MaxPool2d", "Hardtanh", "fronteur", "Flatten"} & set(fused)), fused
+        assert fused.count("FlattenCodes") == 1 and fused[-1] == "LinearDorefa"
+    head = Q.fuse_inference(nn.Sequential(F.BinaryConnect(), L.LinearBin(4096, 4096)))
+    assert names(head) == ["FusedActLayer"]
