@@ -1,8 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- quantized-GEMM throughput of the QuantTorch hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+--config (default xnor_mlp = BASELINE configs[1], the one the driver runs):
+    xnor_mlp        XnorNet MLP 4096-4096-4096-1000, batch 8192 per GPU          metric quantized_gemm_gops
+    alexnet_w4a4    DorefaNet AlexNet W4/A4 @224, batch 256 per GPU (configs[2])  metric images_per_sec
+    resnet18_t2a8   TernerNet ResNet-18 W2/A8 @224, batch 512 per GPU (configs[3]: 2048 over 4 GPUs)
+    vgg_w8a8        DorefaNet VGG W8/A8 @32, batch 512 per GPU (configs[4]: 4096 over 8 GPUs)
 
 Workload (BASELINE.json configs[1]): XnorNet 3-layer MLP 4096-4096-4096-1000, 1-bit weights / 1-bit activations,
 batch 8192 per GPU, synthetic N(0,1) inputs (seed 1234), random-init weights.  One "step" = one forward pass of
@@ -39,7 +45,10 @@ WORKLOAD = "XnorNet 3-layer MLP 4096-4096-4096-1000, 1-bit W / 1-bit A, batch 81
 
 
 def peaks():
-    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written: HBM copy, cuBLAS bf16 burst / sustained) and
+    profiles/peaks_r2.json (measured on this pool by profiles/measure_peaks.py: int8 / fp4 tensor rates)."""
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback",
+         "int8_tops": None, "fp4_tops": None, "int8_src": None}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             m = json.load(f)
@@ -47,7 +56,23 @@ def peaks():
         p["src"] = "measured"
     except Exception:
         pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "peaks_r2.json")) as f:
+            m = json.load(f)
+        p["int8_tops"] = m.get("int8_tops_burst")
+        p["fp4_tops"] = m.get("fp4_tops_burst")
+        p["int8_src"] = "profiles/peaks_r2.json (%s)" % m.get("int8_how", "measured")
+    except Exception:
+        pass
     return p
+
+
+def tensor_peak(pk, timed_region_s):
+    """bf16 denominator: the burst figure for a timed region shorter than a second (clocks have not settled under the power
+    cap yet), the sustained one for seconds-long regions."""
+    if timed_region_s < 1.0:
+        return pk["bf16_tflops"], "MEASURED_PEAKS.json bf16_tflops (burst: timed region %.3f s)" % timed_region_s
+    return pk["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (timed region %.1f s)" % timed_region_s
 
 
 # --------------------------------------------------------------------------------------------
@@ -59,10 +84,8 @@ def cpu_reference_gops(batch, reps, warmup=1, seed=1234):
     import quanttorch_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    g = torch.Generator().manual_seed(seed)
-    ws = [torch.empty(DIMS[i + 1], DIMS[i]).uniform_(-DIMS[i] ** -0.5, DIMS[i] ** -0.5, generator=g) for i in range(3)]
-    bs = [torch.empty(DIMS[i + 1]).uniform_(-1, 1, generator=g) for i in range(3)]
-    x = torch.randn(batch, DIMS[0], generator=g)
+    ws, bs = xnor_weights(torch, seed)
+    x = xnor_inputs(torch)[0][:batch]
     times = []
     with torch.no_grad():
         for i in range(warmup + reps):
@@ -101,23 +124,55 @@ def cpu_linearbin_gops(batch=1024, reps=3, seed=99):
                       % (batch, reps)}
 
 
+def xnor_inputs(torch, rank=0, nbuf=1, seed=1234):
+    """The synthetic batch(es) both arms use: N(0,1) fp32 [8192, 4096], CPU generator seeded per rank."""
+    g = torch.Generator().manual_seed(seed + rank)
+    return [torch.randn(BATCH, DIMS[0], generator=g) for _ in range(nbuf)]
+
+
+def xnor_weights(torch, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    ws, bs = [], []
+    for i in range(3):
+        ws.append(torch.empty(DIMS[i + 1], DIMS[i]).uniform_(-DIMS[i] ** -0.5, DIMS[i] ** -0.5, generator=g))
+        bs.append(torch.empty(DIMS[i + 1]).uniform_(-1, 1, generator=g))
+    return ws, bs
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path (fake-quant ops + dense fp32 F.linear: the oracle port, which is
+    checked bit for bit against the live reference in tests/) on all host threads, on the SAME workload as our arm: the full
+    8192-row batch per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 1024
-    r = cpu_reference_gops(sample_b, reps=max(args.steps, 1), warmup=max(args.warmup, 1))
-    ms = 1e3 * sum(r["times"]) / len(r["times"])
-    sample = "oracle port of the reference CPU path, batch %d rows of the same MLP per step, %d torch threads" % (
-        sample_b, r["cores"])
+    if args.config != "xnor_mlp":
+        return run_reference_cnn(args)
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import quanttorch_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ws, bs = xnor_weights(torch)
+    x = xnor_inputs(torch)[0]
+    times = []
+    with torch.no_grad():
+        for i in range(max(args.warmup, 1) + max(args.steps, 1)):
+            t0 = time.perf_counter()
+            O.xnor_mlp_forward(x, ws, bs)
+            if i >= max(args.warmup, 1):
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    gops = 2.0 * BATCH * MACS_PER_ROW / (ms * 1e-3) / 1e9
+    sample = "oracle port of the reference CPU path (fake-quant + fp32 F.linear), the full %d-row batch per step, %d torch threads" % (
+        BATCH, cores)
     line = {
-        "impl": "reference", "metric": "quantized_gemm_gops", "value": round(r["gops_mean"], 2), "unit": "GOPS",
+        "impl": "reference", "metric": "quantized_gemm_gops", "value": round(gops, 2), "unit": "GOPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_batch": sample_b},
-        "cpu_baseline": {"value": round(r["gops_mean"], 2), "unit": "GOPS", "cores": r["cores"], "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": round(r["gops_mean"], 2), "unit": "GOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": round(gops, 2), "unit": "GOPS", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(gops, 2), "unit": "GOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -221,15 +276,12 @@ class gpu_local_numa:
 # our arm
 # --------------------------------------------------------------------------------------------
 def build_xnor_mlp(Q, torch, dev, seed=1234):
-    g = torch.Generator().manual_seed(seed)
-    lays = []
+    ws, bs = xnor_weights(torch, seed)
+    mods = []
     for i in range(3):
         l = Q.layers.LinearXNOR(DIMS[i], DIMS[i + 1])
-        l.weight.data.uniform_(-DIMS[i] ** -0.5, DIMS[i] ** -0.5, generator=g)
-        l.bias.data.uniform_(-1, 1, generator=g)
-        lays.append(l)
-    mods = []
-    for l in lays:
+        l.weight.data.copy_(ws[i])
+        l.bias.data.copy_(bs[i])
         mods += [Q.functions.nnQuantXnor(1), l]
     net = torch.nn.Sequential(*mods).to(dev)
     net.eval()          # inference: weights packed once (2 bit planes + alpha[k]) at the train(False) swap
@@ -290,10 +342,9 @@ def run_ours(args):
     if os.environ.get("QTB200_BENCH_PREFETCH", "1") == "1":
         # the three weight expansions of a step run on a side stream beside the input quantizer (fusion.OperandPrefetch)
         net = Q.prefetch_operands(net)
-    g = torch.Generator().manual_seed(1234 + rank)
     NBUF = 3   # rotate over 3 x 134 MB inputs (> 126 MB L2) so no step finds its input in L2
     with gpu_local_numa(torch, local):          # pinned host buffers on the GPU's NUMA node
-        x_host = [torch.randn(BATCH, DIMS[0], generator=g).pin_memory() for _ in range(NBUF)]
+        x_host = [t.pin_memory() for t in xnor_inputs(torch, rank, NBUF)]
     x_dev = [t.to(dev) for t in x_host]
     gathered = torch.empty(world * BATCH, DIMS[-1], device=dev) if world > 1 else None
     from pytorch_quantize_impls_b200.sharding import PipelinedGather
@@ -442,10 +493,14 @@ def run_ours(args):
                 pgather.submit(y)
         ms_default = timed(step_default)
         ms_code_only = timed(step_code_only)
-        # parity inside the run: fused chain vs the one-kernel-per-module graph on the same batch
+        # parity inside the run: fused chain vs the one-kernel-per-module graph on the same batch, and the logits of the mode
+        # that was timed (fused chain, code-only activations, graph replay) vs the CPU oracle on the first rows of the batch
         y_f = step(0)
         y_p = net_plain(x_dev[0])
         chain_rel = float((y_f - y_p).abs().max() / y_p.abs().max())
+        parity = None
+        if rank == 0:
+            parity = oracle_parity(torch, x_host[0], y_f, rows=256)
         gather_ok = None
         if world > 1:
             # the pipelined gather against a plain NCCL all_gather of the same logits
@@ -464,6 +519,10 @@ def run_ours(args):
                 extra["linearbin_4096x4096_cpu_reference"] = cpu_linearbin_gops()
             except Exception as err:            # a reporting extra must never cost the bench line
                 extra["linearbin_4096x4096_cpu_reference"] = {"error": str(err)}
+            try:
+                extra["reference_on_b200"] = reference_on_b200(torch, dev, x_dev)
+            except Exception as err:
+                extra["reference_on_b200"] = {"error": str(err)}
             extra["xnor_mlp_default_mode_ms_per_step"] = round(ms_default, 4)
             extra["xnor_mlp_code_only_unfused_ms_per_step"] = round(ms_code_only, 4)
             extra["xnor_mlp_fused_vs_unfused_max_rel_diff"] = chain_rel
@@ -485,13 +544,13 @@ def run_ours(args):
     avg_ms = sum(durs) / len(durs)
     flops = 2.0 * M * N * K                         # algorithmic: the logical 1-bit contraction, once
     achieved = flops / (avg_ms * 1e-3) / 1e12
-    peak = pk["bf16_tflops_sustained"]
+    peak, peak_src = tensor_peak(pk, ms_total * 1e-3)
     # graph mode: one (last-replay) sample per GEMM and graph; eager mode: one sample per GEMM and step
     gemm_ms_per_step = sum(sum(v) for v in summ.values()) / (NBUF if graph_mode else args.steps)
     roofline = {"bound": "tensor", "kernel": "tc_gemm2_kernel<BN=256, kind::f16 (fp16 operands, fp32 accumulate), 6 stages>: CTA pairs (tcgen05 cta_group::2, "
                           "256x256 tiles), requant epilogue, M=%d N=%d K=%d" % (M, N, K),
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk["src"] == "measured" else "fallback",
+                "peak_source": peak_src if pk["src"] == "measured" else "fallback",
                 "avg_launch_ms": round(avg_ms, 4), "gemm_share_of_step": round(gemm_ms_per_step / ms_step, 3),
                 "timing": ("CUDA events recorded as external event nodes inside the captured step graphs; mean over the last replay of "
                            "each of the %d graphs within the timed region" % NBUF) if graph_mode else
@@ -502,10 +561,10 @@ def run_ours(args):
                 "traffic": 204.3e6, "traffic_unit": "bytes per launch (ncu, profiles/r1i_ncu_full_summary.json)",
                 "algorithmic_bytes": float(2 * M * K + 2 * N * K + 2 * M * N + 4 * N)}
 
-    cb = cpu_reference_gops(2048, reps=3, warmup=1)
-    cpu_baseline = {"value": round(cb["gops_best"], 2), "unit": "GOPS", "cores": cb["cores"], "kind": "port",
-                    "sample": "oracle port (torch CPU, %d threads) of the same MLP forward on a 2048-row batch, best of 3"
-                              % cb["cores"]}
+    cb = cpu_reference_gops(BATCH, reps=3, warmup=1)
+    cpu_baseline = {"value": round(cb["gops_mean"], 2), "unit": "GOPS", "cores": cb["cores"], "kind": "port",
+                    "sample": "oracle port (torch CPU, %d threads) of the same MLP forward on the full %d-row batch, mean of 3 "
+                              "(the --impl reference arm runs the same thing)" % (cb["cores"], BATCH)}
     line = {
         "metric": "quantized_gemm_gops", "value": round(value, 1), "unit": "GOPS", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
@@ -527,12 +586,348 @@ def run_ours(args):
                                   "nccl": "one NCCL all_gather of the fp32 logits per step on a communication stream",
                                   "sync": "one NCCL all_gather of the fp32 logits per step on the compute stream"}[pgather.mode]
                    if world > 1 else "none"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
         "e2e": {"value": round(e2e, 1), "unit": "GOPS", "ms_per_step": round(ms_e2e, 4),
                 "api": "pipeline.HostPipeline(net).run(pinned inputs, pinned outputs): H2D / kernels / D2H on 3 streams",
                 "ms_per_step_single_stream": round(ms_e2e_serial, 4),
                 "h2d_bytes_per_step": BATCH * DIMS[0] * 4, "d2h_bytes_per_step": BATCH * DIMS[-1] * 4},
         "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def oracle_parity(torch, x_host0, y_dev, rows=256):
+    """Logits of the timed mode against the CPU oracle (the reference's fake-quant + fp32 path) on the first `rows` rows of
+    the batch (every row is independent: the XnorNet activation scale is a per-row mean)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import quanttorch_oracle as O
+    ws, bs = xnor_weights(torch)
+    with torch.no_grad():
+        ref = O.xnor_mlp_forward(x_host0[:rows].clone(), ws, bs)
+    got = y_dev[:rows].float().cpu()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    return {"rel_err_vs_oracle": err, "tolerance": 1e-3, "ok": err <= 1e-3, "rows": rows,
+            "what": "max|y - y_ref| / max|y_ref| of the fused / code-only / graph-replayed logits vs oracle/quanttorch_oracle.py "
+                    "(xnor_mlp_forward) on the first %d rows of input buffer 0" % rows,
+            "argmax_agreement": float((got.argmax(1) == ref.argmax(1)).float().mean())}
+
+
+def reference_on_b200(torch, dev, x_dev, steps=5):
+    """the reference's own code path moved to the B200 -- fake-quant torch ops + dense fp32 F.linear on cuBLAS
+    (the oracle port executed on CUDA tensors; TF32 off, the torch default for matmul) -- as the on-box GPU comparator."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import quanttorch_oracle as O
+    ws, bs = xnor_weights(torch)
+    ws, bs = [w.to(dev) for w in ws], [b.to(dev) for b in bs]
+    with torch.no_grad():
+        for _ in range(2):
+            O.xnor_mlp_forward(x_dev[0], ws, bs)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            O.xnor_mlp_forward(x_dev[i % len(x_dev)], ws, bs)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": round(ms, 3), "gops": round(2.0 * BATCH * MACS_PER_ROW / ms / 1e6, 1),
+            "what": "oracle port of the reference modules on cuda:0 (ATen elementwise kernels + cuBLAS fp32 sgemm), same batch"}
+
+
+# --------------------------------------------------------------------------------------------
+# network configs (BASELINE configs[2..4])
+# --------------------------------------------------------------------------------------------
+CNN = {
+    "alexnet_w4a4": dict(builder="alexnet_dorefa", kw=dict(bit_width=4), shape=(3, 224, 224), batch=256, gmac=4.935, cpu_batch=8,
+                         bits="4-bit W / 4-bit A", lanes="int8 lanes on tcgen05 kind::i8",
+                         workload="DorefaNet AlexNet (models/Alexnet topology, widths x3) 4-bit W / 4-bit A, 224x224 synthetic, "
+                                  "batch 256 per GPU (BASELINE configs[2])"),
+    "resnet18_t2a8": dict(builder="resnet18_ternary", kw=dict(act_bits=8), shape=(3, 224, 224), batch=512, gmac=1.814, cpu_batch=8,
+                          bits="2-bit (ternary) W / 8-bit A", lanes="int8 x uint8 on tcgen05 kind::i8",
+                          workload="TernerNet ResNet-18 (models/Resnet block plan, ImageNet stem) 2-bit W / 8-bit A, 224x224, "
+                                   "batch 512 per GPU = 2048 sharded over 4 GPUs (BASELINE configs[3])"),
+    "vgg_w8a8": dict(builder="vgg_dorefa", kw=dict(bit_width=8), shape=(3, 32, 32), batch=512, gmac=0.158, cpu_batch=64,
+                     bits="8-bit W / 8-bit A", lanes="uint8 x uint8 on tcgen05 kind::i8, zero point in the epilogue",
+                     workload="DorefaNet VGG (models/VGG/VGG_LinQuant topology, 32x32) 8-bit W / 8-bit A, batch 512 per GPU = 4096 "
+                              "sharded over 8 GPUs + logits all-gather (BASELINE configs[4])"),
+}
+
+
+def cnn_twin_and_state(torch, cfg, calib_batch=4):
+    """CPU twin of the network on the oracle (same builder, oracle-backed layers) with BatchNorm statistics calibrated on a
+    few synthetic images so that activations spread over the quantizer range; its state_dict is what the GPU net loads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib
+    from pytorch_quantize_impls_b200 import nets
+    torch.manual_seed(1234)
+    twin = getattr(nets, cfg["builder"])(lib=oracle_lib, **cfg["kw"]).eval()
+    bns = [m for m in twin.modules() if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d))]
+    for m in bns:
+        m.momentum = 1.0
+        m.train()
+    g = torch.Generator().manual_seed(77)
+    with torch.no_grad():
+        twin(torch.rand(calib_batch, *cfg["shape"], generator=g))
+    for m in bns:
+        m.eval()
+        m.bias.data.fill_(0.5)
+        m.weight.data.fill_(0.25)
+    return twin
+
+
+def cnn_inputs(torch, cfg, n, rank=0, seed=4321):
+    g = torch.Generator().manual_seed(seed + rank)
+    return torch.rand(n, *cfg["shape"], generator=g)
+
+
+def run_reference_cnn(args):
+    import torch
+    cfg = CNN[args.config]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    twin = cnn_twin_and_state(torch, cfg)
+    nb = cfg["cpu_batch"]
+    x = cnn_inputs(torch, cfg, nb)
+    times = []
+    with torch.no_grad():
+        for i in range(max(args.warmup, 1) + max(args.steps, 1)):
+            t0 = time.perf_counter()
+            twin(x)
+            if i >= max(args.warmup, 1):
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    ips = nb / (ms * 1e-3)
+    sample = "oracle-backed twin of the same network (fake-quant + fp32 F.conv2d / F.linear), %d images per step, %d torch threads" % (
+        nb, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "images_per_sec", "value": round(ips, 2), "unit": "img/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": cfg["workload"], "sample_batch": nb},
+        "cpu_baseline": {"value": round(ips, 2), "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(ips, 2), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+class LaunchTimer:
+    """CUDA-event timing of every tensor-core contraction launch of one eager forward (current stream)."""
+    NAMES = {"conv_i8": lambda a: (a[0].shape[0] * a[2][9] * a[2][10], a[7], a[2][0] * a[2][1] * (a[0].shape[3] // a[2][8])),
+             "conv_bf16": lambda a: (a[1][0] * a[1][14] * a[1][15], a[4], a[1][4] * a[1][5] * a[1][1]),
+             "gemm_i8": lambda a: (a[6], a[7], a[8]), "gemm_f4": lambda a: (a[4], a[5], a[6]),
+             "gemm_f16": lambda a: (a[7], a[8], a[9])}
+
+    def __init__(self, torch, ops):
+        self.torch, self.ops, self.ev, self.orig = torch, ops, [], {}
+
+    def __enter__(self):
+        for name, mnk in self.NAMES.items():
+            fn = getattr(self.ops, name)
+            self.orig[name] = fn
+
+            def inner(*a, _fn=fn, _name=name, _mnk=mnk, **k):
+                s, e = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+                s.record()
+                r = _fn(*a, **k)
+                e.record()
+                self.ev.append((_name,) + tuple(int(v) for v in _mnk(a)) + (s, e))
+                return r
+            setattr(self.ops, name, inner)
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self.orig.items():
+            setattr(self.ops, name, fn)
+        return False
+
+    def summary(self):
+        self.torch.cuda.synchronize()
+        out = {}
+        for name, M, N, K, s, e in self.ev:
+            out.setdefault((name, M, N, K), []).append(s.elapsed_time(e))
+        return out
+
+
+def run_cnn(args):
+    import contextlib
+    import torch
+    import torch.distributed as dist
+    cfg = CNN[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import pytorch_quantize_impls_b200 as Q
+    from pytorch_quantize_impls_b200 import _lib, _ops, nets, sharding
+    from pytorch_quantize_impls_b200.pipeline import GraphedModule, HostPipeline
+    pk = peaks()
+    B = cfg["batch"]                     # per GPU (weak scaling): the global batch is world * B
+    twin = cnn_twin_and_state(torch, cfg)
+    torch.manual_seed(1234)
+    net = getattr(nets, cfg["builder"])(**cfg["kw"])
+    net.load_state_dict(twin.state_dict())
+    net = Q.fuse_inference(net.to(dev).eval())
+    Q.set_strict("off")                  # inputs are U[0,1) images and every hidden quantizer sits behind a Hardtanh(0, 1)
+
+    def fwd(x):
+        with Q.code_only_activations():
+            return net(x)
+
+    NBUF = 2
+    with gpu_local_numa(torch, local):
+        x_host = [cnn_inputs(torch, cfg, B, rank * 16 + i).pin_memory() for i in range(NBUF)]
+    x_dev = [t.to(dev) for t in x_host]
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2
+    with torch.no_grad():
+        graphs = [GraphedModule(fwd, xb) for xb in x_dev]
+        _lib.launch_count(reset=True)
+        fwd(x_dev[0])
+        launches_per_forward = _lib.launch_count(reset=True)
+
+        def step(i):
+            y = graphs[i % NBUF]()
+            return sharding.gather_logits(y, batch=world * B) if world > 1 else y
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        evs = []
+        for i in range(args.steps):
+            flush.zero_()                                   # L2 flush between timed iterations (outside the event pairs)
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            step(i)
+            e_.record()
+            evs.append((s_, e_))
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_step = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+        t = torch.tensor([ms_step], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+
+        # end to end: pinned host images in, logits back to pinned host memory, every step
+        with gpu_local_numa(torch, local):
+            outs_host = [torch.empty(B, 10).pin_memory() for _ in range(2)]
+        pipe = HostPipeline(fwd, depth=2, graphs=True)
+        ins = [x_host[i % NBUF] for i in range(args.steps)]
+        outs = [outs_host[i % 2] for i in range(args.steps)]
+        pipe.run(ins[:2], outs[:2])
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        pipe.run(ins, outs)
+        e3.record()
+        barrier()
+        t = torch.tensor([e2.elapsed_time(e3) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+
+        # per-launch times of the tensor-core contractions of one eager forward -> dominant kernel
+        timer = LaunchTimer(torch, _ops)
+        fwd(x_dev[0])
+        with timer:
+            y_eager = fwd(x_dev[0])
+        summ = timer.summary()
+
+        # gathered logits of the sharded run == the same global batch on ONE GPU (bit for bit)
+        gathered_equal = None
+        if world > 1:
+            y_loc = graphs[0]().clone()
+            gathered = sharding.gather_logits(y_loc, batch=world * B)
+            ok = 1
+            if rank == 0:
+                x_full = torch.cat([cnn_inputs(torch, cfg, B, r * 16).to(dev) for r in range(world)], 0)
+                ok = 1 if torch.equal(fwd(x_full), gathered) else 0
+            okt = torch.tensor([ok], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            gathered_equal = bool(okt.item())
+        graph_equals_eager = bool(torch.equal(graphs[0](), y_eager))
+        y0 = graphs[0]().float().cpu()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # parity in the same run: the oracle twin on the first images of buffer 0
+    nb = min(cfg["cpu_batch"], B)
+    with torch.no_grad():
+        ref = twin(x_host[0][:nb].clone())
+    got = y0[:nb]
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+    rel = float((got - ref).abs().max() / ref.abs().max())
+    parity = {"cosine_vs_oracle": cos, "rel_err_vs_oracle": rel, "argmax_agreement": float((got.argmax(1) == ref.argmax(1)).float().mean()),
+              "images": nb, "graph_replay_equals_eager": graph_equals_eager,
+              "what": "logits of the timed mode (fuse_inference + code-only + graph replay) vs the oracle-backed CPU twin with the same "
+                      "state_dict.  End to end a deep k-bit net is not a 1e-3 object (a pre-activation on a rounding boundary flips "
+                      "a code and the flips cascade -- the reference's own CUDA path diverges from its CPU path the same way); the "
+                      "1e-3 / bit-exact statements are per layer, teacher-forced: tests/test_gpu_models.py, test_gpu_convchain.py"}
+    # cpu baseline (bounded sample)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    xs = x_host[0][:nb].clone()
+    with torch.no_grad():
+        twin(xs)
+        t0 = time.perf_counter()
+        twin(xs)
+        dt = time.perf_counter() - t0
+    cpu_baseline = {"value": round(nb / dt, 2), "unit": "img/s", "cores": cores, "kind": "port",
+                    "sample": "oracle-backed twin (fake-quant + fp32 F.conv2d / F.linear) on %d images of the same batch, second of two runs" % nb}
+    # roofline of the dominant tensor-core kernel (largest total time among the contraction shapes of one forward)
+    tot = {k: sum(v) for k, v in summ.items()}
+    all_ms = sum(tot.values())
+    (kname, M, N, K), dom_ms = max(tot.items(), key=lambda kv: kv[1])
+    n_launch = len(summ[(kname, M, N, K)])
+    avg_ms = dom_ms / n_launch
+    achieved = 2.0 * M * N * K / (avg_ms * 1e-3) / 1e12
+    if kname in ("conv_bf16", "gemm_f16"):
+        peak, peak_src, unit = pk["bf16_tflops"], "MEASURED_PEAKS.json bf16_tflops (burst)", "TFLOP/s"
+    elif kname == "gemm_f4":
+        peak, peak_src, unit = pk["fp4_tops"] or 9000.0, pk["int8_src"] or "nominal 9 PFLOP/s dense fp4 (no measured file)", "TOP/s"
+    else:
+        peak, peak_src, unit = pk["int8_tops"] or 4500.0, pk["int8_src"] or "nominal 4.5 POP/s dense int8 (no measured file)", "TOP/s"
+    qops = 2.0 * cfg["gmac"] * 1e9 * B * world
+    roofline = {"bound": "tensor", "kernel": "%s M=%d N=%d K=%d (%d launches per forward; tc_gemm_kernel implicit GEMM / GEMM, %s)"
+                          % (kname, M, N, K, n_launch, cfg["lanes"]),
+                "achieved": round(achieved, 1), "peak": peak, "unit": unit, "frac": round(achieved / peak, 4), "peak_source": peak_src,
+                "avg_launch_ms": round(avg_ms, 4), "timing": "CUDA events around every contraction launch of one eager forward",
+                "tensor_kernels_share_of_step": round(all_ms / ms_step, 3) if world == 1 else None,
+                "network_level_tensor_rate": {"value": round(qops / world / (ms_step * 1e-3) / 1e12, 1), "unit": "TOP/s per GPU",
+                                              "frac_of_peak": round(qops / world / (ms_step * 1e-3) / 1e12 / (pk["int8_tops"] or 4500.0), 4)},
+                "traffic": None, "algorithmic_bytes": None}
+    ips = B * world / (ms_step * 1e-3)
+    line = {
+        "metric": "images_per_sec", "value": round(ips, 1), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int8" if "dorefa" in cfg["builder"] or "resnet" in cfg["builder"] else "f16", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "global_batch": B * world, "bits": cfg["bits"],
+                   "mode": "eval, weights pre-packed to their k-bit HBM format; fuse_inference + code_only_activations(): BatchNorm, clamp, "
+                           "quantizer (and the residual add) run in the conv epilogues, pools on 8-bit codes, the first conv as an "
+                           "implicit GEMM on bf16 plane pixels; one CUDA-graph replay per step",
+                   "l2": "256 MB buffer zeroed between timed steps (outside the per-step CUDA-event pairs); inputs rotate over 2 buffers",
+                   "quantized_gops": round(qops / (ms_step * 1e-3) / 1e9, 1),
+                   "collective": "one NCCL all-gather of the fp32 logits per step (20 KB per rank)" if world > 1 else "none",
+                   "gathered_logits_equal_single_gpu_run": gathered_equal},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+        "e2e": {"value": round(B * world / (ms_e2e * 1e-3), 1), "unit": "img/s", "ms_per_step": round(ms_e2e, 4),
+                "api": "pipeline.HostPipeline(net).run(pinned images, pinned logits): H2D / graph replay / D2H on 3 streams",
+                "h2d_bytes_per_step": int(x_host[0].numel() * 4), "d2h_bytes_per_step": B * 10 * 4},
+        "gpu_launches": int(launches_per_forward * args.steps), "clocks": clocks,
+        "extra": {"launches_per_forward": int(launches_per_forward),
+                  "contraction_ms_by_shape": {"%s %dx%dx%d" % k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:12]}},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -617,6 +1012,25 @@ def extra_layers(Q, torch, dev, pk, _ops):
     out["linearbin_4096x4096_b8192_code_only_quantizer"] = {
         "ms": round(ms, 4), "gops": round(ops_ / ms / 1e6, 1), "hbm_gbs_algorithmic": round(bytes_module / ms / 1e6, 1),
         "hbm_frac": round(bytes_module / ms / 1e6 / pk["hbm_gbs"], 4)}
+    # the same pair through fuse_inference (FusedActLayer: banded quantizer / contraction pipeline)
+    pair = Q.fuse_inference(torch.nn.Sequential(act, lay))
+
+    def fp():
+        i[0] += 1
+        with Q.code_only_activations():
+            return pair(xs[i[0] % 3])
+    try:
+        ms = time_fn(torch, fp, iters=20, graph=True)
+        same = bool(torch.equal(fp(), fc()) or True)
+        i[0] = 0
+        ya = fp()
+        i[0] = 0
+        yb = fc()
+        out["linearbin_4096x4096_b8192_fused_head_pair"] = {
+            "ms": round(ms, 4), "gops": round(ops_ / ms / 1e6, 1), "hbm_gbs_algorithmic": round(bytes_module / ms / 1e6, 1),
+            "hbm_frac": round(bytes_module / ms / 1e6 / pk["hbm_gbs"], 4), "equals_unfused": bool(torch.equal(ya, yb))}
+    except Exception as err:
+        out["linearbin_4096x4096_b8192_fused_head_pair"] = {"error": str(err)}
     # contraction kernel alone on pre-quantized operands
     xq = act(xs[0])
     ms = time_fn(torch, lambda: lay(xq), iters=20, graph=True)
@@ -661,11 +1075,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="xnor_mlp", choices=["xnor_mlp"] + list(CNN))
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.config == "xnor_mlp":
         run_ours(args)
+    else:
+        run_cnn(args)
 
 
 if __name__ == "__main__":

@@ -1,5 +1,6 @@
 """CPU twin namespace for pytorch_quantize_impls_b200.nets builders: the same class names as the product layers,
-implemented with the oracle (fake-quant + fp32 F.linear / F.conv2d) -- i.e. the reference's path.  Test infrastructure."""
+implemented with the oracle (fake-quant + fp32 F.linear / F.conv2d) -- i.e. the reference's path.  TEST INFRASTRUCTURE: imported by tests/ and by
+bench.py's CPU-baseline / --impl reference legs only."""
 import torch
 from torch import nn
 

@@ -30,6 +30,11 @@ int check_epi(const QtEpilogue* e, int64_t M, int64_t N) {
                "requant: codes_kind must be 1 (int8), 2 (uint8), 3 (bf16), 5 (fp16) or 7 (fp4)");
     QT_REQUIRE(r->codes_kind != 7 || r->mode == QT_Q_SIGN || r->mode == QT_Q_TERNARY || (r->mode == QT_Q_DOREFA && r->bit_width == 2) ||
                r->mode == QT_Q_XNOR_ROW, "requant: fp4 codes hold integers in [-4, 4] only");
+    QT_REQUIRE(r->mode != QT_Q_DOREFA || r->codes_kind == 1 || r->codes_kind == 2 || r->codes_kind == 7,
+               "requant: DoReFa codes go to int8, uint8 or fp4 lanes");
+    QT_REQUIRE(r->mode == QT_Q_DOREFA || r->codes_kind != 2, "requant: uint8 lanes hold DoReFa codes only");
+    QT_REQUIRE((r->mode == QT_Q_XNOR_ROW) == (r->codes_kind == 3 || r->codes_kind == 5),
+               "requant: XnorNet codes go to bf16 / fp16 lanes, integer codes to int8 / uint8 / fp4 lanes");
     QT_REQUIRE(r->ld_codes % 32 == 0 && r->ld_codes >= (N + 31) / 32 * 32, "requant: ld_codes must be a multiple of 32 and >= N rounded up to 32");
     QT_REQUIRE((reinterpret_cast<uintptr_t>(r->codes) & 15) == 0, "requant: codes must be 16-byte aligned");
     QT_REQUIRE(r->mode != QT_Q_XNOR_ROW || r->row_part != nullptr, "requant: QT_Q_XNOR_ROW needs row_part");

@@ -38,6 +38,7 @@ struct TcArgs {
   Epi ep;
   int tiles_m, tiles_n;
   int tma_store;        // 1: row-major fp32 output goes through swizzled smem + cp.async.bulk.tensor store
+  int epi_fast;         // 1: the epilogue is the plain "fp32 tile -> TMA store" form (tight code path, see epilogue_f32_tma)
   // implicit-GEMM conv (IM2COL kernels): A rows are output pixels (b, oh, ow), K runs over (kh, kw, c-blocks)
   int cv_OW, cv_OHW;            // output width, output pixels per image
   int cv_sh, cv_sw, cv_ph, cv_pw, cv_dh, cv_dw, cv_kw;
@@ -103,6 +104,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+// accumulator hand-off to the pair leader: the TMEM reads were completed by tcgen05.wait::ld and ordered by
+// tcgen05.fence::before_thread_sync, no global / shared data rides on this arrive
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -249,6 +255,17 @@ __device__ __forceinline__ void load_col32(const float* __restrict__ p, int n0, 
 
 // ---- fused re-quantisation of one 32-column chunk of an output row (QtRequant) ------------------------------------
 // Semantics are those of act_quant_kernel (qt_quantize.cu): safeSign / ternary thresholds / rint(n y) / torch.sign.
+template <int MODE>
+__device__ __forceinline__ float rq_quant_t(const Epi& e, float v) {
+  if (MODE == QT_Q_SIGN) return (v < 0.f) ? -1.f : 1.f;
+  if (MODE == QT_Q_TERNARY) {
+    const float s = (v < 0.f) ? -1.f : 1.f;
+    const float t = v - 0.5f * s;
+    return (s + ((t < 0.f) ? -1.f : 1.f)) * 0.5f;
+  }
+  if (MODE == QT_Q_DOREFA) return rintf(e.rq_n * v);
+  return (float)((v > 0.f) - (v < 0.f));   // QT_Q_XNOR_ROW
+}
 __device__ __forceinline__ float rq_quant(const Epi& e, float v) {
   switch (e.rq_mode) {
     case QT_Q_SIGN: return (v < 0.f) ? -1.f : 1.f;
@@ -270,9 +287,10 @@ __device__ __forceinline__ void st_global_v2(void* p, uint32_t a, uint32_t b) {
 // y[0..31]: fp32 outputs of row m, columns n0..n0+31 (valid while n < n_lim).  Writes the codes of columns n0..n0+ncols-1
 // (zeros past n_lim), accumulates the row partial sums.  Works through the chunk 8 columns at a time so that only the packed
 // words, not 32 more floats and 32 more integers, are live beside the caller's registers.
-__device__ __forceinline__ void rq_store_chunk(const Epi& e, const float (&y)[32], int64_t m, int n0, int n_lim, int ncols,
-                                               float& psum, int& isum, bool& ovf) {
-  const int kind = e.rq_codes_kind;
+template <int MODE, int KIND>
+__device__ __forceinline__ void rq_store_chunk_t(const Epi& e, const float (&y)[32], int64_t m, int n0, int n_lim, int ncols,
+                                                 float& psum, int& isum, bool& ovf) {
+  constexpr int kind = KIND;
   const bool f16 = (kind == 3 || kind == 5);
   const float lo = (kind == 7) ? -4.f : ((kind == 1) ? -128.f : 0.f), hi = (kind == 7) ? 4.f : ((kind == 1) ? 127.f : 255.f);
   uint8_t* const base = reinterpret_cast<uint8_t*>(e.rq_codes);
@@ -285,8 +303,8 @@ __device__ __forceinline__ void rq_store_chunk(const Epi& e, const float (&y)[32
       float v = y[8 * q + j];
       if (e.rq_clamp) v = fminf(fmaxf(v, e.rq_lo), e.rq_hi);
       const bool ok = n0 + 8 * q + j < n_lim;
-      const float qv = rq_quant(e, v);
-      if (e.rq_mode == QT_Q_XNOR_ROW && ok) psum += v;
+      const float qv = rq_quant_t<MODE>(e, v);
+      if (MODE == QT_Q_XNOR_ROW && ok) psum += v;
       c[j] = ok ? qv : 0.f;
     }
     if (f16) {                           // bf16 / fp16 lanes: 16 bytes per 8 columns
@@ -335,6 +353,148 @@ __device__ __forceinline__ void rq_store_chunk(const Epi& e, const float (&y)[32
       }
     }
   }
+}
+
+// The quantizer and the lane format are compile-time constants inside the chunk code (no per-element selects); the switch
+// costs one warp-uniform branch per 32 x 32 chunk.
+__device__ __forceinline__ void rq_store_chunk(const Epi& e, const float (&y)[32], int64_t m, int n0, int n_lim, int ncols,
+                                               float& psum, int& isum, bool& ovf) {
+#define QT_RQ(M_, K_) case (M_) * 8 + (K_): rq_store_chunk_t<M_, K_>(e, y, m, n0, n_lim, ncols, psum, isum, ovf); break;
+  switch (e.rq_mode * 8 + e.rq_codes_kind) {
+    QT_RQ(QT_Q_SIGN, 1) QT_RQ(QT_Q_SIGN, 7) QT_RQ(QT_Q_TERNARY, 1) QT_RQ(QT_Q_TERNARY, 7)
+    QT_RQ(QT_Q_DOREFA, 1) QT_RQ(QT_Q_DOREFA, 2) QT_RQ(QT_Q_DOREFA, 7)
+    QT_RQ(QT_Q_XNOR_ROW, 3) QT_RQ(QT_Q_XNOR_ROW, 5)
+    default: break;
+  }
+#undef QT_RQ
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue, tight form: fp32 row-major output through swizzled staging tiles + bulk tensor stores, optional row / column
+// scales, bias and clamp -- no requant, residual, raw-accumulator or NCHW output (those take the general path below).
+// A product with a short K loop (e2m1 operands: 4x the MACs per byte of fp16) is paced by this code, not by the MMAs: the
+// column parameters are requested before the accumulator chunk is waited for, the next chunk's TMEM read is in flight while
+// this one is staged, and nothing but the 32 accumulators, 32 parameters and the next 32 raw values is live.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int KIND, int CG, int EPB>
+__device__ __forceinline__ void epilogue_f32_tma(const CUtensorMap& map_out, const TcArgs& g, uint32_t tmem_base, uint32_t epi_base,
+                                                 uint32_t tfull0, uint32_t tempty0, int worker, int num_workers, uint32_t cta_rank,
+                                                 int warp, int lane) {
+  const int ew = warp - 2, lane_grp = warp & 3, half = ew >> 2;
+  constexpr int CHUNKS = (BN + 31) / 32;
+  constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
+  constexpr bool INT_ACC = (KIND == 0 || KIND == 2);
+  const Epi& e = g.ep;
+  const int num_tiles = g.tiles_m * g.tiles_n;
+  const uint32_t my_buf = epi_base + (uint32_t)ew * (4096u * EPB);
+  uint32_t buf_sel = 0;
+  const int N32 = (int)g.N;
+  const bool plain_acc = (KIND == 2) && e.acc_mul == 1 && e.row_sum == nullptr;
+  const bool has_cs = e.col_scale != nullptr, has_b = e.bias != nullptr;
+  int as = 0;
+  uint32_t aphase = 0;
+  for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    int tm, tn;
+    tile_coords<CG>(g, tile, tm, tn);
+    const int row0 = (tm * CG + (int)cta_rank) * TC_BM + lane_grp * 32;
+    const int64_t m = (int64_t)row0 + lane;
+    const int n_tile = tn * BN;
+    const int n_lim = min(N32, n_tile + BN);
+    const int c_begin = half * CH_PER_WARP;
+    int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
+    while (c_end > c_begin && n_tile + (c_end - 1) * 32 >= n_lim) --c_end;
+    const bool row_ok = m < g.M;
+    float mul = e.scale;
+    int32_t rsum = 0;
+    if (row_ok) {
+      if (e.row_scale) {
+        if (e.row_scale_parts > 0) {
+          float rs = 0.f;
+          for (int p = 0; p < e.row_scale_parts; ++p) rs += __ldg(e.row_scale + (int64_t)p * g.M + m);
+          mul *= rs * e.row_scale_mul;
+        } else {
+          mul *= __ldg(e.row_scale + m);
+        }
+      }
+      if (e.row_sum) {
+        int32_t rs = 0;
+        if (e.row_sum_parts > 0) {
+          for (int p = 0; p < e.row_sum_parts; ++p) rs += __ldg(e.row_sum + (int64_t)p * g.M + m);
+        } else {
+          rs = __ldg(e.row_sum + m);
+        }
+        rsum = e.rs_mul * rs;
+      }
+    }
+    mbar_wait(tfull0 + 8u * as, aphase);
+    tc_fence_after();
+    uint32_t r[32];
+    const uint32_t t_row = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lane_grp * 32) << 16);
+    if (c_begin < c_end) tmem_ld32_issue(t_row + (uint32_t)(c_begin * 32), r);
+#pragma unroll 1
+    for (int cidx = c_begin; cidx < c_end; ++cidx) {
+      const int c0 = cidx * 32;
+      const int n0 = n_tile + c0;
+      const bool full_chunk = (BN % 32 == 0) || (c0 + 32 <= BN);
+      // column parameters first: their (L1 / L2) latency runs under the TMEM read
+      float pb[32];
+      if (has_b) load_col32(e.bias, n0, N32, true, 0.f, pb);
+      tmem_ld_wait(r);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float a;
+        if (!INT_ACC || plain_acc) a = __uint_as_float(r[j]);
+        else if (KIND == 2) a = (float)(e.acc_mul * __float2int_rn(__uint_as_float(r[j])) + rsum);
+        else a = (float)(e.acc_mul * (int32_t)r[j] + rsum);
+        v[j] = a * mul;
+      }
+      if (cidx + 1 < c_end) tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), r);
+      if (has_cs) {
+        float cs[32];
+        load_col32(e.col_scale, n0, N32, true, 1.f, cs);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= cs[j];
+      }
+      if (has_b) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += pb[j];
+      }
+      if (e.out_clamp) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], e.out_lo), e.out_hi);
+      }
+      if (full_chunk) {
+        if (lane == 0) {
+          if (EPB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else tma_store_wait_read0();
+        }
+        __syncwarp();
+        const uint32_t tile_buf = my_buf + buf_sel * 4096u;
+        const uint32_t rowaddr = tile_buf + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(rowaddr + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) tma_store_2d(&map_out, tile_buf, n0, row0);
+        if (EPB == 2) buf_sel ^= 1u;
+      } else if (row_ok) {       // the 16-column tail chunk of a 240-wide tile
+        float* o = e.out + m * e.ldo + n0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (n0 + j + 4 <= n_lim) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (CG == 2) mbar_arrive_remote(mapa_shared(tempty0 + 8u * as, 0));
+      else mbar_arrive(tempty0 + 8u * as);
+    }
+    if (++as == 2) { as = 0; aphase ^= 1u; }
+  }
+  if (lane == 0) tma_store_wait_all();
 }
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile -- each CTA
@@ -496,6 +656,9 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
       }
     }
     __syncwarp();
+  } else if (g.epi_fast == 1) {
+    epilogue_f32_tma<BN, KIND, CG, EPB>(map_out, g, tmem_base, epi_base, tfull_bar(0), tempty_bar(0), worker, num_workers, cta_rank,
+                                        warp, lane);
   } else {
     // ---- epilogue: 8 warps.  Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quadrant split
     // the BN accumulator columns in halves, so each SM sub-partition always has a second warp to hide latencies.
@@ -675,7 +838,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));   // the leader issues the MMAs of both CTAs
+        if (CG == 2) mbar_arrive_remote(mapa_shared(tempty_bar(as), 0));   // the leader issues the MMAs of both CTAs
         else mbar_arrive(tempty_bar(as));
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
@@ -776,6 +939,20 @@ static int num_sms() {
   return g_num_sms;
 }
 
+// the tight epilogue serves: fp32 row-major output via TMA store, 16-byte aligned column vectors whose length covers whole
+// 32-column chunks up to N (N % 4 == 0), nothing else attached
+static bool epi_is_plain_f32(const TcArgs& g) {
+  const Epi& e = g.ep;
+  static int off = -1;
+  if (off < 0) { const char* s = getenv("QTB200_EPI_FAST"); off = (s && atoi(s) == 0) ? 1 : 0; }
+  if (off) return false;
+  if (!g.tma_store || e.rq_mode >= 0 || e.residual || e.acc_out || e.out_mode != 0 || !e.out) return false;
+  if (g.N % 4 != 0) return false;
+  if (e.col_scale && (reinterpret_cast<uintptr_t>(e.col_scale) & 15)) return false;
+  if (e.bias && (reinterpret_cast<uintptr_t>(e.bias) & 15)) return false;
+  return true;
+}
+
 constexpr size_t TC_SMEM_MAX = 232448;    // 227 KB opt-in limit per CTA
 
 template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false, int EPB = 1>
@@ -789,6 +966,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
     if (int rc = make_map(&mo, g.ep.out, (uint64_t)g.M, (uint64_t)g.N * 4, (uint64_t)g.ep.ldo * 4, 32, true)) return rc;
     g.tma_store = 1;
   }
+  g.epi_fast = epi_is_plain_f32(g) ? 1 : 0;
   // the opt-in shared-memory size is a per-device function attribute: remember it per device (one process may drive several)
   static bool attr_set[64] = {};
   int dev = 0;
@@ -817,6 +995,7 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, c
     if (int rc = make_map(&mo, g.ep.out, (uint64_t)g.M, (uint64_t)g.N * 4, (uint64_t)g.ep.ldo * 4, 32, true)) return rc;
     g.tma_store = 1;
   }
+  g.epi_fast = epi_is_plain_f32(g) ? 1 : 0;
   static bool attr_set[64] = {};
   int dev = 0;
   QT_CUDA_OK(cudaGetDevice(&dev));

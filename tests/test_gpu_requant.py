@@ -301,7 +301,10 @@ def test_batchnorm_and_clamp_folded_into_fp32_epilogue(Q, conv, with_act):
     with torch.no_grad():
         ref = net(x.cuda())
         fused = Q.fuse_inference(net)
-        assert isinstance(fused[1], Q.FusedLayerBN) and len(fused) == 2
+        if conv:
+            assert isinstance(fused[1], Q.FusedLayerBN) and len(fused) == 2
+        else:          # quantizer -> Linear head pair: one FusedActLayer around the BatchNorm-folded layer
+            assert isinstance(fused[0], Q.FusedActLayer) and isinstance(fused[0].inner, Q.FusedLayerBN) and len(fused) == 1
         y = fused(x.cuda())
     assert y.shape == ref.shape
     assert float((y - ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max()))
