@@ -327,15 +327,17 @@ int qt_conv_i8(const void* x_nhwc, int a_signed, const QtConvGeom* g, const void
  * whose integer codes are repeated per part -- one pass, 24 significant bits of the input.  ldw in ELEMENTS. */
 int qt_conv_bf16(const void* x_nhwc, const QtConvGeom* g, const void* w, int64_t ldw, int64_t N, const QtEpilogue* ep, void* stream);
 
-/* fp32 NCHW image x[B, C, H, W] -> channels-last bf16 plane pixels out[B, Hp, Wp, 16] with the conv's zero padding
- * materialised: out[b, h + pad_h, w + pad_w, p * C + c] = part p of x[b, c, h, w]  (p = 0 hi, 1 mid, 2 lo; hi + mid + lo == x
- * to 24 significant bits), every other slot / border pixel zero.  planes * C <= 16.  Pixels of the source that fall outside
- * [Hp, Wp] after the shift are dropped (a strided conv never reads them).  Because consecutive pixels of a row are adjacent
- * in memory, the caller may view f pixels as one pixel of 16 f slots: a stride-f filter row of kw taps becomes a stride-1
- * row of floor((kw - 1) / f) + 1 taps (space-to-depth along W), which is how 7x7/2 and 11x11/4 stems keep the number of
- * TMA stages per tile small. */
+/* fp32 NCHW image x[B, C, H, W] -> channels-last bf16 plane pixels with the conv's zero padding materialised:
+ * pixel (h + pad_h, w + pad_w) of the padded [Hp, Wp] image holds 16 slots, slot p * C + c = part p of x[b, c, h, w]
+ * (p = 0 hi, 1 mid, 2 lo; hi + mid + lo == x to 24 significant bits), every other slot / border pixel zero; planes * C <= 16.
+ * Pixels of the source that fall outside [Hp, Wp] after the shift are dropped (a strided conv never reads them).
+ * Space-to-depth: a fold_h x fold_w block of pixels is stored as ONE super pixel of fold_h * fold_w * 16 slots,
+ *   out[b, hp / fold_h, wp / fold_w, ((hp % fold_h) * fold_w + wp % fold_w) * 16 + slot]     (fold_h = fold_w = 1: [B, Hp, Wp, 16]),
+ * so that a stride-f filter of k taps per axis becomes a stride-1 filter of floor((k - 1) / f) + 1 super taps: a 7x7 / 2 stem
+ * reads 4 x 4 taps of 128-byte super pixels instead of 49 taps of 32 bytes, an 11x11 / 4 stem (fold 1 x 4) 11 x 3 taps -- the TMA
+ * im2col engine works per pixel row, so fewer, fatter taps are what keeps the tensor pipe fed. */
 int qt_image_planes(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int planes, int pad_h, int pad_w,
-                    int64_t Hp, int64_t Wp, void* out, void* stream);
+                    int64_t Hp, int64_t Wp, int fold_h, int fold_w, void* out, void* stream);
 
 /* Max-pool (nn.MaxPool2d, ceil_mode = False, dilation 1; OH = floor((H + 2 pad - k) / stride) + 1) on channels-last tensors.
  *   qt_pool_codes      8-bit activation codes [B, H, W, C] -> [B, OH, OW, C].  An activation quantizer is monotone, so

@@ -244,6 +244,7 @@ class RequantSpec:
         self.mode, self.kind, self.bit_width, self.lo, self.hi = mode, kind, bit_width, lo, hi
         self.col_mul, self.col_add = col_mul, col_add
         self.force_8bit = False      # the consumer of the codes cannot read e2m1 operands
+        self.pad_channels = 0        # conv outputs: round the channel pitch of the codes up to this (0: dense) -- see conv_pad_channels
         self._fold = {}
 
     def fold(self, col_scale, bias, n0, n):
@@ -520,6 +521,30 @@ def set_first_layer_implicit(flag):
     _first_layer_implicit[0] = bool(flag)
 
 
+def conv_pad_channels(C):
+    """Channel pitch a conv's channels-last codes should have for the NEXT conv's TMA im2col: the im2col engine works per pixel
+    row, so K blocks of a full 128-byte swizzle row (C % 128 == 0) need a third fewer rows per MAC than 64-byte blocks.  C = 192
+    -> 256, 576 -> 640; small or already aligned counts stay dense.  The pad channels hold zero codes (written by the producer's
+    requant epilogue) and meet zero weights."""
+    if C > 128 and C % 128 != 0:
+        return (C + 127) // 128 * 128
+    return C
+
+
+def _channel_padded_weights(pack, out_kind, N, taps, Cin, Cp):
+    """Expanded conv operand [N, taps * Cin] re-laid as [N, taps * Cp] with zero columns for the pad channels (cached on the pack)."""
+    key = (pack.packed.data_ptr(), pack.packed._version, out_kind, Cp)
+    hit = pack._padw
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    w, ldw = ops._expand_weight(pack, out_kind)
+    wz = torch.zeros((N, taps, Cp), dtype=w.dtype, device=w.device)
+    wz[:, :, :Cin] = w[:N, :taps * Cin].reshape(N, taps, Cin)
+    wz = wz.reshape(N, taps * Cp)
+    pack._padw = (key, wz, taps * Cp)
+    return wz, taps * Cp
+
+
 def _out_clamp(affine, requant, keep_out):
     """Clamp applied to the fp32 value the epilogue WRITES (the requant path clamps its own copy)."""
     if affine is not None and affine.lo is not None:
@@ -529,20 +554,21 @@ def _out_clamp(affine, requant, keep_out):
     return None
 
 
-def _first_layer_weights(pack, O, kh, kw, Cin, P, f, kwf):
-    """bf16 weights of the plane-pixel implicit GEMM: [O, kh, kwf, f, 16] -- the exact integer codes of W_q repeated for each of
-    the P parts (hi / mid / lo) of the input channels, zero in the unused slots and in the taps a folded row adds.
+def _first_layer_weights(pack, O, kh, kw, Cin, P, fh, fw, khf, kwf):
+    """bf16 weights of the plane-pixel implicit GEMM: [O, khf, kwf, fh, fw, 16] -- the exact integer codes of W_q repeated for
+    each of the P parts (hi / mid / lo) of the input channels, zero in the unused slots and in the taps the folds add.
     Cached on the pack while its packed tensor is unchanged."""
-    key = (pack.packed.data_ptr(), pack.packed._version, kh, kw, Cin, P, f)
+    key = (pack.packed.data_ptr(), pack.packed._version, kh, kw, Cin, P, fh, fw)
     hit = getattr(pack, "_first", None)
     if hit is not None and hit[0] == key:
         return hit[1], hit[2]
     w, ldw = ops._expand_weight(pack, L.CODES_BF16)             # [1, O, ld]: exact codes, K order (kh, kw, c)
     wv = w[0, :O, :kh * kw * Cin].reshape(O, kh, kw, Cin)
-    wz = torch.zeros((O, kh, kwf * f, 16), dtype=torch.bfloat16, device=w.device)
+    wz = torch.zeros((O, khf * fh, kwf * fw, 16), dtype=torch.bfloat16, device=w.device)
     for p in range(P):
-        wz[:, :, :kw, p * Cin:(p + 1) * Cin] = wv
-    wz = wz.reshape(O, kh * kwf * f * 16)
+        wz[:, :kh, :kw, p * Cin:(p + 1) * Cin] = wv
+    # (ky' fh + dy, kx' fw + dx) -> [ky', kx', dy, dx]: the K order of a super pixel
+    wz = wz.reshape(O, khf, fh, kwf, fw, 16).permute(0, 1, 3, 2, 4, 5).reshape(O, khf * kwf * fh * fw * 16).contiguous()
     pack._first = (key, wz, wz.shape[1])
     return wz, wz.shape[1]
 
@@ -550,8 +576,9 @@ def _first_layer_weights(pack, O, kh, kw, Cin, P, f, kwf):
 def _conv_first_layer(xf, pack, geom, O, Cin, epi_kw):
     """Real-valued NCHW input with few channels: one pass over the image builds zero-padded channels-last bf16 plane pixels
     (each channel as hi / mid / lo bf16 parts side by side, 32 bytes per pixel), and the conv runs as an implicit GEMM fed by TMA
-    im2col.  A stride-f row of kw taps is read as floor((kw - 1) / f) + 1 taps of f-pixel super pixels.  Returns False when the
-    shape does not fit (the caller gathers explicitly)."""
+    im2col.  Strides are folded into the pixel (space-to-depth): stride 2 on both axes -> 2 x 2 super pixels of 128 bytes and a
+    stride-1 filter of floor((k - 1) / 2) + 1 taps per axis; stride 4 -> 1 x 4 super pixels.  Returns False when the shape does
+    not fit (the caller gathers explicitly)."""
     kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW = geom
     if groups != 1 or Cin > 8 or pack.kind not in ("sign", "ternary", "dorefa", "lin") or pack.packed is None:
         return False
@@ -561,20 +588,28 @@ def _conv_first_layer(xf, pack, geom, O, Cin, epi_kw):
         return False
     B = xf.shape[0]
     P = 3 if 3 * Cin <= 16 else 2
-    f = sw if (sw in (2, 4) and dw == 1) else 1
-    if f > 1:
-        kwf = (kw - 1) // f + 1
-        Wp = f * (OW + kwf - 1)
-        g_w, g_kw, g_sw, g_dw = Wp // f, kwf, 1, 1
+    fw = sw if (sw in (2, 4) and dw == 1) else 1
+    fh = 2 if (sh == 2 and dh == 1 and fw == 2) else 1          # 2 x 2 x 32 B = one 128-byte swizzle row
+    if fw > 1:
+        kwf = (kw - 1) // fw + 1
+        Wp = fw * (OW + kwf - 1)
+        g_w, g_kw, g_sw, g_dw = Wp // fw, kwf, 1, 1
     else:
         kwf = kw
         Wp = (OW - 1) * sw + (kw - 1) * dw + 1
         g_w, g_kw, g_sw, g_dw = Wp, kw, sw, dw
-    Hp = (OH - 1) * sh + (kh - 1) * dh + 1
-    planes = ops.image_planes(xf, P, ph, pw, Hp, Wp)
-    wz, ldw = _first_layer_weights(pack, O, kh, kw, Cin, P, f, kwf)
+    if fh > 1:
+        khf = (kh - 1) // fh + 1
+        Hp = fh * (OH + khf - 1)
+        g_h, g_kh, g_sh, g_dh = Hp // fh, khf, 1, 1
+    else:
+        khf = kh
+        Hp = (OH - 1) * sh + (kh - 1) * dh + 1
+        g_h, g_kh, g_sh, g_dh = Hp, kh, sh, dh
+    planes = ops.image_planes(xf, P, ph, pw, Hp, Wp, fh, fw)
+    wz, ldw = _first_layer_weights(pack, O, kh, kw, Cin, P, fh, fw, khf, kwf)
     epi = ops.make_epi(**epi_kw)
-    ops.conv_bf16(planes, (B, 16 * f, Hp, g_w, kh, g_kw, sh, g_sw, 0, 0, dh, g_dw, 1, 0, OH, OW), wz, ldw, O, epi)
+    ops.conv_bf16(planes, (B, 16 * fh * fw, g_h, g_w, g_kh, g_kw, g_sh, g_sw, 0, 0, g_dh, g_dw, 1, 0, OH, OW), wz, ldw, O, epi)
     return True
 
 
@@ -639,18 +674,25 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
         raise RuntimeError("pytorch_quantize_impls_b200: this conv layer cannot consume the code-only activation it was given")
 
     # implicit GEMM: TMA im2col straight from the channels-last codes (no im2col matrix is materialised)
+    Cp = tag.codes.shape[3] if (tag is not None and tag.codes.dim() == 4) else Cin       # channel pitch of the codes (>= Cin)
+    if tag is not None and Cp != Cin and (groups != 1 or not _implicit_conv[0] or _force_backend["i8"] == L.BACKEND_SIMT):
+        raise RuntimeError("internal: channel-padded codes need the implicit-GEMM route (groups == 1)")
     if (tag is not None and _implicit_conv[0] and Cg % 32 == 0 and Cin % 16 == 0
             and _force_backend["i8"] != L.BACKEND_SIMT):
         a_signed = tag.codes_kind == L.CODES_I8
         # DoReFa-8 weights stay unsigned codes c; the zero point needs the per-pixel patch sums of the activation codes
-        w, ldw = ops.expand_weight(pack, L.CODES_U8 if need_rs else L.CODES_I8)
+        if Cp != Cin:
+            w, ldw = _channel_padded_weights(pack, L.CODES_U8 if need_rs else L.CODES_I8, O, kh * kw, Cin, Cp)
+        else:
+            w, ldw = ops.expand_weight(pack, L.CODES_U8 if need_rs else L.CODES_I8)
         col_scale = pack.col_scale
         done = True
         rq = None
         if requant is not None:
+            Op = max(O, requant.pad_channels) if groups == 1 else O        # channel pitch of the codes (pad channels: zero codes)
             rq = ops.RequantOut(requant.mode, requant.bit_width, requant.codes_kind(False), B * P, O, dev, lo=requant.lo,
-                                hi=requant.hi, ld=O,
-                                codes=torch.empty((B, OH, OW, O), device=dev,
+                                hi=requant.hi, ld=Op,
+                                codes=torch.empty((B, OH, OW, Op), device=dev,
                                                   dtype=torch.uint8 if requant.codes_kind(False) == L.CODES_U8 else torch.int8))
         for g in range(groups):
             rs = ops.patch_rowsum(tag.codes, not a_signed, geom, g) if need_rs else None
@@ -678,8 +720,9 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
         rq = None
         if requant is not None:
             ck = requant.codes_kind(False)
-            rq = ops.RequantOut(requant.mode, requant.bit_width, ck, B * P, O, dev, lo=requant.lo, hi=requant.hi, ld=O,
-                                codes=torch.empty((B, OH, OW, O), device=dev,
+            Op = max(O, requant.pad_channels)
+            rq = ops.RequantOut(requant.mode, requant.bit_width, ck, B * P, O, dev, lo=requant.lo, hi=requant.hi, ld=Op,
+                                codes=torch.empty((B, OH, OW, Op), device=dev,
                                                   dtype=torch.uint8 if ck == L.CODES_U8 else torch.int8))
         cs, bg = pack.col_scale, bias
         if requant is not None or affine is not None:

@@ -197,7 +197,7 @@ class WeightPack:
     """k-bit weight matrix resident in HBM (the persistent format) + what the epilogue needs."""
     __slots__ = ("kind", "bit_width", "n", "k", "packed", "ld_packed", "alpha", "alpha_norm", "alpha_max", "stats",
                  "col_scale", "planes", "ld_planes", "wq", "wscale", "emin", "_prefetch", "_last_kind", "_first", "_hold",
-                 "_hold_on")
+                 "_hold_on", "_padw")
     # kind 'lin' / 'log' (LogLin layers): packed = int8 codes [1, n, ld]; value = code * wscale (lin) or
     # sign(code) * 2^(emin + |code| - 1) (log)
 
@@ -206,6 +206,7 @@ class WeightPack:
         self._prefetch = None        # (out_kind, operand, ld, event): expanded ahead of time on a side stream
         self._last_kind = None       # operand kind the last contraction asked for (what a prefetch expands)
         self._first = None           # cached plane-pixel weights of a first conv layer (engine._first_layer_weights)
+        self._padw = None            # cached channel-padded conv operand (engine._channel_padded_weights)
         self._hold, self._hold_on = None, False   # one expansion shared by the row bands of engine.linear_banded
 
     def nbytes(self):
@@ -485,13 +486,15 @@ def conv_bf16(x_nhwc, geom_args, w, ldw, N, epi):
     L.check(L.lib().qt_conv_bf16(_p(x_nhwc), C.byref(g), _p(w), ldw, N, C.byref(epi), _stream()), "qt_conv_bf16")
 
 
-def image_planes(x, planes, pad_h, pad_w, Hp, Wp):
-    """fp32 NCHW image -> zero-padded channels-last bf16 plane pixels [B, Hp, Wp, 16] (qt_image_planes)."""
+def image_planes(x, planes, pad_h, pad_w, Hp, Wp, fold_h=1, fold_w=1):
+    """fp32 NCHW image -> zero-padded channels-last bf16 plane pixels (qt_image_planes): [B, Hp, Wp, 16], or with a
+    space-to-depth fold [B, Hp / fold_h, Wp / fold_w, fold_h * fold_w * 16]."""
     require_cuda(x, "input")
     x = as_f32c(x)
     B, Cn, Hn, Wn = x.shape
-    out = torch.empty((B, Hp, Wp, 16), dtype=torch.bfloat16, device=x.device)
-    L.check(L.lib().qt_image_planes(_p(x), B, Cn, Hn, Wn, planes, pad_h, pad_w, Hp, Wp, _p(out), _stream()), "qt_image_planes")
+    out = torch.empty((B, Hp // fold_h, Wp // fold_w, fold_h * fold_w * 16), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().qt_image_planes(_p(x), B, Cn, Hn, Wn, planes, pad_h, pad_w, Hp, Wp, fold_h, fold_w, _p(out), _stream()),
+            "qt_image_planes")
     return out
 
 

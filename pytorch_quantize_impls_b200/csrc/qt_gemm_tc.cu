@@ -91,6 +91,13 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap*
       "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_im2col_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c, int w, int h, int n,
+                                                    uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -505,7 +512,6 @@ template <int BN, int KIND, int STAGES, int BKB, bool IM2COL, int CG, int EPB>
 __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUtensorMap& map_w, const CUtensorMap& map_out,
                                              const TcArgs& g) {
   static_assert(CG == 1 || BN % 16 == 0, "cta_group::2 needs N % 16 == 0");
-  static_assert(CG == 1 || !IM2COL, "the implicit-GEMM conv kernels run at cta_group::1");
   constexpr uint32_t A_BYTES = TC_BM * BKB;
   constexpr uint32_t W_BYTES = (BN / CG) * BKB;         // this CTA's share of the B tile
   constexpr uint32_t STAGE_BYTES = A_BYTES + W_BYTES;
@@ -590,8 +596,8 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
           const int a_row = (int)(g.pa[pass] * g.a_plane_rows) + (tm * CG + (int)cta_rank) * TC_BM;
           const int w_row = (int)(g.pw[pass] * g.w_plane_rows) + tn * BN + (int)cta_rank * (BN / CG);
           int cv_n = 0, cv_h = 0, cv_w = 0;
-          if (IM2COL) {   // first output pixel of this M tile -> base position of its filter window
-            const int m0 = tm * TC_BM;
+          if (IM2COL) {   // first output pixel of this CTA's 128 rows -> base position of its filter window
+            const int m0 = (tm * CG + (int)cta_rank) * TC_BM;
             cv_n = m0 / g.cv_OHW;
             const int r = m0 - cv_n * g.cv_OHW;
             const int oh = r / g.cv_OW;
@@ -605,7 +611,14 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
             if (CG == 2) {
               const uint32_t lbar = mapa_shared(full_bar(stage), 0);
-              tma_load_2d_cg2(sa, &map_a, lbar, kb * BKB, a_row);
+              if (IM2COL) {
+                const int tap = kb / g.cv_cblocks, cb = kb - tap * g.cv_cblocks;
+                const int ky = tap / g.cv_kw, kx = tap - ky * g.cv_kw;
+                tma_load_im2col_cg2(sa, &map_a, lbar, g.cv_c0 + cb * BKB, cv_w, cv_h, cv_n, (uint16_t)(kx * g.cv_dw),
+                                    (uint16_t)(ky * g.cv_dh));
+              } else {
+                tma_load_2d_cg2(sa, &map_a, lbar, kb * BKB, a_row);
+              }
               tma_load_2d_cg2(sa + A_BYTES, &map_w, lbar, kb * BKB, w_row);
               if (++stage == STAGES) { stage = 0; phase ^= 1u; }
               continue;
@@ -690,7 +703,10 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
       // chunks of this warp that hold at least one valid column (warp-uniform)
       const int c_begin = half * CH_PER_WARP;
       int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
-      while (c_end > c_begin && n_tile + (c_end - 1) * 32 >= n_lim) --c_end;
+      // a requant row may be wider than N (channel padding for the consumer's 128-byte K blocks): those chunks are visited
+      // too and receive zero codes
+      const int n_cover = (e.rq_mode >= 0) ? max(n_lim, (int)min((int64_t)(n_tile + BN), e.rq_ld)) : n_lim;
+      while (c_end > c_begin && n_tile + (c_end - 1) * 32 >= n_cover) --c_end;
       const bool row_ok = m < g.M;
       float mul = e.scale;
       int32_t rsum = 0;
@@ -864,11 +880,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // CTA-pair variant: 256 x BN tiles, cluster of two CTAs on the two SMs of a TPC.
-template <int BN, int KIND, int STAGES, int EPB = 1>
+template <int BN, int KIND, int STAGES, int EPB = 1, int BKB = TC_BK_BYTES, bool IM2COL = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out, TcArgs g) {
-  tc_gemm_body<BN, KIND, STAGES, TC_BK_BYTES, false, 2, EPB>(map_a, map_w, map_out, g);
+  tc_gemm_body<BN, KIND, STAGES, BKB, IM2COL, 2, EPB>(map_a, map_w, map_out, g);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -985,9 +1001,9 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
 
 // CTA-pair launch: tiles of 256 x BN, grid = 2 x min(#tiles, #SMs / 2); `mw` must have been built with BN / 2 box rows and
 // g.idesc with M = 256.
-template <int BN, int KIND, int STAGES, int EPB = 1>
+template <int BN, int KIND, int STAGES, int EPB = 1, int BKB = TC_BK_BYTES, bool IM2COL = false>
 static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (TC_BM * TC_BK_BYTES + (BN / 2) * TC_BK_BYTES) + (size_t)EPB * 8 * 4096 + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * BKB + (BN / 2) * BKB) + (size_t)EPB * 8 * 4096 + 1024 + 256;
   static_assert(smem <= TC_SMEM_MAX, "tc_gemm2_kernel: shared memory budget");
   CUtensorMap mo = ma;
   g.tma_store = 0;
@@ -1000,13 +1016,13 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, c
   int dev = 0;
   QT_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm2_kernel<BN, KIND, STAGES, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QT_CUDA_OK(cudaFuncSetAttribute(tc_gemm2_kernel<BN, KIND, STAGES, EPB, BKB, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   g.tiles_m = (int)ceil_div(g.M, 2 * TC_BM);
   g.tiles_n = (int)ceil_div(g.N, BN);
   const int grid = 2 * std::min(g.tiles_m * g.tiles_n, num_sms() / 2);
-  tc_gemm2_kernel<BN, KIND, STAGES, EPB><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
+  tc_gemm2_kernel<BN, KIND, STAGES, EPB, BKB, IM2COL><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }
@@ -1209,8 +1225,16 @@ extern "C" int qt_gemm_f16(const void* a, int64_t lda, int64_t a_plane_stride, c
 // ---------------------------------------------------------------------------------------------
 namespace qt {
 template <int KIND, int BKB>
-static int dispatch_conv(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream) {
-  // stage = 128 x BKB (pixels) + BN x BKB (filters)
+static int dispatch_conv(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, int bn, cudaStream_t stream, bool pair) {
+  // stage = 128 x BKB (pixels) + BN x BKB (filters).  CTA pairs (256-pixel tiles, each CTA stages half of the filter rows) for
+  // the 64- and 128-byte channel blocks: the TMA engine works per row, and the filter rows are most of them when N is large
+  if constexpr (BKB >= 64) {
+    if (pair) {
+      if (bn == 64) return launch_tc2<64, KIND, 8, 2, BKB, true>(ma, mw, g, stream);
+      if (bn == 128) return launch_tc2<128, KIND, (BKB == 128 ? 6 : 8), 2, BKB, true>(ma, mw, g, stream);
+      return launch_tc2<256, KIND, (BKB == 128 ? 5 : 8), 2, BKB, true>(ma, mw, g, stream);
+    }
+  }
   if (bn == 64) return launch_tc<64, KIND, (BKB == 128 ? 6 : 8), BKB, true, 2>(ma, mw, g, stream);
   if (bn == 128) return launch_tc<128, KIND, (BKB == 128 ? 5 : 8), BKB, true, 2>(ma, mw, g, stream);
   if constexpr (BKB == 128) return launch_tc<256, KIND, 4, BKB, true, 1>(ma, mw, g, stream);
@@ -1251,7 +1275,10 @@ static int conv_implicit(const void* x_nhwc, int elem_bytes, int a_signed, const
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed with CUresult %d", (int)r); return QT_EUNSUPPORTED; }
   }
   const int bn = pick_bn(N);
-  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)K * elem_bytes, (uint64_t)ldw * elem_bytes, (uint32_t)bn, false, bkb)) return rc;
+  if (g_cta_group < 0) use_cta_pair(0, 0);                     // reads QTB200_CTA_GROUP once
+  const bool pair = bkb >= 64 && g_cta_group != 1 && M >= 148 * 128;     // at least one 256-pixel tile per CTA pair
+  const int cgn = pair ? 2 : 1;
+  if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)K * elem_bytes, (uint64_t)ldw * elem_bytes, (uint32_t)(bn / cgn), false, bkb)) return rc;
   TcArgs g{};
   g.M = M; g.N = N; g.npass = 1; g.pa[0] = g.pw[0] = 0; g.a_plane_rows = g.w_plane_rows = 0; g.is_int = elem_bytes == 1;
   g.ep = make_epi(ep, M, N);
@@ -1263,16 +1290,16 @@ static int conv_implicit(const void* x_nhwc, int elem_bytes, int a_signed, const
   if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
   if (elem_bytes == 1) {
     g.idesc = (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((w_signed ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) |
-              ((uint32_t)(TC_BM >> 4) << 24);
-    if (bkb == 128) return dispatch_conv<0, 128>(ma, mw, g, bn, stream);
-    if (bkb == 64) return dispatch_conv<0, 64>(ma, mw, g, bn, stream);
-    return dispatch_conv<0, 32>(ma, mw, g, bn, stream);
+              ((uint32_t)((TC_BM * cgn) >> 4) << 24);
+    if (bkb == 128) return dispatch_conv<0, 128>(ma, mw, g, bn, stream, pair);
+    if (bkb == 64) return dispatch_conv<0, 64>(ma, mw, g, bn, stream, pair);
+    return dispatch_conv<0, 32>(ma, mw, g, bn, stream, false);
   }
   // D = f32 (1 << 4), A/B = bf16 (1) at bits 7 / 10
-  g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-  if (bkb == 128) return dispatch_conv<1, 128>(ma, mw, g, bn, stream);
-  if (bkb == 64) return dispatch_conv<1, 64>(ma, mw, g, bn, stream);
-  return dispatch_conv<1, 32>(ma, mw, g, bn, stream);
+  g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((TC_BM * cgn) >> 4) << 24);
+  if (bkb == 128) return dispatch_conv<1, 128>(ma, mw, g, bn, stream, pair);
+  if (bkb == 64) return dispatch_conv<1, 64>(ma, mw, g, bn, stream, pair);
+  return dispatch_conv<1, 32>(ma, mw, g, bn, stream, false);
 }
 }  // namespace qt
 

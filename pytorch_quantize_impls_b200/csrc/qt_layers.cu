@@ -17,7 +17,7 @@ static bool al(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p)
 // ---------------------------------------------------------------------------------------------
 template <int P>
 __global__ void __launch_bounds__(256) image_planes_kernel(const float* __restrict__ x, int B, int C, int H, int W, int Hp, int Wp,
-                                                           int pad_h, int pad_w, __nv_bfloat16* __restrict__ out) {
+                                                           int pad_h, int pad_w, int fh, int fw, __nv_bfloat16* __restrict__ out) {
   const int64_t total = (int64_t)B * Hp * Wp;
   for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (int64_t)gridDim.x * blockDim.x) {
     const int wp = (int)(pix % Wp);
@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(256) image_planes_kernel(const float* __restri
         }
       }
     }
-    uint4* o = reinterpret_cast<uint4*>(out + pix * 16);
+    // space-to-depth: an fh x fw block of pixels is one super pixel of fh * fw * 16 slots (fh == 1: plain row-major pixels)
+    const int64_t sp = (b * (Hp / fh) + hp / fh) * (Wp / fw) + wp / fw;
+    uint4* o = reinterpret_cast<uint4*>(out + (sp * (fh * fw) + (hp % fh) * fw + (wp % fw)) * 16);
     o[0] = reinterpret_cast<const uint4*>(s)[0];
     o[1] = reinterpret_cast<const uint4*>(s)[1];
   }
@@ -185,19 +187,20 @@ static unsigned grid_for(int64_t total, int threads) {
 using namespace qt;
 
 extern "C" int qt_image_planes(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int planes, int pad_h, int pad_w,
-                               int64_t Hp, int64_t Wp, void* out, void* stream_) {
+                               int64_t Hp, int64_t Wp, int fold_h, int fold_w, void* out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   QT_REQUIRE(x && out, "qt_image_planes: null argument");
   QT_REQUIRE(planes >= 1 && planes <= 3 && C >= 1 && planes * C <= 16, "qt_image_planes: planes * C must fit the 16 slots of a pixel");
   QT_REQUIRE(B >= 0 && H > 0 && W > 0 && Hp > 0 && Wp > 0 && pad_h >= 0 && pad_w >= 0, "qt_image_planes: bad shape");
   QT_REQUIRE(al(out, 16), "qt_image_planes: out must be 16-byte aligned");
+  QT_REQUIRE(fold_h >= 1 && fold_w >= 1 && Hp % fold_h == 0 && Wp % fold_w == 0, "qt_image_planes: the folds must divide Hp / Wp");
   QT_REQUIRE(B * Hp * Wp < (1ll << 40) && H * W < (1ll << 31), "qt_image_planes: tensor too large");
   if (B == 0) return QT_OK;
   const unsigned grid = grid_for(B * Hp * Wp, 256);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (planes == 1) image_planes_kernel<1><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, o);
-  else if (planes == 2) image_planes_kernel<2><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, o);
-  else image_planes_kernel<3><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, o);
+  if (planes == 1) image_planes_kernel<1><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, fold_h, fold_w, o);
+  else if (planes == 2) image_planes_kernel<2><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, fold_h, fold_w, o);
+  else image_planes_kernel<3><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, fold_h, fold_w, o);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }

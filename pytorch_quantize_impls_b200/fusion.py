@@ -132,6 +132,10 @@ class FusedLayerQuant(nn.Module):
         # the tail on its own is the one-pass BatchNorm+clamp+quantizer kernel: used whenever the epilogue fusion does not apply
         self.tail = FusedBNActQuant(bn, act, quant) if (bn is not None or act is not None) else quant
         self._consumer_needs_i8 = _needs_8bit_lanes(consumer)
+        # a conv consumer reads the codes through TMA im2col: give it whole 128-byte channel rows (engine.conv_pad_channels)
+        self._pad_channels = 0
+        if layer._is_conv and _is_quant_layer(consumer) and consumer._is_conv and consumer.groups == 1:
+            self._pad_channels = eng.conv_pad_channels(layer.out_channels)
         self._spec = None
 
     @property
@@ -167,6 +171,7 @@ class FusedLayerQuant(nn.Module):
         mode = {"sign": L.Q_SIGN, "ternary": L.Q_TERNARY, "dorefa": L.Q_DOREFA, "xnor": L.Q_XNOR_ROW}[kind]
         spec = eng.RequantSpec(mode, kind, bit_width=arg if kind == "dorefa" else 0, lo=lo, hi=hi, col_mul=mul, col_add=add)
         spec.force_8bit = self._consumer_needs_i8
+        spec.pad_channels = self._pad_channels
         self._spec = (key, spec)
         return spec
 
@@ -281,9 +286,9 @@ class FusedLayerPoolQuant(FusedLayerQuant):
                 return self._compose(x)
             tag = eng.get_tag(y)
             pooled = ops.pool_codes(tag.codes, *geo, use_min=self._min_mask(spec))
-            B, PH, PW, Cn = pooled.shape
+            B, PH, PW, Cn = pooled.shape                    # Cn: channel pitch of the codes (>= out_channels when padded)
             tag.codes, tag.rows, tag.cols, tag.ld = pooled, B, Cn * PH * PW, Cn * PH * PW
-            out = torch.empty((B, Cn, PH, PW), dtype=torch.float32, device="meta")
+            out = torch.empty((B, self.layer.out_channels, PH, PW), dtype=torch.float32, device="meta")
             return eng.attach_tag(out, tag)
         return self._compose(x)
 
@@ -300,6 +305,7 @@ class FusedConvPool(nn.Module):
         super().__init__()
         self.inner = FusedLayerBN(layer, bn, act)
         self.pool = pool
+        self._next = None          # _qt_spec of the DoReFa quantizer that reads the pooled tensor next (a residual block's q_in)
 
     def forward(self, x):
         geo = _pool_params(self.pool)
@@ -307,6 +313,22 @@ class FusedConvPool(nn.Module):
         if (geo is not None and not torch.is_grad_enabled() and x.is_cuda and x.dim() == 4 and lay._is_conv
                 and lay.out_channels % 4 == 0 and _bn_ready(self.inner.bn)):
             y = lay._forward_affine(x, self.inner._make_spec(), out_format="nhwc")
+            nxt = self._next
+            lo, hi = _clamp_range(self.inner.act)
+            if (nxt is not None and nxt[0] == "dorefa" and 2 <= nxt[1] <= 8 and eng._code_only[0] and lay.out_channels % 16 == 0):
+                # the pool pass also writes the next quantizer's codes: one read of the conv output, no separate quantizer pass
+                k = nxt[1]
+                ck = L.CODES_U8 if k == 8 else L.CODES_I8
+                out, codes, ovf = ops.pool_quant_f32(y, *geo, want_out=True, mode=L.Q_DOREFA, bit_width=k, codes_kind=ck)
+                tag = ops.ActCodes()
+                B, PH, PW, Cn = codes.shape
+                tag.kind, tag.bit_width, tag.codes, tag.codes_kind = "dorefa", k, codes, ck
+                tag.rows, tag.cols, tag.ld, tag.layout = B, Cn * PH * PW, Cn * PH * PW, "nhwc"
+                tag.scale = _f32(_f32(1.0) / _f32(2 ** k - 1))
+                tag.row_sum = tag.row_scale = tag.bits = None
+                tag.ld_bits, tag.row_parts, tag.row_mul, tag.overflow = 0, 0, 1.0, ovf
+                tag.range_ok = ops.clamp_guarantees_lane(ck, k, lo, hi) if lo is not NotImplemented else False
+                return eng.attach_tag(out, tag)
             return ops.pool_quant_f32(y, *geo)[0]
         return self.pool(self.inner(x))
 
@@ -535,6 +557,11 @@ def fuse_inference(module):
     for name, child in list(module.named_children()):
         fuse_inference(child)
     if not isinstance(module, nn.Sequential):
+        # residual nets (nets.ResNetTer layout): the stem's pool pass also emits the codes of the first block's input quantizer
+        stem, layers = getattr(module, "stem", None), getattr(module, "layers", None)
+        if (isinstance(stem, nn.Sequential) and isinstance(layers, nn.Sequential) and len(stem) and len(layers)
+                and isinstance(stem[-1], FusedConvPool) and isinstance(layers[0], FusedBasicBlock)):
+            stem[-1]._next = getattr(layers[0].block.q_in, "_qt_spec", None)
         return module
     mods = list(module.children())
     out, i = [], 0

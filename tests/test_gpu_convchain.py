@@ -156,14 +156,15 @@ def _code_diff(tag_a, tag_b):
 
 
 @pytest.mark.parametrize("negative", [False, True])
-@pytest.mark.parametrize("k", [4, 8])
-def test_conv_pool_bn_quant_on_codes(Q, k, negative):
-    """conv -> MaxPool -> BatchNorm -> Hardtanh(0, 1) -> quantizer: requant epilogue + pool on codes vs the plain modules."""
+@pytest.mark.parametrize("k,mid", [(4, 64), (8, 64), (4, 192), (8, 192)])
+def test_conv_pool_bn_quant_on_codes(Q, k, mid, negative):
+    """conv -> MaxPool -> BatchNorm -> Hardtanh(0, 1) -> quantizer: requant epilogue + pool on codes vs the plain modules.
+    mid = 192: the codes are written with a 256-channel pitch (zero pad channels) for the next conv's 128-byte K blocks."""
     torch.manual_seed(7 + k)
     F_, L_ = Q.functions, Q.layers
-    net = nn.Sequential(F_.nnDorefaQuant(k), L_.DorefaConv2d(32, 64, 3, padding=1, bit_width=k), nn.MaxPool2d(3, 2, 1),
-                        _calibrated_bn(64, negative=negative), nn.Hardtanh(0.0, 1.0), F_.nnDorefaQuant(k),
-                        L_.DorefaConv2d(64, 32, 3, padding=1, bit_width=k)).cuda().eval()
+    net = nn.Sequential(F_.nnDorefaQuant(k), L_.DorefaConv2d(32, mid, 3, padding=1, bit_width=k), nn.MaxPool2d(3, 2, 1),
+                        _calibrated_bn(mid, negative=negative), nn.Hardtanh(0.0, 1.0), F_.nnDorefaQuant(k),
+                        L_.DorefaConv2d(mid, 32, 3, padding=1, bit_width=k)).cuda().eval()
     x = torch.rand(4, 32, 17, 19).cuda()
     with torch.no_grad():
         ref_codes = net[:6](x)._qt_codes                   # plain graph: NCHW fp32 + channels-last code tag
@@ -171,9 +172,14 @@ def test_conv_pool_bn_quant_on_codes(Q, k, negative):
         fused = Q.fuse_inference(net)
         assert [type(m).__name__ for m in fused] == ["fronteur", "FusedLayerPoolQuant", "DorefaConv2d"]
         with Q.code_only_activations():
-            mid = fused[1](fused[0](x))
-            assert mid.is_meta and mid._qt_codes.codes.shape == ref_codes.codes.shape
-            mx, frac = _code_diff(mid._qt_codes, ref_codes)
+            h = fused[1](fused[0](x))
+            pitch = 256 if mid == 192 else mid
+            assert h.is_meta and h.shape[1] == mid and h._qt_codes.codes.shape[:3] == ref_codes.codes.shape[:3]
+            assert h._qt_codes.codes.shape[3] == pitch
+            got = h._qt_codes.codes
+            assert torch.equal(got[..., mid:], torch.zeros_like(got[..., mid:]))         # pad channels: zero codes
+            d = (got[..., :mid].float() - ref_codes.codes.float()).abs()
+            mx, frac = float(d.max()), float((d > 0).float().mean())
             y = fused(x)
     assert mx <= 1 and frac <= 1e-3                        # folded BatchNorm: one rounding instead of three
     assert rel(y, ref) <= 2e-2
