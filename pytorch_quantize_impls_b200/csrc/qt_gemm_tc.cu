@@ -114,8 +114,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
 }
 // accumulator hand-off to the pair leader: the TMEM reads were completed by tcgen05.wait::ld and ordered by
 // tcgen05.fence::before_thread_sync, no global / shared data rides on this arrive
+// .relaxed: a releasing arrive is a MEMBAR, which waits for every global store the warp still has in flight (the requant codes
+// go out as plain stores) -- per tile, on the critical path of the accumulator ring.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -497,11 +502,191 @@ __device__ __forceinline__ void epilogue_f32_tma(const CUtensorMap& map_out, con
     __syncwarp();
     if (lane == 0) {
       if (CG == 2) mbar_arrive_remote(mapa_shared(tempty0 + 8u * as, 0));
-      else mbar_arrive(tempty0 + 8u * as);
+      else mbar_arrive_relaxed(tempty0 + 8u * as);
     }
     if (++as == 2) { as = 0; aphase ^= 1u; }
   }
   if (lane == 0) tma_store_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue, tight form for the conv / linear chains of k-bit (DoReFa) activations: the output goes out as 8-bit codes
+//   c = rint(n * clamp(y, lo, hi))           y = acc * (scale * row) * col_scale + bias [+ residual]
+// (int8 lane for k <= 7, uint8 for k = 8; the clamp keeps n * y inside the lane, so no overflow bookkeeping), optionally
+// together with the clamped fp32 value (channels-last, TMA store) -- the residual-block form.  Same arithmetic, in the same
+// order, as the general path (bit-identical codes); ~1/3 of its instructions: the quantizer is FMUL + F2I.RN + I2IP per
+// element, no per-element selects, no row-sum / overflow tracking.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack4_sat(bool uns, int k0, int k1, int k2, int k3) {
+  uint32_t t, w;
+  if (uns) {
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(k3), "r"(k2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(k1), "r"(k0), "r"(t));
+  } else {
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(k3), "r"(k2), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(k1), "r"(k0), "r"(t));
+  }
+  return w;
+}
+
+template <int BN, int KIND, int CG, int EPB>
+__device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const TcArgs& g, uint32_t tmem_base, uint32_t epi_base,
+                                             uint32_t tfull0, uint32_t tempty0, int worker, int num_workers, uint32_t cta_rank,
+                                             int warp, int lane) {
+  const int ew = warp - 2, lane_grp = warp & 3, half = ew >> 2;
+  constexpr int CHUNKS = (BN + 31) / 32;
+  constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
+  constexpr bool INT_ACC = (KIND == 0 || KIND == 2);
+  const Epi& e = g.ep;
+  const int num_tiles = g.tiles_m * g.tiles_n;
+  const uint32_t my_buf = epi_base + (uint32_t)ew * (4096u * EPB);
+  uint32_t buf_sel = 0;
+  const int N32 = (int)g.N;
+  const bool plain_acc = (KIND == 2) && e.acc_mul == 1 && e.row_sum == nullptr;
+  const bool has_cs = e.col_scale != nullptr, has_b = e.bias != nullptr, has_res = e.residual != nullptr, has_out = e.out != nullptr;
+  const bool uns = e.rq_codes_kind == 2;
+  const float lo = e.rq_lo, hi = e.rq_hi, qn = e.rq_n;
+  uint8_t* const cbase = reinterpret_cast<uint8_t*>(e.rq_codes);
+  int as = 0;
+  uint32_t aphase = 0;
+  for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    int tm, tn;
+    tile_coords<CG>(g, tile, tm, tn);
+    const int row0 = (tm * CG + (int)cta_rank) * TC_BM + lane_grp * 32;
+    const int64_t m = (int64_t)row0 + lane;
+    const int n_tile = tn * BN;
+    const int n_lim = min(N32, n_tile + BN);
+    const int n_cover = max(n_lim, (int)min((int64_t)(n_tile + BN), e.rq_ld));       // zero codes for pad channels
+    const int c_begin = half * CH_PER_WARP;
+    int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
+    while (c_end > c_begin && n_tile + (c_end - 1) * 32 >= n_cover) --c_end;
+    const bool row_ok = m < g.M;
+    float mul = e.scale;
+    int32_t rsum = 0;
+    if (row_ok) {
+      if (e.row_scale) {
+        if (e.row_scale_parts > 0) {
+          float rs = 0.f;
+          for (int p = 0; p < e.row_scale_parts; ++p) rs += __ldg(e.row_scale + (int64_t)p * g.M + m);
+          mul *= rs * e.row_scale_mul;
+        } else {
+          mul *= __ldg(e.row_scale + m);
+        }
+      }
+      if (e.row_sum) {
+        int32_t rs = 0;
+        if (e.row_sum_parts > 0) {
+          for (int p = 0; p < e.row_sum_parts; ++p) rs += __ldg(e.row_sum + (int64_t)p * g.M + m);
+        } else {
+          rs = __ldg(e.row_sum + m);
+        }
+        rsum = e.rs_mul * rs;
+      }
+      if (has_res) {
+        for (int c = c_begin; c < c_end; ++c)
+          if (n_tile + c * 32 < n_lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.residual + m * e.ld_res + n_tile + c * 32));
+      }
+    }
+    mbar_wait(tfull0 + 8u * as, aphase);
+    tc_fence_after();
+    uint32_t r[32];
+    const uint32_t t_row = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lane_grp * 32) << 16);
+    if (c_begin < c_end) tmem_ld32_issue(t_row + (uint32_t)(c_begin * 32), r);
+#pragma unroll 1
+    for (int cidx = c_begin; cidx < c_end; ++cidx) {
+      const int c0 = cidx * 32;
+      const int n0 = n_tile + c0;
+      const bool whole = n0 + 32 <= n_lim;            // all 32 columns are real outputs (else: tail / pad-channel chunk)
+      float res[32];
+      if (has_res && row_ok && whole) {
+        const float4* rp = reinterpret_cast<const float4*>(e.residual + m * e.ld_res + n0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = __ldcs(rp + q);
+          res[4 * q] = t.x; res[4 * q + 1] = t.y; res[4 * q + 2] = t.z; res[4 * q + 3] = t.w;
+        }
+      }
+      tmem_ld_wait(r);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float a;
+        if (!INT_ACC || plain_acc) a = __uint_as_float(r[j]);
+        else if (KIND == 2) a = (float)(e.acc_mul * __float2int_rn(__uint_as_float(r[j])) + rsum);
+        else a = (float)(e.acc_mul * (int32_t)r[j] + rsum);
+        v[j] = a * mul;
+      }
+      if (cidx + 1 < c_end) tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), r);
+      if (has_cs) {
+        float cs[32];
+        load_col32(e.col_scale, n0, N32, true, 1.f, cs);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= cs[j];
+      }
+      if (has_b) {
+        float pb[32];
+        load_col32(e.bias, n0, N32, true, 0.f, pb);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += pb[j];
+      }
+      if (has_res && row_ok) {
+        if (whole) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += res[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < n_lim) v[j] += __ldg(e.residual + m * e.ld_res + n0 + j);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], lo), hi);
+      // codes: 32 bytes per row chunk, two 16-byte stores
+      if (row_ok) {
+        uint32_t w[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          int k0 = __float2int_rn(qn * v[4 * q]), k1 = __float2int_rn(qn * v[4 * q + 1]);
+          int k2 = __float2int_rn(qn * v[4 * q + 2]), k3 = __float2int_rn(qn * v[4 * q + 3]);
+          if (!whole) {
+            if (n0 + 4 * q >= n_lim) k0 = 0;
+            if (n0 + 4 * q + 1 >= n_lim) k1 = 0;
+            if (n0 + 4 * q + 2 >= n_lim) k2 = 0;
+            if (n0 + 4 * q + 3 >= n_lim) k3 = 0;
+          }
+          w[q] = pack4_sat(uns, k0, k1, k2, k3);
+        }
+        uint8_t* dst = cbase + (m * e.rq_ld + n0);
+        if (n0 < e.rq_ld) st_global_v4(dst, w[0], w[1], w[2], w[3]);
+        if (n0 + 16 < e.rq_ld && c0 + 16 < BN) st_global_v4(dst + 16, w[4], w[5], w[6], w[7]);
+      }
+      if (has_out && n0 < n_lim) {
+        // fp32 tile through the staging buffer (whole chunks; the tensor map clips M / N tails)
+        if (lane == 0) {
+          if (EPB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else tma_store_wait_read0();
+        }
+        __syncwarp();
+        const uint32_t tile_buf = my_buf + buf_sel * 4096u;
+        const uint32_t rowaddr = tile_buf + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(rowaddr + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) tma_store_2d(&map_out, tile_buf, n0, row0);
+        if (EPB == 2) buf_sel ^= 1u;
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (CG == 2) mbar_arrive_remote(mapa_shared(tempty0 + 8u * as, 0));
+      else mbar_arrive_relaxed(tempty0 + 8u * as);
+    }
+    if (++as == 2) { as = 0; aphase ^= 1u; }
+  }
+  if (has_out && lane == 0) tma_store_wait_all();
 }
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile -- each CTA
@@ -518,7 +703,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   // kind::mxf4: 2 x BN accumulator columns (BN <= 240) + 16 columns of unit scale factors at TC_SF_COL
-  constexpr uint32_t TMEM_COLS = (KIND == 2) ? 512u : 2u * BN;
+  constexpr uint32_t TMEM_COLS = (KIND == 2 || 2 * BN > 256) ? 512u : (2 * BN > 128 ? 256u : (2 * BN > 64 ? 128u : 2u * BN));
   static_assert(KIND != 2 || 2 * BN <= TC_SF_COL, "mxf4 tiles must leave the scale-factor columns free");
 
   extern __shared__ uint8_t smem_raw[];
@@ -672,6 +857,10 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
   } else if (g.epi_fast == 1) {
     epilogue_f32_tma<BN, KIND, CG, EPB>(map_out, g, tmem_base, epi_base, tfull_bar(0), tempty_bar(0), worker, num_workers, cta_rank,
                                         warp, lane);
+  } else if (g.epi_fast == 2) {
+    if constexpr (BN % 32 == 0)
+      epilogue_rq8<BN, KIND, CG, EPB>(map_out, g, tmem_base, epi_base, tfull_bar(0), tempty_bar(0), worker, num_workers, cta_rank,
+                                      warp, lane);
   } else {
     // ---- epilogue: 8 warps.  Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quadrant split
     // the BN accumulator columns in halves, so each SM sub-partition always has a second warp to hide latencies.
@@ -855,7 +1044,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
       __syncwarp();
       if (lane == 0) {
         if (CG == 2) mbar_arrive_remote(mapa_shared(tempty_bar(as), 0));   // the leader issues the MMAs of both CTAs
-        else mbar_arrive(tempty_bar(as));
+        else mbar_arrive_relaxed(tempty_bar(as));
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
@@ -969,6 +1158,27 @@ static bool epi_is_plain_f32(const TcArgs& g) {
   return true;
 }
 
+// the tight DoReFa-codes epilogue: 8-bit code lanes behind a clamp that keeps n * y inside the lane, no code row sums, an fp32
+// side output only in the TMA-store form, aligned column vectors / residual rows
+static bool epi_is_rq8(const TcArgs& g) {
+  const Epi& e = g.ep;
+  static int off = -1;
+  if (off < 0) { const char* s = getenv("QTB200_EPI_FAST"); off = (s && atoi(s) == 0) ? 1 : 0; }
+  if (off) return false;
+  if (e.rq_mode != QT_Q_DOREFA || !(e.rq_codes_kind == 1 || e.rq_codes_kind == 2) || !e.rq_clamp) return false;
+  const float lane_lo = e.rq_codes_kind == 1 ? -128.f : 0.f, lane_hi = e.rq_codes_kind == 1 ? 127.f : 255.f;
+  if (!(rintf(e.rq_n * e.rq_lo) >= lane_lo && rintf(e.rq_n * e.rq_hi) <= lane_hi)) return false;
+  if (e.rq_row_sum_part || e.rq_row_part || e.acc_out || g.N % 4 != 0) return false;
+  if (e.out) {
+    if (!g.tma_store || e.out_mode != 0) return false;
+    if (!e.out_clamp || e.out_lo != e.rq_lo || e.out_hi != e.rq_hi) return false;     // one clamp serves both outputs
+  }
+  if (e.residual && ((e.ld_res % 4) || (reinterpret_cast<uintptr_t>(e.residual) & 15))) return false;
+  if (e.col_scale && (reinterpret_cast<uintptr_t>(e.col_scale) & 15)) return false;
+  if (e.bias && (reinterpret_cast<uintptr_t>(e.bias) & 15)) return false;
+  return true;
+}
+
 constexpr size_t TC_SMEM_MAX = 232448;    // 227 KB opt-in limit per CTA
 
 template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false, int EPB = 1>
@@ -982,7 +1192,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
     if (int rc = make_map(&mo, g.ep.out, (uint64_t)g.M, (uint64_t)g.N * 4, (uint64_t)g.ep.ldo * 4, 32, true)) return rc;
     g.tma_store = 1;
   }
-  g.epi_fast = epi_is_plain_f32(g) ? 1 : 0;
+  g.epi_fast = epi_is_plain_f32(g) ? 1 : (epi_is_rq8(g) ? 2 : 0);
   // the opt-in shared-memory size is a per-device function attribute: remember it per device (one process may drive several)
   static bool attr_set[64] = {};
   int dev = 0;
@@ -1011,7 +1221,7 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, c
     if (int rc = make_map(&mo, g.ep.out, (uint64_t)g.M, (uint64_t)g.N * 4, (uint64_t)g.ep.ldo * 4, 32, true)) return rc;
     g.tma_store = 1;
   }
-  g.epi_fast = epi_is_plain_f32(g) ? 1 : 0;
+  g.epi_fast = epi_is_plain_f32(g) ? 1 : (epi_is_rq8(g) ? 2 : 0);
   static bool attr_set[64] = {};
   int dev = 0;
   QT_CUDA_OK(cudaGetDevice(&dev));
@@ -1232,6 +1442,9 @@ static int dispatch_conv(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g
     if (pair) {
       if (bn == 64) return launch_tc2<64, KIND, 8, 2, BKB, true>(ma, mw, g, stream);
       if (bn == 128) return launch_tc2<128, KIND, (BKB == 128 ? 6 : 8), 2, BKB, true>(ma, mw, g, stream);
+      if constexpr (BKB == 128) {
+        if (bn == 192) return launch_tc2<192, KIND, 5, 2, BKB, true>(ma, mw, g, stream);     // N = 192 k: no padded filter columns
+      }
       return launch_tc2<256, KIND, (BKB == 128 ? 5 : 8), 2, BKB, true>(ma, mw, g, stream);
     }
   }
@@ -1274,9 +1487,10 @@ static int conv_implicit(const void* x_nhwc, int elem_bytes, int a_signed, const
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed with CUresult %d", (int)r); return QT_EUNSUPPORTED; }
   }
-  const int bn = pick_bn(N);
   if (g_cta_group < 0) use_cta_pair(0, 0);                     // reads QTB200_CTA_GROUP once
   const bool pair = bkb >= 64 && g_cta_group != 1 && M >= 148 * 128;     // at least one 256-pixel tile per CTA pair
+  int bn = pick_bn(N);
+  if (pair && bkb == 128 && N % 192 == 0 && N % 256 != 0) bn = 192;
   const int cgn = pair ? 2 : 1;
   if (int rc = make_map(&mw, w, (uint64_t)N, (uint64_t)K * elem_bytes, (uint64_t)ldw * elem_bytes, (uint32_t)(bn / cgn), false, bkb)) return rc;
   TcArgs g{};
