@@ -394,6 +394,13 @@ int qt_transpose_split(const float* x, int64_t rows, int64_t cols, int64_t ld_x,
                        void* stream);
 int qt_ste_clip(const float* g, const float* x, float thresh, float* out, int64_t n, void* stream);
 
+/* The one collective of the path (all-gather of the fp32 logits of a batch-sharded run) in push form: copy `bytes`
+ * from `src` (local) to each of the `ndst` (<= 8) destinations -- pointers into PEER GPUs' gathered buffers, mapped into this
+ * process (symmetric memory / cudaIpc) -- with 16-byte stores from `ctas` small CTAs (no shared memory, so they run beside the
+ * persistent tcgen05 kernels of the next step).  Ends with a system-scope fence; the caller signals the peers afterwards
+ * (stream-ordered barrier).  The reference has no collective at all (single process, `device.py:2`). */
+int qt_peer_push(const void* src, void* const* dst, int ndst, int64_t bytes, int ctas, void* stream);
+
 /* Tuning / test knobs (process-wide).  "f4_tile_n": qt_gemm_f4 tile width, 0 = auto, or 64 / 128 / 240.
  * Unknown names or values return QT_EINVAL. */
 int qt_set_option(const char* name, int value);

@@ -109,6 +109,7 @@ SYMBOLS = {
     "qt_expand_loglin": (i32, [vp, i64, i64, i64, i32, i32, vp, i64, vp]),
     "qt_transpose_split": (i32, [vp, i64, i64, i64, vp, i64, i32, vp]),
     "qt_ste_clip": (i32, [vp, vp, f32, vp, i64, vp]),
+    "qt_peer_push": (i32, [vp, C.POINTER(vp), i32, i64, i32, vp]),
     "qt_set_option": (i32, [C.c_char_p, i32]),
     "qt_launch_count": (i64, [i32]),
 }

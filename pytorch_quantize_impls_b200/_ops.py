@@ -514,6 +514,14 @@ def pool_codes(codes_nhwc, k, s, p, use_min=None):
     return out
 
 
+def peer_push(src, dsts, ctas=32):
+    """Copy the contiguous tensor `src` into every tensor of `dsts` (same size; peer-mapped buffers) with one kernel (qt_peer_push)."""
+    require_cuda(src, "source")
+    nbytes = src.numel() * src.element_size()
+    arr = (C.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts])
+    L.check(L.lib().qt_peer_push(_p(src), arr, len(dsts), nbytes, ctas, _stream()), "qt_peer_push")
+
+
 def rowsum_codes(codes2d):
     """int32 row sums of an 8-bit code matrix [rows, ld] (qt_rowsum_codes)."""
     rows, ld = codes2d.shape

@@ -261,3 +261,54 @@ extern "C" int qt_pool_quant_f32(const float* x_nhwc, const QtPoolGeom* g, float
   QT_LAUNCH_CHECK();
   return QT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Logits gather over NVLink, push form (the only collective of the path is one all-gather of the fp32 logits).
+// One small kernel copies this rank's shard into its rows of EVERY peer's gathered buffer with 16-byte stores to peer-mapped
+// addresses: the shard is read once, the stores are posted (no round trip), and a few dozen CTAs without shared memory sit
+// beside the persistent tcgen05 CTAs of the next step, so the transfer overlaps the contractions instead of trailing them.
+// ---------------------------------------------------------------------------------------------
+namespace qt {
+struct PushArgs {
+  const uint4* src;
+  uint4* dst[8];
+  int ndst;
+  int64_t nvec;
+};
+
+__global__ void __launch_bounds__(256) peer_push_kernel(PushArgs a) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.nvec; i += stride * 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < a.nvec) v[u] = __ldcs(a.src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i + u * stride < a.nvec) {
+        for (int d = 0; d < a.ndst; ++d) a.dst[d][i + u * stride] = v[u];
+      }
+    }
+  }
+  __threadfence_system();
+}
+}  // namespace qt
+
+extern "C" int qt_peer_push(const void* src, void* const* dst, int ndst, int64_t bytes, int ctas, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(src && dst && ndst >= 1 && ndst <= 8, "qt_peer_push: 1..8 destinations");
+  QT_REQUIRE(bytes >= 0 && bytes % 16 == 0 && al(src, 16), "qt_peer_push: 16-byte aligned source and size");
+  PushArgs a;
+  a.src = reinterpret_cast<const uint4*>(src);
+  a.ndst = ndst;
+  a.nvec = bytes / 16;
+  for (int d = 0; d < ndst; ++d) {
+    QT_REQUIRE(dst[d] && al(dst[d], 16), "qt_peer_push: destinations must be 16-byte aligned");
+    a.dst[d] = reinterpret_cast<uint4*>(dst[d]);
+  }
+  if (a.nvec == 0) return QT_OK;
+  if (ctas <= 0) ctas = 32;
+  peer_push_kernel<<<ctas, 256, 0, stream>>>(a);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}

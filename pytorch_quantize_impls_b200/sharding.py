@@ -65,6 +65,8 @@ class PipelinedGather:
         (torch.distributed._symmetric_memory).  PUSH form: the gathered buffers themselves are peer-mapped; every rank writes
         its shard straight from the logits tensor into rows [rank*B, (rank+1)*B) of every peer's buffer (posted NVLink
         writes, spread over up to 4 streams), then ONE signal-pad barrier tells everybody that all shards have landed.
+    mode "push": the same protocol with the G copies done by ONE small kernel (qt_peer_push: the shard is read once and stored
+        to all peers with 16-byte stores from ~32 CTAs that hold no shared memory, so they run beside the tcgen05 CTAs).
     mode "ce_pull": every rank stages its logits in a peer-mapped buffer, barrier, each rank pulls the G-1 remote shards,
         a second barrier releases the stage (one more copy and one more barrier per step than the push form).
         No SM is taken from the compute kernels: the tcgen05 GEMMs are persistent one-CTA-per-SM kernels with ~225 KB of
@@ -75,8 +77,8 @@ class PipelinedGather:
     On CPU tensors (gloo tests) it degrades to the synchronous collective."""
 
     def __init__(self, depth=2, mode="ce", pull_streams=None):
-        if mode not in ("ce", "ce_pull", "nccl", "sync"):
-            raise ValueError("mode must be 'ce', 'ce_pull', 'nccl' or 'sync'")
+        if mode not in ("ce", "push", "ce_pull", "nccl", "sync"):
+            raise ValueError("mode must be 'ce', 'push', 'ce_pull', 'nccl' or 'sync'")
         self.depth, self.mode = depth, mode
         # mode "ce": the G-1 peer pulls of one step are spread over this many streams so that several copy engines
         # (and NVLink ports) work at once; 1 = one pull after the other
@@ -135,9 +137,9 @@ class PipelinedGather:
             return out, None
         if self._comm is None:
             self._comm = torch.cuda.Stream(device=y_local.device)
-        if self.mode in ("ce", "ce_pull"):
+        if self.mode in ("ce", "push", "ce_pull"):
             try:
-                if self.mode == "ce":
+                if self.mode in ("ce", "push"):
                     out, hdl = self._symmetric_out(slot, y_local, world)     # collective on first use of a slot
                 else:
                     buf, hdl = self._symmetric_stage(slot, y_local)
@@ -150,7 +152,21 @@ class PipelinedGather:
         ready.record(comp)
         self._comm.wait_event(ready)
         with torch.cuda.stream(self._comm):
-            if self.mode == "ce":
+            if self.mode == "push":
+                # same protocol as "ce" (release barrier, pushes, publish barrier), the pushes being ONE kernel: 16-byte stores
+                # from a few dozen CTAs straight into every peer's gathered buffer (qt_peer_push)
+                from . import _ops as ops
+                n = y_local.shape[0]
+                full_shape = (world * n,) + tuple(y_local.shape[1:])
+                hdl.barrier(channel=self.depth + slot)
+                dsts = []
+                for step in range(world):
+                    dst = (rank + step) % world
+                    peer_out = out if dst == rank else hdl.get_buffer(dst, full_shape, y_local.dtype)
+                    dsts.append(peer_out[rank * n:(rank + 1) * n])
+                ops.peer_push(y_local, dsts, ctas=self.pull_streams or 32)
+                hdl.barrier(channel=slot)
+            elif self.mode == "ce":
                 n = y_local.shape[0]
                 # release barrier: a peer may only overwrite my rows of slot `slot` once I am done with what step i - depth left
                 # there.  Every rank's communication stream reaches this barrier after its own `ready` event, i.e. after all
