@@ -39,6 +39,7 @@ struct TcArgs {
   int tiles_m, tiles_n;
   int tma_store;        // 1: row-major fp32 output goes through swizzled smem + cp.async.bulk.tensor store
   int epi_fast;         // 1: the epilogue is the plain "fp32 tile -> TMA store" form (tight code path, see epilogue_f32_tma)
+  int epi_debug;        // profiling aid (QTB200_EPI_DEBUG): 1 = release the accumulator without reading it, 2 = read TMEM, store nothing
   // implicit-GEMM conv (IM2COL kernels): A rows are output pixels (b, oh, ow), K runs over (kh, kw, c-blocks)
   int cv_OW, cv_OHW;            // output width, output pixels per image
   int cv_sh, cv_sw, cv_ph, cv_pw, cv_dh, cv_dw, cv_kw;
@@ -442,6 +443,7 @@ __device__ __forceinline__ void epilogue_f32_tma(const CUtensorMap& map_out, con
     tc_fence_after();
     uint32_t r[32];
     const uint32_t t_row = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lane_grp * 32) << 16);
+    if (g.epi_debug == 1) c_end = c_begin;
     if (c_begin < c_end) tmem_ld32_issue(t_row + (uint32_t)(c_begin * 32), r);
 #pragma unroll 1
     for (int cidx = c_begin; cidx < c_end; ++cidx) {
@@ -452,6 +454,10 @@ __device__ __forceinline__ void epilogue_f32_tma(const CUtensorMap& map_out, con
       float pb[32];
       if (has_b) load_col32(e.bias, n0, N32, true, 0.f, pb);
       tmem_ld_wait(r);
+      if (g.epi_debug == 2) {
+        if (cidx + 1 < c_end) tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), r);
+        continue;
+      }
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -476,7 +482,13 @@ __device__ __forceinline__ void epilogue_f32_tma(const CUtensorMap& map_out, con
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], e.out_lo), e.out_hi);
       }
-      if (full_chunk) {
+      if (g.epi_debug == 3) {      // profiling aid: registers -> global directly (each lane owns 128 contiguous bytes of its row)
+        if (row_ok && n0 + 32 <= n_lim) {
+          float4* o = reinterpret_cast<float4*>(e.out + m * e.ldo + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) __stcs(o + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
+      } else if (full_chunk) {
         if (lane == 0) {
           if (EPB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else tma_store_wait_read0();
@@ -1193,6 +1205,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
     g.tma_store = 1;
   }
   g.epi_fast = epi_is_plain_f32(g) ? 1 : (epi_is_rq8(g) ? 2 : 0);
+  { const char* dbg = getenv("QTB200_EPI_DEBUG"); g.epi_debug = dbg ? atoi(dbg) : 0; }
   // the opt-in shared-memory size is a per-device function attribute: remember it per device (one process may drive several)
   static bool attr_set[64] = {};
   int dev = 0;
@@ -1222,6 +1235,7 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, c
     g.tma_store = 1;
   }
   g.epi_fast = epi_is_plain_f32(g) ? 1 : (epi_is_rq8(g) ? 2 : 0);
+  { const char* dbg = getenv("QTB200_EPI_DEBUG"); g.epi_debug = dbg ? atoi(dbg) : 0; }
   static bool attr_set[64] = {};
   int dev = 0;
   QT_CUDA_OK(cudaGetDevice(&dev));
