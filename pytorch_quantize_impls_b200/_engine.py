@@ -840,3 +840,51 @@ def grad_weight_linear(g2d, x2d):
     epi = ops.make_epi(out, ldo=K)
     ops.gemm_f16(gT, ldg, gT.stride(0), xT, ldx, xT.stride(0), _GRAD_PASSES, N, K, M, epi, _force_backend["bf16"])
     return out
+
+
+def _conv_geom(input_shape, weight_shape, stride, padding, dilation):
+    B, Cin, H, W = input_shape
+    O, Cg, kh, kw = weight_shape
+    (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
+    OH = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    OW = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    return B, Cin, H, W, O, Cg, kh, kw, (sh, sw), (ph, pw), (dh, dw), OH, OW
+
+
+def grad_input_conv2d(input_shape, wq, grad_output, stride=1, padding=0, dilation=1, groups=1):
+    """d loss / d x of F.conv2d(x, W_q): the transposed convolution as a contraction over the output channels,
+    cols[m, (c, kh, kw)] = sum_o g[m, o] W_q[o, (c, kh, kw)] on the bf16 hi/lo tensor-core route (grad_input_linear), followed by
+    the col2im scatter-add (torch fold: pure data movement).  binary_connect.py:139-142, terner_connect.py:137-139,
+    dorefa_connect.py:181-183, xnor_connect.py:152-154 call torch.nn.grad.conv2d_input for this."""
+    if _grad_backend[0] != "tcgen05" or not grad_output.is_cuda or isinstance(padding, str):
+        return torch.nn.grad.conv2d_input(input_shape, wq, grad_output, stride=stride, padding=padding, dilation=dilation, groups=groups)
+    B, Cin, H, W, O, Cg, kh, kw, st, pd, dl, OH, OW = _conv_geom(input_shape, wq.shape, stride, padding, dilation)
+    Ng, L_ = O // groups, OH * OW
+    g = ops.as_f32c(grad_output)
+    parts = []
+    for gi in range(groups):
+        g2 = g[:, gi * Ng:(gi + 1) * Ng].permute(0, 2, 3, 1).reshape(B * L_, Ng)                 # [M, Ng]
+        w2 = ops.as_f32c(wq[gi * Ng:(gi + 1) * Ng]).reshape(Ng, Cg * kh * kw)
+        cols = grad_input_linear(g2.contiguous(), w2)                                               # [M, Cg*kh*kw]
+        parts.append(cols.reshape(B, L_, Cg * kh * kw).transpose(1, 2))
+    cols = parts[0] if groups == 1 else torch.cat(parts, 1)
+    return torch.nn.functional.fold(cols, (H, W), (kh, kw), dilation=dl, padding=pd, stride=st)
+
+
+def grad_weight_conv2d(x, weight_shape, grad_output, stride=1, padding=0, dilation=1, groups=1):
+    """d loss / d W_q of F.conv2d(x, W_q): gw[o, (c, kh, kw)] = sum_m g[m, o] im2col(x)[m, (c, kh, kw)] -- the reduction runs over
+    the B*OH*OW output pixels, both operands are transposed + split in one pass each (grad_weight_linear).  The im2col view comes
+    from torch unfold (data movement).  binary_connect.py:143-146 etc. call torch.nn.grad.conv2d_weight for this."""
+    if _grad_backend[0] != "tcgen05" or not grad_output.is_cuda or isinstance(padding, str):
+        return torch.nn.grad.conv2d_weight(x, weight_shape, grad_output, stride=stride, padding=padding, dilation=dilation, groups=groups)
+    B, Cin, H, W, O, Cg, kh, kw, st, pd, dl, OH, OW = _conv_geom(x.shape, weight_shape, stride, padding, dilation)
+    Ng, L_ = O // groups, OH * OW
+    g = ops.as_f32c(grad_output)
+    unf = torch.nn.functional.unfold(ops.as_f32c(x), (kh, kw), dilation=dl, padding=pd, stride=st)   # [B, Cin*kh*kw, L]
+    outs = []
+    for gi in range(groups):
+        g2 = g[:, gi * Ng:(gi + 1) * Ng].permute(0, 2, 3, 1).reshape(B * L_, Ng).contiguous()
+        cx = unf[:, gi * Cg * kh * kw:(gi + 1) * Cg * kh * kw].transpose(1, 2).reshape(B * L_, Cg * kh * kw).contiguous()
+        outs.append(grad_weight_linear(g2, cx))                                                        # [Ng, Cg*kh*kw]
+    gw = outs[0] if groups == 1 else torch.cat(outs, 0)
+    return gw.reshape(weight_shape)

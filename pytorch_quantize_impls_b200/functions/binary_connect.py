@@ -97,10 +97,10 @@ def BinaryConv2d(stride=1, padding=1, dilation=1, groups=1):
             weight_b = safeSign(weight)
             gi = gw = gb = None
             if ctx.needs_input_grad[0]:
-                gi = torch.nn.grad.conv2d_input(input.size(), weight_b, grad_output, stride=stride, padding=padding,
+                gi = eng.grad_input_conv2d(input.size(), weight_b, grad_output, stride=stride, padding=padding,
                                                 dilation=dilation, groups=groups)
             if ctx.needs_input_grad[1]:
-                gw = torch.nn.grad.conv2d_weight(input, weight.shape, grad_output, stride=stride, padding=padding,
+                gw = eng.grad_weight_conv2d(input, weight.shape, grad_output, stride=stride, padding=padding,
                                                  dilation=dilation, groups=groups)
             if bias is not None and ctx.needs_input_grad[2]:
                 gb = grad_output.sum((0, 2, 3))

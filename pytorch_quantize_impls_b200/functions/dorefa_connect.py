@@ -199,10 +199,10 @@ def QuantConv2d(stride=1, padding=1, dilation=1, groups=1, bit_width=3):
             input, weight, weight_q, max_weight, bias = ctx.saved_tensors
             gi = gw = gb = None
             if ctx.needs_input_grad[0]:
-                gi = torch.nn.grad.conv2d_input(input.size(), weight_q, grad_output, stride=stride, padding=padding,
+                gi = eng.grad_input_conv2d(input.size(), weight_q, grad_output, stride=stride, padding=padding,
                                                 dilation=dilation, groups=groups)
             if ctx.needs_input_grad[1]:
-                gw = torch.nn.grad.conv2d_weight(input, weight.shape, grad_output, stride=stride, padding=padding,
+                gw = eng.grad_weight_conv2d(input, weight.shape, grad_output, stride=stride, padding=padding,
                                                  dilation=dilation, groups=groups)
                 if 1 < bit_width < 32:
                     gw = gw * (1 - torch.pow(torch.tanh(weight), 2)) / torch.tanh(max_weight)

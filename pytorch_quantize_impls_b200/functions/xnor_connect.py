@@ -147,10 +147,10 @@ def XNORConv2d(dim=[0, 1], quant_input=False, stride=1, padding=1, dilation=1, g
             weight_b = torch.sign(weight) * mean
             gi = gw = gb = None
             if ctx.needs_input_grad[0]:
-                gi = torch.nn.grad.conv2d_input(input.size(), weight_b, grad_output, stride=stride, padding=padding,
+                gi = eng.grad_input_conv2d(input.size(), weight_b, grad_output, stride=stride, padding=padding,
                                                 dilation=dilation, groups=groups)
             if ctx.needs_input_grad[1]:
-                t = torch.nn.grad.conv2d_weight(input, weight.shape, grad_output, stride=stride, padding=padding,
+                t = eng.grad_weight_conv2d(input, weight.shape, grad_output, stride=stride, padding=padding,
                                                 dilation=dilation, groups=groups)
                 gw = mean * t + torch.sign(weight) * torch.mean(t * torch.sign(weight), DIM, keepdim=True)
             if bias is not None and ctx.needs_input_grad[2]:

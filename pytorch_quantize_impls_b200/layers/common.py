@@ -56,10 +56,11 @@ class _Contraction(torch.autograd.Function):
         wqd = ctx.wq_sample if ctx.wq_sample is not None else wq.detach()
         if layer._is_conv:
             kw = dict(stride=layer.stride, padding=layer.padding, dilation=layer.dilation, groups=layer.groups)
+            # both gradient contractions on the bf16 hi/lo tensor-core route (engine.grad_*_conv2d)
             if ctx.needs_input_grad[0]:
-                gi = torch.nn.grad.conv2d_input(input.shape, wqd, grad_output, **kw)
+                gi = eng.grad_input_conv2d(input.shape, wqd, grad_output, **kw)
             if ctx.needs_input_grad[1]:
-                gwq = torch.nn.grad.conv2d_weight(input, weight.shape, grad_output, **kw)
+                gwq = eng.grad_weight_conv2d(input, weight.shape, grad_output, **kw)
             if bias is not None and ctx.needs_input_grad[2]:
                 gb = grad_output.sum((0, 2, 3))
         else:

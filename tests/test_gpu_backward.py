@@ -79,3 +79,28 @@ def test_training_step_grads_match_torch_backend(Q, cls, kw, act):
     Q.set_grad_backend("tcgen05")
     for a, b in zip(grads["tcgen05"], grads["torch"]):
         assert rel(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("geo", [dict(stride=1, padding=1), dict(stride=2, padding=1), dict(stride=1, padding=2, dilation=2),
+                                 dict(stride=1, padding=1, groups=2)])
+def test_conv_gradient_contractions_match_fp64(Q, geo):
+    """engine.grad_input_conv2d / grad_weight_conv2d (im2col view + bf16 hi/lo planes on tcgen05) vs fp64 autograd of F.conv2d."""
+    from pytorch_quantize_impls_b200 import _engine as eng
+    torch.manual_seed(11)
+    groups = geo.get("groups", 1)
+    x = torch.randn(6, 16, 13, 11)
+    w = torch.randn(24, 16 // groups, 3, 3).sign() * torch.rand(24, 1, 1, 1)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    y = torch.nn.functional.conv2d(xd, wd, None, **geo)
+    go = torch.randn(y.shape)
+    y.backward(go.double())
+    gi = eng.grad_input_conv2d(x.shape, w.cuda(), go.cuda(), **geo)
+    gw = eng.grad_weight_conv2d(x.cuda(), w.shape, go.cuda(), **geo)
+    assert gi.shape == x.shape and gw.shape == w.shape
+    assert rel(gi.cpu(), xd.grad) < 3e-5 and rel(gw.cpu(), wd.grad) < 3e-5
+    Q.set_grad_backend("torch")
+    try:
+        gi_t = eng.grad_input_conv2d(x.shape, w.cuda(), go.cuda(), **geo)
+    finally:
+        Q.set_grad_backend("tcgen05")
+    assert rel(gi.cpu(), gi_t.cpu()) < 2e-3          # cuDNN's default conv math is TF32
