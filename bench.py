@@ -577,10 +577,10 @@ def run_ours(args):
                 "timing": ("CUDA events recorded as external event nodes inside the captured step graphs; mean over the last replay of "
                            "each of the %d graphs within the timed region" % NBUF) if graph_mode else
                           "CUDA events around every launch of the timed region",
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` launch
-                # (profiles/r1i_ncu_full_summary.json: 157.9 MB read + 46.5 MB written; algorithmic 100.7 MB of operands +
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` launch of round 2
+                # (profiles/r2_ncu_full_summary.json: 159.4 MB read + 49.9 MB written; algorithmic 100.7 MB of operands +
                 # 67.1 MB of fp16 codes, part of which is still in L2 when the kernel ends)
-                "traffic": 204.3e6, "traffic_unit": "bytes per launch (ncu, profiles/r1i_ncu_full_summary.json)",
+                "traffic": 209.3e6, "traffic_unit": "bytes per launch (ncu --set full of this kernel at this shape, profiles/r2_ncu_full_summary.json)",
                 "algorithmic_bytes": float(2 * M * K + 2 * N * K + 2 * M * N + 4 * N)}
 
     cb = cpu_reference_gops(BATCH, reps=3, warmup=1)
@@ -1049,6 +1049,7 @@ def extra_layers(Q, torch, dev, pk, _ops):
         with Q.code_only_activations():
             return pair(xs[i[0] % 3])
     try:
+        Q.set_banded_head(True)
         ms = time_fn(torch, fp, iters=20, graph=True)
         same = bool(torch.equal(fp(), fc()) or True)
         i[0] = 0
@@ -1057,9 +1058,12 @@ def extra_layers(Q, torch, dev, pk, _ops):
         yb = fc()
         out["linearbin_4096x4096_b8192_fused_head_pair"] = {
             "ms": round(ms, 4), "gops": round(ops_ / ms / 1e6, 1), "hbm_gbs_algorithmic": round(bytes_module / ms / 1e6, 1),
-            "hbm_frac": round(bytes_module / ms / 1e6 / pk["hbm_gbs"], 4), "equals_unfused": bool(torch.equal(ya, yb))}
+            "hbm_frac": round(bytes_module / ms / 1e6 / pk["hbm_gbs"], 4), "equals_unfused": bool(torch.equal(ya, yb)),
+            "what": "two-stream band pipeline (set_banded_head(True)); off by default because it is slower than the plain pair"}
     except Exception as err:
         out["linearbin_4096x4096_b8192_fused_head_pair"] = {"error": str(err)}
+    finally:
+        Q.set_banded_head(False)
     # contraction kernel alone on pre-quantized operands
     xq = act(xs[0])
     ms = time_fn(torch, lambda: lay(xq), iters=20, graph=True)

@@ -457,6 +457,16 @@ def linear(x, pack, bias, requant=None, affine=None):
 
 
 _band_streams = {}
+_banded_head = [os.environ.get("QTB200_BANDED_HEAD", "0") == "1"]
+
+
+def set_banded_head(flag):
+    """True: fusion.FusedActLayer runs `quantizer -> Linear` head pairs of >= 4096 rows as the two-stream band pipeline
+    (linear_banded).  Default False: measured on B200 at the north-star shape the pipeline is slower than the plain pair
+    (134 us vs 94 us: every band pays the prologue / tail of a persistent contraction launch, and the one quantizer CTA per SM
+    that fits beside a 168-register contraction CTA reaches ~1.6 TB/s); the mechanism is kept and tested (bit-exact)."""
+    _banded_head[0] = bool(flag)
+
 
 
 def _tag_tensors(tag):

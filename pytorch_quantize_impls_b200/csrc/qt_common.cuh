@@ -94,8 +94,10 @@ static inline Epi make_epi(const QtEpilogue* e, int64_t M, int64_t N) {
 }
 
 int check_epi(const QtEpilogue* e, int64_t M, int64_t N);
-// true when the epilogue asks for something only the tcgen05 kernels implement (requant, partial-sum row operands)
-static inline bool epi_needs_tc(const Epi& e) { return e.rq_mode >= 0 || e.row_scale_parts > 0 || e.row_sum_parts > 0; }
+// true when the epilogue asks for something only the tcgen05 kernels implement (requant, partial-sum row operands, residual)
+static inline bool epi_needs_tc(const Epi& e) {
+  return e.rq_mode >= 0 || e.row_scale_parts > 0 || e.row_sum_parts > 0 || e.residual != nullptr;
+}
 
 // y = float(acc_mul*acc + rs_mul*row_sum[m]) * scale * row_scale[m] * col_scale[n] + bias[n]
 // The integer part is exact; float(t) * 1.0f + bias is a single rounding, which is what makes the
@@ -107,7 +109,6 @@ __device__ __forceinline__ float epi_int(const Epi& e, int64_t m, int64_t n, int
   if (e.row_scale) y *= __ldg(e.row_scale + m);
   if (e.col_scale) y *= __ldg(e.col_scale + n);
   if (e.bias) y += __ldg(e.bias + n);
-  if (e.residual) y += __ldg(e.residual + m * e.ld_res + n);
   if (e.out_clamp) y = fminf(fmaxf(y, e.out_lo), e.out_hi);
   return y;
 }
@@ -116,7 +117,6 @@ __device__ __forceinline__ float epi_f32(const Epi& e, int64_t m, int64_t n, flo
   if (e.row_scale) y *= __ldg(e.row_scale + m);
   if (e.col_scale) y *= __ldg(e.col_scale + n);
   if (e.bias) y += __ldg(e.bias + n);
-  if (e.residual) y += __ldg(e.residual + m * e.ld_res + n);
   if (e.out_clamp) y = fminf(fmaxf(y, e.out_lo), e.out_hi);
   return y;
 }

@@ -377,7 +377,8 @@ class FlattenCodes(nn.Module):
 
 
 class FusedActLayer(nn.Module):
-    """activation quantizer -> quantized Linear at the head of a chain, where the input is a real fp32 tensor: under
+    """activation quantizer -> quantized Linear at the head of a chain, where the input is a real fp32 tensor.  With
+    `set_banded_head(True)` (off by default: slower than the plain pair on B200, see engine.set_banded_head) and under
     `code_only_activations()` the pair runs as a two-stream pipeline over row bands (engine.linear_banded) -- the HBM-bound
     quantizer of band i+1 beside the tensor-bound contraction of band i -- instead of one after the other."""
     MIN_ROWS = 4096
@@ -392,7 +393,8 @@ class FusedActLayer(nn.Module):
     def forward(self, x):
         lay = self._layer()
         kind, arg = self.quant._qt_spec
-        ok = (eng._code_only[0] and not torch.is_grad_enabled() and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+        ok = (eng._banded_head[0] and eng._code_only[0] and not torch.is_grad_enabled() and x.is_cuda and x.dim() == 2
+              and x.dtype == torch.float32
               and x.shape[0] >= self.MIN_ROWS and x.shape[1] % 1024 == 0 and x.is_contiguous() and not lay.training
               and not (isinstance(self.inner, FusedLayerBN) and not _bn_ready(self.inner.bn)))
         if not ok:

@@ -63,9 +63,10 @@ def test_first_layer_implicit_gemm(Q, shape, fam):
           "dorefa8": lambda: Q.layers.DorefaConv2d(Cin, Oc, k, stride=s, padding=p, dilation=d, bit_width=8)}[fam]
     lay = mk()
     if fam == "ter":
-        lay.weight.data.mul_(4.0)
+        lay.weight.data.mul_(0.7 / float(lay.weight.data.abs().max()))     # all three ternary levels occur
     lay.bias.data.uniform_(-1, 1)
     w, b = lay.weight.data.clone(), lay.bias.data.clone()
+    assert fam != "ter" or float(O.ternary_det(w).abs().mean()) > 0.1
     wq = {"ter": O.ternary_det, "bin": O.binary_det, "dorefa4": lambda t: O.dorefa_weight(t, 4),
           "dorefa8": lambda t: O.dorefa_weight(t, 8)}[fam](w)
     ref = TF.conv2d(x.double(), wq.double(), b.double(), s, p, d)
@@ -91,7 +92,7 @@ def test_first_layer_eval_mode_and_channels_last_output(Q):
     from pytorch_quantize_impls_b200 import _engine as eng
     torch.manual_seed(5)
     lay = Q.layers.TerConv2d(3, 64, 7, stride=2, padding=3, bias=False)
-    lay.weight.data.mul_(4.0)
+    lay.weight.data.mul_(0.7 / float(lay.weight.data.abs().max()))
     x = torch.rand(2, 3, 50, 46)
     ref = TF.conv2d(x.double(), O.ternary_det(lay.weight.data).double(), None, 2, 3)
     lay = lay.cuda().eval()
@@ -289,6 +290,7 @@ def test_banded_head_pair_equals_plain(Q, fam):
         ref = net(x)
         fused = Q.fuse_inference(net)
         assert type(fused[0]).__name__ == "FusedActLayer"
+        Q.set_banded_head(True)
         with Q.code_only_activations():
             y = fused(x)
             g = torch.cuda.CUDAGraph()                      # the two-stream fork / join must be capturable
@@ -302,6 +304,7 @@ def test_banded_head_pair_equals_plain(Q, fam):
             g.replay()
             torch.cuda.synchronize()
         y_small = fused(x[:100])                            # below MIN_ROWS: plain path
+        Q.set_banded_head(False)
     if fam == "xnor":
         assert rel(y, ref) <= 2e-6 and rel(yg, ref) <= 2e-6   # partial row sums are added in a different order
     else:
