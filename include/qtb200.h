@@ -247,6 +247,9 @@ typedef struct QtRequant {
   int32_t* row_sum_part;/* optional: [>= qt_requant_max_parts(N), M] partial sums of the integer codes */
   int row_parts;        /* OUT: number of partial rows written */
   int32_t* overflow;    /* optional sticky device flag (a DoReFa code left its lane) */
+  int64_t cover;        /* 0: columns N .. ld_codes-1 of a row are zero-filled (channel padding).  > 0: only columns N .. cover-1
+                           are (the row pitch is wider than this launch's slice: two output-column phases of a W-folded conv
+                           interleave their pixels, ld_codes = 2 * channel pitch) */
 } QtRequant;
 
 /* upper bound on QtRequant.row_parts for an N-column output */
@@ -314,6 +317,11 @@ typedef struct QtConvGeom {
   int kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
   int groups, group;
   int64_t OH, OW;
+  /* optional explicit bounding box of the filter-window base positions along W (asymmetric padding), used when
+     corner_mode != 0: positions lower_w .. (W - 1) + upper_w in steps of stride_w; pad_w is then ignored.  A W-folded conv
+     (two adjacent pixels of a 64-byte-channel tensor viewed as one 128-byte pixel) runs as two such launches, one per
+     output-column parity, with their own zero-padded filters (see engine.conv2d). */
+  int corner_mode, lower_w, upper_w;
 } QtConvGeom;
 
 int qt_conv_i8(const void* x_nhwc, int a_signed, const QtConvGeom* g, const void* w, int w_signed, int64_t ldw,

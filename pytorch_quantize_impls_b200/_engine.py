@@ -541,18 +541,89 @@ def conv_pad_channels(C):
     return C
 
 
+def _relaid_weights(pack, key, build):
+    """Small per-pack cache of re-laid conv operands (channel padding, W-fold phases), valid while the packed tensor is."""
+    base = (pack.packed.data_ptr(), pack.packed._version)
+    cache = pack._padw
+    if cache is None or cache.get("base") != base:
+        cache = pack._padw = {"base": base}
+    hit = cache.get(key)
+    if hit is None:
+        hit = cache[key] = build()
+    return hit
+
+
 def _channel_padded_weights(pack, out_kind, N, taps, Cin, Cp):
-    """Expanded conv operand [N, taps * Cin] re-laid as [N, taps * Cp] with zero columns for the pad channels (cached on the pack)."""
-    key = (pack.packed.data_ptr(), pack.packed._version, out_kind, Cp)
-    hit = pack._padw
-    if hit is not None and hit[0] == key:
-        return hit[1], hit[2]
-    w, ldw = ops._expand_weight(pack, out_kind)
-    wz = torch.zeros((N, taps, Cp), dtype=w.dtype, device=w.device)
-    wz[:, :, :Cin] = w[:N, :taps * Cin].reshape(N, taps, Cin)
-    wz = wz.reshape(N, taps * Cp)
-    pack._padw = (key, wz, taps * Cp)
-    return wz, taps * Cp
+    """Expanded conv operand [N, taps * Cin] re-laid as [N, taps * Cp] with zero columns for the pad channels."""
+    def build():
+        w, ldw = ops._expand_weight(pack, out_kind)
+        wz = torch.zeros((N, taps, Cp), dtype=w.dtype, device=w.device)
+        wz[:, :, :Cin] = w[:N, :taps * Cin].reshape(N, taps, Cin)
+        return wz.reshape(N, taps * Cp), taps * Cp
+    return _relaid_weights(pack, ("pad", out_kind, Cp), build)
+
+
+_wfold = [os.environ.get("QTB200_WFOLD", "1") != "0"]
+
+
+def set_wfold(flag):
+    """True (default): stride-1 convs on channels-last codes with a 64-byte channel pitch read two horizontally adjacent pixels
+    as one 128-byte pixel (two launches, one per output-column parity): a third fewer TMA im2col rows."""
+    _wfold[0] = bool(flag)
+
+
+def _conv_wfold2(tag, pack, bias, geom, dims, requant, affine, out, residual, keep_out, need_rs, dev):
+    """Implicit-GEMM conv with the W axis folded by two.  Pixels (2s, 2s+1) of a row form super pixel s of 2*Cp channels (the
+    same memory).  Output column ow = 2t + p reads pixels ow - pw .. ow - pw + kw - 1, i.e. super pixels starting at
+    t + floor((p - pw) / 2) with the filter shifted by r = (p - pw) mod 2 positions inside the first one: per parity p a stride-1
+    conv over the super-pixel grid with its own zero-padded filter [kh, kw'_p * 2, Cp], asymmetric padding (explicit TMA corners),
+    M / 2 rows, and outputs interleaved back by addressing (row pitch 2 * channels, offset p * channels)."""
+    kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW = geom
+    B, Cin, Cp, H, W, O = dims
+    a_signed = tag.codes_kind == L.CODES_I8
+    kind = L.CODES_U8 if need_rs else L.CODES_I8
+    x2 = tag.codes.view(B, H, W // 2, 2 * Cp)
+    P = OH * OW
+    rq0 = codes = None
+    Op = O
+    if requant is not None:
+        ck = requant.codes_kind(False)
+        Op = max(O, requant.pad_channels)
+        codes = torch.empty((B, OH, OW, Op), device=dev, dtype=torch.uint8 if ck == L.CODES_U8 else torch.int8)
+    rs_full = ops.patch_rowsum(tag.codes, not a_signed, geom, 0) if need_rs else None
+    res_flat = None if residual is None else residual.permute(0, 2, 3, 1).reshape(-1)
+    cs, bg = pack.col_scale, bias
+    if requant is not None or affine is not None:
+        cs, bg = (requant or affine).fold(cs, bg, 0, O)
+    for p in (0, 1):
+        d = p - pw
+        lo_w = d // 2                        # floor
+        r = d - 2 * lo_w
+        kwf = (r + kw - 1) // 2 + 1
+
+        def build(r=r, kwf=kwf):
+            w, _ = ops._expand_weight(pack, kind)
+            wz = torch.zeros((O, kh, kwf * 2, Cp), dtype=w.dtype, device=w.device)
+            wz[:, :, r:r + kw, :Cin] = w[:O, :kh * kw * Cin].reshape(O, kh, kw, Cin)
+            return wz.reshape(O, kh * kwf * 2 * Cp), kh * kwf * 2 * Cp
+        w, ldw = _relaid_weights(pack, ("wfold", kind, Cp, r, kw), build)
+        rq = None
+        if requant is not None:
+            rq = ops.RequantOut(requant.mode, requant.bit_width, ck, B * P // 2, O, dev, lo=requant.lo, hi=requant.hi,
+                                ld=2 * Op, codes=codes, col_offset=p * Op, cover=Op)
+            if rq0 is None:
+                rq0 = rq
+            elif rq0.overflow is not None:
+                rq.c.overflow = rq0.c.overflow           # one sticky flag for both parities
+        rs = rs_full.view(-1, 2)[:, p].contiguous() if need_rs else None
+        epi = ops.make_epi(out, bias=bg, col_scale=cs, row_sum=rs, acc_mul=2 if need_rs else 1, rs_mul=-255 if need_rs else 0,
+                           scale=tag.scale * pack.wscale, out_offset=p * O, requant=rq, out_clamp=_out_clamp(affine, requant, keep_out),
+                           out_mode=0, ldo=2 * O, nchw_inner=1,
+                           residual=None if res_flat is None else res_flat[p * O:], ld_res=2 * O)
+        g2 = (kh, kwf, sh, 1, ph, 0, dh, 1, 1, OH, OW // 2)
+        if not ops.conv_i8(x2, a_signed, g2, 0, w, not need_rs, ldw, O, epi, corners=(lo_w, lo_w + OW // 2 - W // 2)):
+            raise RuntimeError("internal: W-folded conv rejected by the implicit-GEMM kernel")
+    return rq0, codes
 
 
 def _out_clamp(affine, requant, keep_out):
@@ -691,6 +762,15 @@ def conv2d(x, pack, bias, weight_shape, stride, padding, dilation, groups, requa
             and _force_backend["i8"] != L.BACKEND_SIMT):
         a_signed = tag.codes_kind == L.CODES_I8
         # DoReFa-8 weights stay unsigned codes c; the zero point needs the per-pixel patch sums of the activation codes
+        if (_wfold[0] and groups == 1 and Cp == 64 and sw == 1 and dw == 1 and W % 2 == 0 and OW % 2 == 0 and kw <= 7
+                and (out is None or nhwc_out) and B * P >= 148 * 256):
+            rq, codes = _conv_wfold2(tag, pack, bias, geom, (B, Cin, Cp, H, W, O), requant, affine, out, residual, keep_out, need_rs, dev)
+            if requant is not None:
+                y = out if keep_out else torch.empty((B, O, OH, OW), dtype=torch.float32, device="meta")
+                t = _requant_tag(requant, rq, (B, O, OH, OW), layout="nhwc")
+                t.codes, t.rows, t.cols, t.ld = codes, B, codes.shape[3] * P, codes.shape[3] * P
+                return attach_tag(y, t)
+            return out
         if Cp != Cin:
             w, ldw = _channel_padded_weights(pack, L.CODES_U8 if need_rs else L.CODES_I8, O, kh * kw, Cin, Cp)
         else:

@@ -55,7 +55,8 @@ class QtIm2col(C.Structure):
 class QtConvGeom(C.Structure):
     _fields_ = [("B", i64), ("C", i64), ("H", i64), ("W", i64),
                 ("kh", i32), ("kw", i32), ("stride_h", i32), ("stride_w", i32), ("pad_h", i32), ("pad_w", i32),
-                ("dil_h", i32), ("dil_w", i32), ("groups", i32), ("group", i32), ("OH", i64), ("OW", i64)]
+                ("dil_h", i32), ("dil_w", i32), ("groups", i32), ("group", i32), ("OH", i64), ("OW", i64),
+                ("corner_mode", i32), ("lower_w", i32), ("upper_w", i32)]
 
 
 class QtPoolGeom(C.Structure):
@@ -67,7 +68,7 @@ class QtPoolGeom(C.Structure):
 class QtRequant(C.Structure):
     _fields_ = [("mode", i32), ("bit_width", i32), ("codes", vp), ("codes_kind", i32), ("ld_codes", i64),
                 ("clamp", i32), ("lo", f32), ("hi", f32), ("row_part", vp), ("row_sum_part", vp),
-                ("row_parts", i32), ("overflow", vp)]
+                ("row_parts", i32), ("overflow", vp), ("cover", i64)]
 
 
 class QtEpilogue(C.Structure):

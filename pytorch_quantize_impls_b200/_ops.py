@@ -427,7 +427,7 @@ class RequantOut:
     column slices of one channels-last tensor)."""
 
     def __init__(self, mode, bit_width, codes_kind, rows, cols, dev, lo=None, hi=None, want_row_sum=False, codes=None,
-                 ld=None, col_offset=0):
+                 ld=None, col_offset=0, cover=0):
         self.mode, self.bit_width, self.codes_kind, self.rows, self.cols = mode, bit_width, codes_kind, rows, cols
         self.ld = round_up(max(cols, 1), 32) if ld is None else ld
         if codes is None:
@@ -453,6 +453,7 @@ class RequantOut:
         c.clamp = 0 if lo is None else 1
         c.lo, c.hi = (0.0, 0.0) if lo is None else (float(lo), float(hi))
         c.row_part, c.row_sum_part, c.overflow = _p(self.row_part), _p(self.row_sum_part), _p(self.overflow)
+        c.cover = int(cover)
         self.c = c
 
     @property
@@ -573,11 +574,14 @@ def gemm_f16(a, lda, a_plane_stride, w, ldw, w_plane_stride, passes, M, N, K, ep
                                 C.byref(epi), backend, _stream()), "qt_gemm_f16")
 
 
-def conv_i8(x_nhwc, a_signed, geom, group, w, w_signed, ldw, N, epi):
-    """Implicit-GEMM conv on channels-last codes; returns False when the shape needs the explicit im2col route."""
+def conv_i8(x_nhwc, a_signed, geom, group, w, w_signed, ldw, N, epi, corners=None):
+    """Implicit-GEMM conv on channels-last codes; returns False when the shape needs the explicit im2col route.
+    corners = (lower_w, upper_w): explicit bounding box of the window base positions along W (asymmetric padding)."""
     B, H, W, Cc = x_nhwc.shape
     kh, kw, sh, sw, ph, pw, dh, dw, groups, OH, OW = geom
     g = L.QtConvGeom(B, Cc, H, W, kh, kw, sh, sw, ph, pw, dh, dw, groups, group, OH, OW)
+    if corners is not None:
+        g.corner_mode, g.lower_w, g.upper_w = 1, int(corners[0]), int(corners[1])
     rc = L.lib().qt_conv_i8(_p(x_nhwc), int(a_signed), C.byref(g), _p(w), int(w_signed), ldw, N, C.byref(epi), _stream())
     if rc == -3:
         return False

@@ -38,6 +38,8 @@ int check_epi(const QtEpilogue* e, int64_t M, int64_t N) {
     QT_REQUIRE(r->ld_codes % 32 == 0 && r->ld_codes >= (N + 31) / 32 * 32, "requant: ld_codes must be a multiple of 32 and >= N rounded up to 32");
     QT_REQUIRE((reinterpret_cast<uintptr_t>(r->codes) & 15) == 0, "requant: codes must be 16-byte aligned");
     QT_REQUIRE(r->mode != QT_Q_XNOR_ROW || r->row_part != nullptr, "requant: QT_Q_XNOR_ROW needs row_part");
+    QT_REQUIRE(r->cover == 0 || (r->cover % 32 == 0 && r->cover <= r->ld_codes && r->cover >= (N + 31) / 32 * 32),
+               "requant: cover must be a multiple of 32 in [N rounded up to 32, ld_codes]");
   }
   QT_REQUIRE(e->out_mode == 0 || e->out_mode == 1, "epilogue: out_mode must be 0 or 1");
   if (e->residual) QT_REQUIRE(e->out_mode == 0 && e->ld_res >= N, "epilogue: residual needs out_mode 0 and ld_res >= N");

@@ -60,6 +60,7 @@ struct Epi {
   int rq_codes_kind;
   void* rq_codes;
   int64_t rq_ld;
+  int64_t rq_cover;       // columns [N, rq_cover) of a row receive zero codes (<= rq_ld)
   int rq_clamp;
   float rq_lo, rq_hi, rq_n;
   float* rq_row_part;
@@ -79,10 +80,10 @@ static inline Epi make_epi(const QtEpilogue* e, int64_t M, int64_t N) {
   d.scale = e->scale; d.acc_mul = e->acc_mul; d.rs_mul = e->rs_mul;
   d.out = e->out; d.ldo = e->ldo; d.out_mode = e->out_mode; d.nchw_inner = e->nchw_inner;
   d.acc_out = e->acc_out; d.M = M; d.N = N;
-  d.rq_mode = -1; d.rq_codes_kind = 0; d.rq_codes = nullptr; d.rq_ld = 0; d.rq_clamp = 0; d.rq_lo = d.rq_hi = 0.f; d.rq_n = 1.f;
+  d.rq_mode = -1; d.rq_codes_kind = 0; d.rq_codes = nullptr; d.rq_ld = 0; d.rq_cover = 0; d.rq_clamp = 0; d.rq_lo = d.rq_hi = 0.f; d.rq_n = 1.f;
   d.rq_row_part = nullptr; d.rq_row_sum_part = nullptr; d.rq_overflow = nullptr;
   if (const QtRequant* r = e->requant) {
-    d.rq_mode = r->mode; d.rq_codes_kind = r->codes_kind; d.rq_codes = r->codes; d.rq_ld = r->ld_codes;
+    d.rq_mode = r->mode; d.rq_codes_kind = r->codes_kind; d.rq_codes = r->codes; d.rq_ld = r->ld_codes; d.rq_cover = r->cover > 0 ? r->cover : r->ld_codes;
     d.rq_clamp = r->clamp; d.rq_lo = r->lo; d.rq_hi = r->hi;
     d.rq_n = (r->mode == QT_Q_DOREFA) ? (float)((1u << r->bit_width) - 1u) : 1.f;
     d.rq_row_part = r->row_part; d.rq_row_sum_part = r->row_sum_part; d.rq_overflow = r->overflow;

@@ -332,7 +332,7 @@ __device__ __forceinline__ void rq_store_chunk_t(const Epi& e, const float (&y)[
           h[j] = *reinterpret_cast<uint32_t*>(&t);
         }
       }
-      if (8 * q < ncols && n0 + 8 * q < e.rq_ld) st_global_v4(base + (m * e.rq_ld + n0) * 2 + 16 * q, h[0], h[1], h[2], h[3]);
+      if (8 * q < ncols && n0 + 8 * q < e.rq_cover) st_global_v4(base + (m * e.rq_ld + n0) * 2 + 16 * q, h[0], h[1], h[2], h[3]);
       continue;
     }
     int k[8];
@@ -353,7 +353,7 @@ __device__ __forceinline__ void rq_store_chunk_t(const Epi& e, const float (&y)[
       w[q & 1] = acc;
       if (q & 1) {
         uint8_t* dst = base + ((m * e.rq_ld + n0) >> 1) + 4 * (q - 1);
-        if ((q == 1 && n0 < e.rq_ld) || (q == 3 && 16 < ncols && n0 + 16 < e.rq_ld)) st_global_v2(dst, w[0], w[1]);
+        if ((q == 1 && n0 < e.rq_cover) || (q == 3 && 16 < ncols && n0 + 16 < e.rq_cover)) st_global_v2(dst, w[0], w[1]);
       }
     } else {                             // int8 / uint8 lanes: 8 bytes per 8 columns
       w[2 * (q & 1)] = (uint32_t)(k[0] & 0xff) | ((uint32_t)(k[1] & 0xff) << 8) | ((uint32_t)(k[2] & 0xff) << 16) |
@@ -362,7 +362,7 @@ __device__ __forceinline__ void rq_store_chunk_t(const Epi& e, const float (&y)[
                            ((uint32_t)(k[7] & 0xff) << 24);
       if (q & 1) {
         uint8_t* dst = base + (m * e.rq_ld + n0) + 8 * (q - 1);
-        if ((q == 1 && n0 < e.rq_ld) || (q == 3 && 16 < ncols && n0 + 16 < e.rq_ld)) st_global_v4(dst, w[0], w[1], w[2], w[3]);
+        if ((q == 1 && n0 < e.rq_cover) || (q == 3 && 16 < ncols && n0 + 16 < e.rq_cover)) st_global_v4(dst, w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -568,7 +568,7 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
     const int64_t m = (int64_t)row0 + lane;
     const int n_tile = tn * BN;
     const int n_lim = min(N32, n_tile + BN);
-    const int n_cover = max(n_lim, (int)min((int64_t)(n_tile + BN), e.rq_ld));       // zero codes for pad channels
+    const int n_cover = max(n_lim, (int)min((int64_t)(n_tile + BN), e.rq_cover));       // zero codes for pad channels
     const int c_begin = half * CH_PER_WARP;
     int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
     while (c_end > c_begin && n_tile + (c_end - 1) * 32 >= n_cover) --c_end;
@@ -669,8 +669,8 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
           w[q] = pack4_sat(uns, k0, k1, k2, k3);
         }
         uint8_t* dst = cbase + (m * e.rq_ld + n0);
-        if (n0 < e.rq_ld) st_global_v4(dst, w[0], w[1], w[2], w[3]);
-        if (n0 + 16 < e.rq_ld && c0 + 16 < BN) st_global_v4(dst + 16, w[4], w[5], w[6], w[7]);
+        if (n0 < e.rq_cover) st_global_v4(dst, w[0], w[1], w[2], w[3]);
+        if (n0 + 16 < e.rq_cover && c0 + 16 < BN) st_global_v4(dst + 16, w[4], w[5], w[6], w[7]);
       }
       if (has_out && n0 < n_lim) {
         // fp32 tile through the staging buffer (whole chunks; the tensor map clips M / N tails)
@@ -906,7 +906,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
       int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
       // a requant row may be wider than N (channel padding for the consumer's 128-byte K blocks): those chunks are visited
       // too and receive zero codes
-      const int n_cover = (e.rq_mode >= 0) ? max(n_lim, (int)min((int64_t)(n_tile + BN), e.rq_ld)) : n_lim;
+      const int n_cover = (e.rq_mode >= 0) ? max(n_lim, (int)min((int64_t)(n_tile + BN), e.rq_cover)) : n_lim;
       while (c_end > c_begin && n_tile + (c_end - 1) * 32 >= n_cover) --c_end;
       const bool row_ok = m < g.M;
       float mul = e.scale;
@@ -1495,6 +1495,7 @@ static int conv_implicit(const void* x_nhwc, int elem_bytes, int a_signed, const
     // bounding box of filter-window base positions: [-pad, (size - 1) + pad - (k - 1) * dil]
     int lower[2] = {-cg->pad_w, -cg->pad_h};
     int upper[2] = {cg->pad_w - (cg->kw - 1) * cg->dil_w, cg->pad_h - (cg->kh - 1) * cg->dil_h};
+    if (cg->corner_mode) { lower[0] = cg->lower_w; upper[0] = cg->upper_w; }
     cuuint32_t estr[4] = {1, (cuuint32_t)cg->stride_w, (cuuint32_t)cg->stride_h, 1};
     CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x_nhwc), dims, strides, lower, upper,
                      (cuuint32_t)bkb, (cuuint32_t)TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bkb),
@@ -1513,7 +1514,7 @@ static int conv_implicit(const void* x_nhwc, int elem_bytes, int a_signed, const
   g.cv_cblocks = (int)(cgb / bkb);
   g.num_kblocks = (int)taps * g.cv_cblocks;
   g.cv_OW = (int)cg->OW; g.cv_OHW = (int)P;
-  g.cv_sh = cg->stride_h; g.cv_sw = cg->stride_w; g.cv_ph = cg->pad_h; g.cv_pw = cg->pad_w;
+  g.cv_sh = cg->stride_h; g.cv_sw = cg->stride_w; g.cv_ph = cg->pad_h; g.cv_pw = cg->corner_mode ? -cg->lower_w : cg->pad_w;
   g.cv_dh = cg->dil_h; g.cv_dw = cg->dil_w; g.cv_kw = cg->kw; g.cv_c0 = (int)(cgb * cg->group);
   if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
   if (elem_bytes == 1) {

@@ -310,3 +310,45 @@ def test_banded_head_pair_equals_plain(Q, fam):
     else:
         assert torch.equal(y, ref) and torch.equal(yg, ref)
     assert torch.equal(y_small, ref[:100]) or rel(y_small, ref[:100]) <= 2e-6
+
+
+@pytest.mark.parametrize("case", [("ter", 8, 3, 1, 1), ("dorefa8", 8, 3, 1, 1), ("dorefa4", 4, 5, 2, 1), ("ter", 8, 3, 1, 2), ("dorefa8", 8, 1, 0, 1)])
+def test_w_folded_conv_equals_plain_implicit_gemm(Q, case):
+    """64-channel stride-1 convs read two adjacent pixels as one 128-byte pixel (two parity launches): codes, fp32 side output and
+    residual add must be bit-identical to the unfolded implicit GEMM (integer accumulators, same epilogue arithmetic)."""
+    from pytorch_quantize_impls_b200 import _engine as eng, _lib as L, fusion
+    fam, abits, k, pad, sh = case
+    torch.manual_seed(23 + k)
+    F_ = Q.functions
+    if fam == "ter":
+        conv = Q.layers.TerConv2d(64, 64, k, stride=(sh, 1), padding=pad, bias=False)
+        conv.weight.data.mul_(0.7 / float(conv.weight.data.abs().max()))
+    else:
+        conv = Q.layers.DorefaConv2d(64, 96, k, stride=(sh, 1), padding=pad, bit_width=int(fam[6:]))
+    conv = conv.cuda().eval()
+    O = conv.out_channels
+    bn = _calibrated_bn(O).cuda()
+    x = torch.rand(8, 64, 72, 76).cuda()
+    OH = (72 + 2 * pad - k) // sh + 1
+    OW = 76 + 2 * pad - k + 1
+    res = torch.rand(8, O, OH, OW).cuda().contiguous(memory_format=torch.channels_last)
+    mul, add = fusion._bn_affine(bn)
+    outs = {}
+    with torch.no_grad():
+        for flag in (False, True):
+            Q.set_wfold(flag)
+            try:
+                spec = eng.RequantSpec(L.Q_DOREFA, "dorefa", bit_width=abits, lo=0.0, hi=1.0, col_mul=mul, col_add=add)
+                spec.force_8bit = True
+                with Q.code_only_activations():
+                    xq = F_.nnDorefaQuant(abits)(x)
+                    y1 = conv._forward_requant(xq, spec)                                              # codes only
+                    y2 = conv._forward_requant(F_.nnDorefaQuant(abits)(x), spec, out_format="nhwc", residual=res, keep_out=True)
+                    plain = eng.RequantSpec(-1, None, lo=0.0, hi=1.0, col_mul=mul, col_add=add)
+                    y3 = conv._forward_affine(F_.nnDorefaQuant(abits)(x), plain, out_format="nhwc")
+                outs[flag] = (y1._qt_codes.codes.clone(), y2.clone(), y2._qt_codes.codes.clone(), y3.clone())
+            finally:
+                Q.set_wfold(True)
+    for a, b in zip(outs[False], outs[True]):
+        assert a.shape == b.shape and torch.equal(a, b)
+    assert outs[True][1].is_contiguous(memory_format=torch.channels_last)
