@@ -227,29 +227,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-// tcgen05.ld of one 32-column chunk of this warp's 32 TMEM lanes (thread = lane = accumulator row).  Issue and wait are
-// separate so that the load of chunk i+1 is in flight while chunk i is stored; the wait lists the destination registers as
-// read-write operands, which keeps the compiler from touching them between the two statements.
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+// tcgen05.ld of one 32-column chunk of this warp's 32 TMEM lanes (thread = lane = accumulator row) + the wait for it, as ONE
+// asm statement: the destination registers are written asynchronously until tcgen05.wait::ld retires, and nothing the
+// compiler could schedule between two separate statements (a register move, a spill) may touch them.  (A split issue / wait
+// that keeps the next chunk's read in flight during the stores was measured: the TMEM read is not what the epilogue waits
+// for -- DESIGN.md 3.2 -- so the simple form costs nothing.)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :
-               : "memory");
 }
 // 32 per-column epilogue parameters (col_scale / bias) of columns n0..n0+31 into registers.  Every lane reads the SAME
 // addresses (a lane owns one output row and all 32 columns of the chunk): 8 uniform 16-byte loads, one L1 wavefront each.
@@ -386,8 +380,8 @@ __device__ __forceinline__ void rq_store_chunk(const Epi& e, const float (&y)[32
 // Epilogue, tight form: fp32 row-major output through swizzled staging tiles + bulk tensor stores, optional row / column
 // scales, bias and clamp -- no requant, residual, raw-accumulator or NCHW output (those take the general path below).
 // A product with a short K loop (e2m1 operands: 4x the MACs per byte of fp16) is paced by this code, not by the MMAs: the
-// column parameters are requested before the accumulator chunk is waited for, the next chunk's TMEM read is in flight while
-// this one is staged, and nothing but the 32 accumulators, 32 parameters and the next 32 raw values is live.
+// column parameters are requested before the accumulator chunk is read, the fp32 tile goes out through one or two staging
+// tiles per warp, and nothing but the 32 accumulators and 32 parameters is live.
 // ---------------------------------------------------------------------------------------------
 template <int BN, int KIND, int CG, int EPB>
 __device__ __forceinline__ void epilogue_f32_tma(const CUtensorMap& map_out, const TcArgs& g, uint32_t tmem_base, uint32_t epi_base,
@@ -444,7 +438,6 @@ __device__ __forceinline__ void epilogue_f32_tma(const CUtensorMap& map_out, con
     uint32_t r[32];
     const uint32_t t_row = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lane_grp * 32) << 16);
     if (g.epi_debug == 1) c_end = c_begin;
-    if (c_begin < c_end) tmem_ld32_issue(t_row + (uint32_t)(c_begin * 32), r);
 #pragma unroll 1
     for (int cidx = c_begin; cidx < c_end; ++cidx) {
       const int c0 = cidx * 32;
@@ -453,11 +446,8 @@ __device__ __forceinline__ void epilogue_f32_tma(const CUtensorMap& map_out, con
       // column parameters first: their (L1 / L2) latency runs under the TMEM read
       float pb[32];
       if (has_b) load_col32(e.bias, n0, N32, true, 0.f, pb);
-      tmem_ld_wait(r);
-      if (g.epi_debug == 2) {
-        if (cidx + 1 < c_end) tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), r);
-        continue;
-      }
+      tmem_ld32(t_row + (uint32_t)c0, r);
+      if (g.epi_debug == 2) continue;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -467,7 +457,6 @@ __device__ __forceinline__ void epilogue_f32_tma(const CUtensorMap& map_out, con
         else a = (float)(e.acc_mul * (int32_t)r[j] + rsum);
         v[j] = a * mul;
       }
-      if (cidx + 1 < c_end) tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), r);
       if (has_cs) {
         float cs[32];
         load_col32(e.col_scale, n0, N32, true, 1.f, cs);
@@ -541,10 +530,20 @@ __device__ __forceinline__ uint32_t pack4_sat(bool uns, int k0, int k1, int k2, 
   return w;
 }
 
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// cpc != 0: shared-memory cache of the tile's per-column scale / bias (2 x BN floats).  The column parameters of an output
+// tile are the same for every tile of that N block, but a 16-byte global load per 4 columns in front of every use costs an
+// L1 / L2 round trip per chunk on the epilogue's critical path (ncu: a third of the epilogue warps' stall samples in the conv
+// kernels); the eight epilogue warps refresh the cache together when the N block changes and read it with broadcast LDS.128.
 template <int BN, int KIND, int CG, int EPB>
 __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const TcArgs& g, uint32_t tmem_base, uint32_t epi_base,
                                              uint32_t tfull0, uint32_t tempty0, int worker, int num_workers, uint32_t cta_rank,
-                                             int warp, int lane) {
+                                             int warp, int lane, uint32_t cpc) {
   const int ew = warp - 2, lane_grp = warp & 3, half = ew >> 2;
   constexpr int CHUNKS = (BN + 31) / 32;
   constexpr int CH_PER_WARP = (CHUNKS + 1) / 2;
@@ -561,6 +560,7 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
   uint8_t* const cbase = reinterpret_cast<uint8_t*>(e.rq_codes);
   int as = 0;
   uint32_t aphase = 0;
+  int cached_tn = -1;
   for (int tile = worker; tile < num_tiles; tile += num_workers) {
     int tm, tn;
     tile_coords<CG>(g, tile, tm, tn);
@@ -568,6 +568,18 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
     const int64_t m = (int64_t)row0 + lane;
     const int n_tile = tn * BN;
     const int n_lim = min(N32, n_tile + BN);
+    if (cpc != 0 && tn != cached_tn) {          // every epilogue warp walks the same tile sequence: they all arrive here
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // readers of the previous block are done
+      for (int c = ew * 32 + lane; c < BN; c += 256) {
+        const int n = n_tile + c;
+        const float csv = (has_cs && n < N32) ? __ldg(e.col_scale + n) : 1.f;
+        const float bv = (has_b && n < N32) ? __ldg(e.bias + n) : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cpc + 4u * (uint32_t)c), "f"(csv) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cpc + 4u * (uint32_t)(BN + c)), "f"(bv) : "memory");
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      cached_tn = tn;
+    }
     const int n_cover = max(n_lim, (int)min((int64_t)(n_tile + BN), e.rq_cover));       // zero codes for pad channels
     const int c_begin = half * CH_PER_WARP;
     int c_end = min(CHUNKS, c_begin + CH_PER_WARP);
@@ -603,7 +615,6 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
     tc_fence_after();
     uint32_t r[32];
     const uint32_t t_row = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lane_grp * 32) << 16);
-    if (c_begin < c_end) tmem_ld32_issue(t_row + (uint32_t)(c_begin * 32), r);
 #pragma unroll 1
     for (int cidx = c_begin; cidx < c_end; ++cidx) {
       const int c0 = cidx * 32;
@@ -618,7 +629,7 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
           res[4 * q] = t.x; res[4 * q + 1] = t.y; res[4 * q + 2] = t.z; res[4 * q + 3] = t.w;
         }
       }
-      tmem_ld_wait(r);
+      tmem_ld32(t_row + (uint32_t)c0, r);
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -628,18 +639,34 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
         else a = (float)(e.acc_mul * (int32_t)r[j] + rsum);
         v[j] = a * mul;
       }
-      if (cidx + 1 < c_end) tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), r);
-      if (has_cs) {
-        float cs[32];
-        load_col32(e.col_scale, n0, N32, true, 1.f, cs);
+      if (cpc != 0) {
+        if (has_cs) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= cs[j];
-      }
-      if (has_b) {
-        float pb[32];
-        load_col32(e.bias, n0, N32, true, 0.f, pb);
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = lds_v4(cpc + 4u * (uint32_t)(c0 + 4 * q));
+            v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
+          }
+        }
+        if (has_b) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += pb[j];
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = lds_v4(cpc + 4u * (uint32_t)(BN + c0 + 4 * q));
+            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+          }
+        }
+      } else {
+        if (has_cs) {
+          float cs[32];
+          load_col32(e.col_scale, n0, N32, true, 1.f, cs);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= cs[j];
+        }
+        if (has_b) {
+          float pb[32];
+          load_col32(e.bias, n0, N32, true, 0.f, pb);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += pb[j];
+        }
       }
       if (has_res && row_ok) {
         if (whole) {
@@ -731,6 +758,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t cpc_base = IM2COL ? bar_base + 256u : 0u;       // column-parameter cache of the conv kernels (2 x BN floats)
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + EPI_BYTES + 8u * (2 * STAGES + 4));
@@ -872,7 +900,7 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
   } else if (g.epi_fast == 2) {
     if constexpr (BN % 32 == 0)
       epilogue_rq8<BN, KIND, CG, EPB>(map_out, g, tmem_base, epi_base, tfull_bar(0), tempty_bar(0), worker, num_workers, cta_rank,
-                                      warp, lane);
+                                      warp, lane, cpc_base);
   } else {
     // ---- epilogue: 8 warps.  Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quadrant split
     // the BN accumulator columns in halves, so each SM sub-partition always has a second warp to hide latencies.
@@ -947,14 +975,13 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
       bool rq_ovf = false;
       uint32_t r[32];
       const uint32_t t_row = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(lane_grp * 32) << 16);
-      if (c_begin < c_end) tmem_ld32_issue(t_row + (uint32_t)(c_begin * 32), r);
 #pragma unroll 1
       for (int cidx = c_begin; cidx < c_end; ++cidx) {
         const int c0 = cidx * 32;
         const int n0 = n_tile + c0;
         const bool full_chunk = (BN % 32 == 0) || (c0 + 32 <= BN);
         const bool add_res = e.residual != nullptr && row_ok;
-        tmem_ld_wait(r);
+        tmem_ld32(t_row + (uint32_t)c0, r);
         if (INT_ACC && e.acc_out && row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -971,8 +998,6 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
           // float(acc) + bias is one rounding (BinaryNet / Terner bit-exactness)
           v[j] = a * mul;
         }
-        // the accumulator chunk is in v: let the next chunk's TMEM read run beside the stores of this one
-        if (cidx + 1 < c_end) tmem_ld32_issue(t_row + (uint32_t)(c0 + 32), r);
         if (!e.out && e.rq_mode < 0) continue;
         if (e.col_scale) {
           float cs[32];
@@ -1195,7 +1220,7 @@ constexpr size_t TC_SMEM_MAX = 232448;    // 227 KB opt-in limit per CTA
 
 template <int BN, int KIND, int STAGES, int BKB = TC_BK_BYTES, bool IM2COL = false, int EPB = 1>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (TC_BM * BKB + BN * BKB) + (size_t)EPB * 8 * 4096 + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * BKB + BN * BKB) + (size_t)EPB * 8 * 4096 + 1024 + 256 + (IM2COL ? 8 * BN : 0);
   static_assert(smem <= TC_SMEM_MAX, "tc_gemm_kernel: shared memory budget");
   // output tensor map (row-major fp32): only when every row pitch / base is 16-byte aligned
   CUtensorMap mo = ma;
@@ -1226,7 +1251,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
 // g.idesc with M = 256.
 template <int BN, int KIND, int STAGES, int EPB = 1, int BKB = TC_BK_BYTES, bool IM2COL = false>
 static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES * (TC_BM * BKB + (BN / 2) * BKB) + (size_t)EPB * 8 * 4096 + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (TC_BM * BKB + (BN / 2) * BKB) + (size_t)EPB * 8 * 4096 + 1024 + 256 + (IM2COL ? 8 * BN : 0);
   static_assert(smem <= TC_SMEM_MAX, "tc_gemm2_kernel: shared memory budget");
   CUtensorMap mo = ma;
   g.tma_store = 0;
@@ -1459,12 +1484,13 @@ static int dispatch_conv(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g
       if constexpr (BKB == 128) {
         if (bn == 192) return launch_tc2<192, KIND, 5, 2, BKB, true>(ma, mw, g, stream);     // N = 192 k: no padded filter columns
       }
-      return launch_tc2<256, KIND, (BKB == 128 ? 5 : 8), 2, BKB, true>(ma, mw, g, stream);
+      if constexpr (BKB == 128) return launch_tc2<256, KIND, 5, 1, BKB, true>(ma, mw, g, stream);
+      else return launch_tc2<256, KIND, 8, 2, BKB, true>(ma, mw, g, stream);
     }
   }
   if (bn == 64) return launch_tc<64, KIND, (BKB == 128 ? 6 : 8), BKB, true, 2>(ma, mw, g, stream);
   if (bn == 128) return launch_tc<128, KIND, (BKB == 128 ? 5 : 8), BKB, true, 2>(ma, mw, g, stream);
-  if constexpr (BKB == 128) return launch_tc<256, KIND, 4, BKB, true, 1>(ma, mw, g, stream);
+  if constexpr (BKB == 128) return launch_tc<256, KIND, 3, BKB, true, 2>(ma, mw, g, stream);
   else return launch_tc<256, KIND, (BKB == 64 ? 6 : 8), BKB, true, 2>(ma, mw, g, stream);
 }
 
