@@ -45,7 +45,23 @@ struct TcArgs {
   int cv_sh, cv_sw, cv_ph, cv_pw, cv_dh, cv_dw, cv_kw;
   int cv_cblocks;               // channel blocks (of BKB bytes) per filter tap
   int cv_c0;                    // first channel of the conv group
+  // division by run-time constants as multiply-high + shift (a 32-bit integer division is ~40 dependent instructions; the
+  // single TMA-issuing lane executed two per k-block and four per tile, which bounded the conv kernels -- see DESIGN.md 3.2)
+  uint32_t fd_band[2], fd_ohw[2], fd_ow[2];
 };
+
+// n / d for 0 <= n < 2^31: q = umulhi(n, mul) >> shr, mul == 0 encodes d == 1
+static inline void fastdiv_make(uint32_t d, uint32_t out[2]) {
+  if (d <= 1) { out[0] = 0; out[1] = 0; return; }
+  uint32_t lg = 0;
+  while ((1ull << lg) < d) ++lg;
+  const uint32_t p = 31 + lg;
+  out[0] = (uint32_t)(((1ull << p) + d - 1) / d);
+  out[1] = p - 32;
+}
+__device__ __forceinline__ int fastdiv(int n, const uint32_t fd[2]) {
+  return fd[0] ? (int)(__umulhi((uint32_t)n, fd[0]) >> fd[1]) : n;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -57,6 +73,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// One lane of a converged warp (elect.sync): the TMA / MMA issuing warps run their loops with all 32 lanes so that stage
+// indices, shared-memory addresses and descriptors stay warp-uniform (uniform registers feed UTMALDG / UTCxMMA directly);
+// under `if (lane == 0)` the same values count as divergent and every issue costs an ELECT + R2UR broadcast loop
+// (~15 instructions per MMA: the single issuing thread, not the tensor pipe, bounded the kernels -- DESIGN.md 3.2).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -159,10 +184,10 @@ template <int CG = 1>
 __device__ __forceinline__ void tile_coords(const TcArgs& g, int tile, int& tm, int& tn) {
   constexpr int BAND = TC_BAND_M / CG;                            // the band is 2048 rows either way
   const int band_tiles = BAND * g.tiles_n;
-  const int band = tile / band_tiles;
+  const int band = fastdiv(tile, g.fd_band);
   const int t = tile - band * band_tiles;
   const int bm = min(BAND, g.tiles_m - band * BAND);             // last band may be shorter
-  tn = t / bm;
+  tn = (bm == BAND) ? t / BAND : t / bm;                         // BAND is a power of two
   tm = band * BAND + (t - tn * bm);
 }
 
@@ -558,6 +583,18 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
   const bool uns = e.rq_codes_kind == 2;
   const float lo = e.rq_lo, hi = e.rq_hi, qn = e.rq_n;
   uint8_t* const cbase = reinterpret_cast<uint8_t*>(e.rq_codes);
+  // Folded column parameters (the BatchNorm-folded conv chains): with nothing per-row attached the pre-activation is
+  // acc * (scale * col_scale[n]) + bias[n] -- one FFMA per element against the cached products instead of FMUL, FMUL, FADD.
+  // `lean` (no fp32 side output, no residual): the quantizer's scale goes into the cache as well and the float clamp becomes
+  // an integer clamp on the code (rn(n * clamp(v, lo, hi)) == clamp(rn(n * v), rn(n * lo), rn(n * hi)): rounding is
+  // monotonic), of which the saturating pack supplies whichever side coincides with the lane's range.  The fold removes
+  // float roundings, it does not add any: codes differ from the three-rounding form only where a pre-activation sits within
+  // an ulp of a rounding boundary (the documented <= 1 code on <= 0.1 % tolerance of a folded BatchNorm).
+  const bool fold = cpc != 0 && has_cs && e.row_scale == nullptr &&
+                    (KIND == 1 || (KIND == 0 && e.acc_mul == 1 && e.row_sum == nullptr));
+  const int klo = __float2int_rn(qn * lo), khi = __float2int_rn(qn * hi);
+  const bool lean = fold && !has_res && !has_out && klo <= 0 && khi >= 0;      // pad columns must quantize to code 0
+  const bool clamp_lo = klo != (uns ? 0 : -128), clamp_hi = khi != (uns ? 255 : 127);
   int as = 0;
   uint32_t aphase = 0;
   int cached_tn = -1;
@@ -572,8 +609,13 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
       asm volatile("bar.sync 1, 256;" ::: "memory");           // readers of the previous block are done
       for (int c = ew * 32 + lane; c < BN; c += 256) {
         const int n = n_tile + c;
-        const float csv = (has_cs && n < N32) ? __ldg(e.col_scale + n) : 1.f;
-        const float bv = (has_b && n < N32) ? __ldg(e.bias + n) : 0.f;
+        float csv = (has_cs && n < N32) ? __ldg(e.col_scale + n) : 1.f;
+        float bv = (has_b && n < N32) ? __ldg(e.bias + n) : 0.f;
+        if (fold) csv *= e.scale;
+        if (lean) {                                  // columns past N quantize to code 0 without a per-element test
+          csv = n < N32 ? qn * csv : 0.f;
+          bv = n < N32 ? qn * bv : 0.f;
+        }
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(cpc + 4u * (uint32_t)c), "f"(csv) : "memory");
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(cpc + 4u * (uint32_t)(BN + c)), "f"(bv) : "memory");
       }
@@ -620,6 +662,30 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
       const int c0 = cidx * 32;
       const int n0 = n_tile + c0;
       const bool whole = n0 + 32 <= n_lim;            // all 32 columns are real outputs (else: tail / pad-channel chunk)
+      if (lean) {
+        tmem_ld32(t_row + (uint32_t)c0, r);
+        uint32_t w[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 ca = lds_v4(cpc + 4u * (uint32_t)(c0 + 4 * q));
+          const float4 cb = lds_v4(cpc + 4u * (uint32_t)(BN + c0 + 4 * q));
+          const float a0 = KIND == 1 ? __uint_as_float(r[4 * q]) : (float)(int32_t)r[4 * q];
+          const float a1 = KIND == 1 ? __uint_as_float(r[4 * q + 1]) : (float)(int32_t)r[4 * q + 1];
+          const float a2 = KIND == 1 ? __uint_as_float(r[4 * q + 2]) : (float)(int32_t)r[4 * q + 2];
+          const float a3 = KIND == 1 ? __uint_as_float(r[4 * q + 3]) : (float)(int32_t)r[4 * q + 3];
+          int k0 = __float2int_rn(fmaf(a0, ca.x, cb.x)), k1 = __float2int_rn(fmaf(a1, ca.y, cb.y));
+          int k2 = __float2int_rn(fmaf(a2, ca.z, cb.z)), k3 = __float2int_rn(fmaf(a3, ca.w, cb.w));
+          if (clamp_lo) { k0 = max(k0, klo); k1 = max(k1, klo); k2 = max(k2, klo); k3 = max(k3, klo); }
+          if (clamp_hi) { k0 = min(k0, khi); k1 = min(k1, khi); k2 = min(k2, khi); k3 = min(k3, khi); }
+          w[q] = pack4_sat(uns, k0, k1, k2, k3);
+        }
+        if (row_ok) {
+          uint8_t* dst = cbase + (m * e.rq_ld + n0);
+          if (n0 < e.rq_cover) st_global_v4(dst, w[0], w[1], w[2], w[3]);
+          if (n0 + 16 < e.rq_cover && c0 + 16 < BN) st_global_v4(dst + 16, w[4], w[5], w[6], w[7]);
+        }
+        continue;
+      }
       float res[32];
       if (has_res && row_ok && whole) {
         const float4* rp = reinterpret_cast<const float4*>(e.residual + m * e.ld_res + n0);
@@ -637,9 +703,21 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
         if (!INT_ACC || plain_acc) a = __uint_as_float(r[j]);
         else if (KIND == 2) a = (float)(e.acc_mul * __float2int_rn(__uint_as_float(r[j])) + rsum);
         else a = (float)(e.acc_mul * (int32_t)r[j] + rsum);
-        v[j] = a * mul;
+        v[j] = a;
       }
-      if (cpc != 0) {
+      if (!fold) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= mul;
+      }
+      if (fold) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 ca = lds_v4(cpc + 4u * (uint32_t)(c0 + 4 * q));
+          const float4 cb = lds_v4(cpc + 4u * (uint32_t)(BN + c0 + 4 * q));
+          v[4 * q] = fmaf(v[4 * q], ca.x, cb.x); v[4 * q + 1] = fmaf(v[4 * q + 1], ca.y, cb.y);
+          v[4 * q + 2] = fmaf(v[4 * q + 2], ca.z, cb.z); v[4 * q + 3] = fmaf(v[4 * q + 3], ca.w, cb.w);
+        }
+      } else if (cpc != 0) {
         if (has_cs) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -811,60 +889,60 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
   const int worker = (int)blockIdx.x / CG, num_workers = (int)gridDim.x / CG;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        int tm, tn;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      int tm, tn;
       tile_coords<CG>(g, tile, tm, tn);
-        for (int pass = 0; pass < g.npass; ++pass) {
-          const int a_row = (int)(g.pa[pass] * g.a_plane_rows) + (tm * CG + (int)cta_rank) * TC_BM;
-          const int w_row = (int)(g.pw[pass] * g.w_plane_rows) + tn * BN + (int)cta_rank * (BN / CG);
-          int cv_n = 0, cv_h = 0, cv_w = 0;
-          if (IM2COL) {   // first output pixel of this CTA's 128 rows -> base position of its filter window
-            const int m0 = (tm * CG + (int)cta_rank) * TC_BM;
-            cv_n = m0 / g.cv_OHW;
-            const int r = m0 - cv_n * g.cv_OHW;
-            const int oh = r / g.cv_OW;
-            cv_h = oh * g.cv_sh - g.cv_ph;
-            cv_w = (r - oh * g.cv_OW) * g.cv_sw - g.cv_pw;
-          }
-          for (int kb = 0; kb < g.num_kblocks; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
+      for (int pass = 0; pass < g.npass; ++pass) {
+        const int a_row = (int)(g.pa[pass] * g.a_plane_rows) + (tm * CG + (int)cta_rank) * TC_BM;
+        const int w_row = (int)(g.pw[pass] * g.w_plane_rows) + tn * BN + (int)cta_rank * (BN / CG);
+        int cv_n = 0, cv_h = 0, cv_w = 0;
+        if (IM2COL) {   // first output pixel of this CTA's 128 rows -> base position of its filter window
+          const int m0 = (tm * CG + (int)cta_rank) * TC_BM;
+          cv_n = fastdiv(m0, g.fd_ohw);
+          const int r = m0 - cv_n * g.cv_OHW;
+          const int oh = fastdiv(r, g.fd_ow);
+          cv_h = oh * g.cv_sh - g.cv_ph;
+          cv_w = (r - oh * g.cv_OW) * g.cv_sw - g.cv_pw;
+        }
+        int cb = 0, off_w = 0, off_h = 0, kx = 0;              // k-block -> (filter tap, channel block), kept incrementally
+        for (int kb = 0; kb < g.num_kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          if (elect_one()) {
             // cta_group::2: the MMA issuer waits on the LEADER's full barrier, which counts the bytes of both CTAs' loads
             if (leader) mbar_expect_tx(full_bar(stage), CG * STAGE_BYTES);
-            const uint32_t sa = smem_base + stage * STAGE_BYTES;
             if (CG == 2) {
               const uint32_t lbar = mapa_shared(full_bar(stage), 0);
               if (IM2COL) {
-                const int tap = kb / g.cv_cblocks, cb = kb - tap * g.cv_cblocks;
-                const int ky = tap / g.cv_kw, kx = tap - ky * g.cv_kw;
-                tma_load_im2col_cg2(sa, &map_a, lbar, g.cv_c0 + cb * BKB, cv_w, cv_h, cv_n, (uint16_t)(kx * g.cv_dw),
-                                    (uint16_t)(ky * g.cv_dh));
+                tma_load_im2col_cg2(sa, &map_a, lbar, g.cv_c0 + cb * BKB, cv_w, cv_h, cv_n, (uint16_t)off_w, (uint16_t)off_h);
               } else {
                 tma_load_2d_cg2(sa, &map_a, lbar, kb * BKB, a_row);
               }
               tma_load_2d_cg2(sa + A_BYTES, &map_w, lbar, kb * BKB, w_row);
-              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-              continue;
-            }
-            if (IM2COL) {
-              const int tap = kb / g.cv_cblocks, cb = kb - tap * g.cv_cblocks;
-              const int ky = tap / g.cv_kw, kx = tap - ky * g.cv_kw;
-              tma_load_im2col(sa, &map_a, full_bar(stage), g.cv_c0 + cb * BKB, cv_w, cv_h, cv_n,
-                              (uint16_t)(kx * g.cv_dw), (uint16_t)(ky * g.cv_dh));
             } else {
-              tma_load_2d(sa, &map_a, full_bar(stage), kb * BKB, a_row);
+              if (IM2COL) {
+                tma_load_im2col(sa, &map_a, full_bar(stage), g.cv_c0 + cb * BKB, cv_w, cv_h, cv_n, (uint16_t)off_w, (uint16_t)off_h);
+              } else {
+                tma_load_2d(sa, &map_a, full_bar(stage), kb * BKB, a_row);
+              }
+              tma_load_2d(sa + A_BYTES, &map_w, full_bar(stage), kb * BKB, w_row);
             }
-            tma_load_2d(sa + A_BYTES, &map_w, full_bar(stage), kb * BKB, w_row);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          if (IM2COL) {
+            if (++cb == g.cv_cblocks) {
+              cb = 0; off_w += g.cv_dw;
+              if (++kx == g.cv_kw) { kx = 0; off_w = 0; off_h += g.cv_dh; }
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -879,21 +957,25 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint64_t adesc = make_smem_desc<BKB>(sa);
           const uint64_t bdesc = make_smem_desc<BKB>(sa + A_BYTES);
+          if (elect_one()) {               // always the same lane: tcgen05.commit tracks the MMAs of the thread that executes it
 #pragma unroll
-          for (int k = 0; k < BKB / 32; ++k) {
-            // +32 B along K inside the swizzle atom == +2 in the (addr >> 4) field
-            tc_mma<KIND, CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), g.idesc, (it > 0 || k > 0) ? 1u : 0u,
-                             tmem_base + TC_SF_COL);
+            for (int k = 0; k < BKB / 32; ++k) {
+              // +32 B along K inside the swizzle atom == +2 in the (addr >> 4) field
+              tc_mma<KIND, CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), g.idesc, (it > 0 || k > 0) ? 1u : 0u,
+                               tmem_base + TC_SF_COL);
+            }
+            // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+            if (CG == 2) tc_commit_cg2(empty_bar(stage)); else tc_commit(empty_bar(stage));
+            if (it == iters - 1) {         // accumulator complete -> epilogue(s)
+              if (CG == 2) tc_commit_cg2(tfull_bar(as)); else tc_commit(tfull_bar(as));
+            }
           }
-          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
-          if (CG == 2) tc_commit_cg2(empty_bar(stage)); else tc_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (CG == 2) tc_commit_cg2(tfull_bar(as)); else tc_commit(tfull_bar(as));   // accumulator complete -> epilogue(s)
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
-    __syncwarp();
   } else if (g.epi_fast == 1) {
     epilogue_f32_tma<BN, KIND, CG, EPB>(map_out, g, tmem_base, epi_base, tfull_bar(0), tempty_bar(0), worker, num_workers, cta_rank,
                                         warp, lane);
@@ -1241,6 +1323,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, cu
   }
   g.tiles_m = (int)ceil_div(g.M, TC_BM);
   g.tiles_n = (int)ceil_div(g.N, BN);
+  fastdiv_make((uint32_t)(TC_BAND_M * g.tiles_n), g.fd_band);
   int grid = std::min(g.tiles_m * g.tiles_n, num_sms());
   tc_gemm_kernel<BN, KIND, STAGES, BKB, IM2COL, EPB><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
   QT_LAUNCH_CHECK();
@@ -1270,6 +1353,7 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mw, TcArgs& g, c
   }
   g.tiles_m = (int)ceil_div(g.M, 2 * TC_BM);
   g.tiles_n = (int)ceil_div(g.N, BN);
+  fastdiv_make((uint32_t)(TC_BAND_M / 2 * g.tiles_n), g.fd_band);
   const int grid = 2 * std::min(g.tiles_m * g.tiles_n, num_sms() / 2);
   tc_gemm2_kernel<BN, KIND, STAGES, EPB, BKB, IM2COL><<<grid, TC_THREADS, smem, stream>>>(ma, mw, mo, g);
   QT_LAUNCH_CHECK();
@@ -1540,6 +1624,8 @@ static int conv_implicit(const void* x_nhwc, int elem_bytes, int a_signed, const
   g.cv_cblocks = (int)(cgb / bkb);
   g.num_kblocks = (int)taps * g.cv_cblocks;
   g.cv_OW = (int)cg->OW; g.cv_OHW = (int)P;
+  fastdiv_make((uint32_t)g.cv_OHW, g.fd_ohw);
+  fastdiv_make((uint32_t)g.cv_OW, g.fd_ow);
   g.cv_sh = cg->stride_h; g.cv_sw = cg->stride_w; g.cv_ph = cg->pad_h; g.cv_pw = cg->corner_mode ? -cg->lower_w : cg->pad_w;
   g.cv_dh = cg->dil_h; g.cv_dw = cg->dil_w; g.cv_kw = cg->kw; g.cv_c0 = (int)(cgb * cg->group);
   if (ep->requant) ep->requant->row_parts = 2 * (int)ceil_div(N, bn);
