@@ -347,6 +347,15 @@ int qt_conv_bf16(const void* x_nhwc, const QtConvGeom* g, const void* w, int64_t
 int qt_image_planes(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int planes, int pad_h, int pad_w,
                     int64_t Hp, int64_t Wp, int fold_h, int fold_w, void* out, void* stream);
 
+/* Row-window records of the same image, for filters whose whole row fits one record (kw * planes * C <= slots, slots * 2 bytes
+ * = 32 / 64 / 128): out[b, hp, ow, slots] (bf16), slot kx * planes * C + p * C + c = part p of x[b, c, hp - pad_h,
+ * ow * stride_w - pad_w + kx], zero outside the image and in the unused slots.  The conv over the record grid has kw = 1,
+ * stride_w = 1 and one k-block per filter ROW: the 7x7 / 2 stem of models/Resnet/Resnet_bin.py:68 reads 7 x 128 bytes per
+ * output pixel instead of the 16 x 128 bytes of its 2 x 2 space-to-depth form (63 of 64 slots used instead of 441 of 1024) --
+ * the implicit GEMM is bound by L2 -> shared-memory bytes, not by the tensor pipe. */
+int qt_image_windows(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int planes, int kw, int stride_w,
+                     int pad_h, int pad_w, int64_t Hp, int64_t OW, int slots, void* out, void* stream);
+
 /* Max-pool (nn.MaxPool2d, ceil_mode = False, dilation 1; OH = floor((H + 2 pad - k) / stride) + 1) on channels-last tensors.
  *   qt_pool_codes      8-bit activation codes [B, H, W, C] -> [B, OH, OW, C].  An activation quantizer is monotone, so
  *                      pool(quantize(clamp(bn(y)))) == quantize(clamp(bn(pool(y)))) whenever the BatchNorm scale of the channel

@@ -654,6 +654,31 @@ def _first_layer_weights(pack, O, kh, kw, Cin, P, fh, fw, khf, kwf):
     return wz, wz.shape[1]
 
 
+_first_layer_windows = [os.environ.get("QTB200_FIRST_LAYER_WINDOWS", "1") != "0"]
+
+
+def set_first_layer_windows(flag):
+    """True (default): image layers whose filter row fits one 128-byte record (kw * parts * Cin <= 64 slots) read row-window
+    records (qt_image_windows) with one k-block per filter row; False: plane pixels with the space-to-depth folds only."""
+    _first_layer_windows[0] = bool(flag)
+
+
+def _window_weights(pack, O, kh, kw, Cin, P, slots):
+    """bf16 weights against row-window records: [O, kh, slots], slot kx * P * Cin + p * Cin + c = code of W_q[o, c, ky, kx] for
+    every part p, zero in the unused slots.  Cached on the pack while its packed tensor is unchanged."""
+    key = (pack.packed.data_ptr(), pack.packed._version, kh, kw, Cin, P, "win", slots)
+    hit = getattr(pack, "_first", None)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    w, ldw = ops._expand_weight(pack, L.CODES_BF16)             # [1, O, ld]: exact codes, K order (kh, kw, c)
+    wv = w[0, :O, :kh * kw * Cin].reshape(O, kh, kw, 1, Cin)
+    wz = torch.zeros((O, kh, slots), dtype=torch.bfloat16, device=w.device)
+    wz[:, :, :kw * P * Cin] = wv.expand(O, kh, kw, P, Cin).reshape(O, kh, kw * P * Cin)
+    wz = wz.reshape(O, kh * slots).contiguous()
+    pack._first = (key, wz, wz.shape[1])
+    return wz, wz.shape[1]
+
+
 def _conv_first_layer(xf, pack, geom, O, Cin, epi_kw):
     """Real-valued NCHW input with few channels: one pass over the image builds zero-padded channels-last bf16 plane pixels
     (each channel as hi / mid / lo bf16 parts side by side, 32 bytes per pixel), and the conv runs as an implicit GEMM fed by TMA
@@ -669,6 +694,16 @@ def _conv_first_layer(xf, pack, geom, O, Cin, epi_kw):
         return False
     B = xf.shape[0]
     P = 3 if 3 * Cin <= 16 else 2
+    if _first_layer_windows[0] and dw == 1 and kw * P * Cin <= 64 and kw > 1:
+        # row-window records: K = kh k-blocks of one record each (bytes per output pixel: kh * slots * 2)
+        used = kw * P * Cin
+        slots = 16 if used <= 16 else (32 if used <= 32 else 64)
+        Hp = (OH - 1) * sh + (kh - 1) * dh + 1
+        rec = ops.image_windows(xf, P, kw, sw, ph, pw, Hp, OW, slots)
+        wz, ldw = _window_weights(pack, O, kh, kw, Cin, P, slots)
+        epi = ops.make_epi(**epi_kw)
+        ops.conv_bf16(rec, (B, slots, Hp, OW, kh, 1, sh, 1, 0, 0, dh, 1, 1, 0, OH, OW), wz, ldw, O, epi)
+        return True
     fw = sw if (sw in (2, 4) and dw == 1) else 1
     fh = 2 if (sh == 2 and dh == 1 and fw == 2) else 1          # 2 x 2 x 32 B = one 128-byte swizzle row
     if fw > 1:

@@ -101,6 +101,7 @@ SYMBOLS = {
     "qt_patch_rowsum": (i32, [vp, i32, C.POINTER(QtConvGeom), vp, vp, vp]),
     "qt_conv_bf16": (i32, [vp, C.POINTER(QtConvGeom), vp, i64, i64, C.POINTER(QtEpilogue), vp]),
     "qt_image_planes": (i32, [vp, i64, i64, i64, i64, i32, i32, i32, i64, i64, i32, i32, vp, vp]),
+    "qt_image_windows": (i32, [vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, i64, i64, i32, vp, vp]),
     "qt_rowsum_codes": (i32, [vp, i32, i64, i64, vp, vp]),
     "qt_pool_codes": (i32, [vp, i32, C.POINTER(QtPoolGeom), vp, vp, vp]),
     "qt_pool_quant_f32": (i32, [vp, C.POINTER(QtPoolGeom), vp, i32, i32, vp, i32, vp, vp]),

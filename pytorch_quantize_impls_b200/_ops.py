@@ -499,6 +499,18 @@ def image_planes(x, planes, pad_h, pad_w, Hp, Wp, fold_h=1, fold_w=1):
     return out
 
 
+def image_windows(x, planes, kw, stride_w, pad_h, pad_w, Hp, OW, slots):
+    """fp32 NCHW image -> row-window records (qt_image_windows): [B, Hp, OW, slots] bf16, record (hp, ow) = the kw pixels
+    w = ow * stride_w - pad_w + kx of row hp - pad_h, each as planes * C slots."""
+    require_cuda(x, "input")
+    x = as_f32c(x)
+    B, Cn, Hn, Wn = x.shape
+    out = torch.empty((B, Hp, OW, slots), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().qt_image_windows(_p(x), B, Cn, Hn, Wn, planes, kw, stride_w, pad_h, pad_w, Hp, OW, slots, _p(out), _stream()),
+            "qt_image_windows")
+    return out
+
+
 def _pool_geom(B, H, W, Cn, k, s, p):
     (kh, kw), (sh, sw), (ph, pw) = k, s, p
     OH, OW = (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1

@@ -2,6 +2,8 @@
 //
 //   qt_image_planes   fp32 NCHW image -> zero-padded channels-last bf16 "plane pixel" tensor (hi / mid / lo parts of every
 //                     channel side by side in one 32-byte pixel): the A operand of the first-layer implicit GEMM
+//   qt_image_windows  the same image as row-window records (the kw pixels of a filter row side by side): one k-block per
+//                     filter ROW instead of per tap
 //   qt_pool_codes     max-pool on channels-last 8-bit activation codes (per-channel max or min)
 //   qt_pool_quant_f32 max-pool of a channels-last fp32 activation fused with the next activation quantizer
 #include "qt_common.cuh"
@@ -47,6 +49,60 @@ __global__ void __launch_bounds__(256) image_planes_kernel(const float* __restri
     uint4* o = reinterpret_cast<uint4*>(out + (sp * (fh * fw) + (hp % fh) * fw + (wp % fw)) * 16);
     o[0] = reinterpret_cast<const uint4*>(s)[0];
     o[1] = reinterpret_cast<const uint4*>(s)[1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// image row windows.  Record (b, hp, ow) holds the kw horizontally adjacent pixels output column ow of a conv row reads
+// (w = ow * sw - pad_w + kx), each as P * C plane slots: slot kx * P * C + p * C + c.  With the row's plane pixels laid out
+// pixel after pixel (P * C slots each, zero padded borders) a record is the CONTIGUOUS slice starting at pixel ow * sw:
+// one block per image row stages that array in shared memory (coalesced reads of the C channel rows, every value split
+// once), then every thread assembles 16-byte chunks of records from it -- consecutive threads write consecutive 16 bytes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) image_windows_kernel(const float* __restrict__ x, int C, int H, int W, int P, int kw,
+                                                            int sw, int pad_h, int pad_w, int Hp, int OW, int slots,
+                                                            __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __nv_bfloat16 row[];          // [n_pix][P * C]
+  const int pc = P * C, used = kw * pc, chunks = slots >> 3;
+  const int n_pix = (OW - 1) * sw + kw;
+  const int64_t bh = blockIdx.x;                  // b * Hp + hp
+  const int hp = (int)(bh % Hp);
+  const int64_t b = bh / Hp;
+  const int h = hp - pad_h;
+  uint4* orow = reinterpret_cast<uint4*>(out) + bh * OW * chunks;
+  if (h < 0 || h >= H) {                          // a row of the conv's zero padding
+    for (int id = threadIdx.x; id < OW * chunks; id += blockDim.x) orow[id] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const float* xrow = x + ((b * C) * H + h) * (int64_t)W;
+  for (int idx = threadIdx.x; idx < C * n_pix; idx += blockDim.x) {
+    const int c = idx / n_pix, i = idx - c * n_pix;
+    const int w = i - pad_w;
+    const float v = (w >= 0 && w < W) ? __ldg(xrow + (int64_t)c * H * W + w) : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    __nv_bfloat16* dst = row + i * pc + c;
+    dst[0] = hi;
+    if (P >= 2) {
+      const float r1 = v - __bfloat162float(hi);
+      const __nv_bfloat16 mi = __float2bfloat16_rn(r1);
+      dst[C] = mi;
+      if (P >= 3) dst[2 * C] = __float2bfloat16_rn(r1 - __bfloat162float(mi));
+    }
+  }
+  __syncthreads();
+  const unsigned short* r16 = reinterpret_cast<const unsigned short*>(row);
+  for (int id = threadIdx.x; id < OW * chunks; id += blockDim.x) {
+    const int ow = id / chunks, q = id - ow * chunks;
+    const int base = ow * sw * pc + q * 8;
+    uint32_t w4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int s0 = q * 8 + 2 * j;
+      const uint32_t e0 = s0 < used ? r16[base + 2 * j] : 0u;
+      const uint32_t e1 = s0 + 1 < used ? r16[base + 2 * j + 1] : 0u;
+      w4[j] = e0 | (e1 << 16);
+    }
+    orow[id] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
   }
 }
 
@@ -137,10 +193,14 @@ __device__ __forceinline__ int pq_code(int mode, float n, float v, float lo, flo
   return (int)c;
 }
 
+// KH x KW > 0: compile-time window, every tap's load issued before the first compare (the run-time loops serialise one 16-byte
+// load per branch: a third of HBM speed on the 3 x 3 / 2 stem pool); KH == 0: run-time window.
+template <int KH, int KW>
 __global__ void __launch_bounds__(256) pool_quant_f32_kernel(PoolQuantArgs a) {
   const int cv = a.C >> 2;
   const int64_t total = (int64_t)a.B * a.OH * a.OW * cv;
   const float lo = (a.codes_kind == 1) ? -128.f : 0.f, hi = (a.codes_kind == 1) ? 127.f : 255.f;
+  const float ninf = -__int_as_float(0x7f800000);
   bool ovf = false;
   for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
     const int v = (int)(id % cv);
@@ -149,23 +209,41 @@ __global__ void __launch_bounds__(256) pool_quant_f32_kernel(PoolQuantArgs a) {
     t /= a.OW;
     const int oh = (int)(t % a.OH);
     const int64_t b = t / a.OH;
-    const float ninf = -__int_as_float(0x7f800000);
     float4 m = make_float4(ninf, ninf, ninf, ninf);
     const int h0 = oh * a.sh - a.ph, w0 = ow * a.sw - a.pw;
-    for (int ky = 0; ky < a.kh; ++ky) {
-      const int h = h0 + ky;
-      if (h < 0 || h >= a.H) continue;
-      for (int kx = 0; kx < a.kw; ++kx) {
-        const int w = w0 + kx;
-        if (w < 0 || w >= a.W) continue;
-        const float4 q = __ldcs(reinterpret_cast<const float4*>(a.x + (((b * a.H + h) * a.W + w) * (int64_t)a.C)) + v);
-        // NaN-propagating like torch's max_pool2d
-        m.x = (q.x > m.x || q.x != q.x) ? q.x : m.x; m.y = (q.y > m.y || q.y != q.y) ? q.y : m.y;
-        m.z = (q.z > m.z || q.z != q.z) ? q.z : m.z; m.w = (q.w > m.w || q.w != q.w) ? q.w : m.w;
+    // NaN-propagating like torch's max_pool2d
+#define QT_POOL_TAKE(q)                                                                              \
+    m.x = (q.x > m.x || q.x != q.x) ? q.x : m.x; m.y = (q.y > m.y || q.y != q.y) ? q.y : m.y;       \
+    m.z = (q.z > m.z || q.z != q.z) ? q.z : m.z; m.w = (q.w > m.w || q.w != q.w) ? q.w : m.w;
+    if (KH > 0) {
+      float4 q[(KH > 0 ? KH * KW : 1)];
+#pragma unroll
+      for (int ky = 0; ky < KH; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < KW; ++kx) {
+          const int h = h0 + ky, w = w0 + kx;
+          const bool in = h >= 0 && h < a.H && w >= 0 && w < a.W;
+          q[ky * KW + kx] = in ? __ldg(reinterpret_cast<const float4*>(a.x + (((b * a.H + h) * a.W + w) * (int64_t)a.C)) + v)
+                               : make_float4(ninf, ninf, ninf, ninf);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < KH * KW; ++i) { QT_POOL_TAKE(q[i]) }
+    } else {
+      for (int ky = 0; ky < a.kh; ++ky) {
+        const int h = h0 + ky;
+        if (h < 0 || h >= a.H) continue;
+        for (int kx = 0; kx < a.kw; ++kx) {
+          const int w = w0 + kx;
+          if (w < 0 || w >= a.W) continue;
+          const float4 q = __ldg(reinterpret_cast<const float4*>(a.x + (((b * a.H + h) * a.W + w) * (int64_t)a.C)) + v);
+          QT_POOL_TAKE(q)
+        }
       }
     }
+#undef QT_POOL_TAKE
     const int64_t o = ((b * a.OH + oh) * a.OW + ow) * (int64_t)a.C;
-    if (a.out) reinterpret_cast<float4*>(a.out + o)[v] = m;
+    if (a.out) __stcs(reinterpret_cast<float4*>(a.out + o) + v, m);
     if (a.codes) {
       const int k0 = pq_code(a.mode, a.n, m.x, lo, hi, ovf), k1 = pq_code(a.mode, a.n, m.y, lo, hi, ovf);
       const int k2 = pq_code(a.mode, a.n, m.z, lo, hi, ovf), k3 = pq_code(a.mode, a.n, m.w, lo, hi, ovf);
@@ -201,6 +279,25 @@ extern "C" int qt_image_planes(const float* x, int64_t B, int64_t C, int64_t H, 
   if (planes == 1) image_planes_kernel<1><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, fold_h, fold_w, o);
   else if (planes == 2) image_planes_kernel<2><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, fold_h, fold_w, o);
   else image_planes_kernel<3><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, fold_h, fold_w, o);
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+extern "C" int qt_image_windows(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int planes, int kw, int stride_w,
+                                int pad_h, int pad_w, int64_t Hp, int64_t OW, int slots, void* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(x && out, "qt_image_windows: null argument");
+  QT_REQUIRE(planes >= 1 && planes <= 3 && C >= 1 && kw >= 1 && stride_w >= 1, "qt_image_windows: bad planes / kw / stride");
+  QT_REQUIRE(slots > 0 && slots % 8 == 0 && (int64_t)kw * planes * C <= slots, "qt_image_windows: kw * planes * C must fit the record's slots (a multiple of 8)");
+  QT_REQUIRE(B >= 0 && H > 0 && W > 0 && Hp > 0 && OW > 0 && pad_h >= 0 && pad_w >= 0, "qt_image_windows: bad shape");
+  QT_REQUIRE(al(out, 16), "qt_image_windows: out must be 16-byte aligned");
+  QT_REQUIRE(B * Hp * OW * slots < (1ll << 42) && C * H * W < (1ll << 31), "qt_image_windows: tensor too large");
+  if (B == 0) return QT_OK;
+  const int64_t n_pix = (OW - 1) * stride_w + kw;
+  const size_t smem = (size_t)(n_pix * planes * C) * 2;
+  QT_REQUIRE(smem <= 48 * 1024 && B * Hp < (1ll << 31), "qt_image_windows: image row too wide for the shared-memory row buffer");
+  image_windows_kernel<<<(unsigned)(B * Hp), 256, smem, stream>>>(x, (int)C, (int)H, (int)W, planes, kw, stride_w, pad_h, pad_w, (int)Hp,
+                                                                    (int)OW, slots, reinterpret_cast<__nv_bfloat16*>(out));
   QT_LAUNCH_CHECK();
   return QT_OK;
 }
@@ -257,7 +354,10 @@ extern "C" int qt_pool_quant_f32(const float* x_nhwc, const QtPoolGeom* g, float
   a.n = (mode == QT_Q_DOREFA) ? (float)((1 << bit_width) - 1) : 1.f;
   a.B = (int)g->B; a.H = (int)g->H; a.W = (int)g->W; a.C = (int)g->C; a.OH = (int)g->OH; a.OW = (int)g->OW;
   a.kh = g->kh; a.kw = g->kw; a.sh = g->stride_h; a.sw = g->stride_w; a.ph = g->pad_h; a.pw = g->pad_w;
-  pool_quant_f32_kernel<<<grid_for(g->B * g->OH * g->OW * (g->C / 4), 256), 256, 0, stream>>>(a);
+  const unsigned grid = grid_for(g->B * g->OH * g->OW * (g->C / 4), 256);
+  if (g->kh == 3 && g->kw == 3) pool_quant_f32_kernel<3, 3><<<grid, 256, 0, stream>>>(a);
+  else if (g->kh == 2 && g->kw == 2) pool_quant_f32_kernel<2, 2><<<grid, 256, 0, stream>>>(a);
+  else pool_quant_f32_kernel<0, 0><<<grid, 256, 0, stream>>>(a);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }

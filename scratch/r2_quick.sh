@@ -10,3 +10,11 @@ import json; d=json.load(open("$O/q_${c}.json")); print("$c", d["value"], d["uni
 PY
 done
 timeout 300 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | cut -c1-200
+QTB200_BENCH_GRAPH=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 75 --csv --log-file $O/q_launches_resnet.csv python bench.py --config resnet18_t2a8 --steps 1 --warmup 3 > /dev/null 2>&1
+python - <<'PY'
+import csv
+rows=[r for r in csv.reader(open("gpurun_out/q_launches_resnet.csv")) if len(r)>10]
+hdr=rows[0]; ki=hdr.index("Kernel Name"); vi=hdr.index("Metric Value")
+for r in rows[1:75]:
+    print(r[ki][:70], r[vi])
+PY

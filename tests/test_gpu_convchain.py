@@ -45,6 +45,29 @@ def test_image_planes_reconstruct_the_image(Q):
     assert torch.equal(small[:, 1:8, 1:9, :3], x.permute(0, 2, 3, 1)[:, :7, :8].bfloat16().float())
 
 
+def test_image_windows_hold_the_filter_rows(Q):
+    from pytorch_quantize_impls_b200 import _ops as ops
+    torch.manual_seed(1)
+    B, C, H, W = 2, 3, 11, 19
+    x = (torch.randn(B, C, H, W) * 3).cuda()
+    for P, kw, sw, pw, slots in ((3, 7, 2, 3, 64), (3, 3, 1, 1, 32), (2, 3, 2, 0, 32), (1, 5, 1, 2, 16)):
+        ph = 2
+        OW = (W + 2 * pw - kw) // sw + 1
+        Hp = H + 2 * ph - 1                                  # the last padded row is never read by a strided filter: dropped
+        rec = ops.image_windows(x, P, kw, sw, ph, pw, Hp, OW, slots).float()            # [B, Hp, OW, slots]
+        assert rec.shape == (B, Hp, OW, slots)
+        assert torch.equal(rec[..., kw * P * C:], torch.zeros_like(rec[..., kw * P * C:]))
+        parts = rec[..., :kw * P * C].reshape(B, Hp, OW, kw, P, C)
+        recon = parts.sum(4)                                  # [B, Hp, OW, kw, C]
+        xp = TF.pad(x, (pw, pw + sw, ph, ph))                 # zero padding as the conv sees it
+        want = torch.stack([xp[:, :, :Hp, kx:kx + (OW - 1) * sw + 1:sw] for kx in range(kw)], -1)      # [B, C, Hp, OW, kw]
+        want = want.permute(0, 2, 3, 4, 1)
+        tol = {1: 2.0 ** -8, 2: 2.0 ** -16, 3: 2.0 ** -23}[P]
+        assert float((recon - want).abs().max() / x.abs().max()) <= tol
+        hi = parts[:, :, :, :, 0]
+        assert torch.equal(hi, want.bfloat16().float())
+
+
 FIRST = [  # Cin, O, k, stride, pad, dil, H, W
     (3, 64, 3, 1, 1, 1, 32, 32), (3, 64, 7, 2, 3, 1, 64, 64), (3, 192, 11, 4, 2, 1, 99, 99), (5, 32, 5, 1, 2, 1, 20, 23),
     (3, 64, 3, 3, 0, 1, 31, 29), (1, 32, 3, 1, 2, 2, 18, 18), (3, 40, 7, 2, 3, 1, 37, 41), (8, 32, 3, 2, 1, 1, 21, 21),
@@ -85,6 +108,12 @@ def test_first_layer_implicit_gemm(Q, shape, fam):
         finally:
             Q.set_first_layer_implicit(True)
         assert rel(y, y_old) <= 5e-5                      # the explicit two-plane gather carries 16 significant bits
+        Q.set_first_layer_windows(False)                  # plane pixels + space-to-depth folds (the route of filters whose row
+        try:                                              # does not fit one record)
+            y_fold = lay(x.cuda())
+        finally:
+            Q.set_first_layer_windows(True)
+        assert rel(y_fold, ref) <= (5e-6 if fam in ("ter", "bin") else 2e-3) and rel(y, y_fold) <= 5e-6
     assert n_launch <= 8                                   # pack (stats + codes), expand, image planes, implicit GEMM: no gather
 
 
