@@ -53,6 +53,14 @@ def clamp_guarantees_lane(codes_kind, bit_width, lo, hi):
     return round(n * lo) >= r[0] and round(n * hi) <= r[1]
 
 
+def _overflow_flag(dev, mode, guaranteed=False):
+    """Sticky lane-overflow flag of a DoReFa quantizer, or None when nobody will look at it: other quantizers, a clamp that
+    keeps the codes inside the lane, or set_strict("off") -- one memset launch per quantizer saved on the inference chains."""
+    if mode != L.Q_DOREFA or guaranteed or _strict == "off":
+        return None
+    return torch.zeros(1, dtype=torch.int32, device=dev)
+
+
 def round_up(a, b):
     return (a + b - 1) // b * b
 
@@ -136,16 +144,16 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
         rows, cols = Bn, Cn * Hn * Wn
         a.rows, a.cols, a.ld_x, a.ld_y, a.nhwc_c = rows, cols, cols, cols, Cn
         codes = torch.empty((Bn, Hn, Wn, Cn), dtype=torch.int8 if codes_kind == L.CODES_I8 else torch.uint8, device=dev)
-        overflow = torch.zeros(1, dtype=torch.int32, device=dev) if mode == L.Q_DOREFA else None
+        overflow = _overflow_flag(dev, mode)
         ld = cols
     elif codes_kind in (L.CODES_I8, L.CODES_U8):
         ld = round_up(max(cols, 1), 16)
         codes = torch.empty((rows, ld), dtype=torch.int8 if codes_kind == L.CODES_I8 else torch.uint8, device=dev)
-        overflow = torch.zeros(1, dtype=torch.int32, device=dev) if mode == L.Q_DOREFA else None
+        overflow = _overflow_flag(dev, mode)
     elif codes_kind == L.CODES_F4:
         ld = round_up(max(cols, 1), 32)        # elements; two e2m1 codes per byte -> 16-byte rows
         codes = torch.empty((rows, ld // 2), dtype=torch.uint8, device=dev)
-        overflow = torch.zeros(1, dtype=torch.int32, device=dev) if mode == L.Q_DOREFA else None
+        overflow = _overflow_flag(dev, mode)
     elif codes_kind == L.CODES_BF16:
         ld = round_up(max(cols, 1), 8)
         codes = torch.empty((rows, ld), dtype=torch.bfloat16, device=dev)
@@ -445,7 +453,7 @@ class RequantOut:
         cap = int(L.lib().qt_requant_max_parts(cols))
         self.row_part = torch.empty((cap, rows), dtype=torch.float32, device=dev) if mode == L.Q_XNOR_ROW else None
         self.row_sum_part = torch.empty((cap, rows), dtype=torch.int32, device=dev) if want_row_sum else None
-        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev) if mode == L.Q_DOREFA else None
+        self.overflow = _overflow_flag(dev, mode, lo is not None and clamp_guarantees_lane(codes_kind, bit_width, lo, hi))
         c = L.QtRequant()
         c.mode, c.bit_width, c.codes_kind, c.ld_codes = mode, bit_width, codes_kind, self.ld
         elem_num, elem_den = {L.CODES_F4: (1, 2), L.CODES_I8: (1, 1), L.CODES_U8: (1, 1)}.get(codes_kind, (2, 1))
@@ -552,7 +560,7 @@ def pool_quant_f32(x_cl, k, s, p, want_out=True, mode=None, bit_width=0, codes_k
     codes = overflow = None
     if mode is not None:
         codes = torch.empty((B, OH, OW, Cn), dtype=torch.int8 if codes_kind == L.CODES_I8 else torch.uint8, device=x_cl.device)
-        overflow = torch.zeros(1, dtype=torch.int32, device=x_cl.device) if mode == L.Q_DOREFA else None
+        overflow = _overflow_flag(x_cl.device, mode)
     L.check(L.lib().qt_pool_quant_f32(_p(x_cl), C.byref(g), _p(out), -1 if mode is None else mode, bit_width, _p(codes),
                                       codes_kind, _p(overflow), _stream()), "qt_pool_quant_f32")
     return out, codes, overflow
