@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QT_VERSION 103
+#define QT_VERSION 104
 
 enum {
   QT_OK = 0,
@@ -355,6 +355,14 @@ int qt_image_planes(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, 
  * the implicit GEMM is bound by L2 -> shared-memory bytes, not by the tensor pipe. */
 int qt_image_windows(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int planes, int kw, int stride_w,
                      int pad_h, int pad_w, int64_t Hp, int64_t OW, int slots, void* out, void* stream);
+
+/* fp32 classifier head of the residual nets (models/Resnet/Resnet_bin.py:104-107: avg_pool2d -> view -> nn.Linear):
+ * out[b, n] = bias[n] + sum_c (mean over hw of x[b, hw, c]) * w[n, c], x channels-last [B, HW, C] (HW = 1: a plain fp32
+ * Linear on [B, C]); bias may be NULL.  Every sum runs in a fixed order that depends on (HW, C) only, so a sample's logits do
+ * not depend on the batch it is part of (library GEMMs choose split-K by batch size): the gathered logits of a sharded run
+ * equal the single-GPU run bit for bit. */
+int qt_head_f32(const float* x, int64_t B, int64_t HW, int64_t C, const float* w, int64_t ldw, const float* bias,
+                int64_t N, float* out, int64_t ldo, void* stream);
 
 /* Max-pool (nn.MaxPool2d, ceil_mode = False, dilation 1; OH = floor((H + 2 pad - k) / stride) + 1) on channels-last tensors.
  *   qt_pool_codes      8-bit activation codes [B, H, W, C] -> [B, OH, OW, C].  An activation quantizer is monotone, so

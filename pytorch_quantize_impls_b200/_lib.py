@@ -105,6 +105,7 @@ SYMBOLS = {
     "qt_rowsum_codes": (i32, [vp, i32, i64, i64, vp, vp]),
     "qt_pool_codes": (i32, [vp, i32, C.POINTER(QtPoolGeom), vp, vp, vp]),
     "qt_pool_quant_f32": (i32, [vp, C.POINTER(QtPoolGeom), vp, i32, i32, vp, i32, vp, vp]),
+    "qt_head_f32": (i32, [vp, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),
     "qt_gemm_f16": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, C.POINTER(i32), C.POINTER(i32),
                           i64, i64, i64, C.POINTER(QtEpilogue), i32, vp]),
     "qt_gemm_f32": (i32, [vp, i64, vp, i64, i64, i64, i64, C.POINTER(QtEpilogue), vp]),

@@ -519,6 +519,27 @@ def image_windows(x, planes, kw, stride_w, pad_h, pad_w, Hp, OW, slots):
     return out
 
 
+def head_f32(x, weight, bias):
+    """Global average pool + fp32 Linear (qt_head_f32), batch-invariant: x channels-last [B, C, H, W] (or [B, C]) fp32,
+    weight [N, C], bias [N] or None -> [B, N]."""
+    require_cuda(x, "input")
+    if x.dim() == 4:
+        if not is_channels_last(x) and not (x.shape[2] == 1 and x.shape[3] == 1):
+            x = x.contiguous(memory_format=torch.channels_last)
+        B, Cn, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    else:
+        x = as_f32c(x)
+        B, Cn, HW = x.shape[0], x.shape[1], 1
+    if x.dtype != torch.float32:
+        x = x.float()
+    w = as_f32c(weight)
+    b = None if bias is None else as_f32c(bias)
+    out = torch.empty((B, w.shape[0]), dtype=torch.float32, device=x.device)
+    L.check(L.lib().qt_head_f32(_p(x), B, HW, Cn, _p(w), w.stride(0), _p(b), w.shape[0], _p(out), out.stride(0), _stream()),
+            "qt_head_f32")
+    return out
+
+
 def _pool_geom(B, H, W, Cn, k, s, p):
     (kh, kw), (sh, sw), (ph, pw) = k, s, p
     OH, OW = (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1

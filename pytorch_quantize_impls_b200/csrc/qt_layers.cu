@@ -6,6 +6,7 @@
 //                     filter ROW instead of per tap
 //   qt_pool_codes     max-pool on channels-last 8-bit activation codes (per-channel max or min)
 //   qt_pool_quant_f32 max-pool of a channels-last fp32 activation fused with the next activation quantizer
+//   qt_head_f32       global average pool + fp32 Linear head, batch-invariant summation order
 #include "qt_common.cuh"
 
 namespace qt {
@@ -254,6 +255,36 @@ __global__ void __launch_bounds__(256) pool_quant_f32_kernel(PoolQuantArgs a) {
   if (a.overflow && ovf) atomicOr(a.overflow, 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 classifier head: out[b, n] = bias[n] + sum_c mean_hw(x[b, hw, c]) * w[n, c]   (global average pool + nn.Linear of the
+// residual nets, models/Resnet/Resnet_bin.py:104-107; hw = 1: a plain fp32 Linear).  One block per sample, every sum in a
+// FIXED order that depends on (HW, C) only: the result for a sample does not depend on the batch it arrives in -- a library
+// GEMM picks split-K by batch size, which made the logits of a 2048-image batch differ in the last bit from the same images
+// run as four shards.  The work is tiny (B x N x C MACs).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_f32_kernel(const float* __restrict__ x, int HW, int C, const float* __restrict__ w,
+                                                       int64_t ldw, const float* __restrict__ bias, int N, float* __restrict__ out,
+                                                       int64_t ldo) {
+  extern __shared__ float mean[];              // [C]
+  const int64_t b = blockIdx.x;
+  const float* xb = x + b * (int64_t)HW * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < HW; ++i) s += __ldg(xb + (int64_t)i * C + c);
+    mean[c] = HW > 1 ? s / (float)HW : s;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = warp; n < N; n += 8) {
+    const float* wn = w + n * ldw;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(mean[c], __ldg(wn + c), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[b * ldo + n] = acc + (bias ? __ldg(bias + n) : 0.f);
+  }
+}
+
 static unsigned grid_for(int64_t total, int threads) {
   int64_t blocks = ceil_div(total, threads);
   const int64_t cap = 148ll * 64;          // grid-stride beyond ~8 resident waves
@@ -331,6 +362,18 @@ extern "C" int qt_pool_codes(const void* x_nhwc, int is_unsigned, const QtPoolGe
     if (use_min) pool_codes_kernel<false, true><<<grid, 256, 0, stream>>>(a);
     else pool_codes_kernel<false, false><<<grid, 256, 0, stream>>>(a);
   }
+  QT_LAUNCH_CHECK();
+  return QT_OK;
+}
+
+extern "C" int qt_head_f32(const float* x, int64_t B, int64_t HW, int64_t C, const float* w, int64_t ldw, const float* bias,
+                           int64_t N, float* out, int64_t ldo, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  QT_REQUIRE(x && w && out, "qt_head_f32: null argument");
+  QT_REQUIRE(B >= 0 && HW >= 1 && C >= 1 && N >= 1 && ldw >= C && ldo >= N, "qt_head_f32: bad shape");
+  QT_REQUIRE(C <= 12288 && HW < (1 << 20) && N < (1 << 20) && B < (1ll << 31), "qt_head_f32: C must fit the 48 KB mean buffer");
+  if (B == 0) return QT_OK;
+  head_f32_kernel<<<(unsigned)B, 256, (size_t)C * 4, stream>>>(x, (int)HW, (int)C, w, ldw, bias, (int)N, out, ldo);
   QT_LAUNCH_CHECK();
   return QT_OK;
 }

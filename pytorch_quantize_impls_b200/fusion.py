@@ -543,6 +543,22 @@ def _is_block(m):
     return all(hasattr(m, a) for a in ("q_in", "branch1", "branch2", "clip", "shortcut")) and not isinstance(m, FusedBasicBlock)
 
 
+class FusedAvgLinear:
+    """AdaptiveAvgPool2d(1) -> flatten -> nn.Linear (fp32 head of the residual nets) as ONE batch-invariant kernel (qt_head_f32)
+    on the inference path; anything else (autograd, CPU, other dtypes) runs the two modules.  Not an nn.Module: it only
+    borrows the parameters of the modules it was built from."""
+
+    def __init__(self, avg, linear):
+        self.avg, self.linear = avg, linear
+
+    def __call__(self, x):
+        lin = self.linear
+        if (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and not torch.is_grad_enabled()
+                and lin.weight.dtype == torch.float32 and lin.weight.is_cuda):
+            return ops.head_f32(x, lin.weight, lin.bias)
+        return lin(self.avg(x).flatten(1))
+
+
 def fuse_inference(module):
     """Rewrite, in place and recursively, the inter-layer patterns of the reference nets found inside nn.Sequential containers:
 
@@ -564,6 +580,10 @@ def fuse_inference(module):
         if (isinstance(stem, nn.Sequential) and isinstance(layers, nn.Sequential) and len(stem) and len(layers)
                 and isinstance(stem[-1], FusedConvPool) and isinstance(layers[0], FusedBasicBlock)):
             stem[-1]._next = getattr(layers[0].block.q_in, "_qt_spec", None)
+        avg, lin = getattr(module, "avg", None), getattr(module, "linear", None)
+        if (getattr(type(module), "_uses_fused_head", False) and isinstance(avg, nn.AdaptiveAvgPool2d)
+                and avg.output_size in (1, (1, 1)) and type(lin) is nn.Linear):
+            module.__dict__["_fused_head"] = FusedAvgLinear(avg, lin)
         return module
     mods = list(module.children())
     out, i = [], 0

@@ -112,6 +112,8 @@ class TerBasicBlock(nn.Module):
 
 
 class ResNetTer(nn.Module):
+    _uses_fused_head = True        # forward() calls the head fuse_inference leaves in __dict__["_fused_head"]
+
     def __init__(self, lib, num_blocks, num_classes, act_bits):
         super().__init__()
         self.in_planes = 64
@@ -130,7 +132,8 @@ class ResNetTer(nn.Module):
 
     def forward(self, x):
         out = self.layers(self.stem(x))
-        return self.linear(self.avg(out).flatten(1))
+        head = self.__dict__.get("_fused_head")        # set by fuse_inference (not a registered child: same state_dict keys)
+        return head(out) if head is not None else self.linear(self.avg(out).flatten(1))
 
 
 def resnet18_ternary(act_bits=8, num_classes=10, lib=None):

@@ -45,6 +45,7 @@ def test_resnet_blocks_and_unknown_modules_are_left_alone():
     blk = net.layers[2].block                 # first down-sampling block
     assert names(blk.branch1) == ["FusedLayerQuant"] and names(blk.branch2) == ["FusedLayerBN"]
     assert names(blk.shortcut) == ["FusedLayerBN"] and isinstance(net.linear, nn.Linear)
+    assert type(net.__dict__["_fused_head"]).__name__ == "FusedAvgLinear" and "_fused_head" not in dict(net.named_children())
     plain = nn.Sequential(nn.Linear(4, 4), nn.BatchNorm1d(4), nn.ReLU())
     assert names(Q.fuse_inference(plain)) == ["Linear", "BatchNorm1d", "ReLU"]          # not a quantized layer: untouched
 

@@ -381,3 +381,33 @@ def test_w_folded_conv_equals_plain_implicit_gemm(Q, case):
     for a, b in zip(outs[False], outs[True]):
         assert a.shape == b.shape and torch.equal(a, b)
     assert outs[True][1].is_contiguous(memory_format=torch.channels_last)
+
+
+def test_fp32_head_is_batch_invariant(Q):
+    """Global average pool + nn.Linear as one kernel: equals torch to fp32 accuracy, and a sample's logits do not depend on the
+    batch it is part of (the property the sharded-run == single-GPU-run check of bench.py --config needs)."""
+    from pytorch_quantize_impls_b200 import _ops as ops
+    torch.manual_seed(11)
+    lin = torch.nn.Linear(512, 10).cuda()
+    x = torch.rand(96, 512, 7, 7).cuda().contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y = ops.head_f32(x, lin.weight, lin.bias)
+        ref = torch.nn.functional.linear(x.double().mean((2, 3)), lin.weight.double(), lin.bias.double())
+        assert rel(y, ref) <= 2e-6
+        for n in (1, 5, 32):
+            assert torch.equal(ops.head_f32(x[:n].contiguous(memory_format=torch.channels_last), lin.weight, lin.bias), y[:n])
+        y2 = ops.head_f32(x[:, :, :1, :1].reshape(96, 512), lin.weight, None)          # plain Linear, no bias
+        assert rel(y2, torch.nn.functional.linear(x[:, :, 0, 0].double(), lin.weight.double())) <= 2e-6
+    net = Q.fuse_inference(nets_resnet().cuda().eval())
+    assert net.__dict__.get("_fused_head") is not None
+    xi = torch.rand(6, 3, 64, 64).cuda()
+    with torch.no_grad():
+        a = net(xi)
+        b = torch.cat([net(xi[:2]), net(xi[2:])])
+    assert torch.equal(a, b)
+
+
+def nets_resnet():
+    from pytorch_quantize_impls_b200 import nets
+    torch.manual_seed(3)
+    return nets.resnet18_ternary()
