@@ -578,9 +578,9 @@ def run_ours(args):
                            "each of the %d graphs within the timed region" % NBUF) if graph_mode else
                           "CUDA events around every launch of the timed region",
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` launch of round 2
-                # (profiles/r2_ncu_full_summary.json: 159.4 MB read + 49.9 MB written; algorithmic 100.7 MB of operands +
+                # (profiles/r2_ncu_full_headline.json: 161.2 MB read + 48.4 MB written; algorithmic 100.7 MB of operands +
                 # 67.1 MB of fp16 codes, part of which is still in L2 when the kernel ends)
-                "traffic": 209.3e6, "traffic_unit": "bytes per launch (ncu --set full of this kernel at this shape, profiles/r2_ncu_full_summary.json)",
+                "traffic": 209.6e6, "traffic_unit": "bytes per launch (ncu --set full of this kernel at this shape, profiles/r2_ncu_full_headline.json)",
                 "algorithmic_bytes": float(2 * M * K + 2 * N * K + 2 * M * N + 4 * N)}
 
     cb = cpu_reference_gops(BATCH, reps=3, warmup=1)
