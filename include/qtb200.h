@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QT_VERSION 104
+#define QT_VERSION 105
 
 enum {
   QT_OK = 0,
@@ -106,6 +106,11 @@ typedef struct QtActQuant {
                            CTAs, each looping over row chunks -- a bounded footprint (8 warps, ~8 K registers, no shared memory
                            per CTA) that shares every SM with a persistent tcgen05 contraction running on another stream
                            (the quantizer of row band i+1 beside the product of band i).  Code-only calls only (no y / bits) */
+  int32_t* ready;       /* optional progress counters (device, zeroed by the caller): after the codes of a 1024-column chunk of row r
+                           are stored (and fenced), ready[r / ready_rows] is incremented -- a consumer kernel running CONCURRENTLY
+                           (QtEpilogue.a_ready) starts on a row block as soon as its count reaches ready_rows * cols / 1024.
+                           Lean code-only calls only (cols % 1024 == 0); ignored otherwise is an error */
+  int ready_rows;
 } QtActQuant;
 
 int qt_quant_act(const QtActQuant* p, void* stream);
@@ -281,6 +286,13 @@ typedef struct QtEpilogue {
                              `out += self.shortcut(x); out = F.relu(out)`) folded into the second conv's epilogue, with the
                              channels-last fp32 activation as [pixels, channels] matrix.  out_mode 0 only */
   int64_t ld_res;
+  /* Operand dependency (tcgen05 GEMM routes, plain row-major A): the A rows are being produced by a kernel running on another
+     stream at the same time (qt_quant_act with `ready` counters).  Before the TMA producer loads rows of block
+     b = row / a_ready_rows it waits until a_ready[b] >= a_ready_target (acquire at gpu scope + proxy fence).  The quantizer of
+     a layer then runs BESIDE its contraction instead of in front of it (HBM-bound pass hidden behind the tensor-bound one)
+     without cutting the product into bands.  a_ready_rows must be a multiple of 128.  NULL: no dependency. */
+  const int32_t* a_ready;
+  int a_ready_rows, a_ready_target;
 } QtEpilogue;
 
 /* 1-bit x 1-bit: acc = K - 2 popc(a ^ w).  CUDA-core XNOR + popcount. */

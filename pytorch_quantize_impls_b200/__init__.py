@@ -10,7 +10,7 @@ from . import _lib  # noqa: F401  (defines the loud failure when libqtb200.so is
 from . import functions, layers  # noqa: F401
 from . import BinaryNet, DorefaNet, LogLinNet, TernerNet, XnorNet  # noqa: F401
 from ._engine import (code_only_activations, set_backend, set_banded_head, set_first_layer_implicit,  # noqa: F401
-                      set_first_layer_windows,
+                      set_first_layer_windows, set_overlap_head,
                       set_first_layer_planes, set_fp4, set_grad_backend, set_implicit_conv, set_wfold, set_xnor_mode)
 from ._ops import device_caps, set_strict  # noqa: F401
 from .fusion import (FlattenCodes, FusedActLayer, FusedBasicBlock, FusedBNActQuant, FusedConvPool, FusedLayerBN,  # noqa: F401

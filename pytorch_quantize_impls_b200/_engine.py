@@ -165,7 +165,7 @@ def attach_tag(y, tag):
 class _A:
     """Activation operand handed to the contraction."""
     __slots__ = ("form", "t", "ld", "signed", "scale", "row_sum", "row_scale", "planes", "bits", "ld_bits",
-                 "row_parts", "row_mul")
+                 "row_parts", "row_mul", "ready")
 
 
 def _a_from_tag(tag):
@@ -327,6 +327,8 @@ def _contract_impl(a, pack, M, N, K, out, *, w_row0=0, bias=None, out_mode=0, ld
     if pack.wscale != 1.0:           # LogLin 'lin' weights: value = code * step
         a = _scaled(a, pack.wscale)
     rp = dict(row_parts=a.row_parts, row_mul=a.row_mul, requant=requant)
+    if getattr(a, "ready", None) is not None:
+        rp["a_ready"] = a.ready          # the operand is still being written by a quantizer on another stream (linear_overlapped)
     if requant is None and rq_spec is not None and rq_spec.lo is not None:
         rp["out_clamp"] = (rq_spec.lo, rq_spec.hi)       # a clamp activation folded behind the (BatchNorm-folded) layer
 
@@ -516,6 +518,73 @@ def linear_banded(x, quantize, pack, bias, nbands=4, affine=None):
         pack._hold_on, pack._hold = False, None
         cur.wait_stream(side)
     return out
+
+
+_overlap_head = [os.environ.get("QTB200_OVERLAP_HEAD", "0") == "1"]
+
+
+def set_overlap_head(flag):
+    """True: a `sign / ternary quantizer -> quantized Linear` pair on a large fp32 input (fusion.FusedActLayer, code-only
+    inference) runs (part of) the quantizer on a side stream BESIDE the contraction; the contraction's TMA producer follows
+    per-row-block progress counters (QtActQuant.ready / QtEpilogue.a_ready).  False (default): one kernel after the other.
+    Off by default because it is slower on B200 at the north-star shape (85.7 us plain; 105 - 127 us with 75 % - 0 % of the rows
+    quantized up front): beside a 168-register contraction CTA one 8-warp quantizer CTA fits per SM, it pulls ~1.3 TB/s and
+    slows the shared-memory-bound product it runs beside.  Bit-identical to the plain pair."""
+    _overlap_head[0] = bool(flag)
+
+
+OVERLAP_ROWS = 256          # rows per progress counter: one CTA-pair tile
+
+
+def linear_overlapped(x, quantize, codes_kind, pack, bias, affine=None):
+    """`activation quantizer -> F.linear(., W_q, bias)` on an fp32 [M, K] input with the two kernels running CONCURRENTLY: the
+    quantizer (bounded grid: one 8-warp CTA per SM, no shared memory -- it fits beside the persistent tcgen05 CTA) walks the
+    rows in order and bumps one counter per 256-row block; the contraction, launched right behind it on the calling stream,
+    waits per tile for its block's counter.  The HBM-bound pass (read fp32, write codes) hides behind the shared-memory-bound
+    product instead of preceding it.  quantize(x_rows, max_ctas, ready, ready_rows, codes_out) -> ActCodes (code-only, sign / ternary:
+    no row vectors); codes_kind: its lane format.  fp32 result [M, N]."""
+    dev = x.device
+    M, K = x.shape
+    N = pack.n
+    if M % OVERLAP_ROWS or K % 1024:
+        raise RuntimeError("internal: linear_overlapped needs M % 256 == 0 and K % 1024 == 0")
+    out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    if bias is not None:
+        bias = ops.as_f32c(bias)
+    nblk = -(-M // OVERLAP_ROWS)
+    flags = torch.zeros(nblk, dtype=torch.int32, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    side = _band_streams.get(dev)
+    if side is None:
+        side = _band_streams[dev] = torch.cuda.Stream(device=dev)
+    sms = ops.device_caps(dev.index if dev.index is not None else torch.cuda.current_device())["num_sms"]
+    # Beside a 168-register contraction CTA only ONE 8-warp quantizer CTA fits per SM, and its loads in flight live in
+    # registers: the co-resident quantizer pulls ~1.3 TB/s, slower than the contraction consumes rows.  So the first
+    # OVERLAP_SPLIT of the rows are quantized at full speed in front of the contraction (same stream), the rest beside it.
+    head = int(M * OVERLAP_SPLIT[0]) // OVERLAP_ROWS * OVERLAP_ROWS
+    full = ops.codes_buffer(M, K, codes_kind, dev)
+    tag = None
+    try:
+        if head > 0:
+            tag = quantize(x[:head], 0, flags, OVERLAP_ROWS, full[:head])
+        fork = torch.cuda.Event()
+        fork.record(cur)                                  # x, the zeroed counters and the head rows are ready
+        side.wait_event(fork)
+        if head < M:
+            with torch.cuda.stream(side):
+                tag = quantize(x[head:], sms, flags[head // OVERLAP_ROWS:], OVERLAP_ROWS, full[head:])
+            full.record_stream(side)
+            flags.record_stream(side)
+        tag.codes, tag.rows = full, M
+        a = _a_from_tag(tag)
+        a.ready = (flags, OVERLAP_ROWS, OVERLAP_ROWS * (K // 1024))      # chunk tasks per complete 256-row block
+        _contract(a, pack, M, N, K, out, bias=bias, rq_spec=affine)
+    finally:
+        cur.wait_stream(side)
+    return out
+
+
+OVERLAP_SPLIT = [float(os.environ.get("QTB200_OVERLAP_SPLIT", "0.4"))]
 
 
 def _pair(v):

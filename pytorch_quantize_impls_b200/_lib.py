@@ -30,7 +30,7 @@ class QtActQuant(C.Structure):
                 ("bits", vp), ("ld_bits", i64),
                 ("row_sum", vp), ("row_scale", vp), ("overflow", vp),
                 ("pre_scale", vp), ("pre_shift", vp), ("pre_channels", i64), ("pre_hw", i64), ("pre_clamp", i32),
-                ("pre_lo", f32), ("pre_hi", f32), ("nhwc_c", i64), ("row_parts", i32), ("max_ctas", i32)]
+                ("pre_lo", f32), ("pre_hi", f32), ("nhwc_c", i64), ("row_parts", i32), ("max_ctas", i32), ("ready", vp), ("ready_rows", i32)]
 
 
 class QtWeightPack(C.Structure):
@@ -77,7 +77,7 @@ class QtEpilogue(C.Structure):
                 ("out", vp), ("ldo", i64), ("out_mode", i32), ("nchw_inner", i64), ("acc_out", vp),
                 ("requant", C.POINTER(QtRequant)), ("row_scale_parts", i32), ("row_scale_mul", f32),
                 ("row_sum_parts", i32), ("out_clamp", i32), ("out_lo", f32), ("out_hi", f32),
-                ("residual", vp), ("ld_res", i64)]
+                ("residual", vp), ("ld_res", i64), ("a_ready", vp), ("a_ready_rows", i32), ("a_ready_target", i32)]
 
 
 # every symbol include/qtb200.h declares: name -> (restype, argtypes)

@@ -114,7 +114,8 @@ class ActCodes:
 
 
 def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_kind=L.CODES_NONE,
-              want_bits=False, want_row_sum=False, want_row_scale=False, kind=None, pre=None, max_ctas=0):
+              want_bits=False, want_row_sum=False, want_row_scale=False, kind=None, pre=None, max_ctas=0, ready=None,
+              ready_rows=0, codes_out=None):
     """Run one activation-quantizer pass.  Returns (y or None, ActCodes or None).
     pre = (scale[C], shift[C], lo, hi) fuses x' = clamp(x*scale[ch] + shift[ch], lo, hi) in front (lo/hi None: no clamp)."""
     require_cuda(x, "input")
@@ -163,6 +164,10 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
     elif codes_kind in (L.CODES_BF16X2, L.CODES_BF16X3):
         ld = round_up(max(cols, 1), 8)
         codes = torch.empty((2 if codes_kind == L.CODES_BF16X2 else 3, rows, ld), dtype=torch.bfloat16, device=dev)
+    if codes_out is not None:            # row range of a larger operand (codes_buffer): 2-D code matrices only
+        if layout != "rows" or codes is None or codes_out.shape != codes.shape or codes_out.dtype != codes.dtype:
+            raise ValueError("quant_act: codes_out does not match the operand this call produces")
+        codes = codes_out
     if want_bits:
         ldb = round_up((cols + 31) // 32, 4)
         bits = torch.empty((rows, ldb), dtype=torch.int32, device=dev)
@@ -180,6 +185,8 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
             row_parts = 0
             row_scale = torch.empty(rows, dtype=torch.float32, device=dev)
     a.max_ctas = int(max_ctas)
+    if ready is not None:                # progress counters for a consumer running beside this call (QtActQuant.ready)
+        a.ready, a.ready_rows = _p(ready), int(ready_rows)
     a.codes, a.codes_kind, a.ld_codes = _p(codes), codes_kind, ld
     a.bits, a.ld_bits = _p(bits), ldb
     a.row_sum, a.row_scale, a.overflow = _p(row_sum), _p(row_scale), _p(overflow)
@@ -199,6 +206,17 @@ def quant_act(x, mode, *, bit_width=0, fsr=0, with_sign=1, want_y=True, codes_ki
         if _strict is True:
             tag.check()
     return y, tag
+
+
+def codes_buffer(rows, cols, codes_kind, dev):
+    """Uninitialised [rows, ld] code matrix as quant_act lays it out (8-bit or e2m1 lanes), for calls that fill row ranges of
+    it (codes_out)."""
+    if codes_kind == L.CODES_F4:
+        return torch.empty((rows, round_up(max(cols, 1), 32) // 2), dtype=torch.uint8, device=dev)
+    if codes_kind in (L.CODES_I8, L.CODES_U8):
+        return torch.empty((rows, round_up(max(cols, 1), 16)), dtype=torch.int8 if codes_kind == L.CODES_I8 else torch.uint8,
+                           device=dev)
+    raise ValueError("codes_buffer: 8-bit and e2m1 lanes only")
 
 
 class WeightPack:
@@ -402,7 +420,7 @@ def im2col(x4d, elem_bytes, geom, group, out, ld_out, row_sum=None, is_unsigned=
 
 def make_epi(out, *, ldo, out_mode=0, nchw_inner=1, bias=None, row_scale=None, col_scale=None, row_sum=None,
              scale=1.0, acc_mul=1, rs_mul=0, acc_out=None, out_offset=0, row_parts=0, row_mul=1.0, requant=None,
-             out_clamp=None, residual=None, ld_res=0):
+             out_clamp=None, residual=None, ld_res=0, a_ready=None):
     """requant: a RequantOut (fused re-quantisation of the output); row_parts > 0: row_scale / row_sum are partial sums
     left by a previous layer's requant epilogue."""
     e = L.QtEpilogue()
@@ -423,6 +441,9 @@ def make_epi(out, *, ldo, out_mode=0, nchw_inner=1, bias=None, row_scale=None, c
         e._keep = requant        # keep the ctypes struct alive as long as the epilogue
     if residual is not None:
         e.residual, e.ld_res = _p(residual), int(ld_res)
+    if a_ready is not None:              # (int32 counters, rows per counter, count that means "block complete")
+        e.a_ready, e.a_ready_rows, e.a_ready_target = _p(a_ready[0]), int(a_ready[1]), int(a_ready[2])
+        e._keep_ready = a_ready[0]
     return e
 
 

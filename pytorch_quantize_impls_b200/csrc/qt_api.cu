@@ -43,6 +43,7 @@ int check_epi(const QtEpilogue* e, int64_t M, int64_t N) {
   }
   QT_REQUIRE(e->out_mode == 0 || e->out_mode == 1, "epilogue: out_mode must be 0 or 1");
   if (e->residual) QT_REQUIRE(e->out_mode == 0 && e->ld_res >= N, "epilogue: residual needs out_mode 0 and ld_res >= N");
+  if (e->a_ready) QT_REQUIRE(e->a_ready_rows >= 128 && e->a_ready_rows % 128 == 0 && e->a_ready_target > 0, "epilogue: a_ready needs a_ready_rows % 128 == 0 and a positive target");
   if (e->out && e->out_mode == 0) QT_REQUIRE(e->ldo >= N, "epilogue: ldo (%lld) < N (%lld)", (long long)e->ldo, (long long)N);
   if (e->out && e->out_mode == 1)
     QT_REQUIRE(e->ldo >= N && e->nchw_inner > 0 && M % e->nchw_inner == 0, "epilogue: NCHW inner (%lld) must divide M (%lld)",

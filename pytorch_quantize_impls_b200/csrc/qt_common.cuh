@@ -72,6 +72,8 @@ struct Epi {
   float out_lo, out_hi;
   const float* residual;   // optional fp32 [M, ld_res] added to y before the clamp (row-major outputs only)
   int64_t ld_res;
+  const int32_t* a_ready;  // progress counters of a concurrently running producer of the A rows (tcgen05 GEMM routes)
+  int a_ready_rows, a_ready_target;
 };
 
 static inline Epi make_epi(const QtEpilogue* e, int64_t M, int64_t N) {
@@ -91,13 +93,14 @@ static inline Epi make_epi(const QtEpilogue* e, int64_t M, int64_t N) {
   d.row_scale_parts = e->row_scale_parts; d.row_sum_parts = e->row_sum_parts; d.row_scale_mul = e->row_scale_mul;
   d.out_clamp = e->out_clamp; d.out_lo = e->out_lo; d.out_hi = e->out_hi;
   d.residual = e->residual; d.ld_res = e->ld_res;
+  d.a_ready = e->a_ready; d.a_ready_rows = e->a_ready_rows; d.a_ready_target = e->a_ready_target;
   return d;
 }
 
 int check_epi(const QtEpilogue* e, int64_t M, int64_t N);
 // true when the epilogue asks for something only the tcgen05 kernels implement (requant, partial-sum row operands, residual)
 static inline bool epi_needs_tc(const Epi& e) {
-  return e.rq_mode >= 0 || e.row_scale_parts > 0 || e.row_sum_parts > 0 || e.residual != nullptr;
+  return e.rq_mode >= 0 || e.row_scale_parts > 0 || e.row_sum_parts > 0 || e.residual != nullptr || e.a_ready != nullptr;
 }
 
 // y = float(acc_mul*acc + rs_mul*row_sum[m]) * scale * row_scale[m] * col_scale[n] + bias[n]

@@ -906,6 +906,23 @@ __device__ __forceinline__ void tc_gemm_body(const CUtensorMap& map_a, const CUt
           cv_h = oh * g.cv_sh - g.cv_ph;
           cv_w = (r - oh * g.cv_OW) * g.cv_sw - g.cv_pw;
         }
+        if (!IM2COL && g.ep.a_ready != nullptr) {
+          // the A rows of this tile are being written by a kernel on another stream: wait for their progress counter
+          const int blk = a_row / g.ep.a_ready_rows;
+          if (lane == 0) {
+            const int32_t* flag = g.ep.a_ready + blk;
+            int32_t v;
+            unsigned spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+              if (v >= g.ep.a_ready_target) break;
+              __nanosleep(200);
+              if (++spins > (1u << 24)) asm volatile("trap;");      // ~ seconds: the producer is not running -- fail loudly, do not hang
+            } while (true);
+            asm volatile("fence.proxy.async.global;" ::: "memory");  // the generic-proxy writes become visible to the TMA reads
+          }
+          __syncwarp();
+        }
         int cb = 0, off_w = 0, off_h = 0, kx = 0;              // k-block -> (filter tap, channel block), kept incrementally
         for (int kb = 0; kb < g.num_kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);

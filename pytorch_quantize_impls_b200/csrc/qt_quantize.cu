@@ -1144,6 +1144,8 @@ struct LeanArgs {
   float n;               // DoReFa levels
   float inv_cols;
   int max_ctas;          // 0: one CTA per 8 tasks; > 0: grid bound (persistent form)
+  int32_t* ready;        // optional progress counters: ready[row / ready_rows] += 1 per finished task
+  uint32_t ready_rows;
 };
 
 template <int MODE, int CK>
@@ -1230,6 +1232,13 @@ __global__ void __launch_bounds__(256) act_quant_lean_kernel(LeanArgs a) {
       else atomicAdd(a.row_sum + row, isum);
     }
   }
+  if (a.ready) {           // publish the chunk: every lane's stores (and the row vectors above) before the counter
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(a.ready + row / a.ready_rows, 1);
+    }
+  }
   }   // task loop
   if (MODE == QT_Q_DOREFA && a.overflow) {
     const unsigned any = __ballot_sync(0xffffffffu, ovf);
@@ -1264,6 +1273,7 @@ static int try_lean_quant(const QtActQuant* p, cudaStream_t stream) {
   a.x = p->x; a.codes = p->codes; a.row_sum = p->row_sum; a.row_scale = p->row_scale; a.overflow = p->overflow;
   a.rows = (uint32_t)p->rows; a.nchunks = (uint32_t)(p->cols / 1024); a.ld_x = p->ld_x; a.ld_codes = p->ld_codes;
   a.n = 1.f; a.inv_cols = 1.f / (float)p->cols; a.max_ctas = p->max_ctas;
+  a.ready = p->ready; a.ready_rows = p->ready ? (uint32_t)p->ready_rows : 1u;
   if (p->mode == QT_Q_XNOR_ROW) {
     if (!(ck == 3 || ck == 5)) return 0;
     // the partial-sum contract of qt_quant_xnor_parts: chunks of 1024 columns only when the caller provided room for them
@@ -1349,7 +1359,9 @@ extern "C" int qt_quant_act(const QtActQuant* p, void* stream_) {
   a.y = p->y; a.ld_y = p->ld_y; a.codes = p->codes; a.codes_kind = p->codes_kind; a.ld_codes = p->ld_codes;
   a.bits = p->bits; a.ld_bits = p->ld_bits; a.row_sum = p->row_sum; a.row_scale = p->row_scale; a.overflow = p->overflow;
 
+  if (p->ready) QT_REQUIRE(p->ready_rows > 0, "qt_quant_act: ready needs ready_rows > 0");
   if (int lean = try_lean_quant(p, stream)) return lean > 0 ? QT_OK : lean;
+  if (p->ready) { set_error("qt_quant_act: progress counters (ready) are served by the lean code-only kernels only (cols %% 1024 == 0, no y / bits)"); return QT_EUNSUPPORTED; }
 
   if (p->nhwc_c > 0) {
     QT_REQUIRE(p->codes && (p->codes_kind == 1 || p->codes_kind == 2), "qt_quant_act: NHWC output needs int8/uint8 codes");

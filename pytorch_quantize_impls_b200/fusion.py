@@ -393,7 +393,8 @@ class FusedActLayer(nn.Module):
     def forward(self, x):
         lay = self._layer()
         kind, arg = self.quant._qt_spec
-        ok = (eng._banded_head[0] and eng._code_only[0] and not torch.is_grad_enabled() and x.is_cuda and x.dim() == 2
+        ok = ((eng._banded_head[0] or eng._overlap_head[0]) and eng._code_only[0] and not torch.is_grad_enabled() and x.is_cuda
+              and x.dim() == 2
               and x.dtype == torch.float32
               and x.shape[0] >= self.MIN_ROWS and x.shape[1] % 1024 == 0 and x.is_contiguous() and not lay.training
               and not (isinstance(self.inner, FusedLayerBN) and not _bn_ready(self.inner.bn)))
@@ -412,25 +413,29 @@ class FusedActLayer(nn.Module):
         f4 = eng._fp4[0] and eng._f4_weight_ok(pack) and (kind in ("sign", "ternary") or arg == 2)
         small = L.CODES_F4 if f4 else L.CODES_I8
 
-        def quantize(rows, max_ctas):
+        def quantize(rows, max_ctas, ready=None, ready_rows=0, codes_out=None):
+            kw = dict(want_y=False, max_ctas=max_ctas, ready=ready, ready_rows=ready_rows, codes_out=codes_out)
             if kind == "sign":
-                return ops.quant_act(rows, L.Q_SIGN, want_y=False, codes_kind=small, kind="sign", max_ctas=max_ctas)[1]
+                return ops.quant_act(rows, L.Q_SIGN, codes_kind=small, kind="sign", **kw)[1]
             if kind == "ternary":
-                return ops.quant_act(rows, L.Q_TERNARY, want_y=False, codes_kind=small, kind="ternary", max_ctas=max_ctas)[1]
+                return ops.quant_act(rows, L.Q_TERNARY, codes_kind=small, kind="ternary", **kw)[1]
             if kind == "xnor":
-                return ops.quant_act(rows, L.Q_XNOR_ROW, want_y=False, codes_kind=eng.xnor_codes_kind(), want_row_scale=True,
-                                     kind="xnor", max_ctas=max_ctas)[1]
+                return ops.quant_act(rows, L.Q_XNOR_ROW, codes_kind=eng.xnor_codes_kind(), want_row_scale=True, kind="xnor", **kw)[1]
             ck = small if arg == 2 else (L.CODES_I8 if arg <= 7 else L.CODES_U8)
-            tag = ops.quant_act(rows, L.Q_DOREFA, bit_width=arg, want_y=False, codes_kind=ck, want_row_sum=True, kind="dorefa",
-                                max_ctas=max_ctas)[1]
+            tag = ops.quant_act(rows, L.Q_DOREFA, bit_width=arg, codes_kind=ck, want_row_sum=True, kind="dorefa", **kw)[1]
             tag.scale = _f32(_f32(1.0) / _f32(2 ** arg - 1))
             return tag
 
         affine = self.inner._make_spec() if isinstance(self.inner, FusedLayerBN) else None
+        if (eng._overlap_head[0] and not eng._banded_head[0] and x.shape[0] % eng.OVERLAP_ROWS == 0
+                and kind in ("sign", "ternary")):
+            return eng.linear_overlapped(x, quantize, small, pack, lay.bias, affine=affine)
+        if not eng._banded_head[0]:
+            return self.inner(self.quant(x))
         return eng.linear_banded(x, quantize, pack, lay.bias, affine=affine)
 
     def extra_repr(self):
-        return "banded quantizer / contraction pipeline"
+        return "quantizer beside the contraction (progress counters) / banded pipeline"
 
 
 class FusedBasicBlock(nn.Module):

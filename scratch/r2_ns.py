@@ -46,21 +46,30 @@ with torch.no_grad():
         with Q.code_only_activations():
             return act(xs[i[0] % 3])
     rec("quantizer_code_only", bench.time_fn(torch, f_q, iters=40, graph=True))
-    ref = f_plain()
-    for nb in (2, 3, 4, 6, 8):
+    def f_pair():
+        i[0] += 1
+        with Q.code_only_activations():
+            return pair(xs[i[0] % 3])
+
+    Q.set_overlap_head(False)
+    i[0] = 0
+    ref = f_pair().clone()                                   # plain pair: one kernel after the other
+    Q.set_overlap_head(True)                                 # quantizer beside the contraction (progress counters)
+    i[0] = 0
+    y = f_pair()
+    out["overlapped_equals_plain"] = bool(torch.equal(y, ref))
+    rec("overlapped", bench.time_fn(torch, f_pair, iters=40, graph=True))
+    Q.set_overlap_head(False)
+    Q.set_banded_head(True)
+    for nb in (2, 4, 8):
         orig = eng.linear_banded
 
         def banded(x, quantize, pack, bias, nbands=4, affine=None, _nb=nb):
             return orig(x, quantize, pack, bias, nbands=_nb, affine=affine)
         eng.linear_banded = banded
-
-        def f_band():
-            i[0] += 1
-            with Q.code_only_activations():
-                return pair(xs[i[0] % 3])
-        y = f_band()
-        rec("banded_%d" % nb, bench.time_fn(torch, f_band, iters=40, graph=True))
+        f_pair()
+        rec("banded_%d" % nb, bench.time_fn(torch, f_pair, iters=40, graph=True))
         eng.linear_banded = orig
-    i[0] = 2
-    ok = torch.equal(f_plain(), (lambda: (i.__setitem__(0, 2), pair(xs[0]))[1])()) if False else None
+    Q.set_banded_head(False)
+    Q.set_overlap_head(True)
 print(json.dumps(out, indent=1))

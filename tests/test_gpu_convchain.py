@@ -411,3 +411,29 @@ def nets_resnet():
     from pytorch_quantize_impls_b200 import nets
     torch.manual_seed(3)
     return nets.resnet18_ternary()
+
+
+@pytest.mark.parametrize("fam", ["bin", "ter"])
+@pytest.mark.parametrize("split", [0.0, 0.5])
+def test_quantizer_beside_contraction_equals_plain(Q, fam, split):
+    """set_overlap_head(True): the quantizer runs on a side stream while the contraction's TMA producer follows its progress
+    counters (QtActQuant.ready -> QtEpilogue.a_ready) -- same bits as one kernel after the other."""
+    from pytorch_quantize_impls_b200 import _engine as eng
+    torch.manual_seed(21)
+    M, K, N = 4096, 2048, 384
+    lay = (Q.layers.LinearBin(K, N) if fam == "bin" else Q.layers.LinearTer(K, N)).cuda().eval()
+    act = Q.functions.BinaryConnect() if fam == "bin" else Q.functions.TernaryConnect()
+    pair = Q.fuse_inference(torch.nn.Sequential(act, lay))
+    x = torch.randn(M, K).cuda()
+    old = eng.OVERLAP_SPLIT[0]
+    with torch.no_grad(), Q.code_only_activations():
+        ref = pair(x).clone()
+        Q.set_overlap_head(True)
+        eng.OVERLAP_SPLIT[0] = split
+        try:
+            y = pair(x)
+            torch.cuda.synchronize()
+        finally:
+            Q.set_overlap_head(False)
+            eng.OVERLAP_SPLIT[0] = old
+    assert torch.equal(y, ref)
