@@ -653,6 +653,19 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
           if (n_tile + c * 32 < n_lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.residual + m * e.ld_res + n_tile + c * 32));
       }
     }
+    // the residual rows of the warp's FIRST chunk are requested before the accumulator wait: their L2 / HBM latency runs under
+    // this tile's MMAs instead of on the epilogue's critical path (ncu: a quarter of the epilogue warps' time in the second
+    // convs of the residual blocks was the scoreboard wait of `y += residual`)
+    float res[32];
+    const bool res_pre = has_res && row_ok && c_end > c_begin && n_tile + c_begin * 32 + 32 <= n_lim;
+    if (res_pre) {
+      const float4* rp = reinterpret_cast<const float4*>(e.residual + m * e.ld_res + n_tile + c_begin * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = __ldcs(rp + q);
+        res[4 * q] = t.x; res[4 * q + 1] = t.y; res[4 * q + 2] = t.z; res[4 * q + 3] = t.w;
+      }
+    }
     mbar_wait(tfull0 + 8u * as, aphase);
     tc_fence_after();
     uint32_t r[32];
@@ -686,8 +699,7 @@ __device__ __forceinline__ void epilogue_rq8(const CUtensorMap& map_out, const T
         }
         continue;
       }
-      float res[32];
-      if (has_res && row_ok && whole) {
+      if (has_res && row_ok && whole && !(res_pre && cidx == c_begin)) {
         const float4* rp = reinterpret_cast<const float4*>(e.residual + m * e.ld_res + n0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) image_planes_kernel(const float* __restri
 // one block per image row stages that array in shared memory (coalesced reads of the C channel rows, every value split
 // once), then every thread assembles 16-byte chunks of records from it -- consecutive threads write consecutive 16 bytes.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) image_windows_kernel(const float* __restrict__ x, int C, int H, int W, int P, int kw,
+__global__ void __launch_bounds__(128) image_windows_kernel(const float* __restrict__ x, int C, int H, int W, int P, int kw,
                                                             int sw, int pad_h, int pad_w, int Hp, int OW, int slots,
                                                             __nv_bfloat16* __restrict__ out) {
   extern __shared__ __nv_bfloat16 row[];          // [n_pix][P * C]
@@ -96,12 +96,18 @@ __global__ void __launch_bounds__(256) image_windows_kernel(const float* __restr
     const int ow = id / chunks, q = id - ow * chunks;
     const int base = ow * sw * pc + q * 8;
     uint32_t w4[4];
+    if ((base & 1) == 0 && q * 8 + 8 <= used) {          // aligned, fully used chunk: four 32-bit shared loads
+      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row) + (base >> 1);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int s0 = q * 8 + 2 * j;
-      const uint32_t e0 = s0 < used ? r16[base + 2 * j] : 0u;
-      const uint32_t e1 = s0 + 1 < used ? r16[base + 2 * j + 1] : 0u;
-      w4[j] = e0 | (e1 << 16);
+      for (int j = 0; j < 4; ++j) w4[j] = r32[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int s0 = q * 8 + 2 * j;
+        const uint32_t e0 = s0 < used ? r16[base + 2 * j] : 0u;
+        const uint32_t e1 = s0 + 1 < used ? r16[base + 2 * j + 1] : 0u;
+        w4[j] = e0 | (e1 << 16);
+      }
     }
     orow[id] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
   }
@@ -327,7 +333,7 @@ extern "C" int qt_image_windows(const float* x, int64_t B, int64_t C, int64_t H,
   const int64_t n_pix = (OW - 1) * stride_w + kw;
   const size_t smem = (size_t)(n_pix * planes * C) * 2;
   QT_REQUIRE(smem <= 48 * 1024 && B * Hp < (1ll << 31), "qt_image_windows: image row too wide for the shared-memory row buffer");
-  image_windows_kernel<<<(unsigned)(B * Hp), 256, smem, stream>>>(x, (int)C, (int)H, (int)W, planes, kw, stride_w, pad_h, pad_w, (int)Hp,
+  image_windows_kernel<<<(unsigned)(B * Hp), 128, smem, stream>>>(x, (int)C, (int)H, (int)W, planes, kw, stride_w, pad_h, pad_w, (int)Hp,
                                                                     (int)OW, slots, reinterpret_cast<__nv_bfloat16*>(out));
   QT_LAUNCH_CHECK();
   return QT_OK;
