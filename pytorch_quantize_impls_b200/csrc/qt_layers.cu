@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(128) image_windows_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ out) {
   extern __shared__ __nv_bfloat16 row[];          // [n_pix][P * C]
   const int pc = P * C, used = kw * pc, chunks = slots >> 3;
+  const int chunk_shift = 31 - __clz(chunks);
   const int n_pix = (OW - 1) * sw + kw;
   const int64_t bh = blockIdx.x;                  // b * Hp + hp
   const int hp = (int)(bh % Hp);
@@ -76,8 +77,8 @@ __global__ void __launch_bounds__(128) image_windows_kernel(const float* __restr
     return;
   }
   const float* xrow = x + ((b * C) * H + h) * (int64_t)W;
-  for (int idx = threadIdx.x; idx < C * n_pix; idx += blockDim.x) {
-    const int c = idx / n_pix, i = idx - c * n_pix;
+  for (int c = 0; c < C; ++c)
+  for (int i = threadIdx.x; i < n_pix; i += blockDim.x) {
     const int w = i - pad_w;
     const float v = (w >= 0 && w < W) ? __ldg(xrow + (int64_t)c * H * W + w) : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(128) image_windows_kernel(const float* __restr
   __syncthreads();
   const unsigned short* r16 = reinterpret_cast<const unsigned short*>(row);
   for (int id = threadIdx.x; id < OW * chunks; id += blockDim.x) {
-    const int ow = id / chunks, q = id - ow * chunks;
+    const int ow = id >> chunk_shift, q = id - (ow << chunk_shift);      // chunks is 2, 4 or 8
     const int base = ow * sw * pc + q * 8;
     uint32_t w4[4];
     if ((base & 1) == 0 && q * 8 + 8 <= used) {          // aligned, fully used chunk: four 32-bit shared loads
@@ -133,15 +134,14 @@ __device__ __forceinline__ uint32_t vmin4(uint32_t a, uint32_t b) { return UNSIG
 
 template <bool UNSIGNED, bool HAS_MIN>
 __global__ void __launch_bounds__(256) pool_codes_kernel(PoolArgs a) {
+  // grid: x = (b, oh) output rows, y = 256-thread slabs of the row's (ow, 16-channel vector) items
   const int cv = a.C >> 4;
-  const int64_t total = (int64_t)a.B * a.OH * a.OW * cv;
-  for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(id % cv);
-    int64_t t = id / cv;
-    const int ow = (int)(t % a.OW);
-    t /= a.OW;
-    const int oh = (int)(t % a.OH);
-    const int64_t b = t / a.OH;
+  const int item = (int)(blockIdx.y * blockDim.x + threadIdx.x);
+  if (item < a.OW * cv) {
+    const int ow = item / cv, v = item - ow * cv;
+    const int64_t bo = blockIdx.x;
+    const int oh = (int)(bo % a.OH);
+    const int64_t b = bo / a.OH;
     const uint32_t lo_id = UNSIGNED ? 0u : 0x80808080u, hi_id = UNSIGNED ? 0xFFFFFFFFu : 0x7F7F7F7Fu;
     uint4 mx = make_uint4(lo_id, lo_id, lo_id, lo_id), mn = make_uint4(hi_id, hi_id, hi_id, hi_id);
     const int h0 = oh * a.sh - a.ph, w0 = ow * a.sw - a.pw;
@@ -202,26 +202,31 @@ __device__ __forceinline__ int pq_code(int mode, float n, float v, float lo, flo
 
 // KH x KW > 0: compile-time window, every tap's load issued before the first compare (the run-time loops serialise one 16-byte
 // load per branch: a third of HBM speed on the 3 x 3 / 2 stem pool); KH == 0: run-time window.
+// Grid: x = (b, oh) output rows, y = 256-thread slabs of the row's (ow, 4-channel vector) items -- one 32-bit division per
+// thread instead of three 64-bit ones (the kernel was issue-bound on its index arithmetic), max.NaN.f32 for torch's
+// NaN-propagating max.
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
 template <int KH, int KW>
 __global__ void __launch_bounds__(256) pool_quant_f32_kernel(PoolQuantArgs a) {
   const int cv = a.C >> 2;
-  const int64_t total = (int64_t)a.B * a.OH * a.OW * cv;
+  const int item = (int)(blockIdx.y * blockDim.x + threadIdx.x);
   const float lo = (a.codes_kind == 1) ? -128.f : 0.f, hi = (a.codes_kind == 1) ? 127.f : 255.f;
   const float ninf = -__int_as_float(0x7f800000);
   bool ovf = false;
-  for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(id % cv);
-    int64_t t = id / cv;
-    const int ow = (int)(t % a.OW);
-    t /= a.OW;
-    const int oh = (int)(t % a.OH);
-    const int64_t b = t / a.OH;
+  if (item < a.OW * cv) {
+    const int ow = item / cv, v = item - ow * cv;
+    const int64_t bo = blockIdx.x;                 // b * OH + oh
+    const int oh = (int)(bo % a.OH);
+    const int64_t b = bo / a.OH;
     float4 m = make_float4(ninf, ninf, ninf, ninf);
     const int h0 = oh * a.sh - a.ph, w0 = ow * a.sw - a.pw;
-    // NaN-propagating like torch's max_pool2d
-#define QT_POOL_TAKE(q)                                                                              \
-    m.x = (q.x > m.x || q.x != q.x) ? q.x : m.x; m.y = (q.y > m.y || q.y != q.y) ? q.y : m.y;       \
-    m.z = (q.z > m.z || q.z != q.z) ? q.z : m.z; m.w = (q.w > m.w || q.w != q.w) ? q.w : m.w;
+    const float4* xb = reinterpret_cast<const float4*>(a.x + b * a.H * a.W * (int64_t)a.C) + v;
+#define QT_POOL_TAKE(q) m.x = max_nan(m.x, q.x); m.y = max_nan(m.y, q.y); m.z = max_nan(m.z, q.z); m.w = max_nan(m.w, q.w);
     if (KH > 0) {
       float4 q[(KH > 0 ? KH * KW : 1)];
 #pragma unroll
@@ -230,8 +235,7 @@ __global__ void __launch_bounds__(256) pool_quant_f32_kernel(PoolQuantArgs a) {
         for (int kx = 0; kx < KW; ++kx) {
           const int h = h0 + ky, w = w0 + kx;
           const bool in = h >= 0 && h < a.H && w >= 0 && w < a.W;
-          q[ky * KW + kx] = in ? __ldg(reinterpret_cast<const float4*>(a.x + (((b * a.H + h) * a.W + w) * (int64_t)a.C)) + v)
-                               : make_float4(ninf, ninf, ninf, ninf);
+          q[ky * KW + kx] = in ? __ldg(xb + (h * a.W + w) * cv) : make_float4(ninf, ninf, ninf, ninf);
         }
       }
 #pragma unroll
@@ -243,13 +247,13 @@ __global__ void __launch_bounds__(256) pool_quant_f32_kernel(PoolQuantArgs a) {
         for (int kx = 0; kx < a.kw; ++kx) {
           const int w = w0 + kx;
           if (w < 0 || w >= a.W) continue;
-          const float4 q = __ldg(reinterpret_cast<const float4*>(a.x + (((b * a.H + h) * a.W + w) * (int64_t)a.C)) + v);
+          const float4 q = __ldg(xb + (h * a.W + w) * cv);
           QT_POOL_TAKE(q)
         }
       }
     }
 #undef QT_POOL_TAKE
-    const int64_t o = ((b * a.OH + oh) * a.OW + ow) * (int64_t)a.C;
+    const int64_t o = (bo * a.OW + ow) * (int64_t)a.C;
     if (a.out) __stcs(reinterpret_cast<float4*>(a.out + o) + v, m);
     if (a.codes) {
       const int k0 = pq_code(a.mode, a.n, m.x, lo, hi, ovf), k1 = pq_code(a.mode, a.n, m.y, lo, hi, ovf);
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(256) pool_quant_f32_kernel(PoolQuantArgs a) {
           (uint32_t)(k0 & 0xff) | ((uint32_t)(k1 & 0xff) << 8) | ((uint32_t)(k2 & 0xff) << 16) | ((uint32_t)(k3 & 0xff) << 24);
     }
   }
-  if (a.overflow && ovf) atomicOr(a.overflow, 1);
+  if (a.overflow && __syncthreads_or(ovf) && threadIdx.x == 0) atomicOr(a.overflow, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -325,7 +329,7 @@ extern "C" int qt_image_windows(const float* x, int64_t B, int64_t C, int64_t H,
   cudaStream_t stream = (cudaStream_t)stream_;
   QT_REQUIRE(x && out, "qt_image_windows: null argument");
   QT_REQUIRE(planes >= 1 && planes <= 3 && C >= 1 && kw >= 1 && stride_w >= 1, "qt_image_windows: bad planes / kw / stride");
-  QT_REQUIRE(slots > 0 && slots % 8 == 0 && (int64_t)kw * planes * C <= slots, "qt_image_windows: kw * planes * C must fit the record's slots (a multiple of 8)");
+  QT_REQUIRE((slots == 16 || slots == 32 || slots == 64) && (int64_t)kw * planes * C <= slots, "qt_image_windows: kw * planes * C must fit the record's slots (16, 32 or 64)");
   QT_REQUIRE(B >= 0 && H > 0 && W > 0 && Hp > 0 && OW > 0 && pad_h >= 0 && pad_w >= 0, "qt_image_windows: bad shape");
   QT_REQUIRE(al(out, 16), "qt_image_windows: out must be 16-byte aligned");
   QT_REQUIRE(B * Hp * OW * slots < (1ll << 42) && C * H * W < (1ll << 31), "qt_image_windows: tensor too large");
@@ -360,7 +364,8 @@ extern "C" int qt_pool_codes(const void* x_nhwc, int is_unsigned, const QtPoolGe
   a.x = x_nhwc; a.out = out; a.use_min = use_min;
   a.B = (int)g->B; a.H = (int)g->H; a.W = (int)g->W; a.C = (int)g->C; a.OH = (int)g->OH; a.OW = (int)g->OW;
   a.kh = g->kh; a.kw = g->kw; a.sh = g->stride_h; a.sw = g->stride_w; a.ph = g->pad_h; a.pw = g->pad_w;
-  const unsigned grid = grid_for(g->B * g->OH * g->OW * (g->C / 16), 256);
+  QT_REQUIRE(ceil_div(g->OW * (g->C / 16), 256) <= 65535, "qt_pool_codes: image too large");
+  const dim3 grid((unsigned)(g->B * g->OH), (unsigned)ceil_div(g->OW * (g->C / 16), 256));
   if (is_unsigned) {
     if (use_min) pool_codes_kernel<true, true><<<grid, 256, 0, stream>>>(a);
     else pool_codes_kernel<true, false><<<grid, 256, 0, stream>>>(a);
@@ -403,7 +408,8 @@ extern "C" int qt_pool_quant_f32(const float* x_nhwc, const QtPoolGeom* g, float
   a.n = (mode == QT_Q_DOREFA) ? (float)((1 << bit_width) - 1) : 1.f;
   a.B = (int)g->B; a.H = (int)g->H; a.W = (int)g->W; a.C = (int)g->C; a.OH = (int)g->OH; a.OW = (int)g->OW;
   a.kh = g->kh; a.kw = g->kw; a.sh = g->stride_h; a.sw = g->stride_w; a.ph = g->pad_h; a.pw = g->pad_w;
-  const unsigned grid = grid_for(g->B * g->OH * g->OW * (g->C / 4), 256);
+  QT_REQUIRE(g->H * g->W * (g->C / 4) < (1ll << 31) && ceil_div(g->OW * (g->C / 4), 256) <= 65535, "qt_pool_quant_f32: image too large");
+  const dim3 grid((unsigned)(g->B * g->OH), (unsigned)ceil_div(g->OW * (g->C / 4), 256));
   if (g->kh == 3 && g->kw == 3) pool_quant_f32_kernel<3, 3><<<grid, 256, 0, stream>>>(a);
   else if (g->kh == 2 && g->kw == 2) pool_quant_f32_kernel<2, 2><<<grid, 256, 0, stream>>>(a);
   else pool_quant_f32_kernel<0, 0><<<grid, 256, 0, stream>>>(a);
