@@ -659,7 +659,8 @@ def _conv_wfold2(tag, pack, bias, geom, dims, requant, affine, out, residual, ke
         ck = requant.codes_kind(False)
         Op = max(O, requant.pad_channels)
         codes = torch.empty((B, OH, OW, Op), device=dev, dtype=torch.uint8 if ck == L.CODES_U8 else torch.int8)
-    rs_full = ops.patch_rowsum(tag.codes, not a_signed, geom, 0) if need_rs else None
+    # row sums of both output-column parities, parity-major (one strided copy instead of one per launch)
+    rs_par = ops.patch_rowsum(tag.codes, not a_signed, geom, 0).view(-1, 2).t().contiguous() if need_rs else None
     res_flat = None if residual is None else residual.permute(0, 2, 3, 1).reshape(-1)
     cs, bg = pack.col_scale, bias
     if requant is not None or affine is not None:
@@ -684,7 +685,7 @@ def _conv_wfold2(tag, pack, bias, geom, dims, requant, affine, out, residual, ke
                 rq0 = rq
             elif rq0.overflow is not None:
                 rq.c.overflow = rq0.c.overflow           # one sticky flag for both parities
-        rs = rs_full.view(-1, 2)[:, p].contiguous() if need_rs else None
+        rs = rs_par[p] if need_rs else None
         epi = ops.make_epi(out, bias=bg, col_scale=cs, row_sum=rs, acc_mul=2 if need_rs else 1, rs_mul=-255 if need_rs else 0,
                            scale=tag.scale * pack.wscale, out_offset=p * O, requant=rq, out_clamp=_out_clamp(affine, requant, keep_out),
                            out_mode=0, ldo=2 * O, nchw_inner=1,

@@ -21,10 +21,10 @@ static bool al(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p)
 template <int P>
 __global__ void __launch_bounds__(256) image_planes_kernel(const float* __restrict__ x, int B, int C, int H, int W, int Hp, int Wp,
                                                            int pad_h, int pad_w, int fh, int fw, __nv_bfloat16* __restrict__ out) {
-  const int64_t total = (int64_t)B * Hp * Wp;
-  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (int64_t)gridDim.x * blockDim.x) {
-    const int wp = (int)(pix % Wp);
-    const int64_t t = pix / Wp;
+  // grid: x = (b, hp) padded rows, y = 256-pixel slabs of the row (no per-pixel 64-bit divisions)
+  const int wp = (int)(blockIdx.y * blockDim.x + threadIdx.x);
+  if (wp < Wp) {
+    const int64_t t = blockIdx.x;
     const int hp = (int)(t % Hp);
     const int64_t b = t / Hp;
     const int h = hp - pad_h, w = wp - pad_w;
@@ -315,7 +315,8 @@ extern "C" int qt_image_planes(const float* x, int64_t B, int64_t C, int64_t H, 
   QT_REQUIRE(fold_h >= 1 && fold_w >= 1 && Hp % fold_h == 0 && Wp % fold_w == 0, "qt_image_planes: the folds must divide Hp / Wp");
   QT_REQUIRE(B * Hp * Wp < (1ll << 40) && H * W < (1ll << 31), "qt_image_planes: tensor too large");
   if (B == 0) return QT_OK;
-  const unsigned grid = grid_for(B * Hp * Wp, 256);
+  QT_REQUIRE(B * Hp < (1ll << 31) && ceil_div(Wp, 256) <= 65535, "qt_image_planes: image too large");
+  const dim3 grid((unsigned)(B * Hp), (unsigned)ceil_div(Wp, 256));
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (planes == 1) image_planes_kernel<1><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, fold_h, fold_w, o);
   else if (planes == 2) image_planes_kernel<2><<<grid, 256, 0, stream>>>(x, (int)B, (int)C, (int)H, (int)W, (int)Hp, (int)Wp, pad_h, pad_w, fold_h, fold_w, o);
