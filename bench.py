@@ -615,7 +615,10 @@ def run_ours(args):
         "e2e": {"value": round(e2e, 1), "unit": "GOPS", "ms_per_step": round(ms_e2e, 4),
                 "api": "pipeline.HostPipeline(net).run(pinned inputs, pinned outputs): H2D / kernels / D2H on 3 streams",
                 "ms_per_step_single_stream": round(ms_e2e_serial, 4),
-                "h2d_bytes_per_step": BATCH * DIMS[0] * 4, "d2h_bytes_per_step": BATCH * DIMS[-1] * 4},
+                "h2d_bytes_per_step": BATCH * DIMS[0] * 4, "d2h_bytes_per_step": BATCH * DIMS[-1] * 4,
+                "h2d_gbs_per_rank": round(BATCH * DIMS[0] * 4 / (ms_e2e * 1e-3) / 1e9, 1),
+                "note": "per-rank bytes; every rank moves its own shard over its own PCIe link, the ranks share the host's memory "
+                        "and PCIe switches (at 8 ranks the host side, not the GPUs, sets this number)"},
         "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
     }
     print(json.dumps(line), flush=True)
@@ -976,7 +979,8 @@ def run_cnn(args):
         "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
         "e2e": {"value": round(B * world / (ms_e2e * 1e-3), 1), "unit": "img/s", "ms_per_step": round(ms_e2e, 4),
                 "api": "pipeline.HostPipeline(net).run(pinned images, pinned logits): H2D / graph replay / D2H on 3 streams",
-                "h2d_bytes_per_step": int(x_host[0].numel() * 4), "d2h_bytes_per_step": B * 10 * 4},
+                "h2d_bytes_per_step": int(x_host[0].numel() * 4), "d2h_bytes_per_step": B * 10 * 4,
+                "h2d_gbs_per_rank": round(x_host[0].numel() * 4 / (ms_e2e * 1e-3) / 1e9, 1)},
         "gpu_launches": int(launches_per_forward * args.steps), "clocks": clocks,
         "extra": {"launches_per_forward": int(launches_per_forward),
                   "contraction_ms_by_shape": {"%s %dx%dx%d" % k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:12]}},

@@ -360,7 +360,7 @@ int qt_image_planes(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, 
                     int64_t Hp, int64_t Wp, int fold_h, int fold_w, void* out, void* stream);
 
 /* Row-window records of the same image, for filters whose whole row fits one record (kw * planes * C <= slots, slots * 2 bytes
- * = 32 / 64 / 128): out[b, hp, ow, slots] (bf16), slot kx * planes * C + p * C + c = part p of x[b, c, hp - pad_h,
+ * = 32 / 64 / 128 / 256): out[b, hp, ow, slots] (bf16), slot kx * planes * C + p * C + c = part p of x[b, c, hp - pad_h,
  * ow * stride_w - pad_w + kx], zero outside the image and in the unused slots.  The conv over the record grid has kw = 1,
  * stride_w = 1 and one k-block per filter ROW: the 7x7 / 2 stem of models/Resnet/Resnet_bin.py:68 reads 7 x 128 bytes per
  * output pixel instead of the 16 x 128 bytes of its 2 x 2 space-to-depth form (63 of 64 slots used instead of 441 of 1024) --

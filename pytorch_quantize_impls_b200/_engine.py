@@ -728,8 +728,8 @@ _first_layer_windows = [os.environ.get("QTB200_FIRST_LAYER_WINDOWS", "1") != "0"
 
 
 def set_first_layer_windows(flag):
-    """True (default): image layers whose filter row fits one 128-byte record (kw * parts * Cin <= 64 slots) read row-window
-    records (qt_image_windows) with one k-block per filter row; False: plane pixels with the space-to-depth folds only."""
+    """True (default): image layers whose filter row fits one record (kw * parts * Cin <= 128 slots) read row-window records
+    (qt_image_windows) with one or two k-blocks per filter row; False: plane pixels with the space-to-depth folds only."""
     _first_layer_windows[0] = bool(flag)
 
 
@@ -764,10 +764,11 @@ def _conv_first_layer(xf, pack, geom, O, Cin, epi_kw):
         return False
     B = xf.shape[0]
     P = 3 if 3 * Cin <= 16 else 2
-    if _first_layer_windows[0] and dw == 1 and kw * P * Cin <= 64 and kw > 1:
-        # row-window records: K = kh k-blocks of one record each (bytes per output pixel: kh * slots * 2)
+    if _first_layer_windows[0] and dw == 1 and kw * P * Cin <= 128 and kw > 1:
+        # row-window records: K = kh records (bytes per output pixel: kh * slots * 2; 128 slots = two 128-byte k-blocks per
+        # filter row: AlexNet's 11x11 / 4 reads 11 x 256 B per output instead of 33 x 128 B in the 1 x 4 space-to-depth form)
         used = kw * P * Cin
-        slots = 16 if used <= 16 else (32 if used <= 32 else 64)
+        slots = 16 if used <= 16 else (32 if used <= 32 else (64 if used <= 64 else 128))
         Hp = (OH - 1) * sh + (kh - 1) * dh + 1
         rec = ops.image_windows(xf, P, kw, sw, ph, pw, Hp, OW, slots)
         wz, ldw = _window_weights(pack, O, kh, kw, Cin, P, slots)

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) image_windows_kernel(const float* __restr
   __syncthreads();
   const unsigned short* r16 = reinterpret_cast<const unsigned short*>(row);
   for (int id = threadIdx.x; id < OW * chunks; id += blockDim.x) {
-    const int ow = id >> chunk_shift, q = id - (ow << chunk_shift);      // chunks is 2, 4 or 8
+    const int ow = id >> chunk_shift, q = id - (ow << chunk_shift);      // chunks is 2, 4, 8 or 16
     const int base = ow * sw * pc + q * 8;
     uint32_t w4[4];
     if ((base & 1) == 0 && q * 8 + 8 <= used) {          // aligned, fully used chunk: four 32-bit shared loads
@@ -330,7 +330,7 @@ extern "C" int qt_image_windows(const float* x, int64_t B, int64_t C, int64_t H,
   cudaStream_t stream = (cudaStream_t)stream_;
   QT_REQUIRE(x && out, "qt_image_windows: null argument");
   QT_REQUIRE(planes >= 1 && planes <= 3 && C >= 1 && kw >= 1 && stride_w >= 1, "qt_image_windows: bad planes / kw / stride");
-  QT_REQUIRE((slots == 16 || slots == 32 || slots == 64) && (int64_t)kw * planes * C <= slots, "qt_image_windows: kw * planes * C must fit the record's slots (16, 32 or 64)");
+  QT_REQUIRE((slots == 16 || slots == 32 || slots == 64 || slots == 128) && (int64_t)kw * planes * C <= slots, "qt_image_windows: kw * planes * C must fit the record's slots (16, 32, 64 or 128)");
   QT_REQUIRE(B >= 0 && H > 0 && W > 0 && Hp > 0 && OW > 0 && pad_h >= 0 && pad_w >= 0, "qt_image_windows: bad shape");
   QT_REQUIRE(al(out, 16), "qt_image_windows: out must be 16-byte aligned");
   QT_REQUIRE(B * Hp * OW * slots < (1ll << 42) && C * H * W < (1ll << 31), "qt_image_windows: tensor too large");

@@ -50,7 +50,7 @@ def test_image_windows_hold_the_filter_rows(Q):
     torch.manual_seed(1)
     B, C, H, W = 2, 3, 11, 19
     x = (torch.randn(B, C, H, W) * 3).cuda()
-    for P, kw, sw, pw, slots in ((3, 7, 2, 3, 64), (3, 3, 1, 1, 32), (2, 3, 2, 0, 32), (1, 5, 1, 2, 16)):
+    for P, kw, sw, pw, slots in ((3, 7, 2, 3, 64), (3, 3, 1, 1, 32), (2, 3, 2, 0, 32), (1, 5, 1, 2, 16), (3, 11, 4, 2, 128)):
         ph = 2
         OW = (W + 2 * pw - kw) // sw + 1
         Hp = H + 2 * ph - 1                                  # the last padded row is never read by a strided filter: dropped
