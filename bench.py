@@ -751,15 +751,17 @@ class LaunchTimer:
 
     def __enter__(self):
         from pytorch_quantize_impls_b200 import _engine as eng
-        self._eng, self._first = eng, eng._conv_first_layer
+        self._eng = eng
 
-        def first_layer(xf, pack, geom, O, Cin, epi_kw, _fn=eng._conv_first_layer):
-            self._real_k = geom[0] * geom[1] * Cin           # kh * kw * Cin of the fp32 convolution
+        self._conv2d = eng.conv2d
+
+        def conv2d(x, pack, bias, weight_shape, *a, _fn=eng.conv2d, **k):
+            self._real_k = int(weight_shape[1] * weight_shape[2] * weight_shape[3])       # Cin/groups * kh * kw of the convolution
             try:
-                return _fn(xf, pack, geom, O, Cin, epi_kw)
+                return _fn(x, pack, bias, weight_shape, *a, **k)
             finally:
                 self._real_k = None
-        eng._conv_first_layer = first_layer
+        eng.conv2d = conv2d
         for name, mnk in self.NAMES.items():
             fn = getattr(self.ops, name)
             self.orig[name] = fn
@@ -770,7 +772,7 @@ class LaunchTimer:
                 r = _fn(*a, **k)
                 e.record()
                 M, N, K = (int(v) for v in _mnk(a))
-                if _name == "conv_bf16" and self._real_k:
+                if _name in ("conv_bf16", "conv_i8") and self._real_k and K != self._real_k:
                     self.executed_k[(_name, M, N, int(self._real_k))] = K
                     K = int(self._real_k)
                 self.ev.append((_name, M, N, K, s, e))
@@ -781,7 +783,7 @@ class LaunchTimer:
     def __exit__(self, *exc):
         for name, fn in self.orig.items():
             setattr(self.ops, name, fn)
-        self._eng._conv_first_layer = self._first
+        self._eng.conv2d = self._conv2d
         return False
 
     def summary(self):
@@ -960,9 +962,10 @@ def run_cnn(args):
                 "traffic": None, "algorithmic_bytes": None}
     if k_exec:
         roofline["executed"] = {"K": k_exec, "tflops": round(achieved * k_exec / K, 1),
-                                "why": "the fp32 image enters as 3 bf16 parts per value (24 significant bits) in padded slots: the "
-                                       "tensor pipe executes K=%d per output for the K=%d of the fp32 convolution; `achieved` "
-                                       "counts the algorithmic flops" % (k_exec, K)}
+                                "why": "`achieved` counts the flops of the convolution (K = Cin/groups * kh * kw = %d); the tensor "
+                                       "pipe executes K = %d per output: channel pitch padded to whole 128-byte k-blocks / zero "
+                                       "taps of a folded filter, or (first layer) 3 bf16 parts per fp32 value in padded slots"
+                                       % (K, k_exec)}
     ips = B * world / (ms_step * 1e-3)
     line = {
         "metric": "images_per_sec", "value": round(ips, 1), "unit": "img/s", "n_gpus": world, "steps": args.steps,
