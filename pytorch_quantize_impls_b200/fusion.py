@@ -450,10 +450,13 @@ class FusedBasicBlock(nn.Module):
     so the residual stream is read once and written once per block (plus 1 byte of codes) instead of the add / clamp / quantizer
     passes.  Outside code-only inference it is the wrapped block."""
 
-    def __init__(self, block, next_spec=None):
+    def __init__(self, block, next_spec=None, next_reads_fp32=True):
         super().__init__()
         self.block = block
         self._next = next_spec                 # _qt_spec of the next block's input quantizer (None: no codes needed)
+        # False: the next block has a shortcut conv (it reads this block's output through its input quantizer only), so the
+        # fp32 block output is not written at all -- only the codes
+        self._next_reads_fp32 = next_reads_fp32
         self._spec2 = None
 
     def _parts(self):
@@ -486,7 +489,11 @@ class FusedBasicBlock(nn.Module):
         b = self.block
         spec_in = getattr(b.q_in, "_qt_spec", None)
         lo, hi = _clamp_range(b.clip)
-        ok = (parts is not None and eng._code_only[0] and not torch.is_grad_enabled() and x.dim() == 4 and x.is_cuda
+        tag = eng.get_tag(x)
+        # a code-only input (no fp32 tensor) is enough when the shortcut is a conv on the codes
+        codes_only_in = bool(x.is_meta and tag is not None and parts is not None and parts[2] is not None)
+        ok = (parts is not None and eng._code_only[0] and not torch.is_grad_enabled() and x.dim() == 4
+              and (x.is_cuda or codes_only_in)
               and x.dtype == torch.float32 and spec_in is not None and spec_in[0] == "dorefa" and 2 <= spec_in[1] <= 8
               and lo is not NotImplemented and x.shape[1] % 16 == 0
               and (self._next is None or (self._next[0] == "dorefa" and 2 <= self._next[1] <= 8)))
@@ -494,11 +501,16 @@ class FusedBasicBlock(nn.Module):
             f1, f2, fs = parts
             ok = _bn_ready(f1.bn) and _bn_ready(f2.bn) and (fs is None or _bn_ready(fs.bn)) and f2.act is None \
                 and f2.layer.out_channels % 32 == 0
+        abits = spec_in[1] if ok else 0
+        tag_ok = tag is not None and tag.layout == "nhwc" and tag.kind == "dorefa" and tag.bit_width == abits
+        if ok and x.is_meta and not tag_ok:
+            ok = False
         if not ok:
+            if x.is_meta:
+                raise RuntimeError("FusedBasicBlock: received a code-only activation it cannot consume (the producer block was "
+                                   "told that this block reads codes only)")
             return b(x)
-        abits = spec_in[1]
-        tag = eng.get_tag(x)
-        if not (tag is not None and tag.layout == "nhwc" and tag.kind == "dorefa" and tag.bit_width == abits):
+        if not tag_ok:
             if not ops.is_channels_last(x):
                 x = x.contiguous(memory_format=torch.channels_last)
             tag = ops.quant_act_nhwc(x, L.Q_DOREFA, bit_width=abits, codes_kind=L.CODES_U8 if abits == 8 else L.CODES_I8,
@@ -509,12 +521,14 @@ class FusedBasicBlock(nn.Module):
         xq = eng.attach_tag(torch.empty(x.shape, dtype=torch.float32, device="meta"), tag)
         c1 = f1(xq)
         if eng.get_tag(c1) is None or not c1.is_meta:
+            if x.is_meta:
+                raise RuntimeError("FusedBasicBlock: the first conv declined the fused epilogue on a code-only input")
             return b(x)                        # the first conv declined the fused epilogue: plain block
         res = x if fs is None else fs.layer._forward_affine(xq, fs._make_spec(), out_format="nhwc")
         plain, rq = self._make_spec2(f2, lo, hi)
         if rq is not None:
             try:
-                return f2.layer._forward_requant(c1, rq, out_format="nhwc", residual=res, keep_out=True)
+                return f2.layer._forward_requant(c1, rq, out_format="nhwc", residual=res, keep_out=self._next_reads_fp32)
             except eng.RequantUnsupported:
                 pass
         return f2.layer._forward_affine(c1, plain, out_format="nhwc", residual=res)
@@ -541,6 +555,14 @@ def _is_quant_layer(m):
 
 def _is_flatten(m):
     return isinstance(m, nn.Flatten) and m.start_dim == 1 and m.end_dim == -1 or type(m).__name__ == "Flatten" and not list(m.parameters())
+
+
+def _codes_only_consumer(blk):
+    """The block can run from its input CODES alone: fusable parts (checked again at run time) and a conv shortcut."""
+    if blk.shortcut is None or len(blk.shortcut) != 1 or not isinstance(blk.shortcut[0], FusedLayerBN):
+        return False
+    return (len(blk.branch1) == 1 and isinstance(blk.branch1[0], FusedLayerQuant)
+            and len(blk.branch2) == 1 and isinstance(blk.branch2[0], FusedLayerBN))
 
 
 def _is_block(m):
@@ -664,7 +686,9 @@ def fuse_inference(module):
             continue
         if _is_block(m):
             nspec = getattr(nxt.q_in, "_qt_spec", None) if (nxt is not None and _is_block(nxt)) else None
-            res.append(FusedBasicBlock(m, nspec))
+            # the next block adds `shortcut(q_in(x))` instead of x itself: it never reads this block's fp32 output
+            reads_fp32 = not (nspec is not None and nxt.shortcut is not None and _codes_only_consumer(nxt))
+            res.append(FusedBasicBlock(m, nspec, reads_fp32))
             i += 1
             continue
         res.append(m)

@@ -42,6 +42,8 @@ def test_resnet_blocks_and_unknown_modules_are_left_alone():
     assert names(net.stem) == ["FusedConvPool"] and isinstance(net.stem[0].inner.act, nn.Hardtanh)
     assert set(names(net.layers)) == {"FusedBasicBlock"}
     assert net.layers[0]._next == ("dorefa", 8) and net.layers[-1]._next is None
+    # blocks in front of a down-sampling block (conv shortcut) hand over codes only
+    assert [b._next_reads_fp32 for b in net.layers] == [True, False, True, False, True, False, True, True]
     blk = net.layers[2].block                 # first down-sampling block
     assert names(blk.branch1) == ["FusedLayerQuant"] and names(blk.branch2) == ["FusedLayerBN"]
     assert names(blk.shortcut) == ["FusedLayerBN"] and isinstance(net.linear, nn.Linear)

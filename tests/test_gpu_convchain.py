@@ -294,8 +294,17 @@ def test_fused_basic_blocks_match_plain_blocks(Q):
         assert cos > 0.999, cos
         # teacher-forced single block: same input -> same output up to the fold rounding
         b0 = fused[0]
+        # the block in front of a down-sampling block (conv shortcut) writes codes only: its fp32 output has no reader
+        assert b0._next_reads_fp32 is False and fused[1]._next_reads_fp32 is True and fused[2]._next_reads_fp32 is True
         with Q.code_only_activations():
-            y0 = b0(x)
+            c0 = b0(x)
+            assert c0.is_meta and c0._qt_codes is not None
+            b0._next_reads_fp32 = True
+            try:
+                y0 = b0(x)
+            finally:
+                b0._next_reads_fp32 = False
+        assert torch.equal(c0._qt_codes.codes, y0._qt_codes.codes)
         r0 = b0.block(x)
         assert float((y0 - r0).abs().max()) <= 5e-2 and float(((y0 - r0).abs() > 1e-5).float().mean()) <= 5e-3
         assert y0._qt_codes is not None and torch.equal(y0._qt_codes.codes.float().permute(0, 3, 1, 2), torch.round(255 * y0))
