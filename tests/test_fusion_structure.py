@@ -71,3 +71,30 @@ def test_network_configs_fuse_into_code_chains():
         assert fused.count("FlattenCodes") == 1 and fused[-1] == "LinearDorefa"
     head = Q.fuse_inference(nn.Sequential(F.BinaryConnect(), L.LinearBin(4096, 4096)))
     assert names(head) == ["FusedActLayer"]
+
+
+def test_resnet_head_falls_back_to_the_two_modules_off_the_gpu():
+    """FusedAvgLinear is one batch-invariant kernel on CUDA inference; anywhere else it must be avg-pool -> flatten -> Linear."""
+    torch.manual_seed(0)
+    net = Q.fuse_inference(nets.resnet18_ternary())
+    head = net.__dict__["_fused_head"]
+    x = torch.randn(3, 512, 4, 5)
+    with torch.no_grad():
+        assert torch.equal(head(x), net.linear(net.avg(x).flatten(1)))
+    assert "_fused_head" not in net.state_dict() and all(not k.startswith("_fused_head") for k in net.state_dict())
+
+
+def test_overflow_flag_policy():
+    """The sticky lane-overflow flag exists only where somebody can look at it (ops.set_strict)."""
+    from pytorch_quantize_impls_b200 import _lib as lib
+    from pytorch_quantize_impls_b200 import _ops as ops
+    dev = torch.device("cpu")
+    try:
+        ops.set_strict(False)
+        assert ops._overflow_flag(dev, lib.Q_DOREFA) is not None and ops._overflow_flag(dev, lib.Q_SIGN) is None
+        assert ops._overflow_flag(dev, lib.Q_DOREFA, guaranteed=True) is None
+        ops.set_strict("off")
+        assert ops._overflow_flag(dev, lib.Q_DOREFA) is None
+    finally:
+        ops.set_strict(False)
+    assert ops.clamp_guarantees_lane(lib.CODES_U8, 8, 0.0, 1.0) and not ops.clamp_guarantees_lane(lib.CODES_I8, 8, 0.0, 1.0)
