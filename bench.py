@@ -922,6 +922,10 @@ def run_cnn(args):
     rel = float((got - ref).abs().max() / ref.abs().max())
     parity = {"cosine_vs_oracle": cos, "rel_err_vs_oracle": rel, "argmax_agreement": float((got.argmax(1) == ref.argmax(1)).float().mean()),
               "images": nb, "graph_replay_equals_eager": graph_equals_eager,
+              "weight_codes": ("DoReFa weight codes (nnQuantWeight): the device evaluates tanh in fp64, CPU torch uses Sleef's 1-ulp tanhf -- "
+                               "<= 1 level on <= 0.1 % of the weights may differ (tests/test_gpu_parity.py::test_weight_quantizer), which "
+                               "is part of the end-to-end difference above") if "dorefa" in cfg["builder"] else
+                              "ternary weight codes are bit-exact (thresholds at +-0.5)",
               "what": "logits of the timed mode (fuse_inference + code-only + graph replay) vs the oracle-backed CPU twin with the same "
                       "state_dict.  End to end a deep k-bit net is not a 1e-3 object (a pre-activation on a rounding boundary flips "
                       "a code and the flips cascade -- the reference's own CUDA path diverges from its CPU path the same way); the "
