@@ -354,8 +354,9 @@ int qt_conv_bf16(const void* x_nhwc, const QtConvGeom* g, const void* w, int64_t
  * Space-to-depth: a fold_h x fold_w block of pixels is stored as ONE super pixel of fold_h * fold_w * 16 slots,
  *   out[b, hp / fold_h, wp / fold_w, ((hp % fold_h) * fold_w + wp % fold_w) * 16 + slot]     (fold_h = fold_w = 1: [B, Hp, Wp, 16]),
  * so that a stride-f filter of k taps per axis becomes a stride-1 filter of floor((k - 1) / f) + 1 super taps: a 7x7 / 2 stem
- * reads 4 x 4 taps of 128-byte super pixels instead of 49 taps of 32 bytes, an 11x11 / 4 stem (fold 1 x 4) 11 x 3 taps -- the TMA
- * im2col engine works per pixel row, so fewer, fatter taps are what keeps the tensor pipe fed. */
+ * reads 4 x 4 taps of 128-byte super pixels instead of 49 taps of 32 bytes, an 11x11 / 4 stem (fold 1 x 4) 11 x 3 taps: whole
+ * 128-byte k-blocks, a fraction of the TMA / MMA issues per output.  (Filters whose row fits a record use qt_image_windows,
+ * which moves fewer bytes through L2.) */
 int qt_image_planes(const float* x, int64_t B, int64_t C, int64_t H, int64_t W, int planes, int pad_h, int pad_w,
                     int64_t Hp, int64_t Wp, int fold_h, int fold_w, void* out, void* stream);
 
